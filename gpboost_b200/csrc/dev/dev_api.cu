@@ -1,0 +1,412 @@
+// Device engine for the Vecchia-approximated Gaussian process: C ABI of include/gpboost_b200_dev.h.
+// sm_100a only; there is no CPU fallback (every entry fails loudly without a CUDA device).
+#include "../../../include/gpboost_b200_dev.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "knn.cuh"
+#include "vecchia_factor.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return -1;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess) {                                                                     \
+      return fail(std::string("CUDA error at " __FILE__ ":") + std::to_string(__LINE__) + ": " +    \
+                  cudaGetErrorString(err__));                                                       \
+    }                                                                                               \
+  } while (0)
+
+// ---- small kernels around the factor kernel -------------------------------------------------------
+
+// y_ord[i] = y_orig[perm[i]]  (the per-cluster re-ordering SetY does, re_model_template.h:6185-6200)
+__global__ void gather_perm_kernel(const double* __restrict__ src, const int32_t* __restrict__ perm,
+                                   double* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[perm[i]];
+}
+
+// fixed-order reduction of the per-warp partial sums: deterministic for a given grid
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int64_t nrows, double* __restrict__ out) {
+  __shared__ double sh[256];
+  for (int k = 0; k < gpb::kNumAcc; ++k) {
+    double s = 0.;
+    for (int64_t r = threadIdx.x; r < nrows; r += blockDim.x) s += partials[r * gpb::kNumAcc + k];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k] = sh[0];
+    __syncthreads();
+  }
+}
+
+// y_aux = B^T u with u = D^-1 B y (CalcYAux, re_model_template.h:9772), gather form over the CSC view of
+// B's pattern: one warp per column, deterministic; result scattered back to the original observation order.
+__global__ void bt_apply_kernel(const double* __restrict__ A, const double* __restrict__ u,
+                                const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
+                                const int32_t* __restrict__ perm, double* __restrict__ out_orig, int64_t n, int m,
+                                int64_t row_begin, int64_t row_end) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < n; j += nwarps) {
+    const int32_t b = colptr[j], e = colptr[j + 1];
+    double s = 0.;
+    for (int32_t p = b + lane; p < e; p += 32) {
+      const int32_t pos = csc_pos[p];
+      s -= A[pos] * u[pos / m];
+    }
+    s = gpb::warp_sum(s);
+    if (lane == 0) {
+      if (j >= row_begin && j < row_end) s += u[j];  // unit diagonal of B
+      out_orig[perm[j]] = s;
+    }
+  }
+}
+
+__global__ void fill_kernel(double* p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+using FactorKernel = void (*)(const gpb::FactorArgs);
+
+template <int COV, int MODE>
+FactorKernel pick_dim(int d) {
+  return d == 2 ? gpb::vecchia_factor_kernel<COV, MODE, 2> : gpb::vecchia_factor_kernel<COV, MODE, 0>;
+}
+template <int COV>
+FactorKernel pick_mode(int mode, int d) {
+  switch (mode) {
+    case gpb::MODE_NLL: return pick_dim<COV, gpb::MODE_NLL>(d);
+    case gpb::MODE_STORE: return pick_dim<COV, gpb::MODE_STORE>(d);
+    default: return pick_dim<COV, gpb::MODE_GRAD>(d);
+  }
+}
+FactorKernel pick_kernel(int cov, int mode, int d) {
+  switch (cov) {
+    case gpb::COV_EXPONENTIAL: return pick_mode<gpb::COV_EXPONENTIAL>(mode, d);
+    case gpb::COV_MATERN15: return pick_mode<gpb::COV_MATERN15>(mode, d);
+    case gpb::COV_MATERN25: return pick_mode<gpb::COV_MATERN25>(mode, d);
+    default: return pick_mode<gpb::COV_GAUSSIAN>(mode, d);
+  }
+}
+
+}  // namespace
+
+struct gpbdev_vecchia {
+  int device = 0;
+  int64_t n = 0;
+  int d = 0, m = 0;
+  int64_t row_begin = 0, row_end = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double* coords = nullptr;   // n x d
+  int32_t* nn = nullptr;      // n x m
+  int32_t* perm = nullptr;    // n
+  double* y_in = nullptr;     // n staging (original order)
+  double* y = nullptr;        // n ordered
+  double* A = nullptr;        // n x m   (lazy)
+  double* Dinv = nullptr;     // n       (lazy)
+  double* u = nullptr;        // n       (lazy)
+  double* yaux = nullptr;     // n       (lazy, original order)
+  int32_t* colptr = nullptr;  // n + 1   (lazy)
+  int32_t* csc_pos = nullptr; // nnz     (lazy)
+  double* partials = nullptr;
+  double* sums = nullptr;     // kNumAcc (device)
+  double* sums_host = nullptr;  // pinned
+  double* stage_host = nullptr; // pinned n doubles
+  double* flush = nullptr;
+  int64_t flush_n = 0;
+  int grid = 0;
+  int64_t launches = 0;
+  bool factor_stored = false;
+  std::vector<int32_t> nn_host;  // kept for the lazy CSC build
+};
+
+namespace {
+
+int ensure_store_buffers(gpbdev_vecchia* h) {
+  if (h->A) return 0;
+  CUDA_TRY(cudaMalloc(&h->A, sizeof(double) * h->n * h->m));
+  CUDA_TRY(cudaMalloc(&h->Dinv, sizeof(double) * h->n));
+  CUDA_TRY(cudaMalloc(&h->u, sizeof(double) * h->n));
+  CUDA_TRY(cudaMemsetAsync(h->A, 0, sizeof(double) * h->n * h->m, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->u, 0, sizeof(double) * h->n, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->Dinv, 0, sizeof(double) * h->n, h->stream));
+  return 0;
+}
+
+// CSC view of the pattern of B restricted to this shard's rows: for column j the positions i*m+k with nn[i,k]==j
+int ensure_csc(gpbdev_vecchia* h) {
+  if (h->colptr) return 0;
+  const int64_t n = h->n;
+  const int m = h->m;
+  if (h->nn_host.empty()) {
+    h->nn_host.resize((size_t)n * m);
+    CUDA_TRY(cudaMemcpy(h->nn_host.data(), h->nn, sizeof(int32_t) * n * m, cudaMemcpyDeviceToHost));
+  }
+  std::vector<int32_t> colptr(n + 1, 0);
+  for (int64_t i = h->row_begin; i < h->row_end; ++i)
+    for (int k = 0; k < m; ++k) {
+      const int32_t j = h->nn_host[(size_t)i * m + k];
+      if (j >= 0) ++colptr[j + 1];
+    }
+  for (int64_t j = 0; j < n; ++j) colptr[j + 1] += colptr[j];
+  std::vector<int32_t> pos((size_t)colptr[n]);
+  std::vector<int32_t> fill(colptr.begin(), colptr.end() - 1);
+  for (int64_t i = h->row_begin; i < h->row_end; ++i)
+    for (int k = 0; k < m; ++k) {
+      const int32_t j = h->nn_host[(size_t)i * m + k];
+      if (j >= 0) pos[fill[j]++] = (int32_t)(i * m + k);
+    }
+  CUDA_TRY(cudaMalloc(&h->colptr, sizeof(int32_t) * (n + 1)));
+  CUDA_TRY(cudaMalloc(&h->csc_pos, sizeof(int32_t) * std::max<size_t>(pos.size(), 1)));
+  CUDA_TRY(cudaMemcpy(h->colptr, colptr.data(), sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->csc_pos, pos.data(), sizeof(int32_t) * pos.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->yaux, sizeof(double) * n));
+  return 0;
+}
+
+int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int mode) {
+  if (cov_type < 0 || cov_type > 3) return fail("gpbdev_vecchia_eval: unknown covariance id");
+  if (mode < 0 || mode > 2) return fail("gpbdev_vecchia_eval: unknown mode");
+  if (!(var > 0.) || !(range > 0.)) return fail("gpbdev_vecchia_eval: covariance parameters must be positive");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (mode == gpb::MODE_STORE) {
+    if (ensure_store_buffers(h)) return -1;
+  }
+  gpb::FactorArgs a;
+  a.coords = h->coords; a.nn = h->nn; a.y = h->y;
+  a.A = h->A; a.Dinv = h->Dinv; a.w = h->u;
+  a.partials = h->partials;
+  a.n = h->n; a.row_begin = h->row_begin; a.row_end = h->row_end;
+  a.m = h->m; a.d = h->d; a.var = var; a.range = range;
+  FactorKernel k = pick_kernel(cov_type, mode, h->d);
+  const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 96);
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  k<<<h->grid, gpb::kWarpsPerBlock * 32, smem, h->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)h->grid * gpb::kWarpsPerBlock, h->sums);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  if (mode == gpb::MODE_STORE) h->factor_stored = true;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gpbdev_last_error(void) { return g_last_error.c_str(); }
+
+int gpbdev_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, int m, const double* coords_ordered,
+                          const int32_t* perm, const int32_t* nn, int64_t row_begin, int64_t row_end) {
+  if (!out || !coords_ordered || !perm) return fail("gpbdev_vecchia_create: null argument");
+  if (n <= 0 || d <= 0 || d > 16) return fail("gpbdev_vecchia_create: need n > 0 and 1 <= dim <= 16");
+  if (m < 1 || m > gpb::kMaxNeighbors)
+    return fail("gpbdev_vecchia_create: num_neighbors must be in [1, " + std::to_string(gpb::kMaxNeighbors) +
+                "] for the B200 Vecchia engine");
+  if ((int64_t)n * m >= (int64_t)2147483647) return fail("gpbdev_vecchia_create: n * num_neighbors exceeds int32 positions");
+  if (row_begin < 0 || row_end > n || row_begin > row_end) return fail("gpbdev_vecchia_create: bad row shard");
+  if (gpbdev_device_count() <= device)
+    return fail("gpbdev_vecchia_create: no CUDA device " + std::to_string(device) + " — the B200 engine has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(device));
+  gpbdev_vecchia* h = new gpbdev_vecchia();
+  h->device = device; h->n = n; h->d = d; h->m = m; h->row_begin = row_begin; h->row_end = row_end;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  CUDA_TRY(cudaMalloc(&h->coords, sizeof(double) * n * d));
+  CUDA_TRY(cudaMalloc(&h->nn, sizeof(int32_t) * n * m));
+  CUDA_TRY(cudaMalloc(&h->perm, sizeof(int32_t) * n));
+  CUDA_TRY(cudaMalloc(&h->y_in, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&h->y, sizeof(double) * n));
+  CUDA_TRY(cudaMemset(h->y, 0, sizeof(double) * n));
+  // persistent grid: resident CTAs per SM x SM count (4 CTAs of 4 warps; 3 in gradient mode still fills the SMs)
+  h->grid = h->num_sms * 4;
+  const int64_t rows = row_end - row_begin;
+  const int64_t max_blocks = (rows + gpb::kWarpsPerBlock - 1) / gpb::kWarpsPerBlock;
+  if (h->grid > max_blocks) h->grid = (int)std::max<int64_t>(max_blocks, 1);
+  CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * h->grid * gpb::kWarpsPerBlock * gpb::kNumAcc));
+  CUDA_TRY(cudaMalloc(&h->sums, sizeof(double) * gpb::kNumAcc));
+  CUDA_TRY(cudaMallocHost(&h->sums_host, sizeof(double) * gpb::kNumAcc));
+  CUDA_TRY(cudaMallocHost(&h->stage_host, sizeof(double) * n));
+  CUDA_TRY(cudaMemcpy(h->coords, coords_ordered, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->perm, perm, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  if (nn) {
+    CUDA_TRY(cudaMemcpy(h->nn, nn, sizeof(int32_t) * n * m, cudaMemcpyHostToDevice));
+    h->nn_host.assign(nn, nn + (size_t)n * m);
+  } else {
+    // rank of every point in the sorted coordinate sums (Vecchia_utils.cpp:775-786). The permutation of
+    // equal sums is whatever std::sort yields, so the same library call is made on the same input.
+    std::vector<double> csum((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      double sacc = 0.;
+      for (int k = 0; k < d; ++k) sacc += coords_ordered[i * d + k];
+      csum[(size_t)i] = sacc;
+    }
+    std::vector<int> sort_sum((size_t)n);
+    std::iota(sort_sum.begin(), sort_sum.end(), 0);
+    std::sort(sort_sum.begin(), sort_sum.end(), [&csum](int i1, int i2) { return csum[i1] < csum[i2]; });
+    std::vector<int32_t> pos((size_t)n);
+    for (int64_t r = 0; r < n; ++r) pos[(size_t)sort_sum[(size_t)r]] = (int32_t)r;
+    int32_t* pos_dev = nullptr;
+    CUDA_TRY(cudaMalloc(&pos_dev, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMemcpy(pos_dev, pos.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    std::string err;
+    const int nl = gpb::knn_vecchia_device(h->coords, coords_ordered, n, d, m, pos_dev, h->nn, h->stream, h->num_sms, &err);
+    cudaFree(pos_dev);
+    if (nl < 0) { gpbdev_vecchia_free(h); return fail("gpbdev_vecchia_create: device neighbour search failed: " + err); }
+    h->launches += nl;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  *out = h;
+  return 0;
+}
+
+int gpbdev_vecchia_free(gpbdev_vecchia_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->coords); cudaFree(h->nn); cudaFree(h->perm); cudaFree(h->y_in); cudaFree(h->y);
+  cudaFree(h->A); cudaFree(h->Dinv); cudaFree(h->u); cudaFree(h->yaux); cudaFree(h->colptr); cudaFree(h->csc_pos);
+  cudaFree(h->partials); cudaFree(h->sums); cudaFree(h->flush);
+  cudaFreeHost(h->sums_host); cudaFreeHost(h->stage_host);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int gpbdev_vecchia_get_nn(gpbdev_vecchia_t h, int32_t* nn_host) {
+  if (!h || !nn_host) return fail("gpbdev_vecchia_get_nn: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(nn_host, h->nn, sizeof(int32_t) * h->n * h->m, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gpbdev_vecchia_set_y_device(gpbdev_vecchia_t h, const double* y_dev) {
+  if (!h || !y_dev) return fail("gpbdev_vecchia_set_y_device: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gather_perm_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(y_dev, h->perm, h->y, h->n);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  h->factor_stored = false;
+  return 0;
+}
+
+int gpbdev_vecchia_set_y(gpbdev_vecchia_t h, const double* y_host) {
+  if (!h || !y_host) return fail("gpbdev_vecchia_set_y: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // caller memory is pageable: stage through the engine's pinned buffer so the H2D runs at link speed
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::memcpy(h->stage_host, y_host, sizeof(double) * h->n);
+  CUDA_TRY(cudaMemcpyAsync(h->y_in, h->stage_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  return gpbdev_vecchia_set_y_device(h, h->y_in);
+}
+
+int gpbdev_vecchia_eval_async(gpbdev_vecchia_t h, int cov_type, double var, double range, int mode) {
+  if (!h) return fail("gpbdev_vecchia_eval: null handle");
+  return launch_eval(h, cov_type, var, range, mode);
+}
+
+int gpbdev_vecchia_eval(gpbdev_vecchia_t h, int cov_type, double var, double range, int mode, double* out) {
+  if (!h || !out) return fail("gpbdev_vecchia_eval: null argument");
+  if (launch_eval(h, cov_type, var, range, mode)) return -1;
+  CUDA_TRY(cudaMemcpyAsync(h->sums_host, h->sums, sizeof(double) * gpb::kNumAcc, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::memcpy(out, h->sums_host, sizeof(double) * gpb::kNumAcc);
+  return 0;
+}
+
+int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host) {
+  if (!h || !yaux_host) return fail("gpbdev_vecchia_yaux: null argument");
+  if (!h->factor_stored) return fail("gpbdev_vecchia_yaux: call gpbdev_vecchia_eval(mode=STORE) first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (ensure_csc(h)) return -1;
+  bt_apply_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->A, h->u, h->colptr, h->csc_pos, h->perm, h->yaux, h->n,
+                                                         h->m, h->row_begin, h->row_end);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  CUDA_TRY(cudaMemcpyAsync(h->stage_host, h->yaux, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::memcpy(yaux_host, h->stage_host, sizeof(double) * h->n);
+  return 0;
+}
+
+int gpbdev_vecchia_get_factor(gpbdev_vecchia_t h, double* A_host, double* Dinv_host) {
+  if (!h || !A_host || !Dinv_host) return fail("gpbdev_vecchia_get_factor: null argument");
+  if (!h->factor_stored) return fail("gpbdev_vecchia_get_factor: call gpbdev_vecchia_eval(mode=STORE) first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(A_host, h->A, sizeof(double) * h->n * h->m, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(Dinv_host, h->Dinv, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gpbdev_vecchia_timer_start(gpbdev_vecchia_t h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  return 0;
+}
+int gpbdev_vecchia_timer_stop(gpbdev_vecchia_t h, float* ms) {
+  if (!h || !ms) return fail("null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+int gpbdev_vecchia_sync(gpbdev_vecchia_t h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int64_t gpbdev_vecchia_launch_count(gpbdev_vecchia_t h) { return h ? h->launches : 0; }
+
+int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->flush) {
+    h->flush_n = (int64_t)(256 << 20) / sizeof(double);  // 256 MiB > 126 MB L2
+    CUDA_TRY(cudaMalloc(&h->flush, sizeof(double) * h->flush_n));
+  }
+  fill_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->flush, h->flush_n, 1.0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// Vecchia neighbour search on the device: for every ordered point i, the m nearest among points j < i.
+//
+// Replaces find_nearest_neighbors_Vecchia_fast / find_nearest_neighbors_fast_internal
+// (src/GPBoost/Vecchia_utils.cpp:733-985, :1029-1093) and the reference's own CUDA variant
+// find_neighbors_kernel (src/GPBoost/cuda_kernel.cu:440-494: one THREAD per query walking the sorted
+// coordinate sums, serial insertion sort). The result must be the same int32 sets in the same order:
+//   * squared distances use the reference's arithmetic: sequential sum of unfused products
+//     (Eigen row redux, x86-64 baseline has no FMA)  -> __dmul_rn / __dadd_rn here;
+//   * ties in squared distance are resolved like the reference's walk: candidates are visited alternately
+//     below/above the query in the order of the sorted coordinate sums, a later candidate only displaces on
+//     strictly smaller distance (:1066) and the insertion sort is stable (utils.h:250-262). That is the
+//     lexicographic order (sed, visit_rank) with visit_rank = 2*|pos_j - pos_i| + (pos_j > pos_i), where pos
+//     is the rank in the sorted sums (computed by the caller with the same std::sort the reference uses).
+//
+// B200 design: a uniform cell list (counting/radix sort by cell, stable so that every cell lists its points
+// by increasing index => the "j < i" constraint is a prefix of each cell), one WARP per query scanning
+// Chebyshev rings of cells outward until the m-th best distance is inside the scanned radius; the running
+// top-m lives one-entry-per-lane and is updated by ballot/shuffle insertion. Early points (few candidates,
+// huge search radius) are done by a warp-cooperative brute force.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+#include <string>
+
+namespace gpb {
+
+struct KnnGrid {
+  double lo[3];
+  double inv_h[3];
+  double hmin;
+  int g[3];
+  int dim;
+};
+
+__device__ __forceinline__ double knn_sqdist(const double* __restrict__ a, const double* __restrict__ b, int d) {
+  double s = 0.;
+  for (int k = 0; k < d; ++k) {
+    const double t = __dsub_rn(a[k], b[k]);
+    s = __dadd_rn(s, __dmul_rn(t, t));
+  }
+  return s;
+}
+
+// lexicographic (sed, rank) "a before b"
+__device__ __forceinline__ bool knn_before(double sa, int ra, double sb, int rb) {
+  return sa < sb || (sa == sb && ra < rb);
+}
+
+// one entry per lane, ascending over lanes; insert (s, r, id) if it sorts before the entry of lane m-1
+__device__ __forceinline__ void knn_insert(double& ks, int& kr, int& ki, double s, int r, int id, int lane, int m) {
+  const unsigned before = __ballot_sync(0xffffffffu, knn_before(ks, kr, s, r) || (ks == s && kr == r));
+  const int posn = __popc(before);  // entries are sorted: the first posn lanes stay
+  if (posn >= m) return;
+  const double us = __shfl_up_sync(0xffffffffu, ks, 1);
+  const int ur = __shfl_up_sync(0xffffffffu, kr, 1);
+  const int ui = __shfl_up_sync(0xffffffffu, ki, 1);
+  if (lane > posn) { ks = us; kr = ur; ki = ui; }
+  else if (lane == posn) { ks = s; kr = r; ki = id; }
+}
+
+__device__ __forceinline__ int knn_rank(int pj, int pi) {
+  const int dlt = pj - pi;
+  return dlt < 0 ? (-2 * dlt) : (2 * dlt + 1);
+}
+
+// offer one candidate per lane (valid flag), serialised through the warp in lane order
+__device__ __forceinline__ void knn_offer(double& ks, int& kr, int& ki, bool valid, double s, int r, int id, int lane, int m) {
+  // threshold = entry of lane m-1
+  double ts = __shfl_sync(0xffffffffu, ks, m - 1);
+  int tr = __shfl_sync(0xffffffffu, kr, m - 1);
+  unsigned mask = __ballot_sync(0xffffffffu, valid && knn_before(s, r, ts, tr));
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const double cs = __shfl_sync(0xffffffffu, s, src);
+    const int cr = __shfl_sync(0xffffffffu, r, src);
+    const int ci = __shfl_sync(0xffffffffu, id, src);
+    knn_insert(ks, kr, ki, cs, cr, ci, lane, m);
+  }
+}
+
+__global__ void knn_cell_id_kernel(const double* __restrict__ coords, int64_t n, KnnGrid gr, uint32_t* __restrict__ cell,
+                                   int32_t* __restrict__ idx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    for (int k = gr.dim - 1; k >= 0; --k) {
+      int ck = (int)floor((coords[i * gr.dim + k] - gr.lo[k]) * gr.inv_h[k]);
+      ck = min(max(ck, 0), gr.g[k] - 1);
+      c = c * (uint32_t)gr.g[k] + (uint32_t)ck;
+    }
+    cell[i] = c;
+    idx[i] = (int32_t)i;
+  }
+}
+
+__global__ void knn_cell_start_kernel(const uint32_t* __restrict__ sorted_cell, int64_t n, int64_t ncell,
+                                      int32_t* __restrict__ cell_start) {
+  // cell_start[c] = first position p with sorted_cell[p] >= c ; cell_start[ncell] = n
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cur = p < n ? (int64_t)sorted_cell[p] : ncell;
+    const int64_t prev = p > 0 ? (int64_t)sorted_cell[p - 1] : -1;
+    for (int64_t c = prev + 1; c <= cur; ++c) cell_start[c] = (int32_t)p;
+  }
+}
+
+// queries i in [q_begin, q_end): brute force over all j < i (early points) — warp per query
+__global__ void knn_brute_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos, int d, int m,
+                                 int64_t q_begin, int64_t q_end, int32_t* __restrict__ nn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = q_begin + warp; i < q_end; i += nwarps) {
+    if (i <= m) {  // Vecchia_utils.cpp:788-813: all predecessors, in index order
+      if (lane < m) nn[i * m + lane] = lane < i ? lane : -1;
+      continue;
+    }
+    double ks = INFINITY; int kr = 0x7fffffff, ki = -1;
+    const int pi = pos[i];
+    for (int64_t j0 = 0; j0 < i; j0 += 32) {
+      const int64_t j = j0 + lane;
+      const bool valid = j < i;
+      double s = 0.; int r = 0;
+      if (valid) { s = knn_sqdist(coords + j * d, coords + i * d, d); r = knn_rank(pos[j], pi); }
+      knn_offer(ks, kr, ki, valid, s, r, (int)j, lane, m);
+    }
+    if (lane < m) nn[i * m + lane] = ki;
+  }
+}
+
+// queries i in [q_begin, n): cell-list search — warp per query, DIM in {1,2,3}
+__global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos,
+                                const int32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted_idx,
+                                KnnGrid gr, int m, int64_t q_begin, int64_t n, int32_t* __restrict__ nn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int d = gr.dim;
+  for (int64_t i = q_begin + warp; i < n; i += nwarps) {
+    double ks = INFINITY; int kr = 0x7fffffff, ki = -1;
+    const int pi = pos[i];
+    int qc[3] = {0, 0, 0};
+    for (int k = 0; k < d; ++k) {
+      int ck = (int)floor((coords[i * d + k] - gr.lo[k]) * gr.inv_h[k]);
+      qc[k] = min(max(ck, 0), gr.g[k] - 1);
+    }
+    const int rmax = max(max(gr.g[0], gr.g[1]), gr.g[2]);
+    for (int r = 0; r <= rmax; ++r) {
+      // cells at Chebyshev distance exactly r: enumerate the (2r+1)^d cube, keep the shell
+      const int w = 2 * r + 1;
+      const int64_t ncube = d == 1 ? w : (d == 2 ? (int64_t)w * w : (int64_t)w * w * w);
+      // 2-D shortcut: walk only the 8r ring cells
+      const int64_t ncand = (d == 2 && r > 0) ? 8 * (int64_t)r : ncube;
+      for (int64_t t0 = 0; t0 < ncand; t0 += 32) {
+        const int64_t t = t0 + lane;
+        int32_t pb = 0, pe = 0;
+        if (t < ncand) {
+          int dx = 0, dy = 0, dz = 0;
+          if (d == 2 && r > 0) {
+            const int side = (int)(t / (2 * r)), off = (int)(t % (2 * r));
+            if (side == 0) { dx = -r + off; dy = -r; }
+            else if (side == 1) { dx = r; dy = -r + off; }
+            else if (side == 2) { dx = r - off; dy = r; }
+            else { dx = -r; dy = r - off; }
+          } else {
+            dx = (int)(t % w) - r;
+            dy = d > 1 ? (int)((t / w) % w) - r : 0;
+            dz = d > 2 ? (int)(t / ((int64_t)w * w)) - r : 0;
+          }
+          const bool shell = max(max(abs(dx), abs(dy)), abs(dz)) == r;
+          const int cx = qc[0] + dx, cy = qc[1] + dy, cz = qc[2] + dz;
+          if (shell && cx >= 0 && cx < gr.g[0] && cy >= 0 && cy < gr.g[1] && cz >= 0 && cz < gr.g[2]) {
+            const int64_t c = ((int64_t)cz * gr.g[1] + cy) * gr.g[0] + cx;
+            pb = cell_start[c];
+            pe = cell_start[c + 1];
+          }
+        }
+        // lock-step scan of each lane's cell; the valid part of a cell is a prefix (indices ascending)
+        while (__any_sync(0xffffffffu, pb < pe)) {
+          bool valid = false;
+          double s = 0.; int rk = 0; int id = -1;
+          if (pb < pe) {
+            id = sorted_idx[pb];
+            if (id < i) {
+              valid = true;
+              s = knn_sqdist(coords + (int64_t)id * d, coords + i * d, d);
+              rk = knn_rank(pos[id], pi);
+              ++pb;
+            } else {
+              pb = pe;
+            }
+          }
+          knn_offer(ks, kr, ki, valid, s, rk, id, lane, m);
+        }
+      }
+      // every unscanned point is farther than r*hmin in some coordinate (safety margin for the cell rounding)
+      const double ts = __shfl_sync(0xffffffffu, ks, m - 1);
+      const double reach = (double)r * gr.hmin * (1. - 1e-9);
+      if (ts < reach * reach) break;
+    }
+    if (lane < m) nn[i * m + lane] = ki;
+  }
+}
+
+// Returns the number of kernels launched, or -1 with *err set. coords: device n x d row-major (Vecchia order).
+inline int knn_vecchia_device(const double* coords_dev, const double* coords_host, int64_t n, int d, int m,
+                              const int32_t* pos_dev, int32_t* nn_dev, cudaStream_t stream, int num_sms, std::string* err) {
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
+    return true;
+  };
+  int launches = 0;
+  const int64_t brute_end = std::min<int64_t>(n, d <= 3 ? 4096 : n);
+  {
+    const int blocks = (int)std::min<int64_t>((brute_end + 7) / 8, (int64_t)num_sms * 8);
+    knn_brute_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(coords_dev, pos_dev, d, m, 0, brute_end, nn_dev);
+    if (!ck(cudaGetLastError(), "knn_brute_kernel")) return -1;
+    ++launches;
+  }
+  if (brute_end >= n) return launches;
+  // ---- cell list over all points (host computes the bounding box: one pass over n x d doubles)
+  KnnGrid gr;
+  gr.dim = d;
+  double vol = 1.;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int k = 0; k < d; ++k) { lo[k] = coords_host[k]; hi[k] = coords_host[k]; }
+  for (int64_t i = 0; i < n; ++i)
+    for (int k = 0; k < d; ++k) {
+      const double v = coords_host[i * d + k];
+      lo[k] = std::min(lo[k], v); hi[k] = std::max(hi[k], v);
+    }
+  int active = 0;
+  for (int k = 0; k < d; ++k) { if (hi[k] > lo[k]) { vol *= (hi[k] - lo[k]); ++active; } }
+  const double target_cells = std::max(1.0, (double)n / 8.0);
+  double h = active > 0 ? std::pow(vol / target_cells, 1.0 / active) : 1.0;
+  if (!(h > 0.)) h = 1.0;
+  int64_t ncell = 1;
+  gr.hmin = h;
+  for (int k = 0; k < 3; ++k) {
+    if (k < d && hi[k] > lo[k]) {
+      int gk = (int)std::min<double>(std::ceil((hi[k] - lo[k]) / h), 1 << 20);
+      gk = std::max(gk, 1);
+      gr.g[k] = gk; gr.lo[k] = lo[k]; gr.inv_h[k] = 1.0 / h;
+    } else {
+      gr.g[k] = 1; gr.lo[k] = k < d ? lo[k] : 0.; gr.inv_h[k] = 0.;  // degenerate axis: one slab
+    }
+    ncell *= gr.g[k];
+  }
+  if (ncell >= ((int64_t)1 << 31)) { *err = "cell grid too large"; return -1; }
+  uint32_t *cell = nullptr, *cell_sorted = nullptr;
+  int32_t *idx = nullptr, *idx_sorted = nullptr, *cell_start = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  bool ok = ck(cudaMalloc(&cell, sizeof(uint32_t) * n), "cudaMalloc") && ck(cudaMalloc(&cell_sorted, sizeof(uint32_t) * n), "cudaMalloc") &&
+            ck(cudaMalloc(&idx, sizeof(int32_t) * n), "cudaMalloc") && ck(cudaMalloc(&idx_sorted, sizeof(int32_t) * n), "cudaMalloc") &&
+            ck(cudaMalloc(&cell_start, sizeof(int32_t) * (ncell + 1)), "cudaMalloc");
+  if (ok) {
+    knn_cell_id_kernel<<<num_sms * 8, 256, 0, stream>>>(coords_dev, n, gr, cell, idx);
+    ok = ck(cudaGetLastError(), "knn_cell_id_kernel");
+    ++launches;
+  }
+  int bits = 1;
+  while (((int64_t)1 << bits) < ncell) ++bits;
+  if (ok) ok = ck(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, cell, cell_sorted, idx, idx_sorted, (int)n, 0, bits, stream), "cub size");
+  if (ok) ok = ck(cudaMalloc(&tmp, tmp_bytes), "cudaMalloc");
+  if (ok) {
+    ok = ck(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, cell, cell_sorted, idx, idx_sorted, (int)n, 0, bits, stream), "cub sort");
+    launches += 4;
+  }
+  if (ok) {
+    knn_cell_start_kernel<<<num_sms * 8, 256, 0, stream>>>(cell_sorted, n, ncell, cell_start);
+    ok = ck(cudaGetLastError(), "knn_cell_start_kernel");
+    ++launches;
+  }
+  if (ok) {
+    knn_grid_kernel<<<num_sms * 16, 128, 0, stream>>>(coords_dev, pos_dev, cell_start, idx_sorted, gr, m, brute_end, n, nn_dev);
+    ok = ck(cudaGetLastError(), "knn_grid_kernel");
+    ++launches;
+  }
+  if (ok) ok = ck(cudaStreamSynchronize(stream), "knn sync");
+  cudaFree(cell); cudaFree(cell_sorted); cudaFree(idx); cudaFree(idx_sorted); cudaFree(cell_start); cudaFree(tmp);
+  return ok ? launches : -1;
+}
+
+}  // namespace gpb

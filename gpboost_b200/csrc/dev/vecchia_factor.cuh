@@ -1,0 +1,300 @@
+// Vecchia factor kernel for sm_100a — one warp per observation, matrix rows in registers.
+//
+// Replaces the reference's per-observation loop in CalcCovFactorGradientVecchia
+// (src/GPBoost/Vecchia_utils.cpp:1461-1684) together with the covariance-block construction it calls
+// (include/GPBoost/re_comp.h:1476-1503 -> cov_fcts.h:635-755, gradients cov_fcts.h:1073-1218) and, fused
+// behind it, the reductions the Gaussian likelihood and its gradient need
+// (re_model_template.h:9957-9964 quad form, :2947 log-det, :1988-2010 gradient).
+//
+// Formulation (not a translation of the reference's Eigen code):
+//   * points 0..q-1 = neighbours N(i), point q = observation i itself. The (q+2) x (q+2) matrix
+//         [ S     s     y_N ]      S = Sigma_NN + I (nugget 1 on the transformed scale)
+//         [ s^T   1+v   y_i ]      s = Sigma_iN,  v = sigma_1^2 / sigma^2
+//         [ y_N^T y_i    *  ]
+//     is factorised by ONE right-looking Cholesky with lane j owning row j (registers a[0..31]).
+//     Then  D_i = pivot q before the square root,  z = L[q][0..q) = L_NN^-1 s,
+//           L[q+1][q] = (B y)_i / sqrt(D_i)   =>  (By)_i^2 / D_i = L[q+1][q]^2 :
+//     the likelihood needs NO triangular solve and B is never materialised.
+//   * distances are recomputed from gathered coordinates (the reference keeps 7.2 GB of saved
+//     neighbour distances at n=1e6); the 465 pair covariances are evaluated with a balanced circulant
+//     schedule (lane l handles pairs (l, l+t mod P)) and staged through shared memory, which then
+//     doubles as the column store of L (stride 33 doubles: conflict-free row loads, broadcasts and
+//     transposed reads).
+//   * A_i = L_NN^-T z (and w = S^-1 y_N in gradient mode) by a lane-per-unknown back substitution
+//     reading L by columns from shared memory.
+//   * gradient mode uses the adjoint identities  dD_k = b^T dSigma~_k b,  (dB_k y)_i = -b^T dSigma~_k w~
+//     with b = [-A_i, 1], w~ = [w, 0]: no derivative matrix is factorised or stored; the range-derivative
+//     pair values stay in the registers of the lane that computed them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpb {
+
+enum CovType : int { COV_EXPONENTIAL = 0, COV_MATERN15 = 1, COV_MATERN25 = 2, COV_GAUSSIAN = 3 };
+enum FactorMode : int { MODE_NLL = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kLd = 33;            // column stride (doubles) of the shared matrix
+constexpr int kMaxNeighbors = 30;  // q + 2 rows must fit one warp
+// per-warp accumulators: 0 sum (By)^2/D  1 sum log D  2 #non-positive D
+//   gradient mode: 3,4 sum u_k u   5,6 sum u^2 dD_k   7,8 sum dD_k / D   (k = 0 variance, 1 range)
+constexpr int kNumAcc = 9;
+
+struct FactorArgs {
+  const double* coords;   // n x d row-major, Vecchia order
+  const int32_t* nn;      // n x m, -1 padded
+  const double* y;        // n, Vecchia order
+  double* A;              // n x m  (MODE_STORE): A_i, i.e. -B[i, nn]
+  double* Dinv;           // n      (MODE_STORE)
+  double* w;              // n      (MODE_STORE): D^-1 (B y)
+  double* partials;       // num_warps_total x kNumAcc
+  int64_t n;
+  int64_t row_begin, row_end;  // shard of observations handled by this launch
+  int m;
+  int d;
+  double var;     // sigma_1^2 / sigma^2
+  double range;   // transformed range (cov_fcts.h:485-552)
+};
+
+// covariance value and d/dlog(range) on the transformed scale — closed forms cov_fcts.h:2100-2118,2154;
+// gradient constants cov_fcts.h:2183-2206, element formulas :2535-2563.
+template <int COV, bool GRAD>
+__device__ __forceinline__ double cov_eval(double dist, double var, double range, double& grad) {
+  double val;
+  if (COV == COV_EXPONENTIAL) {
+    val = var * exp(-range * dist);
+    if (GRAD) grad = -range * dist * val;
+  } else if (COV == COV_MATERN15) {
+    const double rd = range * dist;
+    const double e = exp(-rd);
+    val = var * (1. + rd) * e;
+    if (GRAD) grad = -var * range * range * dist * dist * e;
+  } else if (COV == COV_MATERN25) {
+    const double rd = range * dist;
+    const double e = exp(-rd);
+    val = var * (1. + rd + rd * rd / 3.) * e;
+    if (GRAD) grad = -var * range * range / 3. * dist * dist * (1. + rd) * e;
+  } else {
+    val = var * exp(-range * dist * dist);
+    if (GRAD) grad = -range * dist * dist * val;
+  }
+  return val;
+}
+
+__device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <int COV, int MODE, int DIM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 3 : 4)
+vecchia_factor_kernel(const FactorArgs p) {
+  constexpr bool GRAD = (MODE == MODE_GRAD);
+  constexpr bool SOLVE = (MODE != MODE_NLL);
+  extern __shared__ __align__(16) double smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int dim = DIM > 0 ? DIM : p.d;
+  // per-warp shared layout: L/S matrix 32 x kLd | points 32 x dim | ys 32 | xb 32 | xw 32
+  const int per_warp = 32 * kLd + 32 * dim + 96;
+  double* S = smem_raw + (size_t)wib * per_warp;
+  double* pts = S + 32 * kLd;
+  double* ys = pts + 32 * dim;
+  double* xb = ys + 32;
+  double* xw = xb + 32;
+
+  const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const int m = p.m;
+  const double var = p.var, range = p.range;
+
+  double acc[kNumAcc];
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.;
+
+  for (int64_t i = p.row_begin + gwarp; i < p.row_end; i += nwarps) {
+    // ---- gather: neighbour ids, coordinates, responses
+    const int q = i < m ? (int)i : m;  // Vecchia_utils.cpp:788-813: the first m+1 points condition on all predecessors
+    const int P = q + 1;               // points (neighbours + the observation)
+    int64_t src = -1;
+    if (lane < q) src = p.nn[i * m + lane];
+    else if (lane == q) src = i;
+    double yv = 0.;
+    if (src >= 0) {
+      yv = p.y[src];
+      if (DIM == 2) {
+        const double2 c = *reinterpret_cast<const double2*>(p.coords + src * 2);
+        *reinterpret_cast<double2*>(pts + lane * 2) = c;
+      } else {
+        for (int k = 0; k < dim; ++k) pts[lane * dim + k] = p.coords[src * dim + k];
+      }
+    }
+    ys[lane] = yv;
+    __syncwarp();
+
+    // ---- pair covariances, circulant schedule: lane l <-> point (l + t) mod P, t = 1..P/2
+    double gpair[16];
+    double my[DIM > 0 ? DIM : 1];
+    if (DIM > 0) {
+#pragma unroll
+      for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) my[k] = pts[lane * dim + k];
+    }
+    const int half = (P - 1) >> 1;  // t <= half: every lane; t == P/2 (P even): lanes < P/2
+#pragma unroll
+    for (int t = 1; t <= 16; ++t) {
+      if (GRAD) gpair[t - 1] = 0.;
+      if (t <= (P >> 1)) {  // warp-uniform
+        int o = lane + t;
+        if (o >= P) o -= P;
+        const bool valid = lane < P && (t <= half || lane < (P >> 1));
+        if (valid) {
+          double d2 = 0.;
+          if (DIM > 0) {
+#pragma unroll
+            for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) {
+              const double df = my[k] - pts[o * dim + k];
+              d2 += df * df;
+            }
+          } else {
+            for (int k = 0; k < dim; ++k) {
+              const double df = pts[lane * dim + k] - pts[o * dim + k];
+              d2 += df * df;
+            }
+          }
+          const double dist = sqrt(d2);
+          double g = 0.;
+          const double val = cov_eval<COV, GRAD>(dist, var, range, g);
+          const int r = max(lane, o), c = min(lane, o);
+          S[c * kLd + r] = val;
+          if (GRAD) gpair[t - 1] = g;
+        }
+      }
+    }
+    // diagonal (variance + nugget 1; Vecchia_utils.cpp:1601 / :1411,1563) and the response row q+1
+    if (lane < P) {
+      S[lane * kLd + lane] = var + 1.;
+      S[lane * kLd + (q + 1)] = yv;
+    }
+    __syncwarp();
+
+    // ---- row j of the lower triangle -> registers of lane j
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = (c <= q) ? S[c * kLd + lane] : 0.;
+    __syncwarp();
+
+    // ---- right-looking Cholesky, pivots 0..q (row q+1 is eliminated but never a pivot)
+    double Di = 1.;
+#pragma unroll
+    for (int k = 0; k <= kMaxNeighbors; ++k) {
+      if (k <= q) {  // warp-uniform
+        const double dkk = shfl_d(a[k], k);
+        if (k == q) Di = dkk;
+        const double rs = rsqrt(dkk);
+        const double ljk = a[k] * rs;
+        a[k] = ljk;
+        S[k * kLd + lane] = ljk;  // column k of L (rows < k hold don't-care values)
+        __syncwarp();
+        if (k + 1 <= q) a[k + 1] -= ljk * S[k * kLd + k + 1];
+#pragma unroll
+        for (int c = k + 2; c + 1 < 32; c += 2) {
+          if (c <= q) {
+            const double2 l2 = *reinterpret_cast<const double2*>(&S[k * kLd + c]);
+            a[c] -= ljk * l2.x;
+            a[c + 1] -= ljk * l2.y;  // column q+1 is never read: harmless when c == q
+          }
+        }
+      }
+    }
+    // lane q+1 now holds L[q+1][q] = (By)_i / sqrt(D_i) in a[q]; fetch it without dynamic indexing
+    const double r_over_sd = S[q * kLd + (q + 1)];  // written by lane q+1 in step k = q
+    const double quad = r_over_sd * r_over_sd;      // (By)_i^2 / D_i
+    const bool bad = !(Di > 0.);
+    if (lane == 0) {
+      acc[0] += quad;
+      acc[1] += log(Di);
+      acc[2] += bad ? 1. : 0.;
+    }
+
+    if (SOLVE) {
+      // ---- back substitution L_NN^T x = z for z = L[q][.] (-> A_i) and, in gradient mode, L[q+1][.] (-> w)
+      // lane c owns unknown c; L[r][c] is read by columns: S[c*kLd + r]
+      double xa = (lane < q) ? S[lane * kLd + q] : 0.;
+      double xwv = (GRAD && lane < q) ? S[lane * kLd + (q + 1)] : 0.;
+      const double dinv = (lane < q) ? 1. / S[lane * kLd + lane] : 0.;
+#pragma unroll
+      for (int r = kMaxNeighbors - 1; r >= 0; --r) {
+        if (r < q) {  // warp-uniform
+          const double fa = shfl_d(xa * dinv, r);
+          double fw = 0.;
+          if (GRAD) fw = shfl_d(xwv * dinv, r);
+          if (lane == r) { xa = fa; if (GRAD) xwv = fw; }
+          if (lane < r) {
+            const double lrc = S[lane * kLd + r];
+            xa -= lrc * fa;
+            if (GRAD) xwv -= lrc * fw;
+          }
+        }
+      }
+      // xa = A_i[lane] for lane < q
+      const double Dinv_i = 1. / Di;
+      const double By = r_over_sd * sqrt(Di);
+      if (MODE == MODE_STORE) {
+        if (lane < m) p.A[i * m + lane] = (lane < q) ? xa : 0.;
+        if (lane == 0) { p.Dinv[i] = Dinv_i; p.w[i] = By * Dinv_i; }
+      }
+      if (GRAD) {
+        // b = [-A, 1], w~ = [w, 0] over the P points
+        __syncwarp();
+        xb[lane] = (lane < q) ? -xa : (lane == q ? 1. : 0.);
+        xw[lane] = (lane < q) ? xwv : 0.;
+        __syncwarp();
+        // adjoint contractions over this lane's pairs: b^T G b and b^T G w~ (G symmetric, zero diagonal)
+        double bgb = 0., bgw = 0.;
+        const double bl = xb[lane], wl = xw[lane];
+#pragma unroll
+        for (int t = 1; t <= 16; ++t) {
+          if (t <= (P >> 1)) {
+            int o = lane + t;
+            if (o >= P) o -= P;
+            const double g = gpair[t - 1];  // 0 for invalid pairs
+            const double bo = xb[o], wo = xw[o];
+            bgb += g * (bl * bo);
+            bgw += g * (bl * wo + bo * wl);
+          }
+        }
+        bgb = 2. * warp_sum(bgb);
+        bgw = warp_sum(bgw);
+        // variance parameter (dSigma~ = Sigma~ without nugget): dD_0 = v - A.A - A.s ; (dB_0 y)_i = -A.w
+        // A.s = 1 + v - D  (Vecchia_utils.cpp:1623)
+        double aa = (lane < q) ? xa * xa : 0.;
+        double aw = (lane < q) ? xa * xwv : 0.;
+        aa = warp_sum(aa);
+        aw = warp_sum(aw);
+        if (lane == 0) {
+          const double u = By * Dinv_i;  // (D^-1 B y)_i
+          const double dD0 = var - aa - (1. + var - Di);
+          const double dD1 = bgb;
+          const double uk0 = -aw;
+          const double uk1 = -bgw;
+          acc[3] += uk0 * u;
+          acc[4] += uk1 * u;
+          acc[5] += u * u * dD0;
+          acc[6] += u * u * dD1;
+          acc[7] += dD0 * Dinv_i;
+          acc[8] += dD1 * Dinv_i;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumAcc; ++k) p.partials[gwarp * kNumAcc + k] = acc[k];
+  }
+}
+
+}  // namespace gpb

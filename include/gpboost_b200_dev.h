@@ -1,0 +1,97 @@
+/*
+ * gpboost_b200 — device-engine C ABI (plain pointers and sizes, no C++/torch types).
+ *
+ * This is the seam the host-side REModel (gpboost_b200/csrc/host) calls; each entry cites the
+ * reference function(s) whose work it replaces (paths relative to fabsig/GPBoost @ c93fa49).
+ * All functions return 0 on success, non-zero on failure; the message is available from
+ * gpbdev_last_error() (thread-local, like LGBM_GetLastError — include/LightGBM/c_api.h:1837-1849).
+ * There is NO CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef GPBOOST_B200_DEV_H_
+#define GPBOOST_B200_DEV_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPBDEV_EXPORT __attribute__((visibility("default")))
+
+/* covariance function ids (closed forms of include/GPBoost/cov_fcts.h:2100-2118, :2154) */
+enum { GPBDEV_COV_EXPONENTIAL = 0, GPBDEV_COV_MATERN15 = 1, GPBDEV_COV_MATERN25 = 2, GPBDEV_COV_GAUSSIAN = 3 };
+/* evaluation modes of gpbdev_vecchia_eval */
+enum { GPBDEV_MODE_NLL = 0, GPBDEV_MODE_STORE = 1, GPBDEV_MODE_GRAD = 2 };
+/* sums returned by gpbdev_vecchia_eval (out[GPBDEV_NUM_SUMS]) */
+enum {
+  GPBDEV_SUM_QUAD = 0,    /* y^T Psi^-1 y = sum (By)_i^2 / D_i      re_model_template.h:9957-9964 */
+  GPBDEV_SUM_LOGDET = 1,  /* log|Psi| = sum log D_i                  re_model_template.h:2947      */
+  GPBDEV_SUM_NBAD = 2,    /* #(D_i <= 0)                             Vecchia_utils.cpp:1685-1698   */
+  GPBDEV_SUM_UKU0 = 3, GPBDEV_SUM_UKU1 = 4,   /* sum (dB_k y)_i u_i, u = D^-1 B y   re_model_template.h:2002-2004 */
+  GPBDEV_SUM_UDU0 = 5, GPBDEV_SUM_UDU1 = 6,   /* sum u_i^2 dD_k,i                                               */
+  GPBDEV_SUM_TR0 = 7, GPBDEV_SUM_TR1 = 8,     /* sum dD_k,i / D_i                                               */
+  GPBDEV_NUM_SUMS = 9
+};
+
+typedef struct gpbdev_vecchia* gpbdev_vecchia_t;
+
+GPBDEV_EXPORT const char* gpbdev_last_error(void);
+/* number of visible CUDA devices (0 when none / driver missing) */
+GPBDEV_EXPORT int gpbdev_device_count(void);
+
+/*
+ * Create the device-resident state of one Vecchia-approximated GP: ordered coordinates, neighbour sets,
+ * the CSC view of B's sparsity pattern and work buffers.
+ *   coords_ordered : host, n x d ROW-major, already in Vecchia order
+ *   perm           : host, n; ordered position i holds original observation perm[i]
+ *                    (data_indices_per_cluster after Vecchia_utils.cpp:1129-1131)
+ *   nn             : host n x m int32 (-1 padded) or NULL to run the device neighbour search
+ *                    (replaces find_nearest_neighbors_Vecchia_fast, Vecchia_utils.cpp:733-985)
+ *   row_begin/end  : shard [row_begin,row_end) of ordered observations this engine evaluates
+ *                    (whole range on one GPU); coordinates are replicated
+ */
+GPBDEV_EXPORT int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, int m,
+                                        const double* coords_ordered, const int32_t* perm,
+                                        const int32_t* nn, int64_t row_begin, int64_t row_end);
+GPBDEV_EXPORT int gpbdev_vecchia_free(gpbdev_vecchia_t h);
+
+/* copy the neighbour sets back (n x m int32, -1 padded) — parity tests */
+GPBDEV_EXPORT int gpbdev_vecchia_get_nn(gpbdev_vecchia_t h, int32_t* nn_host);
+
+/* y in ORIGINAL observation order; host pointer (H2D inside) or device pointer. Replaces SetY
+ * (re_model_template.h:6185-6200) incl. the per-cluster re-ordering. */
+GPBDEV_EXPORT int gpbdev_vecchia_set_y(gpbdev_vecchia_t h, const double* y_host);
+GPBDEV_EXPORT int gpbdev_vecchia_set_y_device(gpbdev_vecchia_t h, const double* y_dev);
+
+/*
+ * One pass of the hot path at transformed parameters (var = sigma1^2/sigma^2, range per
+ * cov_fcts.h:485-552). Replaces CalcCovFactorVecchia (re_model_template.h:9471) /
+ * CalcCovFactorGradientVecchia (Vecchia_utils.cpp:1367-1699) + CalcYTPsiIInvY (:9938) + the log-det
+ * (:2947) and, in GRAD mode, CalcGradientVecchia (:9601) + the gradient assembly (:1988-2010).
+ *   mode NLL   : sums 0..2
+ *   mode STORE : sums 0..2 and keeps A (= -B off-diagonal), D^-1 and u = D^-1 B y on the device
+ *   mode GRAD  : sums 0..8
+ * Synchronous: returns after the sums reached `out` (host, GPBDEV_NUM_SUMS doubles; shard-local sums).
+ */
+GPBDEV_EXPORT int gpbdev_vecchia_eval(gpbdev_vecchia_t h, int cov_type, double var, double range, int mode,
+                                      double* out);
+/* same, asynchronous on the engine's stream and without the D2H of the sums (bench: device-only timing) */
+GPBDEV_EXPORT int gpbdev_vecchia_eval_async(gpbdev_vecchia_t h, int cov_type, double var, double range, int mode);
+
+/* After a STORE eval: y_aux = Psi^-1 y = B^T D^-1 B y (CalcYAux, re_model_template.h:9772) returned in
+ * ORIGINAL observation order into a host buffer of n doubles. */
+GPBDEV_EXPORT int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host);
+/* After a STORE eval: copy A (n x m) and D^-1 (n) to the host — parity tests against the oracle's B, D^-1 */
+GPBDEV_EXPORT int gpbdev_vecchia_get_factor(gpbdev_vecchia_t h, double* A_host, double* Dinv_host);
+
+/* CUDA-event timing on the engine's stream (bench.py): start, run work, stop -> milliseconds */
+GPBDEV_EXPORT int gpbdev_vecchia_timer_start(gpbdev_vecchia_t h);
+GPBDEV_EXPORT int gpbdev_vecchia_timer_stop(gpbdev_vecchia_t h, float* ms);
+GPBDEV_EXPORT int gpbdev_vecchia_sync(gpbdev_vecchia_t h);
+/* number of kernels this engine has launched so far (bench.py's gpu_launches) */
+GPBDEV_EXPORT int64_t gpbdev_vecchia_launch_count(gpbdev_vecchia_t h);
+/* write > L2-size bytes to evict the L2 between timed iterations */
+GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPBOOST_B200_DEV_H_ */
