@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py — GP log-likelihood evaluations/s on BASELINE.json configs[1]:
+Vecchia GP, n = 1e6, 2-D coords U[0,1]^2, m = 30 neighbours, Matern-1.5, Gaussian likelihood, random ordering.
+
+A "step" = one pass of the hot path = one negative-log-likelihood evaluation at fixed covariance parameters
+(covariance blocks + batched local Cholesky + quadratic form + log-det; SURVEY §8d metric (ii)).
+
+  value : device-resident throughput — y already in HBM, K passes timed with CUDA events on the engine's stream,
+          L2 flushed (256 MiB write) before every timed pass.
+  e2e   : the same metric through the reference-facing C API call GPB_EvalNegLogLikelihood with a pinned HOST
+          response vector: H2D of y (8 MB) + pass + D2H of the sums inside the timed region, every step.
+  N > 1 : one process per GPU (torchrun); the ordered observations are row-sharded, each rank evaluates its rows and
+          the 9 fp64 sums are all-reduced over NCCL (strong scaling at fixed n = 1e6).
+  --impl reference : the UNMODIFIED reference CPU library (oracle/_ref/lib_gpboost.so) on the host cores, same call.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_OBS = 1000000
+M_NEIGH = 30
+COV_PARS = np.array([0.5, 1.0, 0.1])  # (sigma^2, sigma_1^2, rho): SURVEY §8d C2
+WORKLOAD = "configs[1]: Vecchia GP n=1e6, d=2, m=30, Matern-1.5, Gaussian likelihood, random ordering (seed 1)"
+# algorithmic work per observation, SURVEY §8(d): B not materialised (fused NLL): 4m + 8d + 8 = 144 B; ~24 kflop
+ALGO_BYTES_PER_OBS = 4 * M_NEIGH + 8 * 2 + 8
+ALGO_FLOPS_PER_OBS = 24e3
+
+
+def make_data(n):
+    rng = np.random.default_rng(1)
+    return rng.random((n, 2)), rng.standard_normal(n)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.stop_flag = False
+        self.rows = []
+        self.index = index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def time_reference(n, steps, warmup, threads):
+    """The reference's own CPU implementation through the identical C API call."""
+    from gpboost_b200 import GPModel
+    from gpboost_b200.libpath import load_lib
+    from oracle import ref_lib_path
+    if not os.path.exists(ref_lib_path()):
+        return None
+    ref = load_lib(ref_lib_path())
+    coords, y = make_data(n)
+    t0 = time.perf_counter()
+    mdl = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=M_NEIGH,
+                  vecchia_ordering="random", seed=1, num_parallel_threads=threads, _lib=ref)
+    t_create = time.perf_counter() - t0
+    for _ in range(warmup):
+        mdl.neg_log_likelihood(COV_PARS, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        v = mdl.neg_log_likelihood(COV_PARS, y)
+    dt = (time.perf_counter() - t0) / steps
+    return {"sec_per_eval": dt, "negll": v, "create_s": t_create}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-n", type=int, default=250000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = time_reference(N_OBS, args.steps, max(args.warmup, 1), ncores)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lib_gpboost.so missing (build it with oracle/Makefile.ref)"}))
+            return 0
+        v = 1.0 / res["sec_per_eval"]
+        print(json.dumps({
+            "impl": "reference", "metric": "gp_loglik_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": res["sec_per_eval"] * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host_threads": ncores, "model_creation_s": res["create_s"]},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": ncores, "kind": "reference",
+                             "sample": "full workload n=1e6, %d timed GPB_EvalNegLogLikelihood calls" % args.steps},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "negll": res["negll"]}))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from gpboost_b200 import GPModel, load_lib
+    lib = load_lib()
+    if lib.gpbdev_device_count() <= local_rank:
+        raise RuntimeError("bench.py: CUDA device %d not available — the B200 path has no CPU fallback" % local_rank)
+    torch.cuda.set_device(local_rank)
+    cb_keep = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+        from gpboost_b200.parallel import init_collective
+        cb_keep = init_collective(lib, dist, device=torch.device("cuda", local_rank))
+    assert lib.GPB200_SetDevice(local_rank) == 0
+
+    coords, y = make_data(N_OBS)
+    t0 = time.perf_counter()
+    mdl = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=M_NEIGH,
+                  vecchia_ordering="random", seed=1)
+    t_create = time.perf_counter() - t0
+    eng = mdl.device_engine()
+    # pinned host response (the e2e input buffer)
+    y_pin = torch.from_numpy(y).pin_memory()
+    y_ptr = C.cast(y_pin.data_ptr(), C.POINTER(C.c_double))
+    cp = np.ascontiguousarray(COV_PARS)
+    cp_ptr = cp.ctypes.data_as(C.POINTER(C.c_double))
+    negll = C.c_double(0)
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError((lib.gpbdev_last_error() or lib.LGBM_GetLastError()).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        chk(lib.gpbdev_vecchia_sync(eng))
+
+    # transformed parameters for the device-only timing (cov_fcts.h:485-552)
+    var_t, range_t = COV_PARS[1] / COV_PARS[0], np.sqrt(3.) / COV_PARS[2]
+    chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, y_ptr, cp_ptr, None, C.byref(negll)))  # y resident afterwards
+    negll_value = negll.value
+
+    # ---- device-resident timing (value) + per-kernel CUDA-event duration (roofline)
+    for _ in range(W):
+        chk(lib.gpbdev_vecchia_eval_async(eng, 1, C.c_double(var_t), C.c_double(range_t), 0))
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = lib.gpbdev_vecchia_launch_count(eng)
+    ms = C.c_float(0)
+    kernel_ms = []
+    barrier()
+    for _ in range(args.steps):
+        chk(lib.gpbdev_vecchia_flush_l2(eng))
+        chk(lib.gpbdev_vecchia_timer_start(eng))
+        chk(lib.gpbdev_vecchia_eval_async(eng, 1, C.c_double(var_t), C.c_double(range_t), 0))
+        chk(lib.gpbdev_vecchia_timer_stop(eng, C.byref(ms)))
+        kernel_ms.append(ms.value)
+    barrier()
+    dev_ms = float(np.mean(kernel_ms))
+    launches = lib.gpbdev_vecchia_launch_count(eng) - launches0  # factor + reduction kernel per step (L2-flush fills not counted)
+    # ---- e2e timing through the C API with host buffers
+    for _ in range(W):
+        chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, y_ptr, cp_ptr, None, C.byref(negll)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, y_ptr, cp_ptr, None, C.byref(negll)))
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    sampler.stop_flag = True; sampler.join(2)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        rows_per_rank = (N_OBS + world - 1) // world
+        achieved_gbs = ALGO_BYTES_PER_OBS * rows_per_rank / (dev_ms * 1e-3) / 1e9
+        fp64_peak = C.c_double(0)
+        lib.gpbdev_fp64_peak(local_rank, C.byref(fp64_peak))
+        achieved_tf = ALGO_FLOPS_PER_OBS * rows_per_rank / (dev_ms * 1e-3) / 1e12
+        line = {
+            "metric": "gp_loglik_evals_per_sec", "value": 1e3 / dev_ms, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "cov_pars": COV_PARS.tolist(), "l2": "flushed (256 MiB write) before every timed pass",
+                       "sharding": "rows of the ordered observations over %d rank(s); 9 fp64 sums all-reduced" % world,
+                       "model_creation_s": t_create},
+            "e2e": {"value": 1.0 / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(8 * N_OBS + 24), "d2h_bytes_per_step": 72 + 8,
+                    "ms_per_step": e2e_s * 1e3, "call": "GPB_EvalNegLogLikelihood(handle, y_host_pinned, cov_pars, NULL, &negll)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": None, "kernel": "vecchia_factor_kernel<MATERN15, MODE_NLL, DIM=2>", "kernel_ms": dev_ms,
+                         "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS, "peak_source": peak_src,
+                         "note": "this kernel is FP64-pipe bound, not HBM bound (SURVEY §8d, DESIGN.md): see roofline_fp64"},
+            "roofline_fp64": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak.value, "unit": "TFLOP/s",
+                              "frac": achieved_tf / fp64_peak.value if fp64_peak.value > 0 else None,
+                              "flops_per_obs": ALGO_FLOPS_PER_OBS, "peak_source": "measured live: gpbdev_fp64_peak DFMA microbenchmark"},
+            "negll": negll_value,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            ns = args.cpu_sample_n
+            res = time_reference(ns, 3, 1, ncores)
+            if res is not None:
+                v = 1.0 / (res["sec_per_eval"] * (N_OBS / ns))
+                line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": ncores, "kind": "reference",
+                                        "sample": "n=%d sub-problem of the same workload, 3 timed GPB_EvalNegLogLikelihood calls of the "
+                                                  "unmodified reference CPU library; per-eval time scaled linearly to n=1e6" % ns}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    del cb_keep
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -87,26 +87,43 @@ __global__ void fill_kernel(double* p, int64_t n, double v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, no memory traffic. Gives the measured
+// DFMA peak of this chip that the factor kernel (FP64-pipe bound) is compared against in bench.py.
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678) out[0] = x0;
+}
+
 using FactorKernel = void (*)(const gpb::FactorArgs);
 
+template <int COV, int MODE, int DIM>
+FactorKernel pick_cap(int m) {
+  if (m <= 10) return gpb::vecchia_factor_kernel<COV, MODE, DIM, 10>;
+  if (m <= 20) return gpb::vecchia_factor_kernel<COV, MODE, DIM, 20>;
+  return gpb::vecchia_factor_kernel<COV, MODE, DIM, 30>;
+}
 template <int COV, int MODE>
-FactorKernel pick_dim(int d) {
-  return d == 2 ? gpb::vecchia_factor_kernel<COV, MODE, 2> : gpb::vecchia_factor_kernel<COV, MODE, 0>;
+FactorKernel pick_dim(int d, int m) {
+  return d == 2 ? pick_cap<COV, MODE, 2>(m) : pick_cap<COV, MODE, 0>(m);
 }
 template <int COV>
-FactorKernel pick_mode(int mode, int d) {
+FactorKernel pick_mode(int mode, int d, int m) {
   switch (mode) {
-    case gpb::MODE_NLL: return pick_dim<COV, gpb::MODE_NLL>(d);
-    case gpb::MODE_STORE: return pick_dim<COV, gpb::MODE_STORE>(d);
-    default: return pick_dim<COV, gpb::MODE_GRAD>(d);
+    case gpb::MODE_NLL: return pick_dim<COV, gpb::MODE_NLL>(d, m);
+    case gpb::MODE_STORE: return pick_dim<COV, gpb::MODE_STORE>(d, m);
+    default: return pick_dim<COV, gpb::MODE_GRAD>(d, m);
   }
 }
-FactorKernel pick_kernel(int cov, int mode, int d) {
+FactorKernel pick_kernel(int cov, int mode, int d, int m) {
   switch (cov) {
-    case gpb::COV_EXPONENTIAL: return pick_mode<gpb::COV_EXPONENTIAL>(mode, d);
-    case gpb::COV_MATERN15: return pick_mode<gpb::COV_MATERN15>(mode, d);
-    case gpb::COV_MATERN25: return pick_mode<gpb::COV_MATERN25>(mode, d);
-    default: return pick_mode<gpb::COV_GAUSSIAN>(mode, d);
+    case gpb::COV_EXPONENTIAL: return pick_mode<gpb::COV_EXPONENTIAL>(mode, d, m);
+    case gpb::COV_MATERN15: return pick_mode<gpb::COV_MATERN15>(mode, d, m);
+    case gpb::COV_MATERN25: return pick_mode<gpb::COV_MATERN25>(mode, d, m);
+    default: return pick_mode<gpb::COV_GAUSSIAN>(mode, d, m);
   }
 }
 
@@ -140,6 +157,7 @@ struct gpbdev_vecchia {
   int grid = 0;
   int64_t launches = 0;
   bool factor_stored = false;
+  int knn_replayed = 0;  // queries whose neighbour set was re-derived by the exact replay of the reference walk
   std::vector<int32_t> nn_host;  // kept for the lazy CSC build
 };
 
@@ -201,8 +219,8 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   a.partials = h->partials;
   a.n = h->n; a.row_begin = h->row_begin; a.row_end = h->row_end;
   a.m = h->m; a.d = h->d; a.var = var; a.range = range;
-  FactorKernel k = pick_kernel(cov_type, mode, h->d);
-  const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 96);
+  FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);
+  const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 64);
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   k<<<h->grid, gpb::kWarpsPerBlock * 32, smem, h->stream>>>(a);
@@ -280,12 +298,18 @@ int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, i
     std::sort(sort_sum.begin(), sort_sum.end(), [&csum](int i1, int i2) { return csum[i1] < csum[i2]; });
     std::vector<int32_t> pos((size_t)n);
     for (int64_t r = 0; r < n; ++r) pos[(size_t)sort_sum[(size_t)r]] = (int32_t)r;
-    int32_t* pos_dev = nullptr;
+    int32_t *pos_dev = nullptr, *sort_sum_dev = nullptr;
+    double* csum_dev = nullptr;
     CUDA_TRY(cudaMalloc(&pos_dev, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMalloc(&sort_sum_dev, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMalloc(&csum_dev, sizeof(double) * n));
     CUDA_TRY(cudaMemcpy(pos_dev, pos.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sort_sum_dev, sort_sum.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(csum_dev, csum.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     std::string err;
-    const int nl = gpb::knn_vecchia_device(h->coords, coords_ordered, n, d, m, pos_dev, h->nn, h->stream, h->num_sms, &err);
-    cudaFree(pos_dev);
+    const int nl = gpb::knn_vecchia_device(h->coords, coords_ordered, n, d, m, pos_dev, sort_sum_dev, csum_dev, h->nn, h->stream,
+                                           h->num_sms, &h->knn_replayed, &err);
+    cudaFree(pos_dev); cudaFree(sort_sum_dev); cudaFree(csum_dev);
     if (nl < 0) { gpbdev_vecchia_free(h); return fail("gpbdev_vecchia_create: device neighbour search failed: " + err); }
     h->launches += nl;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -329,10 +353,23 @@ int gpbdev_vecchia_set_y_device(gpbdev_vecchia_t h, const double* y_dev) {
 int gpbdev_vecchia_set_y(gpbdev_vecchia_t h, const double* y_host) {
   if (!h || !y_host) return fail("gpbdev_vecchia_set_y: null argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  // caller memory is pageable: stage through the engine's pinned buffer so the H2D runs at link speed
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  std::memcpy(h->stage_host, y_host, sizeof(double) * h->n);
-  CUDA_TRY(cudaMemcpyAsync(h->y_in, h->stage_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned) {  // page-locked caller buffer: DMA straight from it
+    CUDA_TRY(cudaMemcpyAsync(h->y_in, y_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    // pageable caller memory: stage through the engine's pinned buffer (parallel copy) so the H2D runs at link speed
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const int64_t n = h->n;
+    const int64_t chunk = 1 << 16;
+#pragma omp parallel for schedule(static) num_threads(8)
+    for (int64_t b = 0; b < (n + chunk - 1) / chunk; ++b) {
+      const int64_t lo = b * chunk, len = std::min(chunk, n - lo);
+      std::memcpy(h->stage_host + lo, y_host + lo, sizeof(double) * len);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->y_in, h->stage_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  }
   return gpbdev_vecchia_set_y_device(h, h->y_in);
 }
 
@@ -396,6 +433,35 @@ int gpbdev_vecchia_sync(gpbdev_vecchia_t h) {
   return 0;
 }
 int64_t gpbdev_vecchia_launch_count(gpbdev_vecchia_t h) { return h ? h->launches : 0; }
+int gpbdev_vecchia_knn_replayed(gpbdev_vecchia_t h) { return h ? h->knn_replayed : 0; }
+
+int gpbdev_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail("null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, 8));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  fp64_peak_kernel<<<blocks, threads>>>(out, 1 << 10, 1.0000001, 1e-9);
+  double best = 0.;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * (double)iters * blocks * threads;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return 0;
+}
 
 int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h) {
   if (!h) return fail("null handle");

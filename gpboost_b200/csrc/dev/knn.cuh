@@ -83,6 +83,72 @@ __device__ __forceinline__ void knn_offer(double& ks, int& kr, int& ki, bool val
   }
 }
 
+// The reference's walk prunes a direction as soon as a visited candidate has (sum_j - sum_i)^2 > d * (current m-th
+// squared distance) (Vecchia_utils.cpp:1060-1063). In exact arithmetic that never removes a true neighbour; in
+// floating point it can when the comparison is decided by rounding (equidistant points on lattices). If every
+// neighbour found here satisfies smd <= d * T_final the reference provably visited all of them and the results are
+// identical; otherwise the query is queued for knn_walk_kernel, which replays the reference's walk exactly.
+__device__ __forceinline__ void knn_finish(int64_t i, int lane, int m, int d, double ks, int ki, const double* __restrict__ csum,
+                                           int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
+  if (lane < m) nn[i * m + lane] = ki;
+  const double tfin = __shfl_sync(0xffffffffu, ks, m - 1);
+  bool risky = false;
+  if (lane < m && ki >= 0) {
+    const double dd = __dsub_rn(csum[ki], csum[i]);
+    const double smd = __dmul_rn(dd, dd);
+    risky = smd > __dmul_rn((double)d, tfin);
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, risky);
+  if (any && lane == 0) flagged[atomicAdd(nflag, 1)] = (int32_t)i;
+}
+
+// Exact replay of find_nearest_neighbors_fast_internal (Vecchia_utils.cpp:1029-1093) for the queued queries:
+// one thread per query walks the sorted coordinate sums down/up alternately with the reference's pruning rule,
+// strict-'<' replacement and stable insertion (utils.h:250-262).
+__global__ void knn_walk_kernel(const double* __restrict__ coords, const double* __restrict__ csum,
+                                const int32_t* __restrict__ sort_sum, const int32_t* __restrict__ pos, int64_t n, int d, int m,
+                                const int32_t* __restrict__ flagged, const int* __restrict__ nflag, int32_t* __restrict__ nn) {
+  const int nf = *nflag;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    const int64_t i = flagged[f];
+    double sq[32];
+    int id[32];
+    for (int j = 0; j < m; ++j) { sq[j] = INFINITY; id[j] = -1; }
+    bool down = true, up = true;
+    int64_t up_i = pos[i], down_i = pos[i];
+    const int64_t end_search_at = n - 2;
+    while (up || down) {
+      if (down_i == 0) down = false;
+      if (up_i == n - 1) up = false;
+      for (int dir = 0; dir < 2; ++dir) {
+        if (dir == 0 ? !down : !up) continue;
+        const int64_t p = dir == 0 ? --down_i : ++up_i;
+        const int c = sort_sum[p];
+        if (c < i && c <= end_search_at) {
+          const double dd = __dsub_rn(csum[c], csum[i]);
+          const double smd = __dmul_rn(dd, dd);
+          if (smd > __dmul_rn((double)d, sq[m - 1])) {
+            if (dir == 0) down = false; else up = false;
+          } else {
+            const double sed = knn_sqdist(coords + (int64_t)c * d, coords + i * d, d);
+            if (sed < sq[m - 1]) {
+              int k = m - 1;
+              sq[k] = sed; id[k] = c;
+              while (k > 0 && sq[k] < sq[k - 1]) {
+                const double v = sq[k]; const int l = id[k];
+                sq[k] = sq[k - 1]; id[k] = id[k - 1];
+                sq[k - 1] = v; id[k - 1] = l;
+                --k;
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int j = 0; j < m; ++j) nn[i * m + j] = id[j];
+  }
+}
+
 __global__ void knn_cell_id_kernel(const double* __restrict__ coords, int64_t n, KnnGrid gr, uint32_t* __restrict__ cell,
                                    int32_t* __restrict__ idx) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,8 +174,9 @@ __global__ void knn_cell_start_kernel(const uint32_t* __restrict__ sorted_cell, 
 }
 
 // queries i in [q_begin, q_end): brute force over all j < i (early points) — warp per query
-__global__ void knn_brute_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos, int d, int m,
-                                 int64_t q_begin, int64_t q_end, int32_t* __restrict__ nn) {
+__global__ void knn_brute_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos,
+                                 const double* __restrict__ csum, int d, int m, int64_t q_begin, int64_t q_end,
+                                 int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -127,14 +194,15 @@ __global__ void knn_brute_kernel(const double* __restrict__ coords, const int32_
       if (valid) { s = knn_sqdist(coords + j * d, coords + i * d, d); r = knn_rank(pos[j], pi); }
       knn_offer(ks, kr, ki, valid, s, r, (int)j, lane, m);
     }
-    if (lane < m) nn[i * m + lane] = ki;
+    knn_finish(i, lane, m, d, ks, ki, csum, nn, flagged, nflag);
   }
 }
 
 // queries i in [q_begin, n): cell-list search — warp per query, DIM in {1,2,3}
 __global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos,
-                                const int32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted_idx,
-                                KnnGrid gr, int m, int64_t q_begin, int64_t n, int32_t* __restrict__ nn) {
+                                const double* __restrict__ csum, const int32_t* __restrict__ cell_start,
+                                const int32_t* __restrict__ sorted_idx, KnnGrid gr, int m, int64_t q_begin, int64_t n,
+                                int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -201,26 +269,44 @@ __global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t
       const double reach = (double)r * gr.hmin * (1. - 1e-9);
       if (ts < reach * reach) break;
     }
-    if (lane < m) nn[i * m + lane] = ki;
+    knn_finish(i, lane, m, d, ks, ki, csum, nn, flagged, nflag);
   }
 }
 
 // Returns the number of kernels launched, or -1 with *err set. coords: device n x d row-major (Vecchia order).
 inline int knn_vecchia_device(const double* coords_dev, const double* coords_host, int64_t n, int d, int m,
-                              const int32_t* pos_dev, int32_t* nn_dev, cudaStream_t stream, int num_sms, std::string* err) {
+                              const int32_t* pos_dev, const int32_t* sort_sum_dev, const double* csum_dev, int32_t* nn_dev,
+                              cudaStream_t stream, int num_sms, int* num_replayed, std::string* err) {
   auto ck = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
     return true;
   };
   int launches = 0;
+  int32_t* flagged = nullptr;
+  int* nflag = nullptr;
+  if (!ck(cudaMalloc(&flagged, sizeof(int32_t) * n), "cudaMalloc") || !ck(cudaMalloc(&nflag, sizeof(int)), "cudaMalloc") ||
+      !ck(cudaMemsetAsync(nflag, 0, sizeof(int), stream), "memset")) return -1;
+  auto finish = [&](bool ok) -> int {
+    if (ok) {
+      knn_walk_kernel<<<num_sms * 4, 128, 0, stream>>>(coords_dev, csum_dev, sort_sum_dev, pos_dev, n, d, m, flagged, nflag, nn_dev);
+      ok = ck(cudaGetLastError(), "knn_walk_kernel");
+      ++launches;
+      int nf = 0;
+      if (ok) ok = ck(cudaMemcpyAsync(&nf, nflag, sizeof(int), cudaMemcpyDeviceToHost, stream), "memcpy");
+      if (ok) ok = ck(cudaStreamSynchronize(stream), "knn sync");
+      if (num_replayed) *num_replayed = nf;
+    }
+    cudaFree(flagged); cudaFree(nflag);
+    return ok ? launches : -1;
+  };
   const int64_t brute_end = std::min<int64_t>(n, d <= 3 ? 4096 : n);
   {
     const int blocks = (int)std::min<int64_t>((brute_end + 7) / 8, (int64_t)num_sms * 8);
-    knn_brute_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(coords_dev, pos_dev, d, m, 0, brute_end, nn_dev);
-    if (!ck(cudaGetLastError(), "knn_brute_kernel")) return -1;
+    knn_brute_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(coords_dev, pos_dev, csum_dev, d, m, 0, brute_end, nn_dev, flagged, nflag);
+    if (!ck(cudaGetLastError(), "knn_brute_kernel")) return finish(false);
     ++launches;
   }
-  if (brute_end >= n) return launches;
+  if (brute_end >= n) return finish(true);
   // ---- cell list over all points (host computes the bounding box: one pass over n x d doubles)
   KnnGrid gr;
   gr.dim = d;
@@ -249,7 +335,7 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
     }
     ncell *= gr.g[k];
   }
-  if (ncell >= ((int64_t)1 << 31)) { *err = "cell grid too large"; return -1; }
+  if (ncell >= ((int64_t)1 << 31)) { *err = "cell grid too large"; return finish(false); }
   uint32_t *cell = nullptr, *cell_sorted = nullptr;
   int32_t *idx = nullptr, *idx_sorted = nullptr, *cell_start = nullptr;
   void* tmp = nullptr;
@@ -276,13 +362,14 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
     ++launches;
   }
   if (ok) {
-    knn_grid_kernel<<<num_sms * 16, 128, 0, stream>>>(coords_dev, pos_dev, cell_start, idx_sorted, gr, m, brute_end, n, nn_dev);
+    knn_grid_kernel<<<num_sms * 16, 128, 0, stream>>>(coords_dev, pos_dev, csum_dev, cell_start, idx_sorted, gr, m, brute_end, n, nn_dev, flagged, nflag);
     ok = ck(cudaGetLastError(), "knn_grid_kernel");
     ++launches;
   }
   if (ok) ok = ck(cudaStreamSynchronize(stream), "knn sync");
+  const int rc = finish(ok);
   cudaFree(cell); cudaFree(cell_sorted); cudaFree(idx); cudaFree(idx_sorted); cudaFree(cell_start); cudaFree(tmp);
-  return ok ? launches : -1;
+  return rc;
 }
 
 }  // namespace gpb

@@ -22,6 +22,13 @@
 //     transposed reads).
 //   * A_i = L_NN^-T z (and w = S^-1 y_N in gradient mode) by a lane-per-unknown back substitution
 //     reading L by columns from shared memory.
+//   * the kernel is specialised on a compile-time neighbour capacity MT in {10, 20, 30}: a model with m <= MT
+//     neighbours (and the first rows, which have fewer than m predecessors) is padded with "dummy" points that
+//     are uncorrelated with everything (unit diagonal, zero off-diagonal, zero response); the padded
+//     factorisation reproduces the un-padded one exactly. All loops are then fully unrolled without runtime
+//     predicates and the Cholesky is software-pipelined (look-ahead): the pivot chain of column k+1
+//     (shuffle -> rsqrt -> scale -> shared store) is issued right after column k+1 received its update and
+//     overlaps with the remaining rank-1 updates of step k.
 //   * gradient mode uses the adjoint identities  dD_k = b^T dSigma~_k b,  (dB_k y)_i = -b^T dSigma~_k w~
 //     with b = [-A_i, 1], w~ = [w, 0]: no derivative matrix is factorised or stored; the range-derivative
 //     pair values stay in the registers of the lane that computed them.
@@ -82,6 +89,15 @@ __device__ __forceinline__ double cov_eval(double dist, double var, double range
   return val;
 }
 
+// 1/sqrt(x) for x > 0: MUFU.RSQ64H seed + one third-order correction (relative error ~1e-16); no special-case
+// handling (pivots are >= the nugget, squared distances are guarded by the caller).
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);                // 1 - x y^2
+  return fma(y * e, fma(0.375, e, 0.5), y);            // y (1 + e/2 + 3 e^2 / 8)
+}
+
 __device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -89,21 +105,23 @@ __device__ __forceinline__ double warp_sum(double x) {
   return x;
 }
 
-template <int COV, int MODE, int DIM>
+template <int COV, int MODE, int DIM, int MT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 3 : 4)
 vecchia_factor_kernel(const FactorArgs p) {
   constexpr bool GRAD = (MODE == MODE_GRAD);
   constexpr bool SOLVE = (MODE != MODE_NLL);
+  constexpr int P = MT + 1;      // point slots: 0..MT-1 neighbours (real or dummy), MT = the observation
+  constexpr int NT = MT / 2;     // circulant rounds (P is odd)
+  static_assert(MT % 2 == 0 && MT >= 2 && MT <= kMaxNeighbors, "MT must be even and <= 30");
   extern __shared__ __align__(16) double smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int dim = DIM > 0 ? DIM : p.d;
-  // per-warp shared layout: L/S matrix 32 x kLd | points 32 x dim | ys 32 | xb 32 | xw 32
-  const int per_warp = 32 * kLd + 32 * dim + 96;
+  // per-warp shared layout: L/S matrix 32 x kLd | points 32 x dim | xb 32 | xw 32
+  const int per_warp = 32 * kLd + 32 * dim + 64;
   double* S = smem_raw + (size_t)wib * per_warp;
   double* pts = S + 32 * kLd;
-  double* ys = pts + 32 * dim;
-  double* xb = ys + 32;
+  double* xb = pts + 32 * dim;
   double* xw = xb + 32;
 
   const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
@@ -118,12 +136,12 @@ vecchia_factor_kernel(const FactorArgs p) {
   for (int64_t i = p.row_begin + gwarp; i < p.row_end; i += nwarps) {
     // ---- gather: neighbour ids, coordinates, responses
     const int q = i < m ? (int)i : m;  // Vecchia_utils.cpp:788-813: the first m+1 points condition on all predecessors
-    const int P = q + 1;               // points (neighbours + the observation)
     int64_t src = -1;
     if (lane < q) src = p.nn[i * m + lane];
-    else if (lane == q) src = i;
+    else if (lane == MT) src = i;
+    const bool real = src >= 0;  // slots q..MT-1 are dummies
     double yv = 0.;
-    if (src >= 0) {
+    if (real) {
       yv = p.y[src];
       if (DIM == 2) {
         const double2 c = *reinterpret_cast<const double2*>(p.coords + src * 2);
@@ -132,86 +150,87 @@ vecchia_factor_kernel(const FactorArgs p) {
         for (int k = 0; k < dim; ++k) pts[lane * dim + k] = p.coords[src * dim + k];
       }
     }
-    ys[lane] = yv;
+    const unsigned real_mask = __ballot_sync(0xffffffffu, real);
     __syncwarp();
 
-    // ---- pair covariances, circulant schedule: lane l <-> point (l + t) mod P, t = 1..P/2
-    double gpair[16];
+    // ---- pair covariances, circulant schedule: lane l <-> point (l + t) mod P, t = 1..NT
+    double gpair[GRAD ? NT : 1];
     double my[DIM > 0 ? DIM : 1];
     if (DIM > 0) {
 #pragma unroll
       for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) my[k] = pts[lane * dim + k];
     }
-    const int half = (P - 1) >> 1;  // t <= half: every lane; t == P/2 (P even): lanes < P/2
 #pragma unroll
-    for (int t = 1; t <= 16; ++t) {
-      if (GRAD) gpair[t - 1] = 0.;
-      if (t <= (P >> 1)) {  // warp-uniform
-        int o = lane + t;
-        if (o >= P) o -= P;
-        const bool valid = lane < P && (t <= half || lane < (P >> 1));
-        if (valid) {
-          double d2 = 0.;
-          if (DIM > 0) {
+    for (int t = 1; t <= NT; ++t) {
+      int o = lane + t;
+      if (o >= P) o -= P;
+      double val = 0., g = 0.;
+      if (lane < P && real && ((real_mask >> o) & 1u)) {
+        double d2 = 0.;
+        if (DIM > 0) {
 #pragma unroll
-            for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) {
-              const double df = my[k] - pts[o * dim + k];
-              d2 += df * df;
-            }
-          } else {
-            for (int k = 0; k < dim; ++k) {
-              const double df = pts[lane * dim + k] - pts[o * dim + k];
-              d2 += df * df;
-            }
+          for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) {
+            const double df = my[k] - pts[o * dim + k];
+            d2 += df * df;
           }
-          const double dist = sqrt(d2);
-          double g = 0.;
-          const double val = cov_eval<COV, GRAD>(dist, var, range, g);
-          const int r = max(lane, o), c = min(lane, o);
-          S[c * kLd + r] = val;
-          if (GRAD) gpair[t - 1] = g;
+        } else {
+          for (int k = 0; k < dim; ++k) {
+            const double df = pts[lane * dim + k] - pts[o * dim + k];
+            d2 += df * df;
+          }
         }
+        const double dist = d2 > 0. ? d2 * rsqrt_fast(d2) : 0.;
+        val = cov_eval<COV, GRAD>(dist, var, range, g);
       }
+      if (lane < P) S[min(lane, o) * kLd + max(lane, o)] = val;
+      if (GRAD) gpair[t - 1] = g;
     }
-    // diagonal (variance + nugget 1; Vecchia_utils.cpp:1601 / :1411,1563) and the response row q+1
+    // diagonal: variance + nugget 1 (Vecchia_utils.cpp:1601 / :1411,1563), 1 for dummies; response row MT+1
     if (lane < P) {
-      S[lane * kLd + lane] = var + 1.;
-      S[lane * kLd + (q + 1)] = yv;
+      S[lane * kLd + lane] = real ? var + 1. : 1.;
+      S[lane * kLd + (MT + 1)] = yv;
     }
     __syncwarp();
 
     // ---- row j of the lower triangle -> registers of lane j
-    double a[32];
+    double a[MT + 2];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = (c <= q) ? S[c * kLd + lane] : 0.;
+    for (int c = 0; c <= MT; ++c) a[c] = S[c * kLd + lane];
+    a[MT + 1] = 0.;
     __syncwarp();
 
-    // ---- right-looking Cholesky, pivots 0..q (row q+1 is eliminated but never a pivot)
-    double Di = 1.;
-#pragma unroll
-    for (int k = 0; k <= kMaxNeighbors; ++k) {
-      if (k <= q) {  // warp-uniform
-        const double dkk = shfl_d(a[k], k);
-        if (k == q) Di = dkk;
-        const double rs = rsqrt(dkk);
-        const double ljk = a[k] * rs;
-        a[k] = ljk;
-        S[k * kLd + lane] = ljk;  // column k of L (rows < k hold don't-care values)
-        __syncwarp();
-        if (k + 1 <= q) a[k + 1] -= ljk * S[k * kLd + k + 1];
-#pragma unroll
-        for (int c = k + 2; c + 1 < 32; c += 2) {
-          if (c <= q) {
-            const double2 l2 = *reinterpret_cast<const double2*>(&S[k * kLd + c]);
-            a[c] -= ljk * l2.x;
-            a[c + 1] -= ljk * l2.y;  // column q+1 is never read: harmless when c == q
-          }
-        }
-      }
+    // ---- right-looking Cholesky with look-ahead, pivots 0..MT (row MT+1 is eliminated but never a pivot)
+    double Di;
+    double lk;
+    {
+      const double d0 = shfl_d(a[0], 0);
+      lk = a[0] * rsqrt_fast(d0);
+      S[lane] = lk;  // column 0 of L (rows above the diagonal hold don't-care values)
+      Di = d0;
     }
-    // lane q+1 now holds L[q+1][q] = (By)_i / sqrt(D_i) in a[q]; fetch it without dynamic indexing
-    const double r_over_sd = S[q * kLd + (q + 1)];  // written by lane q+1 in step k = q
-    const double quad = r_over_sd * r_over_sd;      // (By)_i^2 / D_i
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+      // column k of L is visible in shared memory; lk = L[lane][k]
+      a[k + 1] -= lk * S[k * kLd + k + 1];
+      // look-ahead: pivot chain of column k+1
+      const double dn = shfl_d(a[k + 1], k + 1);
+      if (k + 1 == MT) Di = dn;
+      const double lk1 = a[k + 1] * rsqrt_fast(dn);
+      S[(k + 1) * kLd + lane] = lk1;
+      // remaining rank-1 updates of step k (columns k+2..MT; the pair load may touch column MT+1: harmless)
+#pragma unroll
+      for (int c = k + 2; c <= MT; c += 2) {
+        const double2 l2 = *reinterpret_cast<const double2*>(&S[k * kLd + c]);
+        a[c] -= lk * l2.x;
+        a[c + 1] -= lk * l2.y;
+      }
+      __syncwarp();
+      lk = lk1;
+    }
+    // lane MT+1 wrote L[MT+1][MT] = (By)_i / sqrt(D_i) into column MT
+    const double r_over_sd = S[MT * kLd + (MT + 1)];
+    const double quad = r_over_sd * r_over_sd;  // (By)_i^2 / D_i
     const bool bad = !(Di > 0.);
     if (lane == 0) {
       acc[0] += quad;
@@ -220,24 +239,20 @@ vecchia_factor_kernel(const FactorArgs p) {
     }
 
     if (SOLVE) {
-      // ---- back substitution L_NN^T x = z for z = L[q][.] (-> A_i) and, in gradient mode, L[q+1][.] (-> w)
-      // lane c owns unknown c; L[r][c] is read by columns: S[c*kLd + r]
-      double xa = (lane < q) ? S[lane * kLd + q] : 0.;
-      double xwv = (GRAD && lane < q) ? S[lane * kLd + (q + 1)] : 0.;
-      const double dinv = (lane < q) ? 1. / S[lane * kLd + lane] : 0.;
+      // ---- back substitution L_NN^T x = z for z = L[MT][.] (-> A_i) and, in gradient mode, L[MT+1][.] (-> w)
+      // lane c owns unknown c; L[r][c] is read by columns: S[c*kLd + r]. Dummy unknowns come out as 0.
+      double xa = (lane < MT) ? S[lane * kLd + MT] : 0.;
+      double xwv = (GRAD && lane < MT) ? S[lane * kLd + (MT + 1)] : 0.;
+      const double dinv = (lane < MT) ? 1. / S[lane * kLd + lane] : 0.;
 #pragma unroll
-      for (int r = kMaxNeighbors - 1; r >= 0; --r) {
-        if (r < q) {  // warp-uniform
-          const double fa = shfl_d(xa * dinv, r);
-          double fw = 0.;
-          if (GRAD) fw = shfl_d(xwv * dinv, r);
-          if (lane == r) { xa = fa; if (GRAD) xwv = fw; }
-          if (lane < r) {
-            const double lrc = S[lane * kLd + r];
-            xa -= lrc * fa;
-            if (GRAD) xwv -= lrc * fw;
-          }
-        }
+      for (int r = MT - 1; r >= 0; --r) {
+        const double fa = shfl_d(xa * dinv, r);
+        double fw = 0.;
+        if (GRAD) fw = shfl_d(xwv * dinv, r);
+        const double lrc = (lane < r) ? S[lane * kLd + r] : 0.;
+        if (lane == r) { xa = fa; if (GRAD) xwv = fw; }
+        xa -= lrc * fa;
+        if (GRAD) xwv -= lrc * fw;
       }
       // xa = A_i[lane] for lane < q
       const double Dinv_i = 1. / Di;
@@ -249,22 +264,21 @@ vecchia_factor_kernel(const FactorArgs p) {
       if (GRAD) {
         // b = [-A, 1], w~ = [w, 0] over the P points
         __syncwarp();
-        xb[lane] = (lane < q) ? -xa : (lane == q ? 1. : 0.);
-        xw[lane] = (lane < q) ? xwv : 0.;
+        xb[lane] = (lane < MT) ? -xa : (lane == MT ? 1. : 0.);
+        xw[lane] = (lane < MT) ? xwv : 0.;
         __syncwarp();
         // adjoint contractions over this lane's pairs: b^T G b and b^T G w~ (G symmetric, zero diagonal)
         double bgb = 0., bgw = 0.;
         const double bl = xb[lane], wl = xw[lane];
 #pragma unroll
-        for (int t = 1; t <= 16; ++t) {
-          if (t <= (P >> 1)) {
-            int o = lane + t;
-            if (o >= P) o -= P;
-            const double g = gpair[t - 1];  // 0 for invalid pairs
-            const double bo = xb[o], wo = xw[o];
-            bgb += g * (bl * bo);
-            bgw += g * (bl * wo + bo * wl);
-          }
+        for (int t = 1; t <= NT; ++t) {
+          int o = lane + t;
+          if (o >= P) o -= P;
+          o = lane < P ? o : 0;
+          const double g = gpair[t - 1];  // 0 for padded / inactive pairs
+          const double bo = xb[o], wo = xw[o];
+          bgb += g * (bl * bo);
+          bgw += g * (bl * wo + bo * wl);
         }
         bgb = 2. * warp_sum(bgb);
         bgw = warp_sum(bgw);

@@ -1,0 +1,397 @@
+// Host-side REModel: configuration parsing, Vecchia ordering, parameter transformations, initial values,
+// the L-BFGS driver and the likelihood algebra around the device sums. See re_model.h.
+#include "re_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+#include "runtime.h"
+
+namespace gpb200 {
+
+namespace {
+
+[[noreturn]] void Fatal(const std::string& msg) { throw std::runtime_error(msg); }
+
+void DevCheck(int rc) {
+  if (rc != 0) Fatal(std::string(gpbdev_last_error()));
+}
+
+bool NearlyEqual(double a, double b) { return std::fabs(a - b) < 1e-10 * std::max({1.0, std::fabs(a), std::fabs(b)}); }
+
+// likelihood aliases: include/GPBoost/likelihoods.h:10255-10280
+std::string ParseLikelihoodAlias(const std::string& l) {
+  if (l == "regression") return "gaussian";
+  if (l == "binary" || l == "binary_logit") return "bernoulli_logit";
+  return l;
+}
+
+}  // namespace
+
+REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* /*re_group_data*/, int32_t num_re_group,
+                 const double* /*re_group_rand_coef_data*/, const int32_t* /*ind_effect_group_rand_coef*/,
+                 int32_t num_re_group_rand_coef, const int* /*drop_intercept_group_rand_effect*/, int32_t num_gp,
+                 const double* gp_coords_data, int dim_gp_coords, const double* /*gp_rand_coef_data*/, int32_t num_gp_rand_coef,
+                 const char* cov_fct, double cov_fct_shape, const char* gp_approx, double /*cov_fct_taper_range*/,
+                 double /*cov_fct_taper_shape*/, int num_neighbors, const char* vecchia_ordering, int /*num_ind_points*/,
+                 double /*cover_tree_radius*/, const char* /*ind_points_selection*/, const char* likelihood,
+                 double /*likelihood_additional_param*/, const char* /*matrix_inversion_method*/, int seed,
+                 int /*num_parallel_threads*/, bool /*GPU_use*/, bool has_weights, const double* /*weights*/,
+                 double likelihood_learning_rate) {
+  // ---- checks in the order of REModelTemplate's constructor (re_model_template.h:102-472)
+  if (!(num_data > 0)) Fatal("Check failed: num_data > 0");
+  if (!(seed >= 0)) Fatal("Check failed: seed >= 0");
+  num_data_ = num_data;
+  rng_ = std::mt19937((uint32_t)seed);  // rng_ = RNG_t(seed), re_model_template.h:160
+  likelihood_ = likelihood == nullptr ? "gaussian" : ParseLikelihoodAlias(likelihood);
+  if (likelihood_ != "gaussian")
+    Fatal("Likelihood '" + likelihood_ + "' is not supported by the B200 engine yet (hot path: 'gaussian')");
+  gp_approx_ = gp_approx == nullptr ? "none" : std::string(gp_approx);
+  if (cluster_ids_data != nullptr) {
+    for (int32_t i = 1; i < num_data; ++i)
+      if (cluster_ids_data[i] != cluster_ids_data[0])
+        Fatal("Multiple independent realizations ('cluster_ids') are not supported by the B200 engine yet");
+  }
+  if (num_re_group > 0 || num_re_group_rand_coef > 0)
+    Fatal("Grouped random effects are not supported by this B200 REModel configuration");
+  if (num_gp != 1) Fatal("num_gp can only be either 0 or 1 in the current implementation");
+  if (num_gp_rand_coef > 0) Fatal("GP random coefficients are not supported by the B200 engine");
+  if (has_weights) Fatal("'weights' are not supported by the B200 engine yet");
+  if (!(likelihood_learning_rate > 0.)) Fatal("Check failed: likelihood_learning_rate > 0.");
+  if (!(dim_gp_coords > 0)) Fatal("Check failed: dim_gp_coords > 0");
+  if (gp_coords_data == nullptr) Fatal("Check failed: gp_coords_data != nullptr");
+  if (cov_fct == nullptr) Fatal("Check failed: cov_fct != nullptr");
+  dim_ = dim_gp_coords;
+  // ---- covariance function (aliases cov_fcts.h:3170-3200; closed forms :2100-2164)
+  cov_fct_ = cov_fct;
+  shape_ = cov_fct_shape;
+  if (cov_fct_ == "exponential" || cov_fct_ == "Matern") { cov_fct_ = "matern"; shape_ = 0.5; }
+  if (cov_fct_ == "Gaussian") cov_fct_ = "gaussian";
+  if (cov_fct_ == "matern") {
+    if (NearlyEqual(shape_, 0.5)) cov_id_ = GPBDEV_COV_EXPONENTIAL;
+    else if (NearlyEqual(shape_, 1.5)) cov_id_ = GPBDEV_COV_MATERN15;
+    else if (NearlyEqual(shape_, 2.5)) cov_id_ = GPBDEV_COV_MATERN25;
+    else Fatal("Only Matern smoothness 0.5, 1.5 and 2.5 are supported by the B200 engine (found " + std::to_string(shape_) + ")");
+  } else if (cov_fct_ == "gaussian") {
+    cov_id_ = GPBDEV_COV_GAUSSIAN;
+  } else {
+    Fatal("Covariance of type '" + cov_fct_ + "' is not supported by the B200 engine.");
+  }
+  num_cov_pars_ = 3;  // nugget, marginal variance, range
+  // ---- GP approximation
+  if (gp_approx_ != "vecchia")
+    Fatal("GP approximation '" + gp_approx_ + "' is currently not supported by the B200 engine (hot path: 'vecchia')");
+  num_neighbors_ = num_neighbors > 0 ? num_neighbors : 20;  // re_model_template.h:288-294
+  vecchia_ordering_ = vecchia_ordering == nullptr ? "none" : std::string(vecchia_ordering);
+  if (vecchia_ordering_ != "none" && vecchia_ordering_ != "random")
+    Fatal("Ordering of type '" + vecchia_ordering_ + "' is not supported for the Veccia approximation ");
+  if (num_neighbors_ > num_data_ - 1) num_neighbors_ = std::max(num_data_ - 1, 1);  // Vecchia_utils.cpp:755-758
+  // ---- ordering: data_indices_per_cluster = 0..n-1, shuffled with rng_ for "random" (Vecchia_utils.cpp:1129-1131)
+  perm_.resize(num_data_);
+  {
+    std::vector<int> idx(num_data_);
+    std::iota(idx.begin(), idx.end(), 0);
+    if (vecchia_ordering_ == "random") std::shuffle(idx.begin(), idx.end(), rng_);
+    for (int32_t i = 0; i < num_data_; ++i) perm_[i] = idx[i];
+  }
+  // coordinates arrive column-major (gp_coords_data[j*num_data+i], Vecchia_utils.cpp:1133-1137); keep them
+  // row-major in Vecchia order for the device
+  coords_ordered_.resize((size_t)num_data_ * dim_);
+  for (int32_t i = 0; i < num_data_; ++i)
+    for (int k = 0; k < dim_; ++k) coords_ordered_[(size_t)i * dim_ + k] = gp_coords_data[(size_t)k * num_data_ + perm_[i]];
+  // ---- device state (+ device neighbour search)
+  const Runtime& rt = GetRuntime();
+  int64_t rb = 0, re = num_data_;
+  if (rt.world_size > 1) {
+    const int64_t chunk = (num_data_ + rt.world_size - 1) / rt.world_size;
+    rb = std::min<int64_t>(num_data_, chunk * rt.rank);
+    re = std::min<int64_t>(num_data_, rb + chunk);
+  }
+  DevCheck(gpbdev_vecchia_create(&engine_, rt.device, num_data_, dim_, num_neighbors_, coords_ordered_.data(), perm_.data(),
+                                 nullptr, rb, re));
+  estimate_cov_par_index_.assign(num_cov_pars_, 1);
+  std::memset(sums_, 0, sizeof(sums_));
+}
+
+REModel::~REModel() {
+  if (engine_) gpbdev_vecchia_free(engine_);
+}
+
+// cov_fcts.h:485-552
+void REModel::TransformCovPars(const double* orig, double* trans) const {
+  const double s2 = orig[0];
+  trans[0] = s2;
+  trans[1] = orig[1] / s2;
+  if (!(orig[2] > 0.)) Fatal("Check failed: pars[1] > 0.");
+  switch (cov_id_) {
+    case GPBDEV_COV_EXPONENTIAL: trans[2] = 1. / orig[2]; break;
+    case GPBDEV_COV_MATERN15: trans[2] = std::sqrt(3.) / orig[2]; break;
+    case GPBDEV_COV_MATERN25: trans[2] = std::sqrt(5.) / orig[2]; break;
+    default: trans[2] = 1. / (orig[2] * orig[2]); break;
+  }
+}
+
+// cov_fcts.h:560-623
+void REModel::TransformBackCovPars(const double* trans, double* orig) const {
+  const double s2 = trans[0];
+  orig[0] = s2;
+  orig[1] = s2 * trans[1];
+  switch (cov_id_) {
+    case GPBDEV_COV_EXPONENTIAL: orig[2] = 1. / trans[2]; break;
+    case GPBDEV_COV_MATERN15: orig[2] = std::sqrt(3.) / trans[2]; break;
+    case GPBDEV_COV_MATERN25: orig[2] = std::sqrt(5.) / trans[2]; break;
+    default: orig[2] = 1. / std::sqrt(trans[2]); break;
+  }
+}
+
+void REModel::SetOptimConfig(const double* init_cov_pars, double lr, int max_iter, double delta_rel_conv, bool trace,
+                             const char* optimizer, const char* convergence_criterion, int m_lbfgs,
+                             const int* estimate_cov_par_index) {
+  // re_model.cpp:SetOptimConfig / re_model_template.h:790-960: -999 and nullptr mean "keep the default"
+  if (init_cov_pars != nullptr) {
+    for (int i = 0; i < num_cov_pars_; ++i)
+      if (!(init_cov_pars[i] > 0.) || std::isnan(init_cov_pars[i]) || std::isinf(init_cov_pars[i]))
+        Fatal("Found negative, zero, NaN or Inf values in 'init_cov_pars'");
+    init_cov_pars_.assign(num_cov_pars_, 0.);
+    TransformCovPars(init_cov_pars, init_cov_pars_.data());
+    cov_pars_ = init_cov_pars_;
+    init_cov_pars_provided_ = true;
+    cov_pars_initialized_ = true;
+  }
+  if (lr > 0.) lr_cov_init_ = lr;
+  else if (!NearlyEqual(lr, -999.)) Fatal("lr_cov is not > 0");
+  if (max_iter >= 0) max_iter_ = max_iter;
+  if (delta_rel_conv > 0.) delta_rel_conv_ = delta_rel_conv;
+  else if (!NearlyEqual(delta_rel_conv, -999.)) Fatal("delta_rel_conv is not > 0");
+  trace_ = trace;
+  if (optimizer != nullptr && std::string(optimizer) != "") {
+    optimizer_ = optimizer;
+    if (optimizer_ != "lbfgs")
+      Fatal("Optimizer option '" + optimizer_ + "' is not supported for covariance parameters by the B200 engine (use 'lbfgs')");
+  }
+  if (convergence_criterion != nullptr && std::string(convergence_criterion) != "" &&
+      std::string(convergence_criterion) != "default") {
+    convergence_criterion_ = convergence_criterion;
+    if (convergence_criterion_ != "relative_change_in_log_likelihood" && convergence_criterion_ != "relative_change_in_parameters")
+      Fatal("Convergence criterion '" + convergence_criterion_ + "' is not supported.");
+  }
+  if (m_lbfgs > 0) m_lbfgs_ = m_lbfgs;
+  if (estimate_cov_par_index != nullptr && estimate_cov_par_index[0] >= 0) {
+    for (int i = 0; i < num_cov_pars_; ++i) {
+      estimate_cov_par_index_[i] = estimate_cov_par_index[i];
+      if (estimate_cov_par_index[i] <= 0) Fatal("Holding covariance parameters fixed ('estimate_cov_par_index') is not supported by the B200 engine yet");
+    }
+  }
+}
+
+// re_model_template.h:4849-4968 (Gaussian branch) + cov_fcts.h:1422-1690 (median-distance range heuristic)
+void REModel::FindInitCovPar(const double* y_data, const double* fixed_effects, double* init_trans) {
+  const int n = num_data_;
+  double mean = 0., var = 0.;
+  for (int i = 0; i < n; ++i) mean += fixed_effects ? y_data[i] - fixed_effects[i] : y_data[i];
+  mean /= n;
+  for (int i = 0; i < n; ++i) {
+    const double r = (fixed_effects ? y_data[i] - fixed_effects[i] : y_data[i]) - mean;
+    var += r * r;
+  }
+  var /= (n - 1);
+  init_trans[0] = var / 2;  // nugget
+  init_trans[1] = 1.;       // marginal variance on the transformed scale (init_marg_var / num_comps_total_)
+  // range: median pairwise distance on (a sub-sample of) the ORDERED coordinates, sampled with the model's rng_
+  const int kMaxPoints = 1000;
+  const int ns = n > kMaxPoints ? kMaxPoints : n;
+  std::vector<int> sample(ns);
+  if (ns < n) {
+    std::uniform_int_distribution<> dis(0, n - 1);
+    for (int i = 0; i < ns; ++i) sample[i] = dis(rng_);
+  } else {
+    std::iota(sample.begin(), sample.end(), 0);
+  }
+  std::vector<double> dists;
+  dists.reserve((size_t)ns * (ns - 1) / 2);
+  for (int i = 0; i < ns - 1; ++i)
+    for (int j = i + 1; j < ns; ++j) {
+      double s = 0.;
+      for (int k = 0; k < dim_; ++k) {
+        const double t = coords_ordered_[(size_t)sample[i] * dim_ + k] - coords_ordered_[(size_t)sample[j] * dim_ + k];
+        s += t * t;
+      }
+      dists.push_back(std::sqrt(s));
+    }
+  if (dists.empty()) Fatal("Cannot find an initial value for the range parameter");
+  const size_t pos_med = dists.size() / 2;
+  std::nth_element(dists.begin(), dists.begin() + pos_med, dists.end());
+  double med = dists[pos_med];
+  if (dists.size() % 2 == 0) {
+    std::nth_element(dists.begin(), dists.begin() + pos_med - 1, dists.end());
+    med = (med + dists[pos_med - 1]) / 2.;
+  }
+  if (med < 1e-10) med = std::accumulate(dists.begin(), dists.end(), 0.) / dists.size();
+  if (med < 1e-10)
+    Fatal("Cannot find an initial value for the range parameter since both the median and the average distances among coordinates are zero ");
+  if (cov_fct_ == "matern") {
+    if (shape_ <= 1.) init_trans[2] = 2. * 3. / med;
+    else if (shape_ <= 2.) init_trans[2] = 2. * 4.7 / med;
+    else init_trans[2] = 2. * 5.9 / med;
+  } else {
+    init_trans[2] = 3. / std::pow(med / 2., 2.);
+  }
+}
+
+// re_model.cpp:1312-1334
+void REModel::InitializeCovParsIfNotDefined(const double* y_data, const double* fixed_effects) {
+  if (cov_pars_initialized_) return;
+  if (init_cov_pars_provided_) {
+    cov_pars_ = init_cov_pars_;
+  } else {
+    cov_pars_.assign(num_cov_pars_, 0.);
+    FindInitCovPar(y_data, fixed_effects, cov_pars_.data());
+    init_cov_pars_ = cov_pars_;
+  }
+  cov_pars_initialized_ = true;
+}
+
+void REModel::SetY(const double* y_data, const double* fixed_effects) {
+  if (fixed_effects == nullptr) {
+    DevCheck(gpbdev_vecchia_set_y(engine_, y_data));
+  } else {  // y - fixed_effects (re_model_template.h:2907-2917)
+    work_.resize(num_data_);
+    for (int32_t i = 0; i < num_data_; ++i) work_[i] = y_data[i] - fixed_effects[i];
+    DevCheck(gpbdev_vecchia_set_y(engine_, work_.data()));
+  }
+}
+
+void REModel::DevicePass(double var, double range, int mode) {
+  DevCheck(gpbdev_vecchia_eval(engine_, cov_id_, var, range, mode, sums_));
+  const Runtime& rt = GetRuntime();
+  if (rt.world_size > 1) {
+    if (rt.allreduce_sum == nullptr) Fatal("world_size > 1 but no all-reduce callback was registered (GPB200_SetCollective)");
+    rt.allreduce_sum(sums_, GPBDEV_NUM_SUMS);
+  }
+  ++num_ll_evals_;
+  if (sums_[GPBDEV_SUM_NBAD] > 0.) {
+    // Vecchia_utils.cpp:1685-1698: warning for Gaussian likelihoods; the likelihood becomes NaN/Inf and the
+    // line search backs off
+  }
+}
+
+// re_model_template.h:3132
+double REModel::NegLLFromSums(double sigma2) const {
+  const double kLog2Pi = std::log(2. * M_PI);
+  return sums_[GPBDEV_SUM_QUAD] / 2. / sigma2 + sums_[GPBDEV_SUM_LOGDET] / 2. + num_data_ / 2. * (std::log(sigma2) + kLog2Pi);
+}
+
+void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects) {
+  double trans[3];
+  if (cov_pars == nullptr) {
+    if (y_data != nullptr) InitializeCovParsIfNotDefined(y_data, fixed_effects);
+    if (!cov_pars_initialized_) Fatal("Check failed: cov_pars_initialized_");
+    for (int i = 0; i < 3; ++i) trans[i] = cov_pars_[i];
+  } else {
+    for (int i = 0; i < num_cov_pars_; ++i)
+      if (!(cov_pars[i] > 0.)) Fatal("Covariance parameters must be positive");
+    TransformCovPars(cov_pars, trans);
+  }
+  if (fixed_effects != nullptr && y_data == nullptr) Fatal("EvalNegLogLikelihoodGauss: 'y_data' cannot nullptr when 'fixed_effects' is provided ");
+  if (y_data != nullptr) SetY(y_data, fixed_effects);
+  DevicePass(trans[1], trans[2], GPBDEV_MODE_NLL);
+  *negll = NegLLFromSums(trans[0]);
+  neg_log_likelihood_ = *negll;
+}
+
+void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
+                          bool reuse_learning_rates_from_previous_call) {
+  if (y_data == nullptr) Fatal("Check failed: y_data != nullptr");
+  for (int32_t i = 0; i < num_data_; ++i)
+    if (std::isnan(y_data[i]) || std::isinf(y_data[i])) Fatal("NaN or Inf in response variable / label ");
+  InitializeCovParsIfNotDefined(y_data, fixed_effects);
+  SetY(y_data, fixed_effects);
+  num_it_ = max_iter_;
+  if (max_iter_ <= 0) return;
+  const bool reuse_mem = reuse_learning_rates_from_previous_call && called_in_GPBoost_algorithm && cov_pars_estimated_once_;
+  // optimisation variables: log of the transformed (variance ratio, range); the error variance is profiled out
+  // (optim_utils.h:244-340, re_model_template.h:1082-1084, :2640-2650)
+  double sigma2 = cov_pars_[0], sigma2_lag1 = cov_pars_[0];
+  bool have_cached_grad = false;
+  std::vector<double> cached_x, cached_grad;
+  double cached_f = 0.;
+  auto grad_from_sums = [&](double s2, std::vector<double>* g) {
+    for (int k = 0; k < 2; ++k)  // re_model_template.h:2002-2004
+      (*g)[k] = (sums_[GPBDEV_SUM_UKU0 + k] - 0.5 * sums_[GPBDEV_SUM_UDU0 + k]) / s2 + 0.5 * sums_[GPBDEV_SUM_TR0 + k];
+  };
+  LbfgsObjective objective = [&](const std::vector<double>& x, std::vector<double>* grad, bool speculative) -> double {
+    if (grad != nullptr && have_cached_grad && cached_x == x) {  // gradient right after an accepted first trial
+      *grad = cached_grad;
+      return cached_f;
+    }
+    const double var = std::exp(x[0]), range = std::exp(x[1]);
+    const bool with_grad = grad != nullptr || speculative;
+    DevicePass(var, range, with_grad ? GPBDEV_MODE_GRAD : GPBDEV_MODE_NLL);
+    sigma2 = sums_[GPBDEV_SUM_QUAD] / num_data_;  // ProfileOutSigma2
+    const double f = NegLLFromSums(sigma2);
+    have_cached_grad = false;
+    if (with_grad) {
+      cached_grad.assign(2, 0.);
+      grad_from_sums(sigma2, &cached_grad);
+      cached_x = x; cached_f = f; have_cached_grad = true;
+      if (grad != nullptr) *grad = cached_grad;
+    }
+    return f;
+  };
+  LbfgsMaxStep max_step = [&](const std::vector<double>& neg_dir) {  // re_model_template.h:5413-5421
+    double mx = 0.;
+    for (double v : neg_dir) mx = std::max(mx, std::fabs(v));
+    return std::log(100.) / mx;
+  };
+  LbfgsHook hook = [&](bool commit) {  // Set/ResetProfiledOutVariables (re_model_template.h:2798-2823)
+    if (commit) sigma2_lag1 = sigma2; else sigma2 = sigma2_lag1;
+  };
+  LbfgsParams par;
+  par.max_iterations = max_iter_;
+  par.delta = delta_rel_conv_;
+  par.m = m_lbfgs_;
+  par.initial_step_factor = lr_cov_init_;
+  std::vector<double> x = {std::log(cov_pars_[1]), std::log(cov_pars_[2])};
+  double fx = 0.;
+  num_it_ = lbfgs_minimize(objective, max_step, hook, par, &x, &fx, &lbfgs_mem_, reuse_mem);
+  cov_pars_[0] = sigma2;
+  cov_pars_[1] = std::exp(x[0]);
+  cov_pars_[2] = std::exp(x[1]);
+  for (double v : cov_pars_)
+    if (std::isnan(v) || std::isinf(v)) Fatal("NaN or Inf occurred in covariance parameter optimization using 'lbfgs'");
+  neg_log_likelihood_ = fx;
+  cov_pars_estimated_once_ = true;
+}
+
+void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_cov_factor*/) {
+  if (y == nullptr) Fatal("Check failed: y != nullptr");
+  InitializeCovParsIfNotDefined(y, fixed_effects);
+  // re_model_template.h:3298-3321: SetY(y); y_aux = Psi^-1 y / sigma^2; written back on y.
+  // The factor is always recomputed here: the device keeps no B between calls unless a STORE pass ran.
+  DevCheck(gpbdev_vecchia_set_y(engine_, y));
+  DevicePass(cov_pars_[1], cov_pars_[2], GPBDEV_MODE_STORE);
+  DevCheck(gpbdev_vecchia_yaux(engine_, y));
+  const Runtime& rt = GetRuntime();
+  if (rt.world_size > 1) rt.allreduce_sum(y, num_data_);
+  const double inv_s2 = 1. / cov_pars_[0];
+  for (int32_t i = 0; i < num_data_; ++i) y[i] *= inv_s2;
+}
+
+void REModel::GetCovPar(double* out, bool calc_std_dev) const {
+  if (!cov_pars_initialized_) Fatal("Covariance parameters have not been estimated or set");
+  if (calc_std_dev) Fatal("Standard deviations of covariance parameters are not available in the B200 engine");
+  TransformBackCovPars(cov_pars_.data(), out);
+}
+
+void REModel::GetInitCovPar(double* out) const {
+  if (init_cov_pars_.empty()) {
+    for (int i = 0; i < num_cov_pars_; ++i) out[i] = -1.;  // re_model.cpp: not yet determined
+    return;
+  }
+  TransformBackCovPars(init_cov_pars_.data(), out);
+}
+
+}  // namespace gpb200

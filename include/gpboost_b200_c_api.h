@@ -1,0 +1,90 @@
+/*
+ * gpboost_b200 — drop-in C API for the GP + tree hot path of fabsig/GPBoost (reference @ c93fa49).
+ *
+ * The entry points below have EXACTLY the names, argument lists, ownership and error behaviour of the
+ * reference's exported C API (include/LightGBM/c_api.h; implementation src/LightGBM/c_api.cpp:2686-3149), so
+ * the reference's language bindings (python-package/gpboost/basic.py ctypes, R-package/src/gpboost_R.cpp) bind
+ * them unchanged. Each returns 0 on success and -1 on failure with the message available from
+ * LGBM_GetLastError() (thread-local buffer, c_api.h:1837-1849). Handles are opaque heap pointers owned by the
+ * caller until *Free. Inputs are copied at creation; outputs go to caller-preallocated buffers.
+ *
+ * Configurations outside the hot path fail with -1 and an explanatory message: there is no CPU
+ * fallback in this library.
+ */
+#ifndef GPBOOST_B200_C_API_H_
+#define GPBOOST_B200_C_API_H_
+#include <stdbool.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define GPB200_EXPORT __attribute__((visibility("default")))
+
+typedef void* REModelHandle;  /* c_api.h:37 */
+
+/* c_api.h:54 */
+GPB200_EXPORT const char* LGBM_GetLastError(void);
+
+/* c_api.h:1359-1391 — creates the device-resident model: Vecchia ordering (std::shuffle with mt19937(seed)),
+ * device neighbour search, coordinates/neighbours uploaded once. */
+GPB200_EXPORT int GPB_CreateREModel(int32_t num_data, const int32_t* cluster_ids_data, const char* re_group_data,
+    int32_t num_re_group, const double* re_group_rand_coef_data, const int32_t* ind_effect_group_rand_coef,
+    int32_t num_re_group_rand_coef, const int* drop_intercept_group_rand_effect, int32_t num_gp,
+    const double* gp_coords_data, const int dim_gp_coords, const double* gp_rand_coef_data, int32_t num_gp_rand_coef,
+    const char* cov_fct, double cov_fct_shape, const char* gp_approx, double cov_fct_taper_range,
+    double cov_fct_taper_shape, int num_neighbors, const char* vecchia_ordering, int num_ind_points,
+    double cover_tree_radius, const char* ind_points_selection, const char* likelihood,
+    double likelihood_additional_param, const char* matrix_inversion_method, int seed, int num_parallel_threads,
+    bool GPU_use, bool has_weights, const double* weights, double likelihood_learning_rate, REModelHandle* out);
+/* c_api.h:1398 */
+GPB200_EXPORT int GPB_REModelFree(REModelHandle handle);
+/* c_api.h:1437-1467 */
+GPB200_EXPORT int GPB_SetOptimConfig(REModelHandle handle, double* init_cov_pars, double lr, double acc_rate_cov,
+    int max_iter, double delta_rel_conv, bool use_nesterov_acc, int nesterov_schedule_version, bool trace,
+    const char* optimizer, int momentum_offset, const char* convergence_criterion, int num_covariates,
+    double* init_coef, double lr_coef, double acc_rate_coef, const char* optimizer_coef, int cg_max_num_it,
+    int cg_max_num_it_tridiag, double cg_delta_conv, int num_rand_vec_trace, bool reuse_rand_vec_trace,
+    const char* cg_preconditioner_type, int seed_rand_vec_trace, int piv_chol_rank, double* init_aux_pars,
+    bool estimate_aux_pars, bool init_coef_aux_pars_from_iid_model, const int* estimate_cov_par_index, int m_lbfgs,
+    double delta_conv_mode_finding);
+/* c_api.h:1476 */
+GPB200_EXPORT int GPB_OptimCovPar(REModelHandle handle, const double* y_data, const double* fixed_effects);
+/* c_api.h:1505 — cov_pars on the original scale (sigma^2, sigma_1^2, rho) */
+GPB200_EXPORT int GPB_EvalNegLogLikelihood(REModelHandle handle, const double* y_data, double* cov_pars,
+    const double* fixed_effects, double* negll);
+/* c_api.h:1517 */
+GPB200_EXPORT int GPB_GetCurrentNegLogLikelihood(REModelHandle handle, double* negll);
+/* c_api.h:1534 */
+GPB200_EXPORT int GPB_GetCovPar(REModelHandle handle, double* optim_cov_pars, bool calc_std_dev);
+/* c_api.h:1545 */
+GPB200_EXPORT int GPB_GetInitCovPar(REModelHandle handle, double* init_cov_pars);
+/* c_api.h:1567 */
+GPB200_EXPORT int GPB_GetNumIt(REModelHandle handle, int* num_it);
+/* c_api.h:1579 */
+GPB200_EXPORT int GPB_HasStdCylBesselK(int* has_bessel);
+/* c_api.h:1686 */
+GPB200_EXPORT int GPB_GetLikelihoodName(REModelHandle handle, char* out_str, int* num_char);
+/* c_api.h:1697 */
+GPB200_EXPORT int GPB_GetOptimizerCovPars(REModelHandle handle, char* out_str, int* num_char);
+/* c_api.h:1520 */
+GPB200_EXPORT int GPB_CanCalculateStandardErrorsCovPars(REModelHandle handle, int* out);
+
+/* ---- extensions of the B200 build (no counterpart in the reference's exported API) ---------------------- */
+/* device ordinal used by models created afterwards in this process (default 0) */
+GPB200_EXPORT int GPB200_SetDevice(int device);
+/* Row sharding of observations over `world_size` processes (one per GPU) + the sum-all-reduce used on shard
+ * boundaries; mirrors LGBM_NetworkInitWithFunctions (c_api.h:1306-1317). allreduce_sum: void(double* buf, int n),
+ * in place, host buffer. Pass world_size = 1 / NULL to reset. */
+GPB200_EXPORT int GPB200_SetCollective(int rank, int world_size, void* allreduce_sum);
+/* y <- Psi^-1 y / sigma^2 at the current covariance parameters: what the reference's objective obtains from
+ * REModel::CalcGradient (regression_objective.hpp:165, re_model.cpp:809); exported for parity tests */
+GPB200_EXPORT int GPB200_CalcGradient(REModelHandle handle, double* y_inout);
+/* number of device likelihood passes so far */
+GPB200_EXPORT int GPB200_GetNumLikelihoodEvals(REModelHandle handle, int64_t* out);
+/* the device engine behind a handle (gpbdev_vecchia_t; include/gpboost_b200_dev.h) — bench.py device-only timing */
+GPB200_EXPORT int GPB200_GetDeviceEngine(REModelHandle handle, void** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPBOOST_B200_C_API_H_ */

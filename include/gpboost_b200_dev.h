@@ -88,6 +88,12 @@ GPBDEV_EXPORT int gpbdev_vecchia_timer_stop(gpbdev_vecchia_t h, float* ms);
 GPBDEV_EXPORT int gpbdev_vecchia_sync(gpbdev_vecchia_t h);
 /* number of kernels this engine has launched so far (bench.py's gpu_launches) */
 GPBDEV_EXPORT int64_t gpbdev_vecchia_launch_count(gpbdev_vecchia_t h);
+/* number of queries of the device neighbour search that were re-derived by the exact replay of the reference's
+ * pruned walk (rounding-decided ties, typically only on lattice data) */
+GPBDEV_EXPORT int gpbdev_vecchia_knn_replayed(gpbdev_vecchia_t h);
+/* measured FP64 FMA peak (TFLOP/s, 2 flops per FMA) of `device`: a register-only DFMA microbenchmark.
+ * The Vecchia factor kernel is FP64-pipe bound, so this is its roofline denominator. */
+GPBDEV_EXPORT int gpbdev_fp64_peak(int device, double* tflops);
 /* write > L2-size bytes to evict the L2 between timed iterations */
 GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
 

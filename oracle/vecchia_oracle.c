@@ -72,32 +72,26 @@ static void orc_sort_increasing(double* a, int* b, int n) {
   }
 }
 
-typedef struct { double v; int i; } orc_pair;
-static int orc_pair_cmp(const void* x, const void* y) {
-  const orc_pair* a = (const orc_pair*)x; const orc_pair* b = (const orc_pair*)y;
-  if (a->v < b->v) return -1;
-  if (a->v > b->v) return 1;
-  return (a->i > b->i) - (a->i < b->i);
-}
+/* std::sort-based index sort of the reference (utils.h:230-238), restated in shuffle_oracle.cpp */
+void orc_sort_indices(const double* v, int n, int32_t* idx_out);
 
 /* ---- Vecchia neighbour search among previously ordered points ("nearest" selection):
  * src/GPBoost/Vecchia_utils.cpp:733-985 (driver) and :1029-1093 (find_nearest_neighbors_fast_internal).
  * coords: column-major n x d (already in Vecchia order). nn: n x m int32, -1 padded.
- * Note: the reference sorts the coordinate sums with std::sort (ties unordered); ties in the sum are
- * broken here by index, which only matters when two candidates have bit-identical squared distance. */
+ * The coordinate sums are sorted by the same std::sort call as the reference (orc_sort_indices), because the
+ * order of equal sums decides which of several equidistant candidates is met first (lattice data). */
 void orc_knn_vecchia(const double* coords, int n, int d, int m, int32_t* nn) {
   for (size_t t = 0; t < (size_t)n * m; ++t) nn[t] = -1;
   double* csum = (double*)malloc(sizeof(double) * n);
-  orc_pair* srt = (orc_pair*)malloc(sizeof(orc_pair) * n);
-  int* sort_sum = (int*)malloc(sizeof(int) * n);
+  int32_t* sort_sum = (int32_t*)malloc(sizeof(int32_t) * n);
   int* sort_inv = (int*)malloc(sizeof(int) * n);
   for (int i = 0; i < n; ++i) {
     double s = 0.;
     for (int k = 0; k < d; ++k) s += coords[(size_t)k * n + i]; /* :778 row sum */
-    csum[i] = s; srt[i].v = s; srt[i].i = i;
+    csum[i] = s;
   }
-  qsort(srt, n, sizeof(orc_pair), orc_pair_cmp);
-  for (int i = 0; i < n; ++i) { sort_sum[i] = srt[i].i; sort_inv[srt[i].i] = i; }
+  orc_sort_indices(csum, n, sort_sum);
+  for (int i = 0; i < n; ++i) sort_inv[sort_sum[i]] = i;
   int end_search_at = n - 2; /* :752-754 */
   /* :788-813 the first m+1 points condition on all predecessors, in index order */
   for (int i = 1; i < n && i <= m; ++i)
@@ -141,7 +135,7 @@ void orc_knn_vecchia(const double* coords, int n, int d, int m, int32_t* nn) {
     }
     free(sq);
   }
-  free(csum); free(srt); free(sort_sum); free(sort_inv);
+  free(csum); free(sort_sum); free(sort_inv);
 }
 
 /* dense Cholesky (lower, in place, row-major ld=m) + solve; stands in for Eigen::LLT at
