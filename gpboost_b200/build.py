@@ -25,17 +25,18 @@ def _sources():
     return cu, cpp, hdr
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out_name=None):
+    """extra_flags / out_name: build an experimental variant next to the product library (tuning runs)."""
     cu, cpp, hdr = _sources()
-    out = lib_path()
+    out = lib_path() if out_name is None else os.path.join(_HERE, out_name)
     deps = cu + cpp + hdr + [os.path.abspath(__file__)]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in deps):
         return out
-    objdir = os.path.join(_HERE, "build")
+    objdir = os.path.join(_HERE, "build" if out_name is None else "build_" + out_name.replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-fvisibility=hidden",
-              "-I", os.path.join(os.path.dirname(_HERE), "include")]
+              "-I", os.path.join(os.path.dirname(_HERE), "include")] + list(extra_flags)
     procs = []
     for s in cu + cpp:
         o = os.path.join(objdir, os.path.basename(s) + ".o")

@@ -154,7 +154,7 @@ struct gpbdev_vecchia {
   double* stage_host = nullptr; // pinned n doubles
   double* flush = nullptr;
   int64_t flush_n = 0;
-  int grid = 0;
+  int grid_cap = 0;
   int64_t launches = 0;
   bool factor_stored = false;
   int knn_replayed = 0;  // queries whose neighbour set was re-derived by the exact replay of the reference walk
@@ -223,9 +223,14 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 64);
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  k<<<h->grid, gpb::kWarpsPerBlock * 32, smem, h->stream>>>(a);
+  // persistent grid = resident CTAs per SM (registers / shared memory of this instantiation) x SM count
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, gpb::kWarpsPerBlock * 32, smem));
+  int grid = std::max(per_sm, 1) * h->num_sms;
+  if (grid > h->grid_cap) grid = h->grid_cap;
+  k<<<grid, gpb::kWarpsPerBlock * 32, smem, h->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
-  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)h->grid * gpb::kWarpsPerBlock, h->sums);
+  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)grid * gpb::kWarpsPerBlock, h->sums);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
   if (mode == gpb::MODE_STORE) h->factor_stored = true;
@@ -270,12 +275,12 @@ int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, i
   CUDA_TRY(cudaMalloc(&h->y_in, sizeof(double) * n));
   CUDA_TRY(cudaMalloc(&h->y, sizeof(double) * n));
   CUDA_TRY(cudaMemset(h->y, 0, sizeof(double) * n));
-  // persistent grid: resident CTAs per SM x SM count (4 CTAs of 4 warps; 3 in gradient mode still fills the SMs)
-  h->grid = h->num_sms * 4;
+  // upper bound of the persistent grid (the launch picks resident-CTAs-per-SM x SM count, see launch_eval)
+  h->grid_cap = h->num_sms * 8;
   const int64_t rows = row_end - row_begin;
   const int64_t max_blocks = (rows + gpb::kWarpsPerBlock - 1) / gpb::kWarpsPerBlock;
-  if (h->grid > max_blocks) h->grid = (int)std::max<int64_t>(max_blocks, 1);
-  CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * h->grid * gpb::kWarpsPerBlock * gpb::kNumAcc));
+  if (h->grid_cap > max_blocks) h->grid_cap = (int)std::max<int64_t>(max_blocks, 1);
+  CUDA_TRY(cudaMalloc(&h->partials, sizeof(double) * h->grid_cap * gpb::kWarpsPerBlock * gpb::kNumAcc));
   CUDA_TRY(cudaMalloc(&h->sums, sizeof(double) * gpb::kNumAcc));
   CUDA_TRY(cudaMallocHost(&h->sums_host, sizeof(double) * gpb::kNumAcc));
   CUDA_TRY(cudaMallocHost(&h->stage_host, sizeof(double) * n));

@@ -41,6 +41,12 @@ namespace gpb {
 enum CovType : int { COV_EXPONENTIAL = 0, COV_MATERN15 = 1, COV_MATERN25 = 2, COV_GAUSSIAN = 3 };
 enum FactorMode : int { MODE_NLL = 0, MODE_STORE = 1, MODE_GRAD = 2 };
 
+#ifndef GPB_NLL_BLOCKS
+#define GPB_NLL_BLOCKS 5
+#endif
+#ifndef GPB_GRAD_BLOCKS
+#define GPB_GRAD_BLOCKS 3
+#endif
 constexpr int kWarpsPerBlock = 4;
 constexpr int kLd = 33;            // column stride (doubles) of the shared matrix
 constexpr int kMaxNeighbors = 30;  // q + 2 rows must fit one warp
@@ -64,26 +70,46 @@ struct FactorArgs {
   double range;   // transformed range (cov_fcts.h:485-552)
 };
 
+// exp(ax) for ax <= 0 (clamped at -700): round-to-nearest range reduction by the 1.5*2^52 trick, degree-13 Taylor
+// polynomial on |r| <= ln2/2 (truncation error 4e-18), scaling by an exponent-field add. No special-case paths and the
+// coefficients are constant-bank operands of the DFMAs — about half the instructions of the library exp().
+__constant__ double kExpC[12] = {1. / 6227020800., 1. / 479001600., 1. / 39916800., 1. / 3628800., 1. / 362880., 1. / 40320.,
+                                 1. / 5040.,       1. / 720.,       1. / 120.,      1. / 24.,      1. / 6.,      0.5};
+__device__ __forceinline__ double exp_neg(double ax) {
+  ax = ax < -700. ? -700. : ax;
+  const double t = fma(ax, 1.4426950408889634074, 6755399441055744.0);
+  const double n = t - 6755399441055744.0;
+  double r = fma(n, -6.93147180369123816490e-01, ax);
+  r = fma(n, -1.90821492927058770002e-10, r);
+  double pl = kExpC[0];
+#pragma unroll
+  for (int k = 1; k < 12; ++k) pl = fma(pl, r, kExpC[k]);
+  pl = fma(pl, r, 1.0);
+  pl = fma(pl, r, 1.0);
+  const int hi = __double2hiint(pl) + (__double2loint(t) << 20);
+  return __hiloint2double(hi, __double2loint(pl));
+}
+
 // covariance value and d/dlog(range) on the transformed scale — closed forms cov_fcts.h:2100-2118,2154;
 // gradient constants cov_fcts.h:2183-2206, element formulas :2535-2563.
 template <int COV, bool GRAD>
 __device__ __forceinline__ double cov_eval(double dist, double var, double range, double& grad) {
   double val;
   if (COV == COV_EXPONENTIAL) {
-    val = var * exp(-range * dist);
+    val = var * exp_neg(-range * dist);
     if (GRAD) grad = -range * dist * val;
   } else if (COV == COV_MATERN15) {
     const double rd = range * dist;
-    const double e = exp(-rd);
+    const double e = exp_neg(-rd);
     val = var * (1. + rd) * e;
     if (GRAD) grad = -var * range * range * dist * dist * e;
   } else if (COV == COV_MATERN25) {
     const double rd = range * dist;
-    const double e = exp(-rd);
+    const double e = exp_neg(-rd);
     val = var * (1. + rd + rd * rd / 3.) * e;
     if (GRAD) grad = -var * range * range / 3. * dist * dist * (1. + rd) * e;
   } else {
-    val = var * exp(-range * dist * dist);
+    val = var * exp_neg(-range * dist * dist);
     if (GRAD) grad = -range * dist * dist * val;
   }
   return val;
@@ -106,7 +132,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 template <int COV, int MODE, int DIM, int MT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 3 : 4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? GPB_GRAD_BLOCKS : GPB_NLL_BLOCKS)
 vecchia_factor_kernel(const FactorArgs p) {
   constexpr bool GRAD = (MODE == MODE_GRAD);
   constexpr bool SOLVE = (MODE != MODE_NLL);
@@ -133,23 +159,43 @@ vecchia_factor_kernel(const FactorArgs p) {
 #pragma unroll
   for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.;
 
+  // slot -> source observation of row ii (or -1 for a dummy slot)
+  auto slot_src = [&](int64_t ii) -> int64_t {
+    const int qq = ii < m ? (int)ii : m;  // Vecchia_utils.cpp:788-813: the first m+1 points condition on all predecessors
+    if (lane < qq) return (int64_t)p.nn[ii * m + lane];
+    return lane == MT ? ii : (int64_t)-1;
+  };
+  // software pipeline over observations (DIM == 2): the gather of row i + nwarps is issued while row i is computed
+  int64_t src_pre = -1;
+  double2 c_pre = make_double2(0., 0.);
+  double y_pre = 0.;
+  if (DIM == 2 && p.row_begin + gwarp < p.row_end) {
+    src_pre = slot_src(p.row_begin + gwarp);
+    if (src_pre >= 0) {
+      y_pre = p.y[src_pre];
+      c_pre = *reinterpret_cast<const double2*>(p.coords + src_pre * 2);
+    }
+  }
+
   for (int64_t i = p.row_begin + gwarp; i < p.row_end; i += nwarps) {
     // ---- gather: neighbour ids, coordinates, responses
-    const int q = i < m ? (int)i : m;  // Vecchia_utils.cpp:788-813: the first m+1 points condition on all predecessors
-    int64_t src = -1;
-    if (lane < q) src = p.nn[i * m + lane];
-    else if (lane == MT) src = i;
-    const bool real = src >= 0;  // slots q..MT-1 are dummies
+    const int q = i < m ? (int)i : m;
+    int64_t src;
     double yv = 0.;
-    if (real) {
-      yv = p.y[src];
-      if (DIM == 2) {
-        const double2 c = *reinterpret_cast<const double2*>(p.coords + src * 2);
-        *reinterpret_cast<double2*>(pts + lane * 2) = c;
-      } else {
+    if (DIM == 2) {
+      src = src_pre;
+      yv = y_pre;
+      if (src >= 0) *reinterpret_cast<double2*>(pts + lane * 2) = c_pre;
+    } else {
+      src = slot_src(i);
+      if (src >= 0) {
+        yv = p.y[src];
         for (int k = 0; k < dim; ++k) pts[lane * dim + k] = p.coords[src * dim + k];
       }
     }
+    const bool real = src >= 0;  // slots q..MT-1 are dummies
+    int64_t src_next = -1;
+    if (DIM == 2 && i + nwarps < p.row_end) src_next = slot_src(i + nwarps);  // consumed after the pair phase
     const unsigned real_mask = __ballot_sync(0xffffffffu, real);
     __syncwarp();
 
@@ -160,30 +206,44 @@ vecchia_factor_kernel(const FactorArgs p) {
 #pragma unroll
       for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) my[k] = pts[lane * dim + k];
     }
+    const bool full = (q == MT);  // warp-uniform: no dummy slots (every row i >= m of a model with m == MT)
 #pragma unroll
     for (int t = 1; t <= NT; ++t) {
       int o = lane + t;
       if (o >= P) o -= P;
-      double val = 0., g = 0.;
-      if (lane < P && real && ((real_mask >> o) & 1u)) {
-        double d2 = 0.;
-        if (DIM > 0) {
+      if (lane >= P) o = 0;  // lane 31 computes a throw-away pair
+      double d2 = 0.;
+      if (DIM > 0) {
 #pragma unroll
-          for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) {
-            const double df = my[k] - pts[o * dim + k];
-            d2 += df * df;
-          }
-        } else {
-          for (int k = 0; k < dim; ++k) {
-            const double df = pts[lane * dim + k] - pts[o * dim + k];
-            d2 += df * df;
-          }
+        for (int k = 0; k < (DIM > 0 ? DIM : 1); ++k) {
+          const double df = my[k] - pts[o * dim + k];
+          d2 = k == 0 ? df * df : fma(df, df, d2);
         }
-        const double dist = d2 > 0. ? d2 * rsqrt_fast(d2) : 0.;
-        val = cov_eval<COV, GRAD>(dist, var, range, g);
+      } else {
+        for (int k = 0; k < dim; ++k) {
+          const double df = pts[lane * dim + k] - pts[o * dim + k];
+          d2 = fma(df, df, d2);
+        }
+      }
+      // dist = d2 / sqrt(d2); the tiny offset makes coincident points come out as exactly 0 without a branch
+      const double dist = d2 * rsqrt_fast(d2 + 1e-300);
+      double g = 0.;
+      double val = cov_eval<COV, GRAD>(dist, var, range, g);
+      if (!full) {
+        const bool both = real && ((real_mask >> o) & 1u);
+        val = both ? val : 0.;
+        g = both ? g : 0.;
       }
       if (lane < P) S[min(lane, o) * kLd + max(lane, o)] = val;
-      if (GRAD) gpair[t - 1] = g;
+      if (GRAD) gpair[t - 1] = (lane < P) ? g : 0.;
+    }
+    if (DIM == 2) {  // dependent gather of the next row; lands during the factorisation
+      src_pre = src_next;
+      y_pre = 0.;
+      if (src_next >= 0) {
+        y_pre = p.y[src_next];
+        c_pre = *reinterpret_cast<const double2*>(p.coords + src_next * 2);
+      }
     }
     // diagonal: variance + nugget 1 (Vecchia_utils.cpp:1601 / :1411,1563), 1 for dummies; response row MT+1
     if (lane < P) {
