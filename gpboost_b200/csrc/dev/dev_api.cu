@@ -64,7 +64,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int6
 __global__ void bt_apply_kernel(const double* __restrict__ A, const double* __restrict__ u,
                                 const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
                                 const int32_t* __restrict__ perm, double* __restrict__ out_orig, int64_t n, int m,
-                                int64_t row_begin, int64_t row_end) {
+                                int64_t row_begin, int64_t row_end, double scale) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -78,7 +78,7 @@ __global__ void bt_apply_kernel(const double* __restrict__ A, const double* __re
     s = gpb::warp_sum(s);
     if (lane == 0) {
       if (j >= row_begin && j < row_end) s += u[j];  // unit diagonal of B
-      out_orig[perm[j]] = s;
+      out_orig[perm[j]] = s * scale;
     }
   }
 }
@@ -398,12 +398,25 @@ int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host) {
   CUDA_TRY(cudaSetDevice(h->device));
   if (ensure_csc(h)) return -1;
   bt_apply_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->A, h->u, h->colptr, h->csc_pos, h->perm, h->yaux, h->n,
-                                                         h->m, h->row_begin, h->row_end);
+                                                         h->m, h->row_begin, h->row_end, 1.0);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   CUDA_TRY(cudaMemcpyAsync(h->stage_host, h->yaux, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   std::memcpy(yaux_host, h->stage_host, sizeof(double) * h->n);
+  return 0;
+}
+
+int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale) {
+  if (!h || !out_dev) return fail("gpbdev_vecchia_yaux_device: null argument");
+  if (!h->factor_stored) return fail("gpbdev_vecchia_yaux_device: call gpbdev_vecchia_eval(mode=STORE) first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (ensure_csc(h)) return -1;
+  bt_apply_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->A, h->u, h->colptr, h->csc_pos, h->perm, out_dev, h->n, h->m,
+                                                         h->row_begin, h->row_end, scale);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -1,0 +1,584 @@
+// Device tree learner: histogram construction, split search and data partition for one leaf-wise tree on dense
+// uint8 bins (numerical features, no missing values, constant hessian). C ABI in include/gpboost_b200_dev.h.
+//
+// Replaces, for that configuration, the reference's SerialTreeLearner::Train loop
+// (src/LightGBM/treelearner/serial_tree_learner.cpp:159-209) and what it calls:
+//   ConstructHistograms :351 -> Dataset::ConstructHistogramsInner (io/dataset.cpp:1143-1245),
+//                               DenseBin::ConstructHistogramInner (io/dense_bin.hpp:98-141)
+//   FindBestSplitsFromHistograms :375 -> FeatureHistogram::FindBestThreshold / FindBestThresholdSequentially
+//                               (feature_histogram.hpp:85-113, 858-960, 1057-1083), Subtract :79, SplitInfo::operator> split_info.hpp:126
+//   SplitInner :565 -> DataPartition::Split (data_partition.hpp:101-120), LeafSplits::Init (leaf_splits.hpp:70-110)
+// and the reference's own device kernels histogram16/64/256 (treelearner/kernels/histogram_16_64_256.cu: float2 atomics in
+// shared memory, sm_60-75 only, split search on the CPU).
+//
+// B200 design:
+//  * bins live row-major n x Fpad (Fpad = 32-multiple) so one warp reads one 32-byte sector per row: lane = feature;
+//  * histogram kernel: one warp per (row chunk, 32-feature group); every lane owns the private shared-memory histogram
+//    of ITS feature (grad fp64 + count u32, 96 KB per warp) and walks the chunk's rows in order: no atomics, no
+//    inter-lane conflicts by construction, deterministic, and the same accumulation order per feature as the reference's
+//    column-wise pass inside a chunk; chunk partials are merged in chunk order by a second kernel;
+//  * split kernel: one thread per feature replays the reference's right-to-left scan with identical arithmetic
+//    (child sums are the scan's running sums, as in the reference), block arg-max with SplitInfo's tie rule;
+//  * partition: flag + exclusive scan (CUB) + scatter = stable, like the reference's ordered partition.
+// The leaf loop runs on the host (one small D2H per split); HBM traffic per split = rows_in_smaller_leaf * (Fpad + 12) bytes.
+#include "../../../include/gpboost_b200_dev.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_tree_err;
+int tfail(const std::string& m) { g_tree_err = m; return -1; }
+#define TCUDA(expr)                                                                                          \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return tfail(std::string("CUDA error at " __FILE__ ":") + std::to_string(__LINE__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kBins = 256;
+constexpr double kEps = (double)1e-15f;  // kEpsilon, include/LightGBM/meta.h:54
+
+struct SplitOut {  // mirrors the fields of SplitInfo the learner consumes (split_info.hpp:22-60)
+  double gain;
+  double left_output, right_output;
+  double left_sum_gradient, left_sum_hessian, right_sum_gradient, right_sum_hessian;
+  int feature, threshold, left_count, right_count;
+};
+
+struct LeafArgs {
+  int leaf;            // -1: inactive; also the row of the per-leaf "splittable" flags
+  int hist_slot;
+  int inherit;         // 1: features flagged unsplittable in the parent (snapshot in parent_flags) are skipped
+  int num_data;
+  double sum_gradients, sum_hessians;
+};
+
+// ---- histogram: lane = feature, private shared histograms, rows of the chunk in order
+__global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bins, int Fpad, const int32_t* __restrict__ idx,
+                                                   int64_t begin, int64_t count, int64_t rows_per_chunk,
+                                                   const double* __restrict__ grad, double* __restrict__ part_g,
+                                                   uint32_t* __restrict__ part_c) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  double* hg = reinterpret_cast<double*>(sm);                        // [32][257]
+  uint32_t* hc = reinterpret_cast<uint32_t*>(sm + 32 * 257 * 8);     // [32][257]
+  const int lane = threadIdx.x;
+  const int chunk = blockIdx.x, fg = blockIdx.y;
+  for (int b = 0; b < 257; ++b) { hg[lane * 257 + b] = 0.; hc[lane * 257 + b] = 0u; }
+  __syncwarp();
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(r0 + rows_per_chunk, count);
+  const uint8_t* bcol = bins + fg * 32 + lane;
+  double* mg = hg + lane * 257;
+  uint32_t* mc = hc + lane * 257;
+  int64_t j = r0;
+  // 4 rows in flight: the loads are independent, the read-modify-writes stay in row order
+  for (; j + 4 <= r1; j += 4) {
+    int64_t r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = idx ? (int64_t)idx[begin + j + u] : (begin + j + u);
+    int b[4];
+    double g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { b[u] = bcol[r[u] * Fpad]; g[u] = grad[r[u]]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { mg[b[u]] += g[u]; mc[b[u]] += 1u; }
+  }
+  for (; j < r1; ++j) {
+    const int64_t r = idx ? (int64_t)idx[begin + j] : (begin + j);
+    const int b = bcol[r * Fpad];
+    mg[b] += grad[r];
+    mc[b] += 1u;
+  }
+  __syncwarp();
+  // partial[chunk][feature][bin], coalesced over bins
+  const int64_t base = ((int64_t)chunk * Fpad + fg * 32) * kBins;
+  for (int f = 0; f < 32; ++f)
+    for (int b = lane; b < kBins; b += 32) {
+      part_g[base + f * kBins + b] = hg[f * 257 + b];
+      part_c[base + f * kBins + b] = hc[f * 257 + b];
+    }
+}
+
+// merge chunk partials in chunk order -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226)
+__global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad,
+                                   int F, double hess_const, double* __restrict__ hist) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= F * kBins) return;
+  double g = 0.;
+  uint64_t c = 0;
+  const int f = t / kBins, b = t % kBins;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int64_t o = ((int64_t)ch * Fpad + f) * kBins + b;
+    g += part_g[o];
+    c += part_c[o];
+  }
+  hist[2 * t] = g;
+  hist[2 * t + 1] = (double)c * hess_const;
+}
+
+// larger = parent - smaller (feature_histogram.hpp:79-83), in place on the parent's slot
+__global__ void hist_subtract_kernel(double* __restrict__ parent, const double* __restrict__ smaller, int n2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n2) parent[t] -= smaller[t];
+}
+
+__device__ __forceinline__ bool split_better(double ga, int fa, double gb, int fb) {  // SplitInfo::operator>
+  if (fa == -1) fa = 2147483647;
+  if (fb == -1) fb = 2147483647;
+  if (ga != gb) return ga > gb;
+  return fa < fb;
+}
+
+// one block per leaf (smaller, larger); thread f scans feature f right-to-left (feature_histogram.hpp:858-960)
+__global__ void split_kernel(const double* __restrict__ hist_base, int64_t slot_stride, const int32_t* __restrict__ num_bin, int F,
+                             LeafArgs a0, LeafArgs a1, int min_data_in_leaf, double min_sum_hessian, double lambda_l2,
+                             double min_gain_to_split, unsigned char* __restrict__ splittable,
+                             const unsigned char* __restrict__ parent_flags, SplitOut* __restrict__ out) {
+  const LeafArgs a = blockIdx.x == 0 ? a0 : a1;
+  if (a.leaf < 0) return;
+  __shared__ SplitOut sh[256];
+  const double* hist = hist_base + (int64_t)a.hist_slot * slot_stride;
+  unsigned char* flags = splittable + (int64_t)a.leaf * F;
+  const unsigned char* pflags = a.inherit ? parent_flags : nullptr;
+  SplitOut best;
+  best.gain = -INFINITY; best.feature = -1; best.threshold = 0; best.left_count = best.right_count = 0;
+  best.left_output = best.right_output = 0.;
+  best.left_sum_gradient = best.left_sum_hessian = best.right_sum_gradient = best.right_sum_hessian = 0.;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    // a feature that had no admissible threshold in the parent is not examined (serial_tree_learner.cpp:329-336)
+    if (pflags && !pflags[f]) { flags[f] = 0; continue; }
+    const double* h = hist + (int64_t)f * kBins * 2;
+    const int nb = num_bin[f];
+    const double sum_gradient = a.sum_gradients;
+    const double sum_hessian = a.sum_hessians + 2 * kEps;
+    const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
+    const double cnt_factor = a.num_data / sum_hessian;
+    double best_lg = NAN, best_lh = NAN, best_gain = -INFINITY;
+    int best_lc = 0, best_thr = nb;
+    double srg = 0., srh = kEps;
+    int rc = 0;
+    bool spl = false;
+    for (int t = nb - 1; t >= 1; --t) {
+      const double g = h[2 * t], hs = h[2 * t + 1];
+      const int cnt = (int)(hs * cnt_factor + 0.5f);
+      srg += g; srh += hs; rc += cnt;
+      if (rc < min_data_in_leaf || srh < min_sum_hessian) continue;
+      const int lc = a.num_data - rc;
+      if (lc < min_data_in_leaf) break;
+      const double slh = sum_hessian - srh;
+      if (slh < min_sum_hessian) break;
+      const double slg = sum_gradient - srg;
+      const double gain = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
+      if (gain <= min_gain_shift) continue;
+      spl = true;
+      if (gain > best_gain) { best_lc = lc; best_lg = slg; best_lh = slh; best_thr = t - 1; best_gain = gain; }
+    }
+    flags[f] = spl ? 1 : 0;
+    if (spl && best_gain > -INFINITY) {
+      SplitOut s;
+      s.feature = f; s.threshold = best_thr;
+      s.left_output = -best_lg / (best_lh + lambda_l2);
+      s.left_count = best_lc;
+      s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
+      s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
+      s.right_count = a.num_data - best_lc;
+      s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
+      s.gain = best_gain - min_gain_shift;
+      if (split_better(s.gain, s.feature, best.gain, best.feature)) best = s;
+    }
+  }
+  sh[threadIdx.x] = best;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const SplitOut& c = sh[threadIdx.x + o];
+      if (split_better(c.gain, c.feature, sh[threadIdx.x].gain, sh[threadIdx.x].feature)) sh[threadIdx.x] = c;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+__global__ void mark_kernel(const uint8_t* __restrict__ bins, int Fpad, int feature, int threshold, const int32_t* __restrict__ idx,
+                            int64_t begin, int64_t count, int32_t* __restrict__ flag) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (int64_t)gridDim.x * blockDim.x)
+    flag[j] = bins[(int64_t)idx[begin + j] * Fpad + feature] <= threshold ? 1 : 0;
+}
+// stable scatter: lefts keep their order at the front, rights theirs behind (data_partition.hpp:101-120)
+__global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, int64_t count, const int32_t* __restrict__ flag,
+                               const int32_t* __restrict__ pos, int32_t nleft, int32_t* __restrict__ out) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = pos[j];
+    const int64_t dst = flag[j] ? p : (nleft + (j - p));
+    out[dst] = idx[begin + j];
+  }
+}
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+// deterministic sum: fixed block partials, then one block
+__global__ void sum_stage1_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ part) {
+  __shared__ double sh[256];
+  double s = 0.;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t b = (int64_t)blockIdx.x * per, e = min(b + per, n);
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void sum_stage2_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+// score[row] += value[leaf] for the rows of every leaf of the last tree (Tree::AddPredictionToScore via the data partition)
+__global__ void add_score_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ leaf_begin,
+                                 const int32_t* __restrict__ leaf_cnt, const double* __restrict__ value, double* __restrict__ score,
+                                 int32_t* __restrict__ leaf_of_row) {
+  const int l = blockIdx.y;
+  const int64_t b = leaf_begin[l], c = leaf_cnt[l];
+  const double v = value[l];
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < c; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = idx[b + j];
+    if (score) score[r] += v;
+    if (leaf_of_row) leaf_of_row[r] = l;
+  }
+}
+
+__global__ void sub_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] - b[i];
+}
+__global__ void add_const_kernel(double* __restrict__ a, double c, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] += c;
+}
+
+}  // namespace
+
+struct gpbdev_tree {
+  int device = 0, num_sms = 0;
+  int64_t n = 0;
+  int F = 0, Fpad = 0, L = 0;
+  gpbdev_tree_config cfg;
+  cudaStream_t stream = nullptr;
+  uint8_t* bins = nullptr;        // n x Fpad row-major
+  int32_t* num_bin = nullptr;     // F
+  int32_t *idx = nullptr, *idx_tmp = nullptr, *flag = nullptr, *pos = nullptr;
+  double* grad = nullptr;         // n (device copy when the caller passes host gradients)
+  double* hist = nullptr;         // (L + 1) slots x F x 256 x 2
+  unsigned char* splittable = nullptr;  // L x F, row = leaf id (FeatureHistogram::is_splittable_)
+  unsigned char* parent_flags = nullptr; // F: snapshot of the parent's flags while its two children are examined
+  double* part_g = nullptr;
+  uint32_t* part_c = nullptr;
+  int max_chunks = 0;
+  double* sum_part = nullptr;
+  SplitOut* split_dev = nullptr;
+  SplitOut* split_host = nullptr;  // pinned
+  double* scalar_host = nullptr;   // pinned
+  void* scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  int32_t *leaf_begin_dev = nullptr, *leaf_cnt_dev = nullptr;
+  double* leaf_val_dev = nullptr;
+  std::vector<int> leaf_begin, leaf_cnt;
+  int last_num_leaves = 0;
+  int64_t launches = 0;
+  std::vector<uint8_t> bins_rm_host;
+};
+
+extern "C" {
+
+const char* gpbdev_tree_last_error(void) { return g_tree_err.c_str(); }
+
+int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major, const int32_t* num_bin,
+                       const gpbdev_tree_config* cfg) {
+  if (!out || !bins_feature_major || !num_bin || !cfg) return tfail("gpbdev_tree_create: null argument");
+  if (n <= 0 || F <= 0) return tfail("gpbdev_tree_create: need n > 0 and F > 0");
+  if (cfg->num_leaves < 2) return tfail("gpbdev_tree_create: num_leaves must be >= 2");
+  for (int f = 0; f < F; ++f)
+    if (num_bin[f] < 1 || num_bin[f] > kBins) return tfail("gpbdev_tree_create: num_bin must be in [1, 256]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
+    cudaGetLastError();
+    return tfail("gpbdev_tree_create: no CUDA device " + std::to_string(device) + " — the B200 tree learner has no CPU fallback");
+  }
+  TCUDA(cudaSetDevice(device));
+  gpbdev_tree* h = new gpbdev_tree();
+  h->device = device; h->n = n; h->F = F; h->Fpad = (F + 31) / 32 * 32; h->L = cfg->num_leaves; h->cfg = *cfg;
+  cudaDeviceProp prop;
+  TCUDA(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  TCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  // feature-major (the reference's dense-bin layout) -> row-major padded (one 32-byte sector per row and feature group)
+  h->bins_rm_host.assign((size_t)n * h->Fpad, 0);
+  for (int f = 0; f < F; ++f)
+    for (int64_t i = 0; i < n; ++i) h->bins_rm_host[(size_t)i * h->Fpad + f] = bins_feature_major[(size_t)f * n + i];
+  TCUDA(cudaMalloc(&h->bins, (size_t)n * h->Fpad));
+  TCUDA(cudaMemcpy(h->bins, h->bins_rm_host.data(), (size_t)n * h->Fpad, cudaMemcpyHostToDevice));
+  h->bins_rm_host.clear(); h->bins_rm_host.shrink_to_fit();
+  TCUDA(cudaMalloc(&h->num_bin, sizeof(int32_t) * F));
+  TCUDA(cudaMemcpy(h->num_bin, num_bin, sizeof(int32_t) * F, cudaMemcpyHostToDevice));
+  TCUDA(cudaMalloc(&h->idx, sizeof(int32_t) * n));
+  TCUDA(cudaMalloc(&h->idx_tmp, sizeof(int32_t) * n));
+  TCUDA(cudaMalloc(&h->flag, sizeof(int32_t) * n));
+  TCUDA(cudaMalloc(&h->pos, sizeof(int32_t) * n));
+  TCUDA(cudaMalloc(&h->grad, sizeof(double) * n));
+  const size_t slot = (size_t)F * kBins * 2;
+  TCUDA(cudaMalloc(&h->hist, sizeof(double) * slot * (h->L + 1)));
+  TCUDA(cudaMalloc(&h->splittable, (size_t)h->L * F));
+  TCUDA(cudaMalloc(&h->parent_flags, (size_t)F));
+  h->max_chunks = h->num_sms * 2;
+  TCUDA(cudaMalloc(&h->part_g, sizeof(double) * (size_t)h->max_chunks * h->Fpad * kBins));
+  TCUDA(cudaMalloc(&h->part_c, sizeof(uint32_t) * (size_t)h->max_chunks * h->Fpad * kBins));
+  TCUDA(cudaMalloc(&h->sum_part, sizeof(double) * 1024));
+  TCUDA(cudaMalloc(&h->split_dev, sizeof(SplitOut) * 2));
+  TCUDA(cudaMallocHost(&h->split_host, sizeof(SplitOut) * 2));
+  TCUDA(cudaMallocHost(&h->scalar_host, sizeof(double) * 4));
+  TCUDA(cub::DeviceScan::ExclusiveSum(nullptr, h->scan_tmp_bytes, h->flag, h->pos, (int)n, h->stream));
+  TCUDA(cudaMalloc(&h->scan_tmp, h->scan_tmp_bytes));
+  TCUDA(cudaMalloc(&h->leaf_begin_dev, sizeof(int32_t) * h->L));
+  TCUDA(cudaMalloc(&h->leaf_cnt_dev, sizeof(int32_t) * h->L));
+  TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
+  TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
+  *out = h;
+  return 0;
+}
+
+int gpbdev_tree_free(gpbdev_tree_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
+  cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
+  cudaFree(h->split_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  cudaFreeHost(h->split_host); cudaFreeHost(h->scalar_host);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int64_t gpbdev_tree_launch_count(gpbdev_tree_t h) { return h ? h->launches : 0; }
+void* gpbdev_tree_stream(gpbdev_tree_t h) { return h ? (void*)h->stream : nullptr; }
+
+int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device, double hess_const, int* num_leaves_out,
+                      int* split_feature, int* threshold_bin, int* left_child, int* right_child, float* split_gain,
+                      double* leaf_value, int* leaf_count) {
+  if (!h || !grad_in || !num_leaves_out) return tfail("gpbdev_tree_train: null argument");
+  TCUDA(cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  const int F = h->F, Fpad = h->Fpad, L = h->L;
+  const gpbdev_tree_config& cfg = h->cfg;
+  const double* grad = grad_in;
+  if (!grad_on_device) {
+    TCUDA(cudaMemcpyAsync(h->grad, grad_in, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    grad = h->grad;
+  }
+  const size_t slot_stride = (size_t)F * kBins * 2;
+  // ---- BeforeTrain: partition = all rows in leaf 0, root sums (leaf_splits.hpp:70-83)
+  iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
+  const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
+  sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
+  sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
+  TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  h->launches += 3;
+  std::vector<int> leaf_begin(L, 0), leaf_cnt(L, 0), leaf_depth(L, 0), leaf_parent(L, -1), slot_of(L, -1);
+  std::vector<double> leaf_sg(L, 0.), leaf_sh(L, 0.);
+  std::vector<SplitOut> best(L);
+  for (auto& b : best) { b.gain = -INFINITY; b.feature = -1; }
+  std::vector<int> free_slots;
+  for (int s = L; s >= 0; --s) free_slots.push_back(s);
+  leaf_cnt[0] = (int)n;
+  leaf_sg[0] = h->scalar_host[0];
+  leaf_sh[0] = hess_const * (double)n;
+  leaf_value[0] = 0.; leaf_count[0] = (int)n;
+  int num_leaves = 1, left_leaf = 0, right_leaf = -1;
+
+  auto build_hist = [&](int leaf, int slot) -> int {
+    const int64_t cnt = leaf_cnt[leaf];
+    int64_t rpc = std::max<int64_t>(2048, (cnt + h->max_chunks - 1) / h->max_chunks);
+    const int nchunks = (int)((cnt + rpc - 1) / rpc);
+    dim3 grid(nchunks, Fpad / 32);
+    hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
+                                                       rpc, grad, h->part_g, h->part_c);
+    TCUDA(cudaGetLastError());
+    hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const,
+                                                                      h->hist + (size_t)slot * slot_stride);
+    TCUDA(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+  };
+
+  for (int split = 0; split < L - 1; ++split) {
+    // ---- BeforeFindBestSplit (serial_tree_learner.cpp:283-322)
+    bool do_find = true;
+    if (cfg.max_depth > 0 && leaf_depth[left_leaf] >= cfg.max_depth) do_find = false;
+    if (do_find) {
+      const int nl = leaf_cnt[left_leaf], nr = right_leaf >= 0 ? leaf_cnt[right_leaf] : 0;
+      if (nr < cfg.min_data_in_leaf * 2 && nl < cfg.min_data_in_leaf * 2) do_find = false;
+    }
+    if (!do_find) {
+      best[left_leaf].gain = -INFINITY;
+      if (right_leaf >= 0) best[right_leaf].gain = -INFINITY;
+    } else {
+      int smaller, larger = -1, parent_slot = -1;
+      if (right_leaf < 0) smaller = left_leaf;
+      else if (leaf_cnt[left_leaf] < leaf_cnt[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
+      else { smaller = right_leaf; larger = left_leaf; }
+      if (right_leaf >= 0) parent_slot = slot_of[left_leaf];  // the parent's histograms sit under the left (= parent) id
+      const int new_slot = free_slots.back();
+      free_slots.pop_back();
+      if (build_hist(smaller, new_slot)) return -1;
+      if (larger >= 0) {  // larger = parent - smaller, in place: the parent's slot becomes the larger leaf's
+        hist_subtract_kernel<<<(int)((slot_stride + 255) / 256), 256, 0, h->stream>>>(h->hist + (size_t)parent_slot * slot_stride,
+                                                                                     h->hist + (size_t)new_slot * slot_stride,
+                                                                                     (int)slot_stride);
+        h->launches += 1;
+        slot_of[larger] = parent_slot;
+      }
+      slot_of[smaller] = new_slot;
+      // both children inherit the parent's flags (the parent's id is the left child's id): snapshot them first
+      if (right_leaf >= 0)
+        TCUDA(cudaMemcpyAsync(h->parent_flags, h->splittable + (size_t)left_leaf * F, F, cudaMemcpyDeviceToDevice, h->stream));
+      LeafArgs a0, a1;
+      a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = leaf_cnt[smaller];
+      a0.sum_gradients = leaf_sg[smaller]; a0.sum_hessians = leaf_sh[smaller];
+      a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt[larger] : 0;
+      a1.sum_gradients = larger >= 0 ? leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? leaf_sh[larger] : 0.;
+      split_kernel<<<2, 256, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
+                                             cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split, h->splittable,
+                                             h->parent_flags, h->split_dev);
+      TCUDA(cudaGetLastError());
+      h->launches += 1;
+      TCUDA(cudaMemcpyAsync(h->split_host, h->split_dev, sizeof(SplitOut) * 2, cudaMemcpyDeviceToHost, h->stream));
+      TCUDA(cudaStreamSynchronize(h->stream));
+      best[smaller] = h->split_host[0];
+      if (larger >= 0) best[larger] = h->split_host[1];
+    }
+    // ---- leaf with the best split (ArrayArgs::ArgMax with SplitInfo::operator>)
+    int best_leaf = 0;
+    for (int l = 1; l < num_leaves; ++l) {
+      int fa = best[l].feature == -1 ? 2147483647 : best[l].feature, fb = best[best_leaf].feature == -1 ? 2147483647 : best[best_leaf].feature;
+      const bool better = best[l].gain != best[best_leaf].gain ? best[l].gain > best[best_leaf].gain : fa < fb;
+      if (better) best_leaf = l;
+    }
+    const SplitOut bs = best[best_leaf];
+    if (!(bs.gain > 0.0)) break;
+    // ---- DataPartition::Split (stable)
+    const int64_t b = leaf_begin[best_leaf], c = leaf_cnt[best_leaf];
+    const int gridp = (int)std::min<int64_t>((c + 255) / 256, (int64_t)h->num_sms * 8);
+    mark_kernel<<<gridp, 256, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, h->flag);
+    TCUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->flag, h->pos, (int)c, h->stream));
+    int32_t last_pos = 0, last_flag = 0;
+    TCUDA(cudaMemcpyAsync(&last_pos, h->pos + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    TCUDA(cudaMemcpyAsync(&last_flag, h->flag + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    TCUDA(cudaStreamSynchronize(h->stream));
+    const int nleft = last_pos + last_flag, nright = (int)c - nleft;
+    scatter_kernel<<<gridp, 256, 0, h->stream>>>(h->idx, b, c, h->flag, h->pos, nleft, h->idx_tmp);
+    TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
+    h->launches += 4;
+    const int new_leaf = num_leaves;
+    leaf_cnt[best_leaf] = nleft; leaf_begin[new_leaf] = (int)(b + nleft); leaf_cnt[new_leaf] = nright;
+    // ---- Tree::Split (tree.h:533-575)
+    const int node = num_leaves - 1;
+    const int parent = leaf_parent[best_leaf];
+    if (parent >= 0) { if (left_child[parent] == ~best_leaf) left_child[parent] = node; else right_child[parent] = node; }
+    split_feature[node] = bs.feature; threshold_bin[node] = bs.threshold;
+    split_gain[node] = (float)(bs.gain + cfg.min_gain_to_split);
+    left_child[node] = ~best_leaf; right_child[node] = ~new_leaf;
+    leaf_parent[best_leaf] = node; leaf_parent[new_leaf] = node;
+    leaf_value[best_leaf] = std::isnan(bs.left_output) ? 0. : bs.left_output; leaf_count[best_leaf] = nleft;
+    leaf_value[new_leaf] = std::isnan(bs.right_output) ? 0. : bs.right_output; leaf_count[new_leaf] = nright;
+    leaf_depth[new_leaf] = leaf_depth[best_leaf] + 1; leaf_depth[best_leaf]++;
+    leaf_sg[best_leaf] = bs.left_sum_gradient; leaf_sh[best_leaf] = bs.left_sum_hessian;
+    leaf_sg[new_leaf] = bs.right_sum_gradient; leaf_sh[new_leaf] = bs.right_sum_hessian;
+    best[best_leaf].gain = -INFINITY; best[best_leaf].feature = -1;
+    best[new_leaf].gain = -INFINITY; best[new_leaf].feature = -1;
+    ++num_leaves;
+    left_leaf = best_leaf; right_leaf = new_leaf;
+  }
+  h->leaf_begin = leaf_begin; h->leaf_cnt = leaf_cnt; h->last_num_leaves = num_leaves;
+  *num_leaves_out = num_leaves;
+  return 0;
+}
+
+int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_leaves, double* score_dev, int32_t* leaf_of_row_dev) {
+  if (!h || !leaf_values) return tfail("gpbdev_tree_add_score: null argument");
+  if (num_leaves != h->last_num_leaves) return tfail("gpbdev_tree_add_score: num_leaves does not match the last trained tree");
+  TCUDA(cudaSetDevice(h->device));
+  std::vector<int32_t> lb(h->leaf_begin.begin(), h->leaf_begin.begin() + num_leaves), lc(h->leaf_cnt.begin(), h->leaf_cnt.begin() + num_leaves);
+  TCUDA(cudaMemcpyAsync(h->leaf_begin_dev, lb.data(), sizeof(int32_t) * num_leaves, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaMemcpyAsync(h->leaf_cnt_dev, lc.data(), sizeof(int32_t) * num_leaves, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaMemcpyAsync(h->leaf_val_dev, leaf_values, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));  // the host vectors above are temporaries
+  dim3 grid((unsigned)std::min<int64_t>((h->n / num_leaves + 255) / 256 + 1, 1024), num_leaves);
+  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, score_dev, leaf_of_row_dev);
+  TCUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+// ---- device vectors owned by the host-side Booster (training score, label, gradient)
+int gpbdev_vec_alloc(gpbdev_tree_t h, double** out, int64_t n) {
+  if (!h || !out) return tfail("gpbdev_vec_alloc: null argument");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaMalloc(out, sizeof(double) * n));
+  TCUDA(cudaMemsetAsync(*out, 0, sizeof(double) * n, h->stream));
+  return 0;
+}
+int gpbdev_vec_free(gpbdev_tree_t h, double* p) {
+  if (h) cudaSetDevice(h->device);
+  cudaFree(p);
+  return 0;
+}
+int gpbdev_vec_upload(gpbdev_tree_t h, double* dst_dev, const double* src_host, int64_t n) {
+  if (!h) return tfail("null handle");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaMemcpyAsync(dst_dev, src_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int gpbdev_vec_download(gpbdev_tree_t h, double* dst_host, const double* src_dev, int64_t n) {
+  if (!h) return tfail("null handle");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaMemcpyAsync(dst_host, src_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+// out = a - b   (RegressionL2loss::GetGradients: grad = score - label, regression_objective.hpp:158-162)
+int gpbdev_vec_sub(gpbdev_tree_t h, const double* a_dev, const double* b_dev, double* out_dev, int64_t n) {
+  if (!h) return tfail("null handle");
+  TCUDA(cudaSetDevice(h->device));
+  sub_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(a_dev, b_dev, out_dev, n);
+  TCUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+int gpbdev_vec_add_const(gpbdev_tree_t h, double* a_dev, double c, int64_t n) {
+  if (!h) return tfail("null handle");
+  TCUDA(cudaSetDevice(h->device));
+  add_const_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(a_dev, c, n);
+  TCUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int gpbdev_tree_sync(gpbdev_tree_t h) {
+  if (!h) return tfail("null handle");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+#include "booster.h"
+
+#include <cmath>
+#include <cstdio>
+#include <sstream>
+#include <stdexcept>
+
+#include "runtime.h"
+
+namespace gpb200 {
+
+namespace {
+[[noreturn]] void Fatal(const std::string& m) { throw std::runtime_error(m); }
+void TreeCheck(int rc) {
+  if (rc != 0) Fatal(std::string(gpbdev_tree_last_error()));
+}
+std::string Num(double v) {
+  char buf[64];
+  std::snprintf(buf, sizeof(buf), "%.17g", v);
+  return buf;
+}
+}  // namespace
+
+double Tree::Predict(const double* row) const {  // Tree::Predict / NumericalDecision (tree.h:577-640), MissingType::None
+  if (num_leaves <= 1) return leaf_value[0];
+  int node = 0;
+  while (node >= 0) {
+    double fval = row[split_feature[node]];
+    if (std::isnan(fval)) fval = 0.0;
+    node = fval <= threshold[node] ? left_child[node] : right_child[node];
+  }
+  return leaf_value[~node];
+}
+
+std::string Tree::ToString() const {  // Tree::ToString (io/tree.cpp:333-400), fields this build carries
+  std::ostringstream s;
+  auto arr_i = [&](const char* k, const std::vector<int>& v, int n) { s << k << "="; for (int i = 0; i < n; ++i) s << (i ? " " : "") << v[i]; s << "\n"; };
+  auto arr_d = [&](const char* k, const std::vector<double>& v, int n) { s << k << "="; for (int i = 0; i < n; ++i) s << (i ? " " : "") << Num(v[i]); s << "\n"; };
+  s << "num_leaves=" << num_leaves << "\n" << "num_cat=0\n";
+  arr_i("split_feature", split_feature, num_leaves - 1);
+  s << "split_gain="; for (int i = 0; i < num_leaves - 1; ++i) s << (i ? " " : "") << Num(split_gain[i]); s << "\n";
+  arr_d("threshold", threshold, num_leaves - 1);
+  s << "decision_type="; for (int i = 0; i < num_leaves - 1; ++i) s << (i ? " " : "") << 2; s << "\n";
+  arr_i("left_child", left_child, num_leaves - 1);
+  arr_i("right_child", right_child, num_leaves - 1);
+  arr_d("leaf_value", leaf_value, num_leaves);
+  arr_i("leaf_count", leaf_count, num_leaves);
+  s << "is_linear=0\n" << "shrinkage=" << Num(shrinkage) << "\n";
+  return s.str();
+}
+
+Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model) : train_(train), re_model_(re_model) {
+  if (train == nullptr) Fatal("Booster: training data is null");
+  if (!train->has_label()) Fatal("Booster: the training Dataset has no label (LGBM_DatasetSetField \"label\")");
+  params_ = train->params();
+  Params p2 = Params::Parse(parameters);
+  for (auto& kv : p2.kv) params_.kv[kv.first] = kv.second;
+  const std::string obj = params_.GetString("objective", "regression", {"objective_type", "app", "application"});
+  if (obj != "regression" && obj != "regression_l2" && obj != "l2" && obj != "mean_squared_error" && obj != "mse")
+    Fatal("Objective '" + obj + "' is not supported by the B200 booster (hot path: 'regression')");
+  n_ = train->num_data();
+  if (re_model_ != nullptr && re_model_->NumData() != n_) Fatal("Different number of data points in the GPModel and the Dataset");  // c_api.cpp:172-233
+  num_leaves_ = params_.GetInt("num_leaves", 31, {"num_leaf", "max_leaves", "max_leaf"});
+  learning_rate_ = params_.GetDouble("learning_rate", 0.1, {"shrinkage_rate", "eta"});
+  boost_from_average_ = params_.GetBool("boost_from_average", true);
+  train_gp_model_cov_pars_ = params_.GetBool("train_gp_model_cov_pars", true);
+  for (const char* k : {"bagging_fraction", "feature_fraction", "feature_fraction_bynode"})
+    if (params_.GetDouble(k, 1.0) < 1.0) Fatal(std::string(k) + " < 1 is not supported by the B200 booster yet");
+  if (params_.GetDouble("lambda_l1", 0., {"reg_alpha"}) > 0.) Fatal("lambda_l1 > 0 is not supported by the B200 booster yet");
+  if (params_.GetBool("leaves_newton_update", false) || params_.GetBool("line_search_step_length", false))
+    Fatal("leaves_newton_update / line_search_step_length are not supported by the B200 booster yet");
+  gpbdev_tree_config cfg;
+  cfg.num_leaves = num_leaves_;
+  cfg.min_data_in_leaf = params_.GetInt("min_data_in_leaf", 20, {"min_data_per_leaf", "min_data", "min_child_samples"});
+  cfg.min_sum_hessian_in_leaf = params_.GetDouble("min_sum_hessian_in_leaf", 1e-3, {"min_sum_hessian_per_leaf", "min_sum_hessian", "min_hessian", "min_child_weight"});
+  cfg.lambda_l2 = params_.GetDouble("lambda_l2", 0., {"reg_lambda", "lambda"});
+  cfg.min_gain_to_split = params_.GetDouble("min_gain_to_split", 0., {"min_split_gain"});
+  cfg.max_depth = params_.GetInt("max_depth", -1);
+  const int F = train->num_features();
+  if (F <= 0) Fatal("All features are trivial (constant): nothing to learn");
+  std::vector<int32_t> num_bin(F);
+  for (int k = 0; k < F; ++k) num_bin[k] = train->feature(k).num_bin;
+  TreeCheck(gpbdev_tree_create(&learner_, GetRuntime().device, n_, F, train->bins_feature_major().data(), num_bin.data(), &cfg));
+  TreeCheck(gpbdev_vec_alloc(learner_, &score_dev_, n_));
+  TreeCheck(gpbdev_vec_alloc(learner_, &label_dev_, n_));
+  TreeCheck(gpbdev_vec_alloc(learner_, &grad_dev_, n_));
+  host_buf_.resize(n_);
+  for (int64_t i = 0; i < n_; ++i) host_buf_[i] = (double)train->label()[i];  // label_t = float (meta.h:49)
+  TreeCheck(gpbdev_vec_upload(learner_, label_dev_, host_buf_.data(), n_));
+}
+
+Booster::~Booster() {
+  if (learner_) {
+    gpbdev_vec_free(learner_, score_dev_);
+    gpbdev_vec_free(learner_, label_dev_);
+    gpbdev_vec_free(learner_, grad_dev_);
+    gpbdev_tree_free(learner_);
+  }
+}
+
+// GBDT::Boosting -> RegressionL2loss::GetGradients (regression_objective.hpp:153-201)
+void Booster::Boosting() {
+  TreeCheck(gpbdev_vec_sub(learner_, score_dev_, label_dev_, grad_dev_, n_));  // grad = score - label, hessian = 1
+  if (re_model_ != nullptr) {
+    // Gaussian likelihood: OptimCovPar(grad) then CalcGradient(grad): grad <- Psi^-1 (F - y) / sigma^2
+    TreeCheck(gpbdev_vec_download(learner_, host_buf_.data(), grad_dev_, n_));
+    if (train_gp_model_cov_pars_) re_model_->OptimCovPar(host_buf_.data(), nullptr, true, true);
+    re_model_->CalcGradient(host_buf_.data(), nullptr, true);
+    TreeCheck(gpbdev_vec_upload(learner_, grad_dev_, host_buf_.data(), n_));
+  }
+  gradients_ready_ = true;
+}
+
+bool Booster::TrainOneIter() {
+  double init_score = 0.;
+  if (models_.empty() && boost_from_average_) {  // BoostFromAverage (gbdt.cpp:376-408): mean label for L2 (also with a Gaussian GP model)
+    double suml = 0.;
+    for (int64_t i = 0; i < n_; ++i) suml += train_->label()[i];
+    init_score = suml / (double)n_;
+    if (std::fabs(init_score) > (double)1e-15f) TreeCheck(gpbdev_vec_add_const(learner_, score_dev_, init_score, n_));
+    else init_score = 0.;
+  }
+  if (re_model_ == nullptr || iter_ == 0 || !gradients_ready_) Boosting();  // gbdt.cpp:428-436
+  auto tree = std::make_unique<Tree>();
+  const int L = num_leaves_;
+  tree->split_feature_inner.assign(L, 0); tree->threshold_bin.assign(L, 0); tree->left_child.assign(L, 0); tree->right_child.assign(L, 0);
+  tree->split_gain.assign(L, 0.f); tree->leaf_value.assign(L, 0.); tree->leaf_count.assign(L, 0);
+  int nl = 1;
+  TreeCheck(gpbdev_tree_train(learner_, grad_dev_, 1, 1.0, &nl, tree->split_feature_inner.data(), tree->threshold_bin.data(),
+                              tree->left_child.data(), tree->right_child.data(), tree->split_gain.data(), tree->leaf_value.data(),
+                              tree->leaf_count.data()));
+  tree->num_leaves = nl;
+  if (nl <= 1) {  // gbdt.cpp:503-523 / :553-562: no split possible
+    if (models_.empty()) {
+      tree->leaf_value[0] = init_score;  // AsConstantTree(init score); the score already carries it
+      models_.push_back(std::move(tree));
+    }
+    return true;
+  }
+  tree->split_feature.resize(nl - 1);
+  tree->threshold.resize(nl - 1);
+  for (int i = 0; i < nl - 1; ++i) {
+    tree->split_feature[i] = train_->real_feature_index(tree->split_feature_inner[i]);
+    tree->threshold[i] = train_->feature(tree->split_feature_inner[i]).upper_bounds[tree->threshold_bin[i]];  // RealThreshold
+  }
+  for (int i = 0; i < nl; ++i) tree->leaf_value[i] *= learning_rate_;  // Tree::Shrinkage
+  tree->shrinkage = learning_rate_;
+  TreeCheck(gpbdev_tree_add_score(learner_, tree->leaf_value.data(), nl, score_dev_, nullptr));  // UpdateScore
+  if (std::fabs(init_score) > (double)1e-15f) {  // Tree::AddBias (tree.h): stored model only
+    for (int i = 0; i < nl; ++i) tree->leaf_value[i] += init_score;
+    tree->shrinkage = 1.;
+  }
+  gradients_ready_ = false;
+  if (re_model_ != nullptr) Boosting();  // gbdt.cpp:543-550: gradients (and covariance parameters) for the next iteration
+  models_.push_back(std::move(tree));
+  ++iter_;
+  return false;
+}
+
+void Booster::GetTrainingScore(double* out) { TreeCheck(gpbdev_vec_download(learner_, out, score_dev_, n_)); }
+
+void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const {
+  if (ncol != train_->num_total_features()) Fatal("The number of features in data is not the same as it was in training data");
+  std::vector<double> row(ncol);
+  for (int64_t i = 0; i < nrow; ++i) {
+    for (int j = 0; j < ncol; ++j) {
+      const int64_t o = is_row_major ? i * ncol + j : (int64_t)j * nrow + i;
+      row[j] = data_type == 0 ? (double)static_cast<const float*>(data)[o] : static_cast<const double*>(data)[o];
+    }
+    double s = 0.;
+    for (const auto& t : models_) s += t->Predict(row.data());
+    out[i] = s;
+  }
+}
+
+std::string Booster::SaveModelToString() const {  // GBDT::SaveModelToString (boosting/gbdt_model_text.cpp), header subset
+  std::ostringstream s;
+  s << "tree\nversion=v3\nnum_class=1\nnum_tree_per_iteration=1\nlabel_index=0\nmax_feature_idx=" << train_->num_total_features() - 1
+    << "\nobjective=regression\n\n";
+  for (size_t i = 0; i < models_.size(); ++i) s << "Tree=" << i << "\n" << models_[i]->ToString() << "\n\n";
+  s << "end of trees\n";
+  return s.str();
+}
+
+}  // namespace gpb200

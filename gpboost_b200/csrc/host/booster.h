@@ -1,0 +1,66 @@
+// Host-side boosting driver of the B200 build: the object behind the LGBM_Booster* C API entries.
+//
+// Restates GBDT::TrainOneIter / Boosting / BoostFromAverage (src/LightGBM/boosting/gbdt.cpp:411-567, :194-203, :376-408),
+// the L2 objective with its GP coupling (src/LightGBM/objective/regression_objective.hpp:153-201, :259-290) and Tree's
+// bookkeeping (include/LightGBM/tree.h, src/LightGBM/io/tree.cpp) for: objective=regression, numerical features, no bagging /
+// feature sampling. Trees are grown by the device learner (gpbdev_tree_*); training scores and gradients stay on the device.
+#ifndef GPB200_BOOSTER_H_
+#define GPB200_BOOSTER_H_
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/gpboost_b200_dev.h"
+#include "dataset.h"
+#include "re_model.h"
+
+namespace gpb200 {
+
+struct Tree {
+  int num_leaves = 1;
+  std::vector<int> split_feature;       // real feature index
+  std::vector<int> split_feature_inner;
+  std::vector<int> threshold_bin;
+  std::vector<double> threshold;        // bin upper bound (Dataset::RealThreshold)
+  std::vector<int> left_child, right_child;
+  std::vector<float> split_gain;
+  std::vector<double> leaf_value;
+  std::vector<int> leaf_count;
+  double shrinkage = 1.;
+  double Predict(const double* row) const;
+  std::string ToString() const;
+};
+
+class Booster {
+ public:
+  Booster(const Dataset* train, const char* parameters, REModel* re_model);
+  ~Booster();
+  bool TrainOneIter();  // returns true when training cannot continue (no split), like GBDT::TrainOneIter
+  int current_iteration() const { return iter_; }
+  int num_models() const { return (int)models_.size(); }
+  int64_t num_data() const { return n_; }
+  void GetTrainingScore(double* out);
+  void Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const;
+  std::string SaveModelToString() const;
+  gpbdev_tree_t learner() const { return learner_; }
+
+ private:
+  void Boosting();  // gradients for the next tree (+ covariance-parameter fit when a GP model is attached)
+  const Dataset* train_;
+  REModel* re_model_;
+  Params params_;
+  int64_t n_ = 0;
+  int num_leaves_ = 31;
+  double learning_rate_ = 0.1;
+  bool boost_from_average_ = true;
+  bool train_gp_model_cov_pars_ = true;
+  gpbdev_tree_t learner_ = nullptr;
+  double *score_dev_ = nullptr, *label_dev_ = nullptr, *grad_dev_ = nullptr;
+  std::vector<double> host_buf_;
+  std::vector<std::unique_ptr<Tree>> models_;
+  int iter_ = 0;
+  bool gradients_ready_ = false;
+};
+
+}  // namespace gpb200
+#endif

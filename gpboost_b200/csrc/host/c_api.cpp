@@ -7,6 +7,8 @@
 #include <exception>
 #include <string>
 
+#include "booster.h"
+#include "dataset.h"
 #include "re_model.h"
 #include "runtime.h"
 
@@ -144,6 +146,123 @@ int GPB_CanCalculateStandardErrorsCovPars(REModelHandle handle, int* out) {
   API_BEGIN();
   M(handle);
   *out = 0;
+  API_END();
+}
+
+// ---------------------------------------------------------------------------------------------- LGBM_* subset
+int LGBM_DatasetCreateFromMat(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, const char* parameters,
+                              const DatasetHandle reference, DatasetHandle* out) {
+  API_BEGIN();
+  if (reference != nullptr) throw std::runtime_error("LGBM_DatasetCreateFromMat: 'reference' datasets are not supported by the B200 build yet");
+  *out = new gpb200::Dataset(data, data_type, nrow, ncol, is_row_major, gpb200::Params::Parse(parameters));
+  API_END();
+}
+
+int LGBM_DatasetSetField(DatasetHandle handle, const char* field_name, const void* field_data, int num_element, int type) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  auto* ds = reinterpret_cast<gpb200::Dataset*>(handle);
+  if (std::string(field_name) == "label" || std::string(field_name) == "target") {
+    if (type != C_API_DTYPE_FLOAT32) throw std::runtime_error("Input data type error: 'label' must be float32");
+    ds->SetLabel(static_cast<const float*>(field_data), num_element);
+  } else {
+    throw std::runtime_error(std::string("Field '") + field_name + "' is not supported by the B200 build yet");
+  }
+  API_END();
+}
+
+int LGBM_DatasetFree(DatasetHandle handle) {
+  API_BEGIN();
+  delete reinterpret_cast<gpb200::Dataset*>(handle);
+  API_END();
+}
+
+int LGBM_DatasetGetNumData(DatasetHandle handle, int* out) {
+  API_BEGIN();
+  *out = reinterpret_cast<gpb200::Dataset*>(handle)->num_data();
+  API_END();
+}
+
+int LGBM_DatasetGetNumFeature(DatasetHandle handle, int* out) {
+  API_BEGIN();
+  *out = reinterpret_cast<gpb200::Dataset*>(handle)->num_total_features();
+  API_END();
+}
+
+int LGBM_BoosterCreate(const DatasetHandle train_data, const char* parameters, BoosterHandle* out) {
+  API_BEGIN();
+  *out = new gpb200::Booster(reinterpret_cast<const gpb200::Dataset*>(train_data), parameters, nullptr);
+  API_END();
+}
+
+int LGBM_GPBoosterCreate(const DatasetHandle train_data, const char* parameters, const REModelHandle re_model, BoosterHandle* out) {
+  API_BEGIN();
+  if (re_model == nullptr) throw std::runtime_error("LGBM_GPBoosterCreate: re_model is null");
+  *out = new gpb200::Booster(reinterpret_cast<const gpb200::Dataset*>(train_data), parameters, reinterpret_cast<gpb200::REModel*>(re_model));
+  API_END();
+}
+
+int LGBM_BoosterFree(BoosterHandle handle) {
+  API_BEGIN();
+  delete reinterpret_cast<gpb200::Booster*>(handle);
+  API_END();
+}
+
+static gpb200::Booster* B(BoosterHandle h) {
+  if (h == nullptr) throw std::runtime_error("Booster handle is null");
+  return reinterpret_cast<gpb200::Booster*>(h);
+}
+
+int LGBM_BoosterUpdateOneIter(BoosterHandle handle, int* is_finished) {
+  API_BEGIN();
+  *is_finished = B(handle)->TrainOneIter() ? 1 : 0;
+  API_END();
+}
+
+int LGBM_BoosterGetCurrentIteration(BoosterHandle handle, int* out_iteration) {
+  API_BEGIN();
+  *out_iteration = B(handle)->current_iteration();
+  API_END();
+}
+
+int LGBM_BoosterNumberOfTotalModel(BoosterHandle handle, int* out_models) {
+  API_BEGIN();
+  *out_models = B(handle)->num_models();
+  API_END();
+}
+
+int LGBM_BoosterGetNumPredict(BoosterHandle handle, int data_idx, int64_t* out_len) {
+  API_BEGIN();
+  if (data_idx != 0) throw std::runtime_error("Only the training data (data_idx = 0) is available in the B200 build");
+  *out_len = B(handle)->num_data();
+  API_END();
+}
+
+int LGBM_BoosterGetPredict(BoosterHandle handle, int data_idx, int64_t* out_len, double* out_result) {
+  API_BEGIN();
+  if (data_idx != 0) throw std::runtime_error("Only the training data (data_idx = 0) is available in the B200 build");
+  B(handle)->GetTrainingScore(out_result);
+  *out_len = B(handle)->num_data();
+  API_END();
+}
+
+int LGBM_BoosterPredictForMat(BoosterHandle handle, const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major,
+                              int predict_type, int /*start_iteration*/, int /*num_iteration*/, const char* /*parameter*/,
+                              int64_t* out_len, double* out_result) {
+  API_BEGIN();
+  if (predict_type != C_API_PREDICT_NORMAL && predict_type != C_API_PREDICT_RAW_SCORE)
+    throw std::runtime_error("Only normal / raw-score prediction is supported by the B200 build");
+  B(handle)->Predict(data, data_type, nrow, ncol, is_row_major, out_result);
+  *out_len = nrow;
+  API_END();
+}
+
+int LGBM_BoosterSaveModelToString(BoosterHandle handle, int /*start_iteration*/, int /*num_iteration*/, int /*feature_importance_type*/,
+                                  int64_t buffer_len, int64_t* out_len, char* out_str) {
+  API_BEGIN();
+  const std::string s = B(handle)->SaveModelToString();
+  *out_len = (int64_t)s.size() + 1;
+  if (*out_len <= buffer_len) std::memcpy(out_str, s.c_str(), *out_len);
   API_END();
 }
 

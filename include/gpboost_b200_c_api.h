@@ -69,6 +69,43 @@ GPB200_EXPORT int GPB_GetOptimizerCovPars(REModelHandle handle, char* out_str, i
 /* c_api.h:1520 */
 GPB200_EXPORT int GPB_CanCalculateStandardErrorsCovPars(REModelHandle handle, int* out);
 
+/* ---- tree boosting entries (dense numerical data, objective=regression, optional GP model) ------------------------ */
+typedef void* DatasetHandle;  /* c_api.h:35 */
+typedef void* BoosterHandle;  /* c_api.h:36 */
+#define C_API_DTYPE_FLOAT32 (0)
+#define C_API_DTYPE_FLOAT64 (1)
+#define C_API_PREDICT_NORMAL (0)
+#define C_API_PREDICT_RAW_SCORE (1)
+/* c_api.h:236 — bin finding (BinMapper::FindBin) + value->bin on the host, bins handed to the device learner */
+GPB200_EXPORT int LGBM_DatasetCreateFromMat(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major,
+    const char* parameters, const DatasetHandle reference, DatasetHandle* out);
+/* c_api.h:351 — field "label" (float32) */
+GPB200_EXPORT int LGBM_DatasetSetField(DatasetHandle handle, const char* field_name, const void* field_data, int num_element, int type);
+/* c_api.h:318, :387, :396 */
+GPB200_EXPORT int LGBM_DatasetFree(DatasetHandle handle);
+GPB200_EXPORT int LGBM_DatasetGetNumData(DatasetHandle handle, int* out);
+GPB200_EXPORT int LGBM_DatasetGetNumFeature(DatasetHandle handle, int* out);
+/* c_api.h:425 / :437 — the Booster holds a non-owning REModel* (c_api.cpp:1673) */
+GPB200_EXPORT int LGBM_BoosterCreate(const DatasetHandle train_data, const char* parameters, BoosterHandle* out);
+GPB200_EXPORT int LGBM_GPBoosterCreate(const DatasetHandle train_data, const char* parameters, const REModelHandle re_model, BoosterHandle* out);
+/* c_api.h:469 */
+GPB200_EXPORT int LGBM_BoosterFree(BoosterHandle handle);
+/* c_api.h:533 — one boosting iteration: gradients (+ GP covariance fit), device tree, score update */
+GPB200_EXPORT int LGBM_BoosterUpdateOneIter(BoosterHandle handle, int* is_finished);
+/* c_api.h:576, :594 */
+GPB200_EXPORT int LGBM_BoosterGetCurrentIteration(BoosterHandle handle, int* out_iteration);
+GPB200_EXPORT int LGBM_BoosterNumberOfTotalModel(BoosterHandle handle, int* out_models);
+/* c_api.h:677, :691 — training scores (data_idx 0) */
+GPB200_EXPORT int LGBM_BoosterGetNumPredict(BoosterHandle handle, int data_idx, int64_t* out_len);
+GPB200_EXPORT int LGBM_BoosterGetPredict(BoosterHandle handle, int data_idx, int64_t* out_len, double* out_result);
+/* c_api.h:1035 — raw-score prediction of the tree ensemble (host traversal; not on the hot path) */
+GPB200_EXPORT int LGBM_BoosterPredictForMat(BoosterHandle handle, const void* data, int data_type, int32_t nrow, int32_t ncol,
+    int is_row_major, int predict_type, int start_iteration, int num_iteration, const char* parameter, int64_t* out_len,
+    double* out_result);
+/* c_api.h:1200 */
+GPB200_EXPORT int LGBM_BoosterSaveModelToString(BoosterHandle handle, int start_iteration, int num_iteration,
+    int feature_importance_type, int64_t buffer_len, int64_t* out_len, char* out_str);
+
 /* ---- extensions of the B200 build (no counterpart in the reference's exported API) ---------------------- */
 /* device ordinal used by models created afterwards in this process (default 0) */
 GPB200_EXPORT int GPB200_SetDevice(int device);

@@ -79,6 +79,9 @@ GPBDEV_EXPORT int gpbdev_vecchia_eval_async(gpbdev_vecchia_t h, int cov_type, do
 /* After a STORE eval: y_aux = Psi^-1 y = B^T D^-1 B y (CalcYAux, re_model_template.h:9772) returned in
  * ORIGINAL observation order into a host buffer of n doubles. */
 GPBDEV_EXPORT int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host);
+/* Same as gpbdev_vecchia_yaux but the result (times `scale`) stays on the device, original order, written to out_dev
+ * (may alias the engine-external gradient buffer of the boosting driver). */
+GPBDEV_EXPORT int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale);
 /* After a STORE eval: copy A (n x m) and D^-1 (n) to the host — parity tests against the oracle's B, D^-1 */
 GPBDEV_EXPORT int gpbdev_vecchia_get_factor(gpbdev_vecchia_t h, double* A_host, double* Dinv_host);
 
@@ -96,6 +99,50 @@ GPBDEV_EXPORT int gpbdev_vecchia_knn_replayed(gpbdev_vecchia_t h);
 GPBDEV_EXPORT int gpbdev_fp64_peak(int device, double* tflops);
 /* write > L2-size bytes to evict the L2 between timed iterations */
 GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device tree learner (dense uint8 bins, numerical features, no missing values, constant hessian).
+ * Seam: the reference's TreeLearner interface (include/LightGBM/tree_learner.h:29-117: Init / Train / AddPredictionToScore /
+ * GetDataLeafIndices), selected there by device_type (src/LightGBM/treelearner/tree_learner.cpp:15-52).
+ */
+typedef struct gpbdev_tree* gpbdev_tree_t;
+typedef struct {
+  int num_leaves;                 /* config.h: num_leaves            */
+  int min_data_in_leaf;           /*           min_data_in_leaf      */
+  double min_sum_hessian_in_leaf; /*           min_sum_hessian_in_leaf */
+  double lambda_l2;               /*           lambda_l2             */
+  double min_gain_to_split;       /*           min_gain_to_split     */
+  int max_depth;                  /*           max_depth (<= 0: unlimited) */
+} gpbdev_tree_config;
+
+GPBDEV_EXPORT const char* gpbdev_tree_last_error(void);
+/* bins_feature_major: host, F x n uint8 (the reference's dense-bin layout: one column per feature); num_bin[f] <= 256.
+ * Replaces TreeLearner::Init (serial_tree_learner.cpp:38-85). */
+GPBDEV_EXPORT int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major,
+                                     const int32_t* num_bin, const gpbdev_tree_config* cfg);
+GPBDEV_EXPORT int gpbdev_tree_free(gpbdev_tree_t h);
+/* Grow one tree from gradients (n doubles; host pointer, or device pointer when grad_on_device != 0) with hessian == hess_const.
+ * Replaces SerialTreeLearner::Train (serial_tree_learner.cpp:159-209). Output arrays are caller-allocated with num_leaves entries:
+ * per internal node split_feature / threshold_bin / left_child / right_child (~leaf for leaves, Tree convention) / split_gain;
+ * per leaf leaf_value (unshrunk) / leaf_count. */
+GPBDEV_EXPORT int gpbdev_tree_train(gpbdev_tree_t h, const double* grad, int grad_on_device, double hess_const, int* num_leaves,
+                                    int* split_feature, int* threshold_bin, int* left_child, int* right_child, float* split_gain,
+                                    double* leaf_value, int* leaf_count);
+/* score_dev[row] += leaf_values[leaf(row)] over the partition of the last trained tree (ScoreUpdater::AddScore(tree_learner, tree),
+ * score_updater.hpp); optionally also writes the leaf index of every row (GetDataLeafIndices). Either pointer may be NULL. */
+GPBDEV_EXPORT int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_leaves, double* score_dev,
+                                        int32_t* leaf_of_row_dev);
+/* device vectors of the boosting driver (training score, label, gradient) on the learner's device/stream */
+GPBDEV_EXPORT int gpbdev_vec_alloc(gpbdev_tree_t h, double** out, int64_t n);
+GPBDEV_EXPORT int gpbdev_vec_free(gpbdev_tree_t h, double* p);
+GPBDEV_EXPORT int gpbdev_vec_upload(gpbdev_tree_t h, double* dst_dev, const double* src_host, int64_t n);
+GPBDEV_EXPORT int gpbdev_vec_download(gpbdev_tree_t h, double* dst_host, const double* src_dev, int64_t n);
+/* out = a - b: the L2 objective's gradient score - label (regression_objective.hpp:158-162) */
+GPBDEV_EXPORT int gpbdev_vec_sub(gpbdev_tree_t h, const double* a_dev, const double* b_dev, double* out_dev, int64_t n);
+GPBDEV_EXPORT int gpbdev_vec_add_const(gpbdev_tree_t h, double* a_dev, double c, int64_t n);
+GPBDEV_EXPORT int gpbdev_tree_sync(gpbdev_tree_t h);
+GPBDEV_EXPORT int64_t gpbdev_tree_launch_count(gpbdev_tree_t h);
+GPBDEV_EXPORT void* gpbdev_tree_stream(gpbdev_tree_t h);
 
 #ifdef __cplusplus
 }
