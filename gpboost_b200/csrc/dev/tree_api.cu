@@ -78,24 +78,35 @@ __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bi
   const uint8_t* bcol = bins + fg * 32 + lane;
   double* mg = hg + lane * 257;
   uint32_t* mc = hc + lane * 257;
-  int64_t j = r0;
-  // 4 rows in flight: the loads are independent, the read-modify-writes stay in row order
-  for (; j + 4 <= r1; j += 4) {
-    int64_t r[4];
+  // batches of 32 rows, software-pipelined: the gather of batch k+1 (row ids -> one 32-byte bin sector + one gradient per
+  // row) is in flight while the read-modify-writes of batch k run in row order
+  constexpr int KB = 32;
+  int bcur[KB];
+  double gcur[KB];
+  auto load_batch = [&](int64_t j0, int* bb, double* gg) {
+    const int64_t jl = j0 + lane;
+    int64_t rid = 0;
+    if (jl < r1) rid = idx ? (int64_t)idx[begin + jl] : (begin + jl);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = idx ? (int64_t)idx[begin + j + u] : (begin + j + u);
-    int b[4];
-    double g[4];
+    for (int u = 0; u < KB; ++u) {
+      const int64_t r = __shfl_sync(0xffffffffu, rid, u);
+      const bool ok = j0 + u < r1;
+      bb[u] = ok ? (int)bcol[r * Fpad] : 256;   // slot 256 = scratch for the tail
+      gg[u] = ok ? grad[r] : 0.;
+    }
+  };
+  if (r0 < r1) load_batch(r0, bcur, gcur);
+  for (int64_t j = r0; j < r1; j += KB) {
+    int bnext[KB];
+    double gnext[KB];
+    const bool more = j + KB < r1;
+    if (more) load_batch(j + KB, bnext, gnext);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { b[u] = bcol[r[u] * Fpad]; g[u] = grad[r[u]]; }
+    for (int u = 0; u < KB; ++u) { mg[bcur[u]] += gcur[u]; mc[bcur[u]] += 1u; }
+    if (more) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { mg[b[u]] += g[u]; mc[b[u]] += 1u; }
-  }
-  for (; j < r1; ++j) {
-    const int64_t r = idx ? (int64_t)idx[begin + j] : (begin + j);
-    const int b = bcol[r * Fpad];
-    mg[b] += grad[r];
-    mc[b] += 1u;
+      for (int u = 0; u < KB; ++u) { bcur[u] = bnext[u]; gcur[u] = gnext[u]; }
+    }
   }
   __syncwarp();
   // partial[chunk][feature][bin], coalesced over bins
@@ -137,63 +148,103 @@ __device__ __forceinline__ bool split_better(double ga, int fa, double gb, int f
   return fa < fb;
 }
 
-// one block per leaf (smaller, larger); thread f scans feature f right-to-left (feature_histogram.hpp:858-960)
-__global__ void split_kernel(const double* __restrict__ hist_base, int64_t slot_stride, const int32_t* __restrict__ num_bin, int F,
-                             LeafArgs a0, LeafArgs a1, int min_data_in_leaf, double min_sum_hessian, double lambda_l2,
-                             double min_gain_to_split, unsigned char* __restrict__ splittable,
-                             const unsigned char* __restrict__ parent_flags, SplitOut* __restrict__ out) {
-  const LeafArgs a = blockIdx.x == 0 ? a0 : a1;
+// block (feature f, leaf slot s): the warp stages the 4 KB histogram row in shared memory, lane 0 replays the reference's
+// right-to-left scan (feature_histogram.hpp:858-960, result :1057-1083); per-feature candidates go to cand[s][f]
+__global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict__ hist_base, int64_t slot_stride,
+                                                        const int32_t* __restrict__ num_bin, int F, LeafArgs a0, LeafArgs a1,
+                                                        int min_data_in_leaf, double min_sum_hessian, double lambda_l2,
+                                                        double min_gain_to_split, unsigned char* __restrict__ splittable,
+                                                        const unsigned char* __restrict__ parent_flags, SplitOut* __restrict__ cand) {
+  const LeafArgs a = blockIdx.y == 0 ? a0 : a1;
   if (a.leaf < 0) return;
-  __shared__ SplitOut sh[256];
-  const double* hist = hist_base + (int64_t)a.hist_slot * slot_stride;
+  const int f = blockIdx.x;
+  __shared__ double h[kBins * 2];
   unsigned char* flags = splittable + (int64_t)a.leaf * F;
-  const unsigned char* pflags = a.inherit ? parent_flags : nullptr;
+  SplitOut s;
+  s.gain = -INFINITY; s.feature = -1; s.threshold = 0; s.left_count = s.right_count = 0;
+  s.left_output = s.right_output = 0.;
+  s.left_sum_gradient = s.left_sum_hessian = s.right_sum_gradient = s.right_sum_hessian = 0.;
+  // a feature that had no admissible threshold in the parent is not examined (serial_tree_learner.cpp:329-336)
+  const bool skip = a.inherit && !parent_flags[f];
+  const int nb = num_bin[f];
+  if (!skip) {
+    const double* src = hist_base + (int64_t)a.hist_slot * slot_stride + (int64_t)f * kBins * 2;
+    for (int t = threadIdx.x; t < nb * 2; t += 32) h[t] = src[t];
+  }
+  __syncwarp();
+  if (skip) {
+    if (threadIdx.x == 0) { flags[f] = 0; cand[blockIdx.y * F + f] = s; }
+    return;
+  }
+  // The reference walks t = nb-1 .. 1 accumulating the right-hand sums in that order and keeps the FIRST strictly larger
+  // gain. Its `continue` / `break` tests are monotone in t (counts and hessian sums only grow), so a threshold is admissible
+  // iff it passes all tests itself: lane 0 reproduces the running sums sequentially (fp64 order matters), then all lanes
+  // evaluate the gains of their thresholds and the warp picks the maximum, ties to the larger t (= the first one met).
+  __shared__ double rsg[kBins], rsh[kBins];
+  __shared__ int rcn[kBins];
+  const double sum_gradient = a.sum_gradients;
+  const double sum_hessian = a.sum_hessians + 2 * kEps;
+  const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
+  const double cnt_factor = a.num_data / sum_hessian;
+  if (threadIdx.x == 0) {
+    double srg = 0., srh = kEps;
+    int rc = 0;
+    for (int t = nb - 1; t >= 1; --t) {
+      const double g = h[2 * t], hs = h[2 * t + 1];
+      srg += g; srh += hs; rc += (int)(hs * cnt_factor + 0.5f);
+      rsg[t] = srg; rsh[t] = srh; rcn[t] = rc;
+    }
+  }
+  __syncwarp();
+  double best_gain = -INFINITY;
+  int best_t = -1;
+  for (int t = nb - 1 - (int)threadIdx.x; t >= 1; t -= 32) {
+    const double srg = rsg[t], srh = rsh[t];
+    const int rc = rcn[t];
+    if (rc < min_data_in_leaf || srh < min_sum_hessian) continue;
+    const int lc = a.num_data - rc;
+    if (lc < min_data_in_leaf) continue;
+    const double slh = sum_hessian - srh;
+    if (slh < min_sum_hessian) continue;
+    const double slg = sum_gradient - srg;
+    const double gain = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
+    if (gain <= min_gain_shift) continue;
+    if (gain > best_gain) { best_gain = gain; best_t = t; }  // this lane visits its t in descending order
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+    const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+    if (og > best_gain || (og == best_gain && ot > best_t)) { best_gain = og; best_t = ot; }
+  }
+  if (threadIdx.x != 0) return;
+  const bool spl = best_t >= 1;
+  flags[f] = spl ? 1 : 0;
+  if (spl) {
+    const double srg = rsg[best_t], srh = rsh[best_t];
+    const double best_lg = sum_gradient - srg, best_lh = sum_hessian - srh;
+    const int best_lc = a.num_data - rcn[best_t];
+    s.feature = f; s.threshold = best_t - 1;
+    s.left_output = -best_lg / (best_lh + lambda_l2);
+    s.left_count = best_lc;
+    s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
+    s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
+    s.right_count = a.num_data - best_lc;
+    s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
+    s.gain = best_gain - min_gain_shift;
+  }
+  cand[blockIdx.y * F + f] = s;
+}
+
+// best candidate per leaf with SplitInfo::operator> (gain, then the smaller feature index)
+__global__ void split_argmax_kernel(const SplitOut* __restrict__ cand, int F, SplitOut* __restrict__ out) {
+  __shared__ SplitOut sh[256];
   SplitOut best;
   best.gain = -INFINITY; best.feature = -1; best.threshold = 0; best.left_count = best.right_count = 0;
   best.left_output = best.right_output = 0.;
   best.left_sum_gradient = best.left_sum_hessian = best.right_sum_gradient = best.right_sum_hessian = 0.;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    // a feature that had no admissible threshold in the parent is not examined (serial_tree_learner.cpp:329-336)
-    if (pflags && !pflags[f]) { flags[f] = 0; continue; }
-    const double* h = hist + (int64_t)f * kBins * 2;
-    const int nb = num_bin[f];
-    const double sum_gradient = a.sum_gradients;
-    const double sum_hessian = a.sum_hessians + 2 * kEps;
-    const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
-    const double cnt_factor = a.num_data / sum_hessian;
-    double best_lg = NAN, best_lh = NAN, best_gain = -INFINITY;
-    int best_lc = 0, best_thr = nb;
-    double srg = 0., srh = kEps;
-    int rc = 0;
-    bool spl = false;
-    for (int t = nb - 1; t >= 1; --t) {
-      const double g = h[2 * t], hs = h[2 * t + 1];
-      const int cnt = (int)(hs * cnt_factor + 0.5f);
-      srg += g; srh += hs; rc += cnt;
-      if (rc < min_data_in_leaf || srh < min_sum_hessian) continue;
-      const int lc = a.num_data - rc;
-      if (lc < min_data_in_leaf) break;
-      const double slh = sum_hessian - srh;
-      if (slh < min_sum_hessian) break;
-      const double slg = sum_gradient - srg;
-      const double gain = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
-      if (gain <= min_gain_shift) continue;
-      spl = true;
-      if (gain > best_gain) { best_lc = lc; best_lg = slg; best_lh = slh; best_thr = t - 1; best_gain = gain; }
-    }
-    flags[f] = spl ? 1 : 0;
-    if (spl && best_gain > -INFINITY) {
-      SplitOut s;
-      s.feature = f; s.threshold = best_thr;
-      s.left_output = -best_lg / (best_lh + lambda_l2);
-      s.left_count = best_lc;
-      s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
-      s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
-      s.right_count = a.num_data - best_lc;
-      s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
-      s.gain = best_gain - min_gain_shift;
-      if (split_better(s.gain, s.feature, best.gain, best.feature)) best = s;
-    }
+    const SplitOut c = cand[blockIdx.x * F + f];
+    if (split_better(c.gain, c.feature, best.gain, best.feature)) best = c;
   }
   sh[threadIdx.x] = best;
   __syncthreads();
@@ -286,6 +337,7 @@ struct gpbdev_tree {
   int max_chunks = 0;
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
+  SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
   SplitOut* split_host = nullptr;  // pinned
   double* scalar_host = nullptr;   // pinned
   void* scan_tmp = nullptr;
@@ -344,6 +396,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->part_c, sizeof(uint32_t) * (size_t)h->max_chunks * h->Fpad * kBins));
   TCUDA(cudaMalloc(&h->sum_part, sizeof(double) * 1024));
   TCUDA(cudaMalloc(&h->split_dev, sizeof(SplitOut) * 2));
+  TCUDA(cudaMalloc(&h->cand_dev, sizeof(SplitOut) * 2 * F));
   TCUDA(cudaMallocHost(&h->split_host, sizeof(SplitOut) * 2));
   TCUDA(cudaMallocHost(&h->scalar_host, sizeof(double) * 4));
   TCUDA(cub::DeviceScan::ExclusiveSum(nullptr, h->scan_tmp_bytes, h->flag, h->pos, (int)n, h->stream));
@@ -361,7 +414,7 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
   cudaSetDevice(h->device);
   cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
-  cudaFree(h->split_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
   cudaFreeHost(h->split_host); cudaFreeHost(h->scalar_host);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -407,7 +460,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
 
   auto build_hist = [&](int leaf, int slot) -> int {
     const int64_t cnt = leaf_cnt[leaf];
-    int64_t rpc = std::max<int64_t>(2048, (cnt + h->max_chunks - 1) / h->max_chunks);
+    int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
     const int nchunks = (int)((cnt + rpc - 1) / rpc);
     dim3 grid(nchunks, Fpad / 32);
     hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
@@ -456,11 +509,14 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       a0.sum_gradients = leaf_sg[smaller]; a0.sum_hessians = leaf_sh[smaller];
       a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt[larger] : 0;
       a1.sum_gradients = larger >= 0 ? leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? leaf_sh[larger] : 0.;
-      split_kernel<<<2, 256, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
-                                             cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split, h->splittable,
-                                             h->parent_flags, h->split_dev);
+      split_scan_kernel<<<dim3(F, 2), 32, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
+                                                          cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                          h->splittable, h->parent_flags, h->cand_dev);
       TCUDA(cudaGetLastError());
-      h->launches += 1;
+      if (larger < 0) TCUDA(cudaMemsetAsync(h->split_dev + 1, 0, sizeof(SplitOut), h->stream));
+      split_argmax_kernel<<<larger >= 0 ? 2 : 1, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
+      TCUDA(cudaGetLastError());
+      h->launches += 2;
       TCUDA(cudaMemcpyAsync(h->split_host, h->split_dev, sizeof(SplitOut) * 2, cudaMemcpyDeviceToHost, h->stream));
       TCUDA(cudaStreamSynchronize(h->stream));
       best[smaller] = h->split_host[0];
