@@ -54,26 +54,40 @@ class GPModel(object):
         self.handle = ctypes.c_void_p()
         if gp_coords is None and group_data is None:
             raise ValueError("Both 'group_data' and 'gp_coords' are None. Provide at least one of them")
-        if group_data is not None:
-            raise ValueError("'group_data' is not supported by gpboost_b200.GPModel yet")
         if weights is not None:
             raise ValueError("'weights' are not supported by gpboost_b200.GPModel yet")
-        gp_coords = np.asarray(gp_coords, dtype=np.float64)
-        if gp_coords.ndim == 1:
-            gp_coords = gp_coords.reshape(-1, 1)
-        if gp_coords.ndim != 2:
-            raise ValueError("'gp_coords' needs to be a 2-D array")
-        self.num_data, self.dim_coords = gp_coords.shape
+        self.num_group_re, self.num_gp, self.dim_coords = 0, 0, 0
+        group_c, coords_ptr = None, None
+        if group_data is not None:
+            group_data = np.asarray(group_data)
+            if group_data.ndim == 1:
+                group_data = group_data.reshape(-1, 1)
+            self.num_data, self.num_group_re = group_data.shape
+            # labels as NUL-terminated strings, column-major (string_array_c_str, basic.py:224-226, :4922-4923)
+            self._group_bytes = "\0".join(str(v) for v in group_data.flatten(order="F")).encode("utf-8") + b"\0"
+            group_c = ctypes.c_char_p(self._group_bytes)
+        if gp_coords is not None:
+            gp_coords = np.asarray(gp_coords, dtype=np.float64)
+            if gp_coords.ndim == 1:
+                gp_coords = gp_coords.reshape(-1, 1)
+            if gp_coords.ndim != 2:
+                raise ValueError("'gp_coords' needs to be a 2-D array")
+            self.num_data, self.dim_coords = gp_coords.shape
+            self.num_gp = 1
         self.likelihood = likelihood
         self.cov_function, self.cov_fct_shape = cov_function, float(cov_fct_shape)
         self.gp_approx, self.vecchia_ordering, self.seed = gp_approx, vecchia_ordering, int(seed)
         self.num_neighbors = -1 if num_neighbors is None else int(num_neighbors)
         self.num_parallel_threads = -1 if num_parallel_threads is None else int(num_parallel_threads)
-        self.num_cov_pars = 3 if likelihood in ("gaussian", "regression") else 2
-        self.cov_par_names = (["Error_term"] if self.num_cov_pars == 3 else []) + ["GP_var", "GP_range"]
+        gauss = likelihood in ("gaussian", "regression")
+        self.num_cov_pars = (1 if gauss else 0) + self.num_group_re + 2 * self.num_gp
+        self.cov_par_names = (["Error_term"] if gauss else []) + ["Group_%d" % (k + 1) for k in range(self.num_group_re)] + \
+            (["GP_var", "GP_range"] if self.num_gp else [])
         self.params = dict(_DEFAULT_PARAMS)
         self.num_coef = 0
-        coords_c = np.asfortranarray(gp_coords)  # column-major, gp_coords_data[j*num_data+i]
+        if self.num_gp:
+            self._coords_c = np.asfortranarray(gp_coords)  # column-major, gp_coords_data[j*num_data+i]
+            coords_ptr = _dptr(self._coords_c)
         cluster_c = None
         if cluster_ids is not None:
             cl = np.ascontiguousarray(np.asarray(cluster_ids).astype(np.int32))
@@ -81,8 +95,8 @@ class GPModel(object):
                 raise ValueError("Incorrect number of data points in 'cluster_ids'")
             cluster_c = cl.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
         self._safe_call(self._LIB.GPB_CreateREModel(
-            ctypes.c_int32(self.num_data), cluster_c, None, ctypes.c_int32(0), None, None, ctypes.c_int32(0), None,
-            ctypes.c_int32(1), _dptr(coords_c), ctypes.c_int(self.dim_coords), None, ctypes.c_int32(0),
+            ctypes.c_int32(self.num_data), cluster_c, group_c, ctypes.c_int32(self.num_group_re), None, None, ctypes.c_int32(0), None,
+            ctypes.c_int32(self.num_gp), coords_ptr, ctypes.c_int(self.dim_coords), None, ctypes.c_int32(0),
             c_str(cov_function), ctypes.c_double(self.cov_fct_shape), c_str(gp_approx), ctypes.c_double(1.),
             ctypes.c_double(1.), ctypes.c_int(self.num_neighbors), c_str(vecchia_ordering), ctypes.c_int(-1),
             ctypes.c_double(1.), c_str("kmeans++"), c_str(likelihood), ctypes.c_double(-999.),

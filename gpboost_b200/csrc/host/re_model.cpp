@@ -7,6 +7,7 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <unordered_map>
 
 #include "runtime.h"
 
@@ -18,6 +19,9 @@ namespace {
 
 void DevCheck(int rc) {
   if (rc != 0) Fatal(std::string(gpbdev_last_error()));
+}
+void GrpCheck(int rc) {
+  if (rc != 0) Fatal(std::string(gpbdev_grouped_last_error()));
 }
 
 bool NearlyEqual(double a, double b) { return std::fabs(a - b) < 1e-10 * std::max({1.0, std::fabs(a), std::fabs(b)}); }
@@ -31,7 +35,7 @@ std::string ParseLikelihoodAlias(const std::string& l) {
 
 }  // namespace
 
-REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* /*re_group_data*/, int32_t num_re_group,
+REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* re_group_data, int32_t num_re_group,
                  const double* /*re_group_rand_coef_data*/, const int32_t* /*ind_effect_group_rand_coef*/,
                  int32_t num_re_group_rand_coef, const int* /*drop_intercept_group_rand_effect*/, int32_t num_gp,
                  const double* gp_coords_data, int dim_gp_coords, const double* /*gp_rand_coef_data*/, int32_t num_gp_rand_coef,
@@ -55,8 +59,18 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
       if (cluster_ids_data[i] != cluster_ids_data[0])
         Fatal("Multiple independent realizations ('cluster_ids') are not supported by the B200 engine yet");
   }
-  if (num_re_group > 0 || num_re_group_rand_coef > 0)
-    Fatal("Grouped random effects are not supported by this B200 REModel configuration");
+  if (num_re_group_rand_coef > 0) Fatal("Grouped random coefficients are not supported by the B200 engine yet");
+  if (num_re_group > 0) {
+    if (num_gp > 0) Fatal("Combined grouped random effects and Gaussian processes are not supported by the B200 engine yet");
+    if (num_re_group != 1) Fatal("Only a single level of grouped random effects is supported by the B200 engine yet (hot path: config 3)");
+    if (has_weights) Fatal("'weights' are not supported by the B200 engine yet");
+    if (re_group_data == nullptr) Fatal("Check failed: re_group_data != nullptr");
+    num_cov_pars_ = 2;  // error variance, group variance
+    CreateGroupedBackend(re_group_data);
+    estimate_cov_par_index_.assign(num_cov_pars_, 1);
+    std::memset(sums_, 0, sizeof(sums_));
+    return;
+  }
   if (num_gp != 1) Fatal("num_gp can only be either 0 or 1 in the current implementation");
   if (num_gp_rand_coef > 0) Fatal("GP random coefficients are not supported by the B200 engine");
   if (has_weights) Fatal("'weights' are not supported by the B200 engine yet");
@@ -118,6 +132,31 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
 
 REModel::~REModel() {
   if (engine_) gpbdev_vecchia_free(engine_);
+  if (grouped_) gpbdev_grouped_free(grouped_);
+}
+
+// group labels arrive as num_data NUL-terminated strings (c_api.h:1325, ConvertCharToStringGroupLevels); Z is kept as an
+// int32 group index per observation (RECompGroup, re_comp.h:228-360)
+void REModel::CreateGroupedBackend(const char* re_group_data) {
+  std::unordered_map<std::string, int32_t> level_of;
+  std::vector<int32_t> gidx(num_data_);
+  const char* p = re_group_data;
+  for (int32_t i = 0; i < num_data_; ++i) {
+    std::string lab(p);
+    p += lab.size() + 1;
+    auto it = level_of.find(lab);
+    if (it == level_of.end()) it = level_of.emplace(lab, (int32_t)level_of.size()).first;
+    gidx[i] = it->second;
+  }
+  num_groups_ = (int)level_of.size();
+  GrpCheck(gpbdev_grouped_create(&grouped_, GetRuntime().device, num_data_, gidx.data(), num_groups_));
+}
+
+void REModel::GroupedPass(double var_ratio) {
+  GrpCheck(gpbdev_grouped_eval(grouped_, var_ratio, gsums_));
+  sums_[GPBDEV_SUM_QUAD] = gsums_[0] - gsums_[1];  // y'Psi^-1 y (Woodbury, re_model_template.h:9966-9985)
+  sums_[GPBDEV_SUM_LOGDET] = gsums_[2];            // log|Psi| (:3029-3031)
+  ++num_ll_evals_;
 }
 
 // cov_fcts.h:485-552
@@ -125,6 +164,7 @@ void REModel::TransformCovPars(const double* orig, double* trans) const {
   const double s2 = orig[0];
   trans[0] = s2;
   trans[1] = orig[1] / s2;
+  if (grouped_) return;  // RECompGroup: only the variance is rescaled (re_comp.h:300-310)
   if (!(orig[2] > 0.)) Fatal("Check failed: pars[1] > 0.");
   switch (cov_id_) {
     case GPBDEV_COV_EXPONENTIAL: trans[2] = 1. / orig[2]; break;
@@ -139,6 +179,7 @@ void REModel::TransformBackCovPars(const double* trans, double* orig) const {
   const double s2 = trans[0];
   orig[0] = s2;
   orig[1] = s2 * trans[1];
+  if (grouped_) return;
   switch (cov_id_) {
     case GPBDEV_COV_EXPONENTIAL: orig[2] = 1. / trans[2]; break;
     case GPBDEV_COV_MATERN15: orig[2] = std::sqrt(3.) / trans[2]; break;
@@ -200,6 +241,7 @@ void REModel::FindInitCovPar(const double* y_data, const double* fixed_effects, 
   var /= (n - 1);
   init_trans[0] = var / 2;  // nugget
   init_trans[1] = 1.;       // marginal variance on the transformed scale (init_marg_var / num_comps_total_)
+  if (grouped_) return;     // RECompGroup::FindInitCovPar: pars[0] = marginal variance only (re_comp.h:411-417)
   // range: median pairwise distance on (a sub-sample of) the ORDERED coordinates, sampled with the model's rng_
   const int kMaxPoints = 1000;
   const int ns = n > kMaxPoints ? kMaxPoints : n;
@@ -255,13 +297,14 @@ void REModel::InitializeCovParsIfNotDefined(const double* y_data, const double* 
 }
 
 void REModel::SetY(const double* y_data, const double* fixed_effects) {
-  if (fixed_effects == nullptr) {
-    DevCheck(gpbdev_vecchia_set_y(engine_, y_data));
-  } else {  // y - fixed_effects (re_model_template.h:2907-2917)
+  const double* src = y_data;
+  if (fixed_effects != nullptr) {  // y - fixed_effects (re_model_template.h:2907-2917)
     work_.resize(num_data_);
     for (int32_t i = 0; i < num_data_; ++i) work_[i] = y_data[i] - fixed_effects[i];
-    DevCheck(gpbdev_vecchia_set_y(engine_, work_.data()));
+    src = work_.data();
   }
+  if (grouped_) GrpCheck(gpbdev_grouped_set_y(grouped_, src));
+  else DevCheck(gpbdev_vecchia_set_y(engine_, src));
 }
 
 void REModel::DevicePass(double var, double range, int mode) {
@@ -285,11 +328,11 @@ double REModel::NegLLFromSums(double sigma2) const {
 }
 
 void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects) {
-  double trans[3];
+  double trans[3] = {0., 0., 1.};
   if (cov_pars == nullptr) {
     if (y_data != nullptr) InitializeCovParsIfNotDefined(y_data, fixed_effects);
     if (!cov_pars_initialized_) Fatal("Check failed: cov_pars_initialized_");
-    for (int i = 0; i < 3; ++i) trans[i] = cov_pars_[i];
+    for (int i = 0; i < num_cov_pars_; ++i) trans[i] = cov_pars_[i];
   } else {
     for (int i = 0; i < num_cov_pars_; ++i)
       if (!(cov_pars[i] > 0.)) Fatal("Covariance parameters must be positive");
@@ -297,7 +340,8 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
   }
   if (fixed_effects != nullptr && y_data == nullptr) Fatal("EvalNegLogLikelihoodGauss: 'y_data' cannot nullptr when 'fixed_effects' is provided ");
   if (y_data != nullptr) SetY(y_data, fixed_effects);
-  DevicePass(trans[1], trans[2], GPBDEV_MODE_NLL);
+  if (grouped_) GroupedPass(trans[1]);
+  else DevicePass(trans[1], trans[2], GPBDEV_MODE_NLL);
   *negll = NegLLFromSums(trans[0]);
   neg_log_likelihood_ = *negll;
 }
@@ -321,6 +365,13 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
   auto grad_from_sums = [&](double s2, std::vector<double>* g) {
     for (int k = 0; k < 2; ++k)  // re_model_template.h:2002-2004
       (*g)[k] = (sums_[GPBDEV_SUM_UKU0 + k] - 0.5 * sums_[GPBDEV_SUM_UDU0 + k]) / s2 + 0.5 * sums_[GPBDEV_SUM_TR0 + k];
+  };
+  LbfgsObjective objective_grouped = [&](const std::vector<double>& x, std::vector<double>* grad, bool) -> double {
+    GroupedPass(std::exp(x[0]));
+    sigma2 = sums_[GPBDEV_SUM_QUAD] / num_data_;  // ProfileOutSigma2
+    // d negll / d log v at the profiled sigma^2: -(d yPy)/(2 sigma^2) ... + (1/2) d log|Psi|
+    if (grad != nullptr) (*grad)[0] = -gsums_[3] / (2. * sigma2) + 0.5 * gsums_[4];
+    return NegLLFromSums(sigma2);
   };
   LbfgsObjective objective = [&](const std::vector<double>& x, std::vector<double>* grad, bool speculative) -> double {
     if (grad != nullptr && have_cached_grad && cached_x == x) {  // gradient right after an accepted first trial
@@ -354,12 +405,13 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
   par.delta = delta_rel_conv_;
   par.m = m_lbfgs_;
   par.initial_step_factor = lr_cov_init_;
-  std::vector<double> x = {std::log(cov_pars_[1]), std::log(cov_pars_[2])};
+  std::vector<double> x = {std::log(cov_pars_[1])};
+  if (!grouped_) x.push_back(std::log(cov_pars_[2]));
   double fx = 0.;
-  num_it_ = lbfgs_minimize(objective, max_step, hook, par, &x, &fx, &lbfgs_mem_, reuse_mem);
+  num_it_ = lbfgs_minimize(grouped_ ? objective_grouped : objective, max_step, hook, par, &x, &fx, &lbfgs_mem_, reuse_mem);
   cov_pars_[0] = sigma2;
   cov_pars_[1] = std::exp(x[0]);
-  cov_pars_[2] = std::exp(x[1]);
+  if (!grouped_) cov_pars_[2] = std::exp(x[1]);
   for (double v : cov_pars_)
     if (std::isnan(v) || std::isinf(v)) Fatal("NaN or Inf occurred in covariance parameter optimization using 'lbfgs'");
   neg_log_likelihood_ = fx;
@@ -371,6 +423,11 @@ void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_c
   InitializeCovParsIfNotDefined(y, fixed_effects);
   // re_model_template.h:3298-3321: SetY(y); y_aux = Psi^-1 y / sigma^2; written back on y.
   // The factor is always recomputed here: the device keeps no B between calls unless a STORE pass ran.
+  if (grouped_) {
+    GrpCheck(gpbdev_grouped_set_y(grouped_, y));
+    GrpCheck(gpbdev_grouped_yaux(grouped_, cov_pars_[1], 1. / cov_pars_[0], y));
+    return;
+  }
   DevCheck(gpbdev_vecchia_set_y(engine_, y));
   DevicePass(cov_pars_[1], cov_pars_[2], GPBDEV_MODE_STORE);
   DevCheck(gpbdev_vecchia_yaux(engine_, y));

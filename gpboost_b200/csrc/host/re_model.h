@@ -56,6 +56,7 @@ class REModel {
   const std::string& OptimizerCovPars() const { return optimizer_; }
   int64_t NumLikelihoodEvals() const { return num_ll_evals_; }
   gpbdev_vecchia_t Engine() const { return engine_; }
+  bool IsGrouped() const { return grouped_ != nullptr; }
   // transformed <-> original scale (cov_fcts.h:485-623)
   void TransformCovPars(const double* orig, double* trans) const;
   void TransformBackCovPars(const double* trans, double* orig) const;
@@ -79,6 +80,11 @@ class REModel {
   std::vector<int32_t> perm_;            // ordered position -> original index (data_indices_per_cluster_)
   std::vector<double> coords_ordered_;   // n x d row-major
   gpbdev_vecchia_t engine_ = nullptr;
+  gpbdev_grouped_t grouped_ = nullptr;   // single-level grouped random effect backend
+  int num_groups_ = 0;
+  double gsums_[5];
+  void CreateGroupedBackend(const char* re_group_data);
+  void GroupedPass(double var_ratio);
 
   // state (all covariance parameters kept on the TRANSFORMED scale like REModel::cov_pars_)
   std::vector<double> cov_pars_, init_cov_pars_;

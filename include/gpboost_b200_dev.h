@@ -101,6 +101,24 @@ GPBDEV_EXPORT int gpbdev_fp64_peak(int device, double* tflops);
 GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Single-level grouped random effect, Gaussian likelihood. group_index: host, n int32 in [0, num_groups).
+ * Replaces InitializeMatricesForUseWoodburyIdentity / CalcZtY / CalcCovFactor single-RE branch / CalcYtilde / CalcYAux /
+ * the Woodbury gradient (re_model_template.h:7174-7308, :6326, :9417-9420, :9907-9918, :9843-9891, :2462-2529).
+ */
+typedef struct gpbdev_grouped* gpbdev_grouped_t;
+GPBDEV_EXPORT const char* gpbdev_grouped_last_error(void);
+GPBDEV_EXPORT int gpbdev_grouped_create(gpbdev_grouped_t* out, int device, int64_t n, const int32_t* group_index, int num_groups);
+GPBDEV_EXPORT int gpbdev_grouped_free(gpbdev_grouped_t h);
+/* y in original order (host): H2D + per-group sums Z^T y (SetY / CalcZtY) */
+GPBDEV_EXPORT int gpbdev_grouped_set_y(gpbdev_grouped_t h, const double* y_host);
+/* sums at variance ratio v = sigma_1^2/sigma^2: out5 = { y'y, sum s_g^2/(1/v+n_g), sum log(1+v n_g),
+ * sum s_g^2 v/(1+v n_g)^2, sum v n_g/(1+v n_g) } */
+GPBDEV_EXPORT int gpbdev_grouped_eval(gpbdev_grouped_t h, double var_ratio, double* out5);
+/* y_aux = Psi^-1 y * scale in original order (CalcYAux single-RE branch) */
+GPBDEV_EXPORT int gpbdev_grouped_yaux(gpbdev_grouped_t h, double var_ratio, double scale, double* yaux_host);
+GPBDEV_EXPORT int64_t gpbdev_grouped_launch_count(gpbdev_grouped_t h);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Device tree learner (dense uint8 bins, numerical features, no missing values, constant hessian).
  * Seam: the reference's TreeLearner interface (include/LightGBM/tree_learner.h:29-117: Init / Train / AddPredictionToScore /
  * GetDataLeafIndices), selected there by device_type (src/LightGBM/treelearner/tree_learner.cpp:15-52).

@@ -39,3 +39,26 @@ def lattice(k):
     g = np.arange(k) / k
     xx, yy = np.meshgrid(g, g, indexing="ij")
     return np.stack([xx.ravel(), yy.ravel()], axis=1)
+
+
+def r_grouped_test_data():
+    """n=1000 single-level grouped data of test_GPModel_grouped_random_effects.R:27-41,62 (LCG modulus 134456)."""
+    from scipy.stats import norm
+    lcg = lambda n, c: sim_rand_unif(n, c, mod=134456.0, a=8121.0, c=28411.0)
+    n, m = 1000, 100
+    group = np.repeat(np.arange(1, m + 1), n // m)
+    b1 = norm.ppf(lcg(m, 0.546))
+    xi = np.sqrt(0.5) * norm.ppf(lcg(n, 0.1))
+    return group, b1[group - 1] + xi
+
+
+def grouped_synth(n, G, seed, balanced=False):
+    rng = np.random.default_rng(seed)
+    if balanced:
+        group = rng.permutation(np.arange(n) % G)
+    else:  # unbalanced group sizes
+        p = rng.dirichlet(np.full(G, 0.7))
+        group = rng.choice(G, size=n, p=p)
+    b = rng.standard_normal(G) * 0.8
+    y = b[group] + 0.6 * rng.standard_normal(n)
+    return group, y
