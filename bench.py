@@ -36,6 +36,19 @@ ALGO_BYTES_PER_OBS = 4 * M_NEIGH + 8 * 2 + 8
 ALGO_FLOPS_PER_OBS = 24e3
 
 
+def host_cores():
+    """Usable host cores: CPU affinity capped by the cgroup CPU quota (the GPU boxes expose 128 CPUs under a 16-CPU quota;
+    running the reference's OpenMP loops with 128 threads there is several hundred times slower than with 16)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return n
+
+
 def make_data(n):
     rng = np.random.default_rng(1)
     return rng.random((n, 2)), rng.standard_normal(n)
@@ -95,6 +108,28 @@ def time_reference(n, steps, warmup, threads):
     return {"sec_per_eval": dt, "negll": v, "create_s": t_create}
 
 
+def time_gpboost(n, iters, lib, threads, F=50):
+    """One GPBoost iteration = LGBM_BoosterUpdateOneIter with a Vecchia GP (m=30) attached: covariance re-fit (L-BFGS) +
+    Psi^-1(F - y) + one 31-leaf tree on n x 50 features (BASELINE configs[3] shape on one GPU, metric (i) of SURVEY §8d)."""
+    from gpboost_b200 import GPModel
+    from gpboost_b200.booster import Booster, Dataset
+    rng = np.random.default_rng(1)
+    coords = rng.random((n, 2)); X = rng.random((n, F))
+    y = 2 * np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + np.sin(5 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.5 * rng.standard_normal(n)
+    params = dict(objective="regression", num_leaves=31, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
+    if lib is not None:
+        params["num_threads"] = threads
+    gp = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=M_NEIGH,
+                 vecchia_ordering="random", seed=1, num_parallel_threads=threads, _lib=lib)
+    b = Booster(params, Dataset(X, y, params=params, _lib=lib), gp_model=gp, _lib=lib)
+    t0 = time.perf_counter(); b.update(); first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        b.update()
+    dt = (time.perf_counter() - t0) / iters
+    return {"sec_per_iter": dt, "first_iter_s": first, "cov_pars": gp.get_cov_pars().tolist()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -103,11 +138,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-n", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--boost-n", type=int, default=1000000, help="n of the GPBoost-iteration measurement (0 = skip)")
+    ap.add_argument("--boost-ref-n", type=int, default=0, help="--impl reference: also time GPBoost iterations at this n (slow)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    ncores = os.cpu_count() or 1
+    ncores = host_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))  # before the reference library (libgomp) is loaded
     W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
@@ -119,7 +157,7 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lib_gpboost.so missing (build it with oracle/Makefile.ref)"}))
             return 0
         v = 1.0 / res["sec_per_eval"]
-        print(json.dumps({
+        line = ({
             "impl": "reference", "metric": "gp_loglik_evals_per_sec", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": res["sec_per_eval"] * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -127,7 +165,14 @@ def main():
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": ncores, "kind": "reference",
                              "sample": "full workload n=1e6, %d timed GPB_EvalNegLogLikelihood calls" % args.steps},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "negll": res["negll"]}))
+            "negll": res["negll"]})
+        if args.boost_ref_n > 0:
+            from gpboost_b200.libpath import load_lib
+            from oracle import ref_lib_path
+            gb = time_gpboost(args.boost_ref_n, 1, load_lib(ref_lib_path()), ncores)
+            line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "n": args.boost_ref_n, "first_iter_s": gb["first_iter_s"],
+                               "note": "GPBoost Vecchia m=30 + 31-leaf trees on n x 50; sub-problem of n=%d, not scaled" % args.boost_ref_n}
+        print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -242,6 +287,12 @@ def main():
                               "flops_per_obs": ALGO_FLOPS_PER_OBS, "peak_source": "measured live: gpbdev_fp64_peak DFMA microbenchmark"},
             "negll": negll_value,
         }
+        if args.boost_n > 0 and world == 1:
+            gb = time_gpboost(args.boost_n, 5, None, ncores)
+            line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "ms_per_iter": gb["sec_per_iter"] * 1e3, "n": args.boost_n,
+                               "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
+                               "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "
+                                       "parameters re-fitted every iteration (BASELINE metric (i)); host buffers, end to end"}
         if not args.no_cpu_baseline and world == 1:
             ns = args.cpu_sample_n
             res = time_reference(ns, 3, 1, ncores)

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bi
 
 // merge chunk partials in chunk order -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226)
 __global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad,
-                                   int F, double hess_const, double* __restrict__ hist) {
+                                   int F, double hess_const, double* __restrict__ hist, double* __restrict__ parent) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= F * kBins) return;
   double g = 0.;
@@ -131,8 +131,13 @@ __global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint
     g += part_g[o];
     c += part_c[o];
   }
+  const double hs = (double)c * hess_const;
   hist[2 * t] = g;
-  hist[2 * t + 1] = (double)c * hess_const;
+  hist[2 * t + 1] = hs;
+  if (parent) {  // larger = parent - smaller (feature_histogram.hpp:79-83), in place on the parent's slot
+    parent[2 * t] -= g;
+    parent[2 * t + 1] -= hs;
+  }
 }
 
 // larger = parent - smaller (feature_histogram.hpp:79-83), in place on the parent's slot
@@ -458,7 +463,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   leaf_value[0] = 0.; leaf_count[0] = (int)n;
   int num_leaves = 1, left_leaf = 0, right_leaf = -1;
 
-  auto build_hist = [&](int leaf, int slot) -> int {
+  auto build_hist = [&](int leaf, int slot, int parent_slot_sub) -> int {
     const int64_t cnt = leaf_cnt[leaf];
     int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
     const int nchunks = (int)((cnt + rpc - 1) / rpc);
@@ -467,7 +472,8 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
                                                        rpc, grad, h->part_g, h->part_c);
     TCUDA(cudaGetLastError());
     hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const,
-                                                                      h->hist + (size_t)slot * slot_stride);
+                                                                      h->hist + (size_t)slot * slot_stride,
+                                                                      parent_slot_sub >= 0 ? h->hist + (size_t)parent_slot_sub * slot_stride : nullptr);
     TCUDA(cudaGetLastError());
     h->launches += 2;
     return 0;
@@ -492,14 +498,9 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       if (right_leaf >= 0) parent_slot = slot_of[left_leaf];  // the parent's histograms sit under the left (= parent) id
       const int new_slot = free_slots.back();
       free_slots.pop_back();
-      if (build_hist(smaller, new_slot)) return -1;
-      if (larger >= 0) {  // larger = parent - smaller, in place: the parent's slot becomes the larger leaf's
-        hist_subtract_kernel<<<(int)((slot_stride + 255) / 256), 256, 0, h->stream>>>(h->hist + (size_t)parent_slot * slot_stride,
-                                                                                     h->hist + (size_t)new_slot * slot_stride,
-                                                                                     (int)slot_stride);
-        h->launches += 1;
-        slot_of[larger] = parent_slot;
-      }
+      // larger = parent - smaller, in place (fused into the merge of the chunk partials): the parent's slot becomes the larger leaf's
+      if (build_hist(smaller, new_slot, larger >= 0 ? parent_slot : -1)) return -1;
+      if (larger >= 0) slot_of[larger] = parent_slot;
       slot_of[smaller] = new_slot;
       // both children inherit the parent's flags (the parent's id is the left child's id): snapshot them first
       if (right_leaf >= 0)
@@ -536,11 +537,11 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     const int gridp = (int)std::min<int64_t>((c + 255) / 256, (int64_t)h->num_sms * 8);
     mark_kernel<<<gridp, 256, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, h->flag);
     TCUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->flag, h->pos, (int)c, h->stream));
-    int32_t last_pos = 0, last_flag = 0;
-    TCUDA(cudaMemcpyAsync(&last_pos, h->pos + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    TCUDA(cudaMemcpyAsync(&last_flag, h->flag + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    TCUDA(cudaStreamSynchronize(h->stream));
-    const int nleft = last_pos + last_flag, nright = (int)c - nleft;
+    // With a constant hessian the histogram's hessian entries are exact multiples of it, so the split scan's
+    // RoundInt(hess * cnt_factor) counts ARE the partition's counts (the reference overwrites them with the
+    // partition's, serial_tree_learner.cpp:589-593 — same numbers). No device round trip is needed for them.
+    const int nleft = bs.left_count, nright = (int)c - nleft;
+    if (nleft <= 0 || nright <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
     scatter_kernel<<<gridp, 256, 0, h->stream>>>(h->idx, b, c, h->flag, h->pos, nleft, h->idx_tmp);
     TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
     h->launches += 4;

@@ -20,7 +20,6 @@ X = rng.random((n_tree, F)); y = 2 * np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.5 * 
 params = dict(objective="regression", num_leaves=31, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
 for name, lib in libs:
     p = dict(params)
-    if lib is not None: p.update(force_col_wise=True, num_threads=os.cpu_count())
     t = time.perf_counter(); ds = Dataset(X, y, params=p, _lib=lib); t_ds = time.perf_counter() - t
     b = Booster(p, ds, _lib=lib)
     b.update()
@@ -29,11 +28,24 @@ for name, lib in libs:
     dt = (time.perf_counter() - t) / 10
     print(f"[{name}] plain boosting n={n_tree} F={F}: dataset {t_ds:.2f}s, {dt*1e3:.2f} ms/iter ({1/dt:.1f} iters/s)", flush=True)
     del b, ds
+# (c) GPBoost with a single-level grouped random effect (BASELINE config 3): 1e4 groups
+group = rng.integers(0, 10000, size=n_tree)
+yg3 = y + rng.standard_normal(10000)[group]
+for name, lib in libs:
+    p = dict(params)
+    gp = GPModel(group_data=group, _lib=lib)
+    ds = Dataset(X, yg3, params=p, _lib=lib)
+    b = Booster(p, ds, gp_model=gp, _lib=lib)
+    t = time.perf_counter(); b.update(); t_first = time.perf_counter() - t
+    t = time.perf_counter()
+    for _ in range(10): b.update()
+    dt = (time.perf_counter() - t) / 10
+    print(f"[{name}] GPBoost grouped RE (1e4 groups) n={n_tree} F={F}: first iter {t_first:.3f}s, then {dt*1e3:.2f} ms/iter ({1/dt:.1f} iters/s) cov_pars {gp.get_cov_pars()}", flush=True)
+    del b, ds, gp
 coords = rng.random((n_gp, 2)); Xg = rng.random((n_gp, F))
 yg = 2 * np.sin(3 * Xg[:, 0]) + Xg[:, 1] ** 2 + np.sin(5 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.5 * rng.standard_normal(n_gp)
 for name, lib in libs:
     p = dict(params)
-    if lib is not None: p.update(force_col_wise=True, num_threads=os.cpu_count())
     t = time.perf_counter()
     gp = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=30, vecchia_ordering="random", seed=1, _lib=lib)
     ds = Dataset(Xg, yg, params=p, _lib=lib)
