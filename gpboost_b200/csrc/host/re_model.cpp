@@ -20,6 +20,9 @@ namespace {
 void DevCheck(int rc) {
   if (rc != 0) Fatal(std::string(gpbdev_last_error()));
 }
+void DenseCheck(int rc) {
+  if (rc != 0) Fatal(std::string(gpbdev_dense_last_error()));
+}
 void GrpCheck(int rc) {
   if (rc != 0) Fatal(std::string(gpbdev_grouped_last_error()));
 }
@@ -96,8 +99,19 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   }
   num_cov_pars_ = 3;  // nugget, marginal variance, range
   // ---- GP approximation
+  if (gp_approx_ == "none") {  // exact GP: dense Gram + Cholesky on the device, original observation order
+    perm_.resize(num_data_);
+    std::iota(perm_.begin(), perm_.end(), 0);
+    coords_ordered_.resize((size_t)num_data_ * dim_);
+    for (int32_t i = 0; i < num_data_; ++i)
+      for (int k = 0; k < dim_; ++k) coords_ordered_[(size_t)i * dim_ + k] = gp_coords_data[(size_t)k * num_data_ + i];
+    DenseCheck(gpbdev_dense_create(&dense_, GetRuntime().device, num_data_, dim_, coords_ordered_.data()));
+    estimate_cov_par_index_.assign(num_cov_pars_, 1);
+    std::memset(sums_, 0, sizeof(sums_));
+    return;
+  }
   if (gp_approx_ != "vecchia")
-    Fatal("GP approximation '" + gp_approx_ + "' is currently not supported by the B200 engine (hot path: 'vecchia')");
+    Fatal("GP approximation '" + gp_approx_ + "' is currently not supported by the B200 engine (hot path: 'vecchia', 'none')");
   num_neighbors_ = num_neighbors > 0 ? num_neighbors : 20;  // re_model_template.h:288-294
   vecchia_ordering_ = vecchia_ordering == nullptr ? "none" : std::string(vecchia_ordering);
   if (vecchia_ordering_ != "none" && vecchia_ordering_ != "random")
@@ -133,6 +147,16 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
 REModel::~REModel() {
   if (engine_) gpbdev_vecchia_free(engine_);
   if (grouped_) gpbdev_grouped_free(grouped_);
+  if (dense_) gpbdev_dense_free(dense_);
+}
+
+void REModel::DensePass(double var, double range) {
+  double o[3];
+  DenseCheck(gpbdev_dense_eval(dense_, cov_id_, var, range, o));
+  sums_[GPBDEV_SUM_QUAD] = o[0];    // y' Psi^-1 y = ||L^-1 y||^2 (re_model_template.h:10002)
+  sums_[GPBDEV_SUM_LOGDET] = o[1];  // 2 sum log L_ii (:3127)
+  sums_[GPBDEV_SUM_NBAD] = o[2];
+  ++num_ll_evals_;
 }
 
 // group labels arrive as num_data NUL-terminated strings (c_api.h:1325, ConvertCharToStringGroupLevels); Z is kept as an
@@ -304,6 +328,7 @@ void REModel::SetY(const double* y_data, const double* fixed_effects) {
     src = work_.data();
   }
   if (grouped_) GrpCheck(gpbdev_grouped_set_y(grouped_, src));
+  else if (dense_) DenseCheck(gpbdev_dense_set_y(dense_, src));
   else DevCheck(gpbdev_vecchia_set_y(engine_, src));
 }
 
@@ -341,6 +366,7 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
   if (fixed_effects != nullptr && y_data == nullptr) Fatal("EvalNegLogLikelihoodGauss: 'y_data' cannot nullptr when 'fixed_effects' is provided ");
   if (y_data != nullptr) SetY(y_data, fixed_effects);
   if (grouped_) GroupedPass(trans[1]);
+  else if (dense_) DensePass(trans[1], trans[2]);
   else DevicePass(trans[1], trans[2], GPBDEV_MODE_NLL);
   *negll = NegLLFromSums(trans[0]);
   neg_log_likelihood_ = *negll;
@@ -355,6 +381,7 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
   SetY(y_data, fixed_effects);
   num_it_ = max_iter_;
   if (max_iter_ <= 0) return;
+  if (dense_) Fatal("Covariance parameter estimation for the exact (dense) GP is not built on the device yet (likelihood evaluation and Psi^-1 y are); use gp_approx = 'vecchia'");
   const bool reuse_mem = reuse_learning_rates_from_previous_call && called_in_GPBoost_algorithm && cov_pars_estimated_once_;
   // optimisation variables: log of the transformed (variance ratio, range); the error variance is profiled out
   // (optim_utils.h:244-340, re_model_template.h:1082-1084, :2640-2650)
@@ -426,6 +453,12 @@ void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_c
   if (grouped_) {
     GrpCheck(gpbdev_grouped_set_y(grouped_, y));
     GrpCheck(gpbdev_grouped_yaux(grouped_, cov_pars_[1], 1. / cov_pars_[0], y));
+    return;
+  }
+  if (dense_) {
+    DenseCheck(gpbdev_dense_set_y(dense_, y));
+    DensePass(cov_pars_[1], cov_pars_[2]);
+    DenseCheck(gpbdev_dense_yaux(dense_, 1. / cov_pars_[0], y));
     return;
   }
   DevCheck(gpbdev_vecchia_set_y(engine_, y));

@@ -81,6 +81,8 @@ class REModel {
   std::vector<double> coords_ordered_;   // n x d row-major
   gpbdev_vecchia_t engine_ = nullptr;
   gpbdev_grouped_t grouped_ = nullptr;   // single-level grouped random effect backend
+  gpbdev_dense_t dense_ = nullptr;       // exact GP backend, gp_approx = "none" 
+  void DensePass(double var, double range);
   int num_groups_ = 0;
   double gsums_[5];
   void CreateGroupedBackend(const char* re_group_data);

@@ -101,6 +101,23 @@ GPBDEV_EXPORT int gpbdev_fp64_peak(int device, double* tflops);
 GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Exact (dense) Gaussian process, Gaussian likelihood (BASELINE config 1). coords: host n x d row-major in the
+ * original observation order. Replaces RECompGP::CalcSigma (re_comp.h:1273), CalcZSigmaZt (re_model_template.h:9273),
+ * CalcChol (:6492), the solves of CalcYAux (:9894) / CalcYTPsiIInvY (:10002) and the log-determinant (:3127).
+ */
+typedef struct gpbdev_dense* gpbdev_dense_t;
+GPBDEV_EXPORT const char* gpbdev_dense_last_error(void);
+GPBDEV_EXPORT int gpbdev_dense_create(gpbdev_dense_t* out, int device, int n, int d, const double* coords_rowmajor);
+GPBDEV_EXPORT int gpbdev_dense_free(gpbdev_dense_t h);
+GPBDEV_EXPORT int gpbdev_dense_set_y(gpbdev_dense_t h, const double* y_host);
+/* Gram build + blocked Cholesky of [[I + Sigma, y],[y^T, *]] at transformed (var, range):
+ * out3 = { y^T Psi^-1 y, log|Psi|, #non-positive pivots } */
+GPBDEV_EXPORT int gpbdev_dense_eval(gpbdev_dense_t h, int cov_type, double var, double range, double* out3);
+/* after an eval: Psi^-1 y * scale (host, n doubles) */
+GPBDEV_EXPORT int gpbdev_dense_yaux(gpbdev_dense_t h, double scale, double* yaux_host);
+GPBDEV_EXPORT int64_t gpbdev_dense_launch_count(gpbdev_dense_t h);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Single-level grouped random effect, Gaussian likelihood. group_index: host, n int32 in [0, num_groups).
  * Replaces InitializeMatricesForUseWoodburyIdentity / CalcZtY / CalcCovFactor single-RE branch / CalcYtilde / CalcYAux /
  * the Woodbury gradient (re_model_template.h:7174-7308, :6326, :9417-9420, :9907-9918, :9843-9891, :2462-2529).
