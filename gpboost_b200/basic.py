@@ -121,7 +121,9 @@ class GPModel(object):
         if params is not None:
             for k, v in params.items():
                 if k in ("optimizer_cov", "init_cov_pars", "maxit", "delta_rel_conv", "lr_cov", "trace",
-                         "convergence_criterion", "m_lbfgs", "estimate_cov_par_index", "std_dev"):
+                         "convergence_criterion", "m_lbfgs", "estimate_cov_par_index", "std_dev", "cg_max_num_it",
+                         "cg_max_num_it_tridiag", "cg_delta_conv", "num_rand_vec_trace", "seed_rand_vec_trace",
+                         "cg_preconditioner_type", "delta_conv_mode_finding"):
                     self.params[k] = v
                 else:
                     raise ValueError("Unknown or unsupported parameter: %s" % k)
@@ -141,7 +143,9 @@ class GPModel(object):
             ctypes.c_double(self.params["lr_coef"]), ctypes.c_double(self.params["acc_rate_coef"]), None,
             ctypes.c_int(self.params["cg_max_num_it"]), ctypes.c_int(self.params["cg_max_num_it_tridiag"]),
             ctypes.c_double(self.params["cg_delta_conv"]), ctypes.c_int(self.params["num_rand_vec_trace"]),
-            ctypes.c_bool(self.params["reuse_rand_vec_trace"]), None, ctypes.c_int(self.params["seed_rand_vec_trace"]),
+            ctypes.c_bool(self.params["reuse_rand_vec_trace"]),
+            c_str(self.params["cg_preconditioner_type"]) if self.params.get("cg_preconditioner_type") else None,
+            ctypes.c_int(self.params["seed_rand_vec_trace"]),
             ctypes.c_int(self.params["fitc_piv_chol_preconditioner_rank"]), None,
             ctypes.c_bool(self.params["estimate_aux_pars"]), ctypes.c_bool(self.params["init_coef_aux_pars_from_iid_model"]),
             est.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_int(self.params["m_lbfgs"]),

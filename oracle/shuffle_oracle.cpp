@@ -26,3 +26,16 @@ extern "C" void orc_sort_indices(const double* v, int n, int32_t* idx_out) {
   std::sort(idx.begin(), idx.end(), [&vv](int i1, int i2) { return vv[i1] < vv[i2]; });
   for (int i = 0; i < n; ++i) idx_out[i] = idx[i];
 }
+
+// Probe vectors of the stochastic Lanczos quadrature, exactly as GenRandVecNormalParallel draws them
+// (src/GPBoost/CG_utils.cpp:978-994): column col_i comes from mt19937 seeded with
+// seed_seq{base_seed, run_id lo, run_id hi, col_i} through std::normal_distribution<double>. Output column-major n x t.
+extern "C" void orc_gen_rand_normal(int base_seed, unsigned long long run_id, int n, int t, double* out) {
+  const uint32_t b32 = static_cast<uint32_t>(base_seed);
+  for (int col = 0; col < t; ++col) {
+    std::normal_distribution<double> ndist(0.0, 1.0);
+    std::seed_seq seq{b32, static_cast<uint32_t>(run_id), static_cast<uint32_t>(run_id >> 32), static_cast<uint32_t>(col)};
+    std::mt19937 gen(seq);
+    for (int row = 0; row < n; ++row) out[(size_t)col * n + row] = ndist(gen);
+  }
+}

@@ -257,6 +257,47 @@ int orc_vecchia_factor(const double* coords, int n, int d, int m, const int32_t*
   return bad;
 }
 
+/* Vecchia factor for a NON-Gaussian likelihood (latent GP, no nugget): Vecchia_utils.cpp:1415-1417 (D starts at 0),
+ * :1555-1563 (+ marginal variance), :1607-1609 (neighbour block diagonal *= JITTER_MULT_VECCHIA = 1 + 1e-10, utils.h:38),
+ * :1618-1623, :1682. pars = {var, range} with var on the ORIGINAL scale (sigma2 = 1) and range transformed. */
+int orc_vecchia_factor_latent(const double* coords, int n, int d, int m, const int32_t* nn, int cov_type,
+                              const double* pars, double* A, double* Dinv) {
+  const double var = pars[0], range = pars[1];
+  int bad = 0;
+#pragma omp parallel
+  {
+    double* S = (double*)malloc(sizeof(double) * m * m);
+    double* s1 = (double*)malloc(sizeof(double) * m);
+    double* a = (double*)malloc(sizeof(double) * m);
+#pragma omp for schedule(static) reduction(+ : bad)
+    for (int i = 0; i < n; ++i) {
+      const int32_t* nb = nn + (size_t)i * m;
+      int q = 0;
+      while (q < m && nb[q] >= 0) ++q;
+      double Di = var;
+      for (int k = 0; k < m; ++k) A[(size_t)i * m + k] = 0.;
+      if (q > 0) {
+        for (int j = 0; j < q; ++j) {
+          s1[j] = orc_cov(cov_type, sqrt(orc_sqdist(coords, n, d, nb[j], i)), var, range);
+          S[j * q + j] = var * (1. + 1e-10);
+          for (int k = j + 1; k < q; ++k)
+            S[j * q + k] = S[k * q + j] = orc_cov(cov_type, sqrt(orc_sqdist(coords, n, d, nb[j], nb[k])), var, range);
+        }
+        if (orc_chol(S, q) != 0) { ++bad; continue; }
+        memcpy(a, s1, sizeof(double) * q);
+        orc_chol_solve(S, q, a);
+        double dot = 0.;
+        for (int j = 0; j < q; ++j) { A[(size_t)i * m + j] = a[j]; dot += a[j] * s1[j]; }
+        Di -= dot;
+      }
+      if (!(Di > 0.)) ++bad;
+      Dinv[i] = 1. / Di;
+    }
+    free(S); free(s1); free(a);
+  }
+  return bad;
+}
+
 /* u = B y  (B = I - A): (B y)_i = y_i - sum_k A[i,k] y[nn[i,k]] */
 void orc_apply_B(int n, int m, const int32_t* nn, const double* A, const double* y, double* u) {
 #pragma omp parallel for schedule(static)

@@ -62,3 +62,25 @@ def grouped_synth(n, G, seed, balanced=False):
     b = rng.standard_normal(G) * 0.8
     y = b[group] + 0.6 * rng.standard_normal(n)
     return group, y
+
+
+def r_binary_test_data():
+    """n=100 coordinates and binary response of test_GPModel_non_Gaussian_data.R:38-47, 2512-2513 (logit link)."""
+    from scipy.stats import norm
+    n, d = 100, 2
+    coords = sim_rand_unif(n * d, 0.1).reshape((n, d), order="F")
+    D = np.sqrt(((coords[:, None, :] - coords[None, :, :]) ** 2).sum(-1))
+    latent = np.linalg.cholesky(np.exp(-D / 0.1) + 1e-20 * np.eye(n)) @ norm.ppf(sim_rand_unif(n, 0.8))
+    probs = 1. / (1. + np.exp(-latent))
+    return coords, (sim_rand_unif(n, 0.2341) < probs).astype(np.float64)
+
+
+def binary_synth(n, seed=1, with_offset=False):
+    """Synthetic coords U[0,1]^2, a smooth latent surface and Bernoulli(logit) labels; optional fixed-effect offset."""
+    rng = np.random.default_rng(seed)
+    coords = rng.random((n, 2))
+    latent = 1.5 * np.sin(6 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.3 * rng.standard_normal(n)
+    offset = 0.5 * np.cos(3 * coords[:, 0]) - 0.2 if with_offset else None
+    eta = latent + (offset if with_offset else 0.)
+    y = (rng.random(n) < 1. / (1. + np.exp(-eta))).astype(np.float64)
+    return coords, y, offset

@@ -1,0 +1,50 @@
+"""Generates tests/golden/laplace_golden.json with the UNMODIFIED reference library (oracle/_ref) through the shared
+frontend: latent Vecchia GP + bernoulli_logit likelihood, Laplace-approximated negative log-likelihood
+with matrix_inversion_method "cholesky" and "iterative" (VADU preconditioner, 50 SLQ probes, seed 1).
+Run in the build container:  python tests/golden/make_laplace_golden.py"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import datagen  # noqa: E402
+from gpboost_b200 import GPModel  # noqa: E402
+from gpboost_b200.libpath import load_lib  # noqa: E402
+from oracle import ref_lib_path  # noqa: E402
+
+ref = load_lib(ref_lib_path())
+CASES = [
+    dict(name="r_binary", cov_function="exponential", shape=0.5, m=20, ordering="none", seed=0, cov_pars=[0.9, 0.2]),
+    dict(name="synth", n=2000, dseed=3, offset=False, cov_function="matern", shape=1.5, m=10, ordering="random", seed=1, cov_pars=[1.0, 0.1]),
+    dict(name="synth", n=3000, dseed=4, offset=True, cov_function="exponential", shape=0.5, m=20, ordering="random", seed=2, cov_pars=[1.7, 0.15]),
+    dict(name="synth", n=2500, dseed=5, offset=False, cov_function="matern", shape=2.5, m=30, ordering="random", seed=3, cov_pars=[0.6, 0.08]),
+    dict(name="synth", n=1500, dseed=6, offset=True, cov_function="gaussian", shape=0., m=15, ordering="random", seed=4, cov_pars=[2.5, 0.05]),
+    dict(name="synth", n=6000, dseed=7, offset=False, cov_function="matern", shape=1.5, m=30, ordering="random", seed=5, cov_pars=[1.2, 0.05]),
+]
+
+
+def case_data(c):
+    if c["name"] == "r_binary":
+        X, y = datagen.r_binary_test_data()
+        return X, y, None
+    return datagen.binary_synth(c["n"], c["dseed"], c["offset"])
+
+
+if __name__ == "__main__":
+    out = {"generator": "tests/golden/make_laplace_golden.py", "cases": []}
+    for c in CASES:
+        X, y, off = case_data(c)
+        rec = dict(c)
+        for method in ("cholesky", "iterative"):
+            m = GPModel(likelihood="bernoulli_logit", gp_coords=X, cov_function=c["cov_function"], cov_fct_shape=c["shape"],
+                        gp_approx="vecchia", num_neighbors=c["m"], vecchia_ordering=c["ordering"], seed=c["seed"],
+                        matrix_inversion_method=method, _lib=ref)
+            rec["negll_" + method] = m.neg_log_likelihood(np.array(c["cov_pars"]), y, fixed_effects=off)
+        print(rec)
+        out["cases"].append(rec)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "laplace_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
