@@ -189,6 +189,18 @@ class GPModel(object):
             return pd.DataFrame(out.reshape(1, -1), columns=self.cov_par_names, index=["Param."])
         return out
 
+    def laplace_info(self):
+        """gpboost_b200 extension: (negll, Newton its, CG its, SLQ its, log det(Sigma W + I), objective at the mode)."""
+        out = np.zeros(6)
+        self._safe_call(self._LIB.GPB200_GetLaplaceInfo(self.handle, _dptr(out)))
+        return out
+
+    def laplace_mode(self):
+        """gpboost_b200 extension: posterior mode of the latent process (original data order)."""
+        out = np.zeros(self.num_data)
+        self._safe_call(self._LIB.GPB200_GetLaplaceMode(self.handle, _dptr(out)))
+        return out
+
     def get_current_neg_log_likelihood(self):
         negll = ctypes.c_double(0)
         self._safe_call(self._LIB.GPB_GetCurrentNegLogLikelihood(self.handle, ctypes.byref(negll)))

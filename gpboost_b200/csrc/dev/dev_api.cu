@@ -129,7 +129,10 @@ FactorKernel pick_kernel(int cov, int mode, int d, int m) {
 
 }  // namespace
 
+struct gpb_laplace_state;
+
 struct gpbdev_vecchia {
+  gpb_laplace_state* lap = nullptr;  // Laplace-Vecchia buffers (laplace.cuh), lazy
   int device = 0;
   int64_t n = 0;
   int d = 0, m = 0;
@@ -162,6 +165,8 @@ struct gpbdev_vecchia {
 };
 
 namespace {
+
+void laplace_release(gpbdev_vecchia* h);  // laplace.cuh
 
 int ensure_store_buffers(gpbdev_vecchia* h) {
   if (h->A) return 0;
@@ -205,7 +210,7 @@ int ensure_csc(gpbdev_vecchia* h) {
   return 0;
 }
 
-int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int mode) {
+int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int mode, bool latent = false) {
   if (cov_type < 0 || cov_type > 3) return fail("gpbdev_vecchia_eval: unknown covariance id");
   if (mode < 0 || mode > 2) return fail("gpbdev_vecchia_eval: unknown mode");
   if (!(var > 0.) || !(range > 0.)) return fail("gpbdev_vecchia_eval: covariance parameters must be positive");
@@ -219,6 +224,9 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   a.partials = h->partials;
   a.n = h->n; a.row_begin = h->row_begin; a.row_end = h->row_end;
   a.m = h->m; a.d = h->d; a.var = var; a.range = range;
+  a.diag_nb = latent ? var * (1. + 1e-10) : var + 1.;
+  a.diag_obs = latent ? var : var + 1.;
+  if (latent && mode == gpb::MODE_GRAD) return fail("gpbdev_vecchia_eval: the gradient pass assumes a Gaussian likelihood");
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);
   const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 64);
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -326,6 +334,7 @@ int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, i
 int gpbdev_vecchia_free(gpbdev_vecchia_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  laplace_release(h);
   cudaFree(h->coords); cudaFree(h->nn); cudaFree(h->perm); cudaFree(h->y_in); cudaFree(h->y);
   cudaFree(h->A); cudaFree(h->Dinv); cudaFree(h->u); cudaFree(h->yaux); cudaFree(h->colptr); cudaFree(h->csc_pos);
   cudaFree(h->partials); cudaFree(h->sums); cudaFree(h->flush);
@@ -494,3 +503,5 @@ int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h) {
 }
 
 }  // extern "C"
+
+#include "laplace.cuh"

@@ -68,6 +68,11 @@ struct FactorArgs {
   int d;
   double var;     // sigma_1^2 / sigma^2
   double range;   // transformed range (cov_fcts.h:485-552)
+  // diagonal of the covariance block: Gaussian likelihood (transformed scale) var + 1 for both; latent GP of a
+  // non-Gaussian likelihood: neighbours var * JITTER_MULT_VECCHIA, the observation itself var
+  // (Vecchia_utils.cpp:1411-1417, 1555-1563, 1599-1609)
+  double diag_nb;
+  double diag_obs;
 };
 
 // exp(ax) for ax <= 0 (clamped at -700): round-to-nearest range reduction by the 1.5*2^52 trick, degree-13 Taylor
@@ -247,7 +252,7 @@ vecchia_factor_kernel(const FactorArgs p) {
     }
     // diagonal: variance + nugget 1 (Vecchia_utils.cpp:1601 / :1411,1563), 1 for dummies; response row MT+1
     if (lane < P) {
-      S[lane * kLd + lane] = real ? var + 1. : 1.;
+      S[lane * kLd + lane] = real ? (lane == MT ? p.diag_obs : p.diag_nb) : 1.;
       S[lane * kLd + (MT + 1)] = yv;
     }
     __syncwarp();

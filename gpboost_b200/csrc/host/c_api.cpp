@@ -76,12 +76,14 @@ int GPB_SetOptimConfig(REModelHandle handle, double* init_cov_pars, double lr, d
                        double delta_rel_conv, bool /*use_nesterov_acc*/, int /*nesterov_schedule_version*/, bool trace,
                        const char* optimizer, int /*momentum_offset*/, const char* convergence_criterion,
                        int /*num_covariates*/, double* /*init_coef*/, double /*lr_coef*/, double /*acc_rate_coef*/,
-                       const char* /*optimizer_coef*/, int /*cg_max_num_it*/, int /*cg_max_num_it_tridiag*/,
-                       double /*cg_delta_conv*/, int /*num_rand_vec_trace*/, bool /*reuse_rand_vec_trace*/,
-                       const char* /*cg_preconditioner_type*/, int /*seed_rand_vec_trace*/, int /*piv_chol_rank*/,
+                       const char* /*optimizer_coef*/, int cg_max_num_it, int cg_max_num_it_tridiag,
+                       double cg_delta_conv, int num_rand_vec_trace, bool /*reuse_rand_vec_trace*/,
+                       const char* cg_preconditioner_type, int seed_rand_vec_trace, int /*piv_chol_rank*/,
                        double* /*init_aux_pars*/, bool /*estimate_aux_pars*/, bool /*init_coef_aux_pars_from_iid_model*/,
-                       const int* estimate_cov_par_index, int m_lbfgs, double /*delta_conv_mode_finding*/) {
+                       const int* estimate_cov_par_index, int m_lbfgs, double delta_conv_mode_finding) {
   API_BEGIN();
+  M(handle)->SetIterativeConfig(cg_max_num_it, cg_max_num_it_tridiag, cg_delta_conv, num_rand_vec_trace, cg_preconditioner_type,
+                                seed_rand_vec_trace, delta_conv_mode_finding);
   M(handle)->SetOptimConfig(init_cov_pars, lr, max_iter, delta_rel_conv, trace, optimizer, convergence_criterion, m_lbfgs,
                             estimate_cov_par_index);
   API_END();
@@ -294,6 +296,19 @@ int GPB200_CalcGradient(REModelHandle handle, double* y_inout) {
 int GPB200_GetNumLikelihoodEvals(REModelHandle handle, int64_t* out) {
   API_BEGIN();
   *out = M(handle)->NumLikelihoodEvals();
+  API_END();
+}
+
+int GPB200_GetLaplaceInfo(REModelHandle handle, double* out6) {
+  API_BEGIN();
+  const double* info = M(handle)->LaplaceInfo();
+  for (int i = 0; i < 6; ++i) out6[i] = info[i];
+  API_END();
+}
+
+int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out) {
+  API_BEGIN();
+  M(handle)->GetLaplaceMode(mode_out);
   API_END();
 }
 

@@ -45,7 +45,7 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
                  const char* cov_fct, double cov_fct_shape, const char* gp_approx, double /*cov_fct_taper_range*/,
                  double /*cov_fct_taper_shape*/, int num_neighbors, const char* vecchia_ordering, int /*num_ind_points*/,
                  double /*cover_tree_radius*/, const char* /*ind_points_selection*/, const char* likelihood,
-                 double /*likelihood_additional_param*/, const char* /*matrix_inversion_method*/, int seed,
+                 double /*likelihood_additional_param*/, const char* matrix_inversion_method, int seed,
                  int /*num_parallel_threads*/, bool /*GPU_use*/, bool has_weights, const double* /*weights*/,
                  double likelihood_learning_rate) {
   // ---- checks in the order of REModelTemplate's constructor (re_model_template.h:102-472)
@@ -54,8 +54,20 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   num_data_ = num_data;
   rng_ = std::mt19937((uint32_t)seed);  // rng_ = RNG_t(seed), re_model_template.h:160
   likelihood_ = likelihood == nullptr ? "gaussian" : ParseLikelihoodAlias(likelihood);
-  if (likelihood_ != "gaussian")
-    Fatal("Likelihood '" + likelihood_ + "' is not supported by the B200 engine yet (hot path: 'gaussian')");
+  if (likelihood_ != "gaussian" && likelihood_ != "bernoulli_logit")
+    Fatal("Likelihood '" + likelihood_ + "' is not supported by the B200 engine yet (hot path: 'gaussian', 'bernoulli_logit')");
+  gauss_ = likelihood_ == "gaussian";
+  if (!gauss_) {
+    // SetDefaultMatrixInversionMethod / UseIterativeByDefault (re_model_template.h:7093-7105, 7431-7444): "default" resolves
+    // to "iterative" for a non-Gaussian likelihood with a Vecchia approximation; only that variant runs on the device
+    const std::string mim = matrix_inversion_method == nullptr ? "default" : std::string(matrix_inversion_method);
+    if (mim != "default" && mim != "iterative")
+      Fatal("matrix_inversion_method = '" + mim + "' is not supported for likelihood '" + likelihood_ +
+            "' by the B200 engine (use 'iterative', the reference's default for this model)");
+    if (num_re_group > 0 || num_gp != 1 || gp_approx == nullptr || std::string(gp_approx) != "vecchia")
+      Fatal("Likelihood '" + likelihood_ + "' is only supported with a single GP and gp_approx = 'vecchia' by the B200 engine");
+    if (GetRuntime().world_size > 1) Fatal("Likelihood '" + likelihood_ + "' is not supported with row-sharded engines yet");
+  }
   gp_approx_ = gp_approx == nullptr ? "none" : std::string(gp_approx);
   if (cluster_ids_data != nullptr) {
     for (int32_t i = 1; i < num_data; ++i)
@@ -97,8 +109,9 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   } else {
     Fatal("Covariance of type '" + cov_fct_ + "' is not supported by the B200 engine.");
   }
-  num_cov_pars_ = 3;  // nugget, marginal variance, range
+  num_cov_pars_ = gauss_ ? 3 : 2;  // (nugget,) marginal variance, range
   // ---- GP approximation
+  std::memset(laplace_out_, 0, sizeof(laplace_out_));
   if (gp_approx_ == "none") {  // exact GP: dense Gram + Cholesky on the device, original observation order
     perm_.resize(num_data_);
     std::iota(perm_.begin(), perm_.end(), 0);
@@ -200,6 +213,16 @@ void REModel::TransformCovPars(const double* orig, double* trans) const {
 
 // cov_fcts.h:560-623
 void REModel::TransformBackCovPars(const double* trans, double* orig) const {
+  if (!gauss_) {  // no nugget: [sigma_1^2, range]
+    orig[0] = trans[0];
+    switch (cov_id_) {
+      case GPBDEV_COV_EXPONENTIAL: orig[1] = 1. / trans[1]; break;
+      case GPBDEV_COV_MATERN15: orig[1] = std::sqrt(3.) / trans[1]; break;
+      case GPBDEV_COV_MATERN25: orig[1] = std::sqrt(5.) / trans[1]; break;
+      default: orig[1] = 1. / std::sqrt(trans[1]); break;
+    }
+    return;
+  }
   const double s2 = trans[0];
   orig[0] = s2;
   orig[1] = s2 * trans[1];
@@ -221,7 +244,8 @@ void REModel::SetOptimConfig(const double* init_cov_pars, double lr, int max_ite
       if (!(init_cov_pars[i] > 0.) || std::isnan(init_cov_pars[i]) || std::isinf(init_cov_pars[i]))
         Fatal("Found negative, zero, NaN or Inf values in 'init_cov_pars'");
     init_cov_pars_.assign(num_cov_pars_, 0.);
-    TransformCovPars(init_cov_pars, init_cov_pars_.data());
+    if (gauss_) TransformCovPars(init_cov_pars, init_cov_pars_.data());
+    else { init_cov_pars_[0] = init_cov_pars[0]; init_cov_pars_[1] = TransformRange(init_cov_pars[1]); }
     cov_pars_ = init_cov_pars_;
     init_cov_pars_provided_ = true;
     cov_pars_initialized_ = true;
@@ -352,7 +376,90 @@ double REModel::NegLLFromSums(double sigma2) const {
   return sums_[GPBDEV_SUM_QUAD] / 2. / sigma2 + sums_[GPBDEV_SUM_LOGDET] / 2. + num_data_ / 2. * (std::log(sigma2) + kLog2Pi);
 }
 
+double REModel::TransformRange(double range) const {
+  if (!(range > 0.)) Fatal("Check failed: pars[1] > 0.");
+  switch (cov_id_) {
+    case GPBDEV_COV_EXPONENTIAL: return 1. / range;
+    case GPBDEV_COV_MATERN15: return std::sqrt(3.) / range;
+    case GPBDEV_COV_MATERN25: return std::sqrt(5.) / range;
+    default: return 1. / (range * range);
+  }
+}
+
+void REModel::SetIterativeConfig(int cg_max_num_it, int cg_max_num_it_tridiag, double cg_delta_conv, int num_rand_vec_trace,
+                                 const char* cg_preconditioner_type, int seed_rand_vec_trace, double delta_conv_mode_finding) {
+  // re_model_template.h:860-900: non-positive / -999 values keep the defaults
+  if (cg_max_num_it > 0) cg_max_num_it_ = cg_max_num_it;
+  if (cg_max_num_it_tridiag > 0) cg_max_num_it_tridiag_ = cg_max_num_it_tridiag;
+  if (cg_delta_conv > 0.) cg_delta_conv_ = cg_delta_conv;
+  if (num_rand_vec_trace > 0) num_rand_vec_trace_ = num_rand_vec_trace;
+  if (seed_rand_vec_trace >= 0) seed_rand_vec_trace_ = seed_rand_vec_trace;
+  if (delta_conv_mode_finding > 0.) delta_conv_mode_finding_ = delta_conv_mode_finding;
+  if (!gauss_ && cg_preconditioner_type != nullptr && std::string(cg_preconditioner_type) != "") {
+    std::string pc(cg_preconditioner_type);
+    if (pc == "Sigma_inv_plus_BtWB" || pc == "vadu" || pc == "VADU") pc = "vadu";  // ParsePreconditionerAlias
+    if (pc != "vadu")
+      Fatal("Preconditioner type '" + pc + "' is not supported by the B200 engine (hot path: 'vadu', the reference's default)");
+  }
+}
+
+// GenRandVecNormalParallel (src/GPBoost/CG_utils.cpp:978-994): column col_i of the probe matrix is drawn from
+// mt19937(seed_seq{seed, run_id lo, run_id hi, col_i}) with std::normal_distribution — the same standard-library calls,
+// so the stochastic Lanczos quadrature sees the reference's probe vectors. Rows index the latent process in Vecchia order.
+void REModel::EnsureProbes() {
+  if (probes_t_ == num_rand_vec_trace_ && probes_seed_ == seed_rand_vec_trace_) return;  // reuse_rand_vec_trace
+  const int t = num_rand_vec_trace_;
+  std::vector<double> probes((size_t)num_data_ * t);
+  const uint64_t run_id = cg_generator_counter_;
+  const uint32_t b32 = static_cast<uint32_t>(seed_rand_vec_trace_);
+#pragma omp parallel for schedule(static) num_threads(16)
+  for (int col = 0; col < t; ++col) {
+    std::normal_distribution<double> ndist(0.0, 1.0);
+    std::seed_seq seq{b32, static_cast<uint32_t>(run_id), static_cast<uint32_t>(run_id >> 32), static_cast<uint32_t>(col)};
+    std::mt19937 gen(seq);
+    double* dst = probes.data() + (size_t)col * num_data_;
+    for (int32_t row = 0; row < num_data_; ++row) dst[row] = ndist(gen);
+  }
+  ++cg_generator_counter_;
+  DevCheck(gpbdev_vecchia_laplace_set_probes(engine_, probes.data(), t));
+  probes_t_ = t;
+  probes_seed_ = seed_rand_vec_trace_;
+}
+
+// EvalLaplaceApproxNegLogLikelihood (re_model_template.h:3175-3214): mode re-initialised to 0, factor at cov_pars, then
+// FindModePostRandEffCalcMLLVecchia on the device
+void REModel::EvalLaplace(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects) {
+  double var, range_t;
+  if (cov_pars == nullptr) {
+    if (!cov_pars_initialized_) Fatal("Check failed: cov_pars != nullptr");
+    var = cov_pars_[0]; range_t = cov_pars_[1];
+  } else {
+    for (int i = 0; i < num_cov_pars_; ++i)
+      if (!(cov_pars[i] > 0.)) Fatal("Covariance parameters must be positive");
+    var = cov_pars[0]; range_t = TransformRange(cov_pars[1]);
+  }
+  if (y_data != nullptr) {
+    for (int32_t i = 0; i < num_data_; ++i)  // CheckY, likelihoods.h:1321-1329
+      if (std::fabs(y_data[i]) >= 1e-10 && !NearlyEqual(y_data[i], 1.))
+        Fatal("The response variable ('y') needs to be 0 or 1 for likelihood = '" + likelihood_ + "' ");
+    DevCheck(gpbdev_vecchia_set_y(engine_, y_data));
+  }
+  EnsureProbes();
+  const double cfg[8] = {1000., delta_conv_mode_finding_, 20., (double)cg_max_num_it_, (double)cg_max_num_it_tridiag_,
+                         cg_delta_conv_, 1., 1e-4};  // likelihoods.h:17316-17332
+  DevCheck(gpbdev_vecchia_laplace_eval(engine_, cov_id_, var, range_t, fixed_effects, cfg, laplace_out_));
+  ++num_ll_evals_;
+  *negll = laplace_out_[0];
+  neg_log_likelihood_ = *negll;
+}
+
+void REModel::GetLaplaceMode(double* out) const {
+  if (gauss_ || engine_ == nullptr) Fatal("The posterior mode is only available for non-Gaussian likelihoods");
+  DevCheck(gpbdev_vecchia_laplace_get_mode(engine_, out));
+}
+
 void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects) {
+  if (!gauss_) { EvalLaplace(y_data, cov_pars, negll, fixed_effects); return; }
   double trans[3] = {0., 0., 1.};
   if (cov_pars == nullptr) {
     if (y_data != nullptr) InitializeCovParsIfNotDefined(y_data, fixed_effects);
@@ -374,6 +481,8 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
 
 void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
                           bool reuse_learning_rates_from_previous_call) {
+  if (!gauss_)
+    Fatal("Covariance parameter estimation for likelihood '" + likelihood_ + "' is not built on the device yet (the Laplace-approximated likelihood and the posterior mode are)");
   if (y_data == nullptr) Fatal("Check failed: y_data != nullptr");
   for (int32_t i = 0; i < num_data_; ++i)
     if (std::isnan(y_data[i]) || std::isinf(y_data[i])) Fatal("NaN or Inf in response variable / label ");
@@ -446,6 +555,7 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
 }
 
 void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_cov_factor*/) {
+  if (!gauss_) Fatal("CalcGradient for likelihood '" + likelihood_ + "' is not built on the device yet");
   if (y == nullptr) Fatal("Check failed: y != nullptr");
   InitializeCovParsIfNotDefined(y, fixed_effects);
   // re_model_template.h:3298-3321: SetY(y); y_aux = Psi^-1 y / sigma^2; written back on y.

@@ -38,6 +38,9 @@ class REModel {
                       const char* optimizer, const char* convergence_criterion, int m_lbfgs,
                       const int* estimate_cov_par_index);
 
+  // iterative-method settings of GPB_SetOptimConfig consumed by the Laplace-Vecchia path (re_model_template.h:860-900)
+  void SetIterativeConfig(int cg_max_num_it, int cg_max_num_it_tridiag, double cg_delta_conv, int num_rand_vec_trace,
+                          const char* cg_preconditioner_type, int seed_rand_vec_trace, double delta_conv_mode_finding);
   // REModel::OptimCovPar (re_model.cpp:483-541)
   void OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
                    bool reuse_learning_rates_from_previous_call);
@@ -83,6 +86,20 @@ class REModel {
   gpbdev_grouped_t grouped_ = nullptr;   // single-level grouped random effect backend
   gpbdev_dense_t dense_ = nullptr;       // exact GP backend, gp_approx = "none" 
   void DensePass(double var, double range);
+  // non-Gaussian likelihood (bernoulli_logit) with a latent Vecchia GP: Laplace approximation on the device
+  bool gauss_ = true;
+  void EvalLaplace(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects);
+  void EnsureProbes();
+  double TransformRange(double range) const;
+  int cg_max_num_it_ = 1000, cg_max_num_it_tridiag_ = 1000, num_rand_vec_trace_ = 50, seed_rand_vec_trace_ = 1;
+  double cg_delta_conv_ = 1e-2, delta_conv_mode_finding_ = 1e-8;
+  uint64_t cg_generator_counter_ = 0;   // likelihoods.h:17395
+  int probes_t_ = 0, probes_seed_ = -1;
+  double laplace_out_[6];
+ public:
+  const double* LaplaceInfo() const { return laplace_out_; }
+  void GetLaplaceMode(double* out) const;
+ private:
   int num_groups_ = 0;
   double gsums_[5];
   void CreateGroupedBackend(const char* re_group_data);

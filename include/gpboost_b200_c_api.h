@@ -118,6 +118,11 @@ GPB200_EXPORT int GPB200_SetCollective(int rank, int world_size, void* allreduce
 GPB200_EXPORT int GPB200_CalcGradient(REModelHandle handle, double* y_inout);
 /* number of device likelihood passes so far */
 GPB200_EXPORT int GPB200_GetNumLikelihoodEvals(REModelHandle handle, int64_t* out);
+/* non-Gaussian likelihoods (Laplace approximation), after GPB_EvalNegLogLikelihood: out6 = {negll, Newton iterations of the
+ * mode finding, CG iterations, SLQ iterations, log det(Sigma W + I), objective at the mode}; and the posterior mode of the
+ * latent process in the original data order (likelihoods.h: mode_, num_it_mode_finding_) */
+GPB200_EXPORT int GPB200_GetLaplaceInfo(REModelHandle handle, double* out6);
+GPB200_EXPORT int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out);
 /* the device engine behind a handle (gpbdev_vecchia_t; include/gpboost_b200_dev.h) — bench.py device-only timing */
 GPB200_EXPORT int GPB200_GetDeviceEngine(REModelHandle handle, void** out);
 

@@ -100,6 +100,22 @@ GPBDEV_EXPORT int gpbdev_fp64_peak(int device, double* tflops);
 /* write > L2-size bytes to evict the L2 between timed iterations */
 GPBDEV_EXPORT int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h);
 
+/* ---- Laplace approximation, latent Vecchia GP + bernoulli_logit likelihood -----------------------
+ * Replaces FindModePostRandEffCalcMLLVecchia (include/GPBoost/likelihoods.h:3773-4059) with
+ * matrix_inversion_method = "iterative", cg_preconditioner_type = "vadu": Newton mode finding with PCG solves
+ * (CGVecchiaLaplaceVec, src/GPBoost/CG_utils.cpp:21-108) and the log-determinant by stochastic Lanczos quadrature
+ * (CalcLogDetStochVecchia likelihoods.h:16376-16521, CGTridiagVecchiaLaplace CG_utils.cpp:110-229).
+ * Labels (0/1 as doubles) are set with gpbdev_vecchia_set_y. */
+/* probe vectors r_i ~ N(0, I): n x t COLUMN-major, rows in the Vecchia order (GenRandVecNormalParallel, CG_utils.cpp:978) */
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_set_probes(gpbdev_vecchia_t h, const double* probes_colmajor, int t);
+/* cfg[8]: 0 maxit_mode_newton, 1 delta_conv_mode_finding, 2 max step halvings, 3 cg_max_num_it, 4 cg_max_num_it_tridiag,
+ *         5 cg_delta_conv, 6 calculate the log-determinant (0/1), 7 c_armijo.  var = sigma_1^2, range transformed.
+ * out[6]: 0 approximate NEGATIVE marginal log-likelihood, 1 Newton iterations, 2 CG iterations, 3 SLQ iterations,
+ *         4 log det(Sigma W + I), 5 objective at the mode. fixed_effects_host: original data order or NULL. */
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, double range,
+                                              const double* fixed_effects_host, const double* cfg, double* out);
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_get_mode(gpbdev_vecchia_t h, double* mode_host);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Exact (dense) Gaussian process, Gaussian likelihood (BASELINE config 1). coords: host n x d row-major in the
  * original observation order. Replaces RECompGP::CalcSigma (re_comp.h:1273), CalcZSigmaZt (re_model_template.h:9273),
