@@ -23,10 +23,13 @@
 // (Eigen triangularView solve). Here they are *synchronisation-free*: the solution buffer is pre-filled with a
 // sentinel NaN payload, a persistent cooperative grid assigns rows to warps in topological (index) order, and a warp
 // simply polls the entries it depends on (ld.relaxed.gpu from L2) until they stop being the sentinel. The dependency
-// depth of B at n = 1e6, m = 30 is ~500 rows, so a solve costs ~500 L2 round trips instead of 500 kernel launches or
-// grid barriers. All of these kernels are HBM/L2 gather bound: algorithmic bytes per row and column = 8(m+1) gathered
+// depth of B at n = 1e6, m = 30 is ~500 rows, so a solve costs ~500 dependency hops of a few L2 round trips each instead
+// of 500 kernel launches or grid barriers. All of these kernels are HBM/L2 gather bound: algorithmic bytes per row and column = 8(m+1) gathered
 // + 8 written, plus 12m for the pattern and A, amortised over the t columns.
 #include <cooperative_groups.h>
+
+#include <chrono>
+#include <cstdlib>
 
 namespace gpl {
 
@@ -34,6 +37,7 @@ constexpr unsigned long long kSentinel = 0x7ff8dead0badf00dULL;  // quiet-NaN pa
 constexpr int kMaxCols = 128;
 constexpr int kBlock = 256;
 constexpr int kSpinLimit = 1 << 22;
+__device__ int g_sleep_ns = 100;  // back-off between polls of a dependency that is still in flight
 
 struct Coef { double v[kMaxCols]; };
 
@@ -57,7 +61,7 @@ __device__ __forceinline__ double poll(const double* p, int* err) {
   int spins = 0;
   while (is_sent(v)) {
     if (++spins > kSpinLimit) { atomicExch(err, 1); return 0.; }
-    __nanosleep(20);
+    __nanosleep(g_sleep_ns);
     v = ld_gpu(p);
   }
   return v;
@@ -85,29 +89,48 @@ __global__ void col_reduce_kernel(const double* __restrict__ partials, int nwarp
   if (threadIdx.x == 0) out[c] = sh[0];
 }
 
-// T[i,:] = s_i * (X[i,:] - sum_k A[i,k] X[nn[i,k],:]),  s_i = Dinv[i] (or 1 when Dinv == nullptr)
-template <int TC>
-__global__ void mv_B_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t,
-                            const double* __restrict__ Dinv, const double* __restrict__ X, double* __restrict__ T) {
-  const int lane = threadIdx.x & 31;
+// ---- multi-vector kernels ----------------------------------------------------------------------------------------
+// Work unit = (row, column group): a warp owns 32 consecutive columns of a row (lane = column), so a row of t = 50 probe
+// columns is two independent units. Warp gw works on column group gw % G and on rows gw / G, gw / G + W / G, ... .
+// All m gathers of a unit are issued before the first use (m loads in flight per lane); per-warp column partials are
+// laid out [row sequence gw / G][column], so every column of a partial row is written by exactly one warp.
+constexpr int kM = 30;  // neighbour capacity of the engine (gpb::kMaxNeighbors)
+
+struct Unit {
+  int lane, c, cc;     // lane, column, clamped column
+  bool active;
+  int64_t r0, rstep;   // first row and row stride of this warp
+  size_t pslot;        // row of the partial buffer
+};
+__device__ __forceinline__ Unit make_unit(int t, int G) {
+  Unit u;
+  u.lane = threadIdx.x & 31;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = gw; i < n; i += nw) {
-    int32_t jk = lane < m ? nn[i * m + lane] : -1;
-    const double ak = jk >= 0 ? A[i * m + lane] : 0.;
+  const int cg = (int)(gw % G);
+  u.c = cg * 32 + u.lane;
+  u.active = u.c < t;
+  u.cc = u.active ? u.c : t - 1;
+  u.r0 = gw / G;
+  u.rstep = nw / G;
+  u.pslot = (size_t)(gw / G);
+  return u;
+}
+
+// T[i,:] = s_i * (X[i,:] - sum_k A[i,k] X[nn[i,k],:]),  s_i = Dinv[i] (or 1 when Dinv == nullptr)
+__global__ void __launch_bounds__(kBlock) mv_B_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t, int G,
+                                                      const double* __restrict__ Dinv, const double* __restrict__ X, double* __restrict__ T) {
+  const Unit u = make_unit(t, G);
+  for (int64_t i = u.r0; i < n; i += u.rstep) {
+    int32_t jk = u.lane < m ? nn[i * m + u.lane] : -1;
+    const double ak = jk >= 0 ? A[i * m + u.lane] : 0.;
     jk = max(jk, 0);
-    double acc[TC];
+    double acc = X[i * t + u.cc];
+    double v[kM];
 #pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; acc[cc] = c < t ? X[i * t + c] : 0.; }
-#pragma unroll 6
-    for (int k = 0; k < m; ++k) {
-      const int64_t j = __shfl_sync(0xffffffffu, jk, k);
-      const double a = __shfl_sync(0xffffffffu, ak, k);
+    for (int k = 0; k < kM; ++k) v[k] = X[(int64_t)__shfl_sync(0xffffffffu, jk, k) * t + u.cc];
 #pragma unroll
-      for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) acc[cc] -= a * X[j * t + c]; }
-    }
-    const double s = Dinv ? Dinv[i] : 1.;
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) T[i * t + c] = s * acc[cc]; }
+    for (int k = 0; k < kM; ++k) acc -= __shfl_sync(0xffffffffu, ak, k) * v[k];
+    if (u.active) T[i * t + u.c] = (Dinv ? Dinv[i] : 1.) * acc;
   }
 }
 
@@ -127,49 +150,38 @@ __global__ void v_mv_B_kernel(const double* __restrict__ A, const int32_t* __res
   }
 }
 
-// V[j,:] = T[j,:] - sum_{(i,k): nn[i,k]=j} A[i,k] T[i,:] + W[j] X[j,:];  partial[warp][c] += X[j,c] V[j,c]
-template <int TC>
-__global__ void mv_Bt_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
-                             int m, int64_t n, int t, const double* __restrict__ T, const double* __restrict__ W,
-                             const double* __restrict__ X, double* __restrict__ V, double* __restrict__ partial) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  double dot[TC];
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc) dot[cc] = 0.;
-  for (int64_t j = gw; j < n; j += nw) {
-    double acc[TC];
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; acc[cc] = c < t ? T[j * t + c] : 0.; }
+// V[j,:] = T[j,:] - sum_{(i,k): nn[i,k]=j} A[i,k] T[i,:] + W[j] X[j,:];  partial[.][c] += X[j,c] V[j,c]
+__global__ void __launch_bounds__(kBlock) mv_Bt_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr,
+                                                       const int32_t* __restrict__ csc_pos, int m, int64_t n, int t, int G,
+                                                       const double* __restrict__ T, const double* __restrict__ W,
+                                                       const double* __restrict__ X, double* __restrict__ V, double* __restrict__ partial) {
+  const Unit u = make_unit(t, G);
+  double dot = 0.;
+  for (int64_t j = u.r0; j < n; j += u.rstep) {
+    double acc = T[j * t + u.cc];
+    const double xj = X[j * t + u.cc];
     const int e0 = colptr[j], e1 = colptr[j + 1];
     for (int eb = e0; eb < e1; eb += 32) {
-      const int e = eb + lane;
+      const int e = eb + u.lane;
       const int32_t pos = e < e1 ? csc_pos[e] : 0;
       const double ap = e < e1 ? A[pos] : 0.;
-      const int64_t rowp = pos / m;
+      const int64_t rowp = e < e1 ? pos / m : j;
       const int cnt = min(32, e1 - eb);
-#pragma unroll 4
-      for (int q = 0; q < cnt; ++q) {
-        const int64_t row = __shfl_sync(0xffffffffu, rowp, q);
-        const double a = __shfl_sync(0xffffffffu, ap, q);
 #pragma unroll
-        for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) acc[cc] -= a * T[row * t + c]; }
+      for (int hb = 0; hb < 32; hb += 16) {
+        if (hb < cnt) {
+          double v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = T[__shfl_sync(0xffffffffu, rowp, hb + q) * t + u.cc];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc -= __shfl_sync(0xffffffffu, ap, hb + q) * v[q];
+        }
       }
     }
-    const double w = W ? W[j] : 0.;
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) {
-      const int c = lane + 32 * cc;
-      if (c < t) {
-        const double x = X[j * t + c];
-        const double v = acc[cc] + w * x;
-        V[j * t + c] = v;
-        dot[cc] += x * v;
-      }
-    }
+    const double v = acc + (W ? W[j] : 0.) * xj;
+    if (u.active) { V[j * t + u.c] = v; dot += xj * v; }
   }
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) partial[(size_t)gw * kMaxCols + c] = dot[cc]; }
+  if (u.active) partial[u.pslot * kMaxCols + u.c] = dot;
 }
 
 __global__ void v_mv_Bt_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
@@ -196,29 +208,21 @@ __global__ void v_mv_Bt_kernel(const double* __restrict__ A, const int32_t* __re
   if (lane == 0) partial[(size_t)gw * kMaxCols] = dot;
 }
 
-// R -= V * a[c]  (and U += H * a[c] when U != nullptr);  partial[warp][c] += R[i,c]^2
-template <int TC>
-__global__ void axpy_norm_kernel(int64_t n, int t, Coef a, const double* __restrict__ V, double* __restrict__ R,
+// R -= V * a[c]  (and U += H * a[c] when U != nullptr);  partial[.][c] += R[i,c]^2
+__global__ void axpy_norm_kernel(int64_t n, int t, int G, Coef a, const double* __restrict__ V, double* __restrict__ R,
                                  const double* __restrict__ H, double* __restrict__ U, double* __restrict__ partial) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  double rr[TC];
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc) rr[cc] = 0.;
-  for (int64_t i = gw; i < n; i += nw) {
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) {
-      const int c = lane + 32 * cc;
-      if (c < t) {
-        const double r = R[i * t + c] - V[i * t + c] * a.v[c];
-        R[i * t + c] = r;
-        rr[cc] += r * r;
-        if (U) U[i * t + c] += H[i * t + c] * a.v[c];
-      }
+  const Unit u = make_unit(t, G);
+  double rr = 0.;
+  if (u.active) {
+    const double ac = a.v[u.c];
+    for (int64_t i = u.r0; i < n; i += u.rstep) {
+      const double r = R[i * t + u.c] - V[i * t + u.c] * ac;
+      R[i * t + u.c] = r;
+      rr += r * r;
+      if (U) U[i * t + u.c] += H[i * t + u.c] * ac;
     }
+    partial[u.pslot * kMaxCols + u.c] = rr;
   }
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) partial[(size_t)gw * kMaxCols + c] = rr[cc]; }
 }
 
 // H = Z + H * b[c]
@@ -228,104 +232,118 @@ __global__ void h_update_kernel(int64_t len, int t, Coef b, const double* __rest
 }
 
 // ---- synchronisation-free sparse triangular solves --------------------------------------------------------------
-// Rows are assigned to the warps of a persistent cooperative grid in topological (index) order: warp w handles rows
-// w, w + W, w + 2W, ... . A row only ever waits for rows with a smaller position in that order, which belong to
-// co-resident warps at an earlier or equal step of their own sequence, so the wait always ends.
-// Multi-vector form: a per-row flag carries an epoch; the producer stores its row (L2, st.cg), then releases the flag;
-// consumers poll the flags of all their dependencies in parallel (one per lane, ld.acquire.gpu), then read the rows from
-// L2 (ld.cg) with all loads in flight.
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Units are assigned to the warps of a persistent cooperative grid in topological (index) order: within a column group,
+// warp w handles rows w, w + W', w + 2W', ... . A unit only ever waits for units of the same column group with a
+// smaller position in that order, which belong to co-resident warps at an earlier or equal step of their own
+// sequence, so the wait always ends.
+// The value itself is the flag: the solution buffer is pre-filled with a sentinel NaN payload. A consumer issues the L2
+// loads (ld.cg) of ALL its dependencies at once; for a dependency that still carries the payload ONE lane polls (so a
+// waiting warp costs one L2 request per back-off period, not 32) and the warp then re-reads that row. No fences and no
+// separate flags: a dependency that finished long ago costs exactly the load the product needs anyway, and a hop of
+// the critical path costs about two L2 round trips.
+// Resolves the dependencies of one unit. On entry v[k] holds a first (weak, L2) load of dependency k's value at this
+// lane's column, dep = this LANE's own dependency row (lane k <-> dependency k), coef != 0 marks real dependencies.
+// Dependencies whose value still carries the payload are polled IN PARALLEL (lane k polls the first column of
+// dependency k), then the rows that became ready are re-read with all loads in flight: a hop of the critical path
+// costs about two L2 round trips no matter how many dependencies were still in flight at the first load.
+__device__ __forceinline__ double ld_gpu_nc(const double* p) {  // strong L2 load without a compiler barrier: loads overlap
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void wait_flag(const int* p, int epoch, int* err) {
+template <int N>
+__device__ __forceinline__ void resolve_deps(double (&v)[N], const double* base, int64_t dep, bool real, int t, int cg0, int cc, int lane,
+                                             int* err) {
+  unsigned pend = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const bool rk = __shfl_sync(0xffffffffu, (int)real, k) != 0;
+    if (rk && __any_sync(0xffffffffu, is_sent(v[k]))) pend |= 1u << k;
+  }
   int spins = 0;
-  while (ld_acquire(p) != epoch) {
-    if (++spins > kSpinLimit) { atomicExch(err, 1); return; }
-    __nanosleep(20);
+  while (pend) {
+    const bool mine = lane < N && ((pend >> lane) & 1u);
+    double w = 0.;
+    if (mine) w = ld_gpu(base + dep * t + cg0);
+    unsigned still = __ballot_sync(0xffffffffu, mine && is_sent(w));
+    const unsigned ready = pend & ~still;
+    if (ready) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int64_t row = __shfl_sync(0xffffffffu, dep, k);
+        if ((ready >> k) & 1u) v[k] = ld_gpu_nc(base + row * t + cc);
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        if (((ready >> k) & 1u) && __any_sync(0xffffffffu, is_sent(v[k]))) still |= 1u << k;  // row only partly visible yet
+    } else {
+      if (++spins > kSpinLimit) { if (lane == 0) atomicExch(err, 1); return; }
+      __nanosleep(g_sleep_ns);
+    }
+    pend = still;
   }
 }
 
 // Y = B^-T R, rows in descending order
-template <int TC>
-__global__ void trs_bwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
-                               int m, int64_t n, int t, const double* __restrict__ R, double* Y, int* flag, int epoch, int* err) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t jj = gw; jj < n; jj += nw) {
+__global__ void __launch_bounds__(kBlock) trs_bwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr,
+                                                         const int32_t* __restrict__ csc_pos, int m, int64_t n, int t, int G,
+                                                         const double* __restrict__ R, double* Y, int* err) {
+  const Unit u = make_unit(t, G);
+  const int cg0 = u.c - u.lane;
+  for (int64_t jj = u.r0; jj < n; jj += u.rstep) {
     const int64_t j = n - 1 - jj;
-    double acc[TC];
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; acc[cc] = c < t ? R[j * t + c] : 0.; }
+    double acc = R[j * t + u.cc];
     const int e0 = colptr[j], e1 = colptr[j + 1];
     for (int eb = e0; eb < e1; eb += 32) {
-      const int e = eb + lane;
-      const int32_t pos = e < e1 ? csc_pos[e] : 0;
-      const double ap = e < e1 ? A[pos] : 0.;
-      const int64_t rowp = pos / m;
-      if (e < e1) wait_flag(flag + rowp, epoch, err);
-      __syncwarp();
-      const int cnt = min(32, e1 - eb);
-#pragma unroll 4
-      for (int q = 0; q < cnt; ++q) {
-        const int64_t row = __shfl_sync(0xffffffffu, rowp, q);
+      const int e = eb + u.lane;
+      const bool real = e < e1;
+      const int32_t pos = real ? csc_pos[e] : 0;
+      const double ap = real ? A[pos] : 0.;
+      const int64_t rowp = real ? pos / m : j;  // idle slots: coefficient 0, value never used
+      double v[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = __ldcg(Y + __shfl_sync(0xffffffffu, rowp, q) * t + u.cc);
+      resolve_deps<32>(v, Y, rowp, real, t, cg0, u.cc, u.lane, err);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
         const double a = __shfl_sync(0xffffffffu, ap, q);
-#pragma unroll
-        for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) acc[cc] += a * __ldcg(Y + row * t + c); }
+        if (a != 0.) acc += a * v[q];
       }
     }
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) __stcg(Y + j * t + c, acc[cc]); }
-    __syncwarp();
-    if (lane == 0) st_release(flag + j, epoch);
+    if (u.active) st_gpu(Y + j * t + u.c, acc);
   }
 }
 
-// Z = B^-1 (Y / dw), rows ascending; partial[warp][c] += R[i,c] Z[i,c]
-template <int TC>
-__global__ void trs_fwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t,
-                               const double* __restrict__ dw, const double* __restrict__ Y, const double* __restrict__ R,
-                               double* Z, double* __restrict__ partial, int* flag, int epoch, int* err) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  double dot[TC];
+// Z = B^-1 (Y / dw), rows ascending; partial[.][c] += R[i,c] Z[i,c]
+__global__ void __launch_bounds__(kBlock) trs_fwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t, int G,
+                                                         const double* __restrict__ dw, const double* __restrict__ Y,
+                                                         const double* __restrict__ R, double* Z, double* __restrict__ partial, int* err) {
+  const Unit u = make_unit(t, G);
+  const int cg0 = u.c - u.lane;
+  double dot = 0.;
+  for (int64_t i = u.r0; i < n; i += u.rstep) {
+    int32_t jk = u.lane < m ? nn[i * m + u.lane] : -1;
+    const bool real = jk >= 0;
+    const double ak = real ? A[i * m + u.lane] : 0.;
+    const int64_t dep = real ? jk : (i > 0 ? i - 1 : 0);  // padded slots: coefficient 0, value never used
+    double acc = Y[i * t + u.cc] / dw[i];
+    const double ri = R[i * t + u.cc];
+    double v[kM];
 #pragma unroll
-  for (int cc = 0; cc < TC; ++cc) dot[cc] = 0.;
-  for (int64_t i = gw; i < n; i += nw) {
-    int32_t jk = lane < m ? nn[i * m + lane] : -1;
-    const double ak = jk >= 0 ? A[i * m + lane] : 0.;
-    const double inv = 1. / dw[i];
-    double acc[TC];
+    for (int k = 0; k < kM; ++k) v[k] = __ldcg(Z + __shfl_sync(0xffffffffu, dep, k) * t + u.cc);
+    resolve_deps<kM>(v, Z, dep, real, t, cg0, u.cc, u.lane, err);
 #pragma unroll
-    for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; acc[cc] = c < t ? Y[i * t + c] * inv : 0.; }
-    if (jk >= 0) wait_flag(flag + jk, epoch, err);
-    jk = jk >= 0 ? jk : (int32_t)i;  // padded slots: coefficient 0, harmless self read
-    __syncwarp();
-    if (i > 0) {
-#pragma unroll 6
-      for (int k = 0; k < m; ++k) {
-        const int64_t j = __shfl_sync(0xffffffffu, jk, k);
-        const double a = __shfl_sync(0xffffffffu, ak, k);
-#pragma unroll
-        for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t && a != 0.) acc[cc] += a * __ldcg(Z + j * t + c); }
-      }
+    for (int k = 0; k < kM; ++k) {
+      const double a = __shfl_sync(0xffffffffu, ak, k);
+      if (a != 0.) acc += a * v[k];
     }
-#pragma unroll
-    for (int cc = 0; cc < TC; ++cc) {
-      const int c = lane + 32 * cc;
-      if (c < t) { __stcg(Z + i * t + c, acc[cc]); dot[cc] += R[i * t + c] * acc[cc]; }
-    }
-    __syncwarp();
-    if (lane == 0) st_release(flag + i, epoch);
+    if (u.active) { st_gpu(Z + i * t + u.c, acc); dot += ri * acc; }
   }
-#pragma unroll
-  for (int cc = 0; cc < TC; ++cc) { const int c = lane + 32 * cc; if (c < t) partial[(size_t)gw * kMaxCols + c] = dot[cc]; }
+  if (u.active) partial[u.pslot * kMaxCols + u.c] = dot;
 }
 
-// Single-vector forms: the value itself is the flag. The solution buffer is pre-filled with a sentinel NaN payload and a
-// consumer lane polls its dependency (ld.relaxed.gpu, L2) until the payload is gone: one L2 round trip per dependency hop.
+// Single-vector forms (lane = dependency): every lane polls its own dependency (ld.relaxed.gpu, L2) until the payload
+// is gone — one L2 round trip per hop of the critical path. The next row's pattern is fetched before the wait.
 __global__ void v_trs_bwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
                                  int m, int64_t n, const double* __restrict__ r, double* y, int* err) {
   const int lane = threadIdx.x & 31;
@@ -333,13 +351,14 @@ __global__ void v_trs_bwd_kernel(const double* __restrict__ A, const int32_t* __
   for (int64_t jj = gw; jj < n; jj += nw) {
     const int64_t j = n - 1 - jj;
     const int e0 = colptr[j], e1 = colptr[j + 1];
+    const double rj = r[j];
     double s = 0.;
     for (int e = e0 + lane; e < e1; e += 32) {
       const int32_t pos = csc_pos[e];
       s += A[pos] * poll(y + pos / m, err);
     }
     s = wsum(s);
-    if (lane == 0) st_gpu(y + j, r[j] + s);
+    if (lane == 0) st_gpu(y + j, rj + s);
   }
 }
 
@@ -349,17 +368,26 @@ __global__ void v_trs_fwd_kernel(const double* __restrict__ A, const int32_t* __
   const int lane = threadIdx.x & 31;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double dot = 0.;
+  int32_t jn = -1; double an = 0., yn = 0., rn = 0.;
+  if (gw < n) {
+    if (lane < m) { jn = nn[gw * m + lane]; an = A[gw * m + lane]; }
+    yn = y[gw] / dw[gw]; rn = r[gw];
+  }
   for (int64_t i = gw; i < n; i += nw) {
-    double s = 0.;
-    if (lane < m) {
-      const int32_t j = nn[i * m + lane];
-      if (j >= 0) s = A[i * m + lane] * poll(z + j, err);
+    const int32_t j = jn; const double a = an, yi = yn, ri = rn;
+    const int64_t ni = i + nw;
+    if (ni < n) {  // next row's pattern and right-hand side: in flight while this row waits
+      jn = lane < m ? nn[ni * m + lane] : -1;
+      an = lane < m ? A[ni * m + lane] : 0.;
+      yn = y[ni] / dw[ni]; rn = r[ni];
     }
+    double s = 0.;
+    if (j >= 0) s = a * poll(z + j, err);
     s = wsum(s);
     if (lane == 0) {
-      const double zi = y[i] / dw[i] + s;
+      const double zi = yi + s;
       st_gpu(z + i, zi);
-      dot += r[i] * zi;
+      dot += ri * zi;
     }
   }
   if (lane == 0) partial[(size_t)gw * kMaxCols] = dot;
@@ -492,7 +520,9 @@ inline double tridiag_e1_log_e1(std::vector<double> d, std::vector<double> e) {
 
 struct gpb_laplace_state {
   int t = 0;              // probe columns
-  int grid = 0;           // persistent cooperative grid (blocks)
+  int grid = 0;           // persistent cooperative grid (blocks): what is co-resident for the polling kernels
+  int grid_mv = 0;        // grid of the ordinary (non-polling) row kernels
+  int grid_v = 0;         // cooperative grid of the single-vector polling kernels (few registers: more resident warps)
   int nwarps = 0;
   double *mode = nullptr, *mode_new = nullptr, *upd = nullptr, *dir = nullptr, *rhs = nullptr, *W = nullptr, *dw = nullptr, *fe = nullptr;
   double *r = nullptr, *z = nullptr, *hv = nullptr, *v = nullptr, *tt = nullptr, *yy = nullptr;  // n-vectors of the Newton CG
@@ -502,8 +532,6 @@ struct gpb_laplace_state {
   double* colsum = nullptr;   // kMaxCols (device)
   double* colsum_host = nullptr;  // pinned
   int* err = nullptr;
-  int* flag = nullptr;        // n row flags of the multi-vector triangular solves
-  int epoch = 0;
   double* stage = nullptr;    // pinned n
 };
 
@@ -516,7 +544,6 @@ void laplace_release(gpbdev_vecchia* h) {
                     L->probes, L->R, L->Z, L->H, L->V, L->T, L->Y, L->partial, L->colsum};
   for (double* b : bufs) cudaFree(b);
   cudaFree(L->err);
-  cudaFree(L->flag);
   cudaFreeHost(L->colsum_host);
   cudaFreeHost(L->stage);
   delete L;
@@ -534,12 +561,17 @@ int laplace_ensure(gpbdev_vecchia* h) {
   const int64_t n = h->n;
   // persistent grid: what is co-resident for the polling kernels (the most register-hungry instantiation bounds all)
   int per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gpl::trs_bwd_kernel<2>, gpl::kBlock, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gpl::trs_bwd_kernel, gpl::kBlock, 0));
   int per_sm2 = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, gpl::trs_fwd_kernel<4>, gpl::kBlock, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, gpl::trs_fwd_kernel, gpl::kBlock, 0));
   per_sm = std::max(1, std::min(std::min(per_sm, per_sm2), 4));
   L->grid = per_sm * h->num_sms;
-  L->nwarps = L->grid * (gpl::kBlock / 32);
+  L->grid_mv = 6 * h->num_sms;
+  int per_v = 0, per_v2 = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v, gpl::v_trs_bwd_kernel, gpl::kBlock, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v2, gpl::v_trs_fwd_kernel, gpl::kBlock, 0));
+  L->grid_v = std::max(1, std::min(std::min(per_v, per_v2), 4)) * h->num_sms;
+  L->nwarps = std::max(std::max(L->grid, L->grid_mv), L->grid_v) * (gpl::kBlock / 32);
   double** vecs[] = {&L->mode, &L->mode_new, &L->upd, &L->dir, &L->rhs, &L->W, &L->dw, &L->fe, &L->r, &L->z, &L->hv, &L->v, &L->tt, &L->yy};
   for (double** p : vecs) {
     CUDA_TRY(cudaMalloc(p, sizeof(double) * n));
@@ -552,15 +584,13 @@ int laplace_ensure(gpbdev_vecchia* h) {
   CUDA_TRY(cudaMalloc(&L->err, sizeof(int)));
   CUDA_TRY(cudaMemsetAsync(L->err, 0, sizeof(int), h->stream));
   CUDA_TRY(cudaMallocHost(&L->stage, sizeof(double) * n));
-  CUDA_TRY(cudaMalloc(&L->flag, sizeof(int) * n));
-  CUDA_TRY(cudaMemsetAsync(L->flag, 0, sizeof(int) * n, h->stream));
   return 0;
 }
 
 // column sums of the per-warp partials -> pinned host (synchronises the stream)
-int laplace_colsums(gpbdev_vecchia* h, int ncols, double* out) {
+int laplace_colsums(gpbdev_vecchia* h, int ncols, double* out, int nrows) {
   gpb_laplace_state* L = h->lap;
-  gpl::col_reduce_kernel<<<ncols, gpl::kBlock, 0, h->stream>>>(L->partial, L->nwarps, gpl::kMaxCols, L->colsum);
+  gpl::col_reduce_kernel<<<ncols, gpl::kBlock, 0, h->stream>>>(L->partial, nrows, gpl::kMaxCols, L->colsum);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(L->colsum_host, L->colsum, sizeof(double) * ncols, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -570,35 +600,46 @@ int laplace_colsums(gpbdev_vecchia* h, int ncols, double* out) {
 }
 
 template <typename K, typename... Args>
-int coop_launch(gpbdev_vecchia* h, K kernel, Args... args) {
+int coop_launch(gpbdev_vecchia* h, int grid, K kernel, Args... args) {
   void* params[] = {(void*)&args...};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3(h->lap->grid), dim3(gpl::kBlock), params, 0, h->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(gpl::kBlock), params, 0, h->stream));
   h->launches += 1;
   return 0;
 }
 
-#define GPL_DISPATCH_TC(t, CALL)                    \
-  do {                                              \
-    if ((t) <= 32) { constexpr int TC = 1; CALL; }  \
-    else if ((t) <= 64) { constexpr int TC = 2; CALL; } \
-    else { constexpr int TC = 4; CALL; }            \
-  } while (0)
+// column groups of a t-column multi-vector and the grid that keeps (warps % groups) == 0
+inline int lap_groups(int t) { return (t + 31) / 32; }
+inline int lap_grid(int grid, int G) { return std::max(G, grid - grid % G); }
+
+// phase timers (GPB200_LAPLACE_TRACE=1 prints them): every timed helper ends with a stream synchronisation
+struct LapTrace {
+  bool on = std::getenv("GPB200_LAPLACE_TRACE") != nullptr;
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+LapTrace g_trace;
+struct LapScope {
+  int id; std::chrono::steady_clock::time_point t0;
+  explicit LapScope(int i) : id(i), t0(std::chrono::steady_clock::now()) {}
+  ~LapScope() { g_trace.t[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_trace.c[id]; }
+};
 
 // V = (B^T D^-1 B + W) X, dots[c] = X[:,c] . V[:,c]
 int lap_apply_op(gpbdev_vecchia* h, int t, const double* X, double* V, double* Tbuf, double* dots) {
   gpb_laplace_state* L = h->lap;
   const int64_t n = h->n;
+  LapScope scope(t == 1 ? 0 : 2);
+  const int G = lap_groups(t), grid = lap_grid(L->grid_mv, G);
   if (t == 1) {
-    gpl::v_mv_B_kernel<<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, h->Dinv, X, Tbuf);
-    gpl::v_mv_Bt_kernel<<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, Tbuf, L->W, X, V, L->partial);
+    gpl::v_mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, h->Dinv, X, Tbuf);
+    gpl::v_mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, Tbuf, L->W, X, V, L->partial);
   } else {
-    GPL_DISPATCH_TC(t, (gpl::mv_B_kernel<TC><<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, h->Dinv, X, Tbuf)));
-    GPL_DISPATCH_TC(t, (gpl::mv_Bt_kernel<TC><<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, Tbuf, L->W, X,
-                                                                                    V, L->partial)));
+    gpl::mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, X, Tbuf);
+    gpl::mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, Tbuf, L->W, X, V, L->partial);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
-  return laplace_colsums(h, t, dots);
+  return laplace_colsums(h, t, dots, grid * (gpl::kBlock / 32) / G);
 }
 
 // Z = P^-1 R with P = B^T (D^-1 + W) B;  dots[c] = R[:,c] . Z[:,c]
@@ -608,30 +649,37 @@ int lap_precond(gpbdev_vecchia* h, int t, const double* R, double* Z, double* Yb
   const double* A = h->A; const int32_t* colptr = h->colptr; const int32_t* csc = h->csc_pos; const int32_t* nn = h->nn;
   int m = h->m; int64_t nn_ = n; int tt = t; const double* dw = L->dw; double* partial = L->partial; int* err = L->err;
   const double* Yc = Ybuf;
+  LapScope scope(t == 1 ? 1 : 3);
   if (t == 1) {
     const int fb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 16);
     gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Ybuf, n);
     gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Z, n);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
-    if (coop_launch(h, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
-    if (coop_launch(h, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
+    if (coop_launch(h, L->grid_v, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
+    if (coop_launch(h, L->grid_v, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
   } else {
-    int* flag = L->flag;
-    int e1 = ++L->epoch;
-    GPL_DISPATCH_TC(t, { if (coop_launch(h, gpl::trs_bwd_kernel<TC>, A, colptr, csc, m, nn_, tt, R, Ybuf, flag, e1, err)) return -1; });
-    int e2 = ++L->epoch;
-    GPL_DISPATCH_TC(t, { if (coop_launch(h, gpl::trs_fwd_kernel<TC>, A, nn, m, nn_, tt, dw, Yc, R, Z, partial, flag, e2, err)) return -1; });
+    const int64_t len = n * t;
+    const int fb = (int)std::min<int64_t>((len + 255) / 256, (int64_t)h->num_sms * 16);
+    gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Ybuf, len);
+    gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Z, len);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    int G = lap_groups(t);
+    const int grid = lap_grid(L->grid, G);
+    if (coop_launch(h, grid, gpl::trs_bwd_kernel, A, colptr, csc, m, nn_, tt, G, R, Ybuf, err)) return -1;
+    if (coop_launch(h, grid, gpl::trs_fwd_kernel, A, nn, m, nn_, tt, G, dw, Yc, R, Z, partial, err)) return -1;
+    return laplace_colsums(h, t, dots, grid * (gpl::kBlock / 32) / G);
   }
-  return laplace_colsums(h, t, dots);
+  return laplace_colsums(h, t, dots, L->grid_v * (gpl::kBlock / 32));
 }
 
 int lap_row_stats(gpbdev_vecchia* h, const double* x, const double* W, const double* y, const double* fe, const double* dw, double* out5) {
   gpb_laplace_state* L = h->lap;
-  gpl::row_stats_kernel<<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, h->n, h->Dinv, x, W, y, fe, dw, L->partial);
+  gpl::row_stats_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, h->n, h->Dinv, x, W, y, fe, dw, L->partial);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
-  return laplace_colsums(h, 5, out5);
+  return laplace_colsums(h, 5, out5, L->grid_mv * (gpl::kBlock / 32));
 }
 
 int lap_check_err(gpbdev_vecchia* h) {
@@ -718,7 +766,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       } else {
         if (lap_apply_op(h, 1, L->upd, L->v, L->tt, &dot)) return -1;
         gpl::Coef one; one.v[0] = 1.;
-        gpl::axpy_norm_kernel<1><<<L->grid, gpl::kBlock, 0, h->stream>>>(n, 1, one, L->v, L->r, nullptr, nullptr, L->partial);
+        gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, one, L->v, L->r, nullptr, nullptr, L->partial);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
       }
@@ -729,10 +777,10 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       for (j = 0; j < cg_max; ++j) {
         if (lap_apply_op(h, 1, L->hv, L->v, L->tt, &hv)) return -1;
         gpl::Coef a; a.v[0] = rz / hv;
-        gpl::axpy_norm_kernel<1><<<L->grid, gpl::kBlock, 0, h->stream>>>(n, 1, a, L->v, L->r, L->hv, L->upd, L->partial);
+        gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, a, L->v, L->r, L->hv, L->upd, L->partial);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
-        if (laplace_colsums(h, 1, &rr)) return -1;
+        if (laplace_colsums(h, 1, &rr, L->grid_mv * (gpl::kBlock / 32))) return -1;
         ++cg_total;
         const double rn = std::sqrt(rr);
         if (!std::isfinite(rn)) { na = true; break; }
@@ -787,8 +835,8 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     // z_i = B^T (D^-1 + W)^0.5 r_i  (likelihoods.h:16480-16490)
     gpl::scale_transpose_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->probes, L->dw, L->T);
     CUDA_TRY(cudaGetLastError());
-    GPL_DISPATCH_TC(t, (gpl::mv_Bt_kernel<TC><<<L->grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, L->T, nullptr,
-                                                                                    L->T, L->R, L->partial)));
+    const int G = lap_groups(t), gridg = lap_grid(L->grid_mv, G), prow = gridg * (gpl::kBlock / 32) / G;
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
     // ---- CGTridiagVecchiaLaplace
@@ -803,10 +851,10 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       a_old = a;
       gpl::Coef ac;
       for (int c = 0; c < t; ++c) { a[c] = rz[c] / hvd[c]; ac.v[c] = a[c]; }
-      GPL_DISPATCH_TC(t, (gpl::axpy_norm_kernel<TC><<<L->grid, gpl::kBlock, 0, h->stream>>>(n, t, ac, L->V, L->R, nullptr, nullptr, L->partial)));
+      gpl::axpy_norm_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, ac, L->V, L->R, nullptr, nullptr, L->partial);
       CUDA_TRY(cudaGetLastError());
       h->launches += 1;
-      if (laplace_colsums(h, t, rr.data())) return -1;
+      if (laplace_colsums(h, t, rr.data(), prow)) return -1;
       double mean_norm = 0.;
       for (int c = 0; c < t; ++c) mean_norm += std::sqrt(rr[c]);
       mean_norm /= t;
@@ -837,6 +885,11 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
   }
   out[4] = logdet;
   out[0] = -(mll - 0.5 * logdet);
+  if (g_trace.on) {
+    std::fprintf(stderr, "[laplace n=%lld] op(t=1) %.3fs/%d  precond(t=1) %.3fs/%d  op(t=%d) %.3fs/%d  precond(t=%d) %.3fs/%d\n", (long long)n,
+                 g_trace.t[0], g_trace.c[0], g_trace.t[1], g_trace.c[1], L->t, g_trace.t[2], g_trace.c[2], L->t, g_trace.t[3], g_trace.c[3]);
+    for (int i = 0; i < 8; ++i) { g_trace.t[i] = 0.; g_trace.c[i] = 0; }
+  }
   return 0;
 }
 

@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+cat > /tmp/lap.py <<'PY'
+import sys, time
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import numpy as np, datagen
+from gpboost_b200 import GPModel
+n = int(sys.argv[1])
+X, y, _ = datagen.binary_synth(n, 5, False)
+gm = GPModel(likelihood="bernoulli_logit", gp_coords=X, gp_approx="vecchia", num_neighbors=30, seed=1)
+for rep in range(2):
+    t = time.time(); v = gm.neg_log_likelihood(np.array([1.0, 0.05]), y); print(n, time.time() - t, v, gm.laplace_info().tolist(), flush=True)
+PY
+timeout 600 python -m pytest tests/test_laplace_gpu.py -x -q -m gpu 2>&1 | tail -5
+export GPB200_LAPLACE_TRACE=1
+echo "== base"; timeout 300 python /tmp/lap.py 100000 2>&1 | tail -2
+echo "== nofill"; GPB200_LAP_NOFILL=1 timeout 300 python /tmp/lap.py 100000 2>&1 | grep laplace | tail -1
+echo "== 1e6"; timeout 300 python /tmp/lap.py 1000000 2>&1 | tail -2
