@@ -130,6 +130,37 @@ def time_gpboost(n, iters, lib, threads, F=50):
     return {"sec_per_iter": dt, "first_iter_s": first, "cov_pars": gp.get_cov_pars().tolist()}
 
 
+def time_laplace(n, lib, threads, reps=1, barrier=None):
+    """BASELINE configs[4]: bernoulli_logit likelihood + latent Vecchia GP (m=30), one Laplace-approximated likelihood
+    evaluation = Newton mode finding (VADU-PCG) + log-determinant by stochastic Lanczos quadrature (50 probes), through
+    GPB_EvalNegLogLikelihood with host buffers. Same call, same defaults for both libraries."""
+    from gpboost_b200 import GPModel
+    rng = np.random.default_rng(5)
+    coords = rng.random((n, 2))
+    latent = 1.5 * np.sin(6 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.3 * rng.standard_normal(n)
+    y = (rng.random(n) < 1. / (1. + np.exp(-latent))).astype(np.float64)
+    t0 = time.perf_counter()
+    gp = GPModel(likelihood="bernoulli_logit", gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia",
+                 num_neighbors=M_NEIGH, vecchia_ordering="random", seed=1, matrix_inversion_method="iterative",
+                 num_parallel_threads=threads, _lib=lib)
+    t_create = time.perf_counter() - t0
+    pars = np.array([1.0, 0.05])
+    t0 = time.perf_counter(); v = gp.neg_log_likelihood(pars, y); first = time.perf_counter() - t0
+    if barrier:
+        barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        v = gp.neg_log_likelihood(pars, y)
+    if barrier:
+        barrier()
+    dt = (time.perf_counter() - t0) / reps
+    out = {"n": n, "sec_per_eval": dt, "first_eval_s": first, "create_s": t_create, "negll": v}
+    if lib is None:
+        info = gp.laplace_info()
+        out.update({"newton_it": int(info[1]), "cg_it": int(info[2]), "slq_it": int(info[3])})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +171,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--boost-n", type=int, default=1000000, help="n of the GPBoost-iteration measurement (0 = skip)")
     ap.add_argument("--boost-ref-n", type=int, default=0, help="--impl reference: also time GPBoost iterations at this n (slow)")
+    ap.add_argument("--laplace-n", type=int, default=100000, help="n of the Laplace-Vecchia (bernoulli_logit) measurement (0 = skip)")
+    ap.add_argument("--laplace-ref-n", type=int, default=0, help="--impl reference: also time one Laplace-Vecchia evaluation at this n (slow)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,6 +205,11 @@ def main():
             gb = time_gpboost(args.boost_ref_n, 1, load_lib(ref_lib_path()), ncores)
             line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "n": args.boost_ref_n, "first_iter_s": gb["first_iter_s"],
                                "note": "GPBoost Vecchia m=30 + 31-leaf trees on n x 50; sub-problem of n=%d, not scaled" % args.boost_ref_n}
+        if args.laplace_ref_n > 0:
+            from gpboost_b200.libpath import load_lib
+            from oracle import ref_lib_path
+            lp = time_laplace(args.laplace_ref_n, load_lib(ref_lib_path()), ncores, reps=1)
+            line["laplace"] = {"evals_per_sec": 1.0 / lp["sec_per_eval"], **lp}
         print(json.dumps(line))
         return 0
 
@@ -254,6 +292,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(t[0]), float(t[1])
 
+    # Laplace-Vecchia (configs[4]); all ranks take part (probe columns are sharded), rank 0 reports
+    laplace_res = None
+    if args.laplace_n > 0:
+        laplace_res = time_laplace(args.laplace_n, None, ncores, reps=2, barrier=barrier if world > 1 else None)
+
     if rank == 0:
         peaks = {}
         try:
@@ -293,6 +336,10 @@ def main():
                                "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
                                "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "
                                        "parameters re-fitted every iteration (BASELINE metric (i)); host buffers, end to end"}
+        if laplace_res is not None:
+            line["laplace"] = {"evals_per_sec": 1.0 / laplace_res["sec_per_eval"], **laplace_res,
+                               "note": "GPB_EvalNegLogLikelihood, bernoulli_logit + latent Vecchia GP m=30 (BASELINE configs[4]); with N GPUs "
+                                       "the 50 SLQ probe columns are sharded over the ranks (every rank holds the whole factor)"}
         if not args.no_cpu_baseline and world == 1:
             ns = args.cpu_sample_n
             res = time_reference(ns, 3, 1, ncores)

@@ -519,7 +519,9 @@ inline double tridiag_e1_log_e1(std::vector<double> d, std::vector<double> e) {
 }  // namespace gpl
 
 struct gpb_laplace_state {
-  int t = 0;              // probe columns
+  int t = 0;              // probe columns held by this process
+  int t_total = 0;        // probe columns of the whole job (columns are sharded over ranks, see set_collective)
+  void (*allreduce)(double*, int) = nullptr;
   int grid = 0;           // persistent cooperative grid (blocks): what is co-resident for the polling kernels
   int grid_mv = 0;        // grid of the ordinary (non-polling) row kernels
   int grid_v = 0;         // cooperative grid of the single-vector polling kernels (few registers: more resident warps)
@@ -706,7 +708,20 @@ int gpbdev_vecchia_laplace_set_probes(gpbdev_vecchia_t h, const double* probes_c
     for (double** b : bufs) { cudaFree(*b); *b = nullptr; CUDA_TRY(cudaMalloc(b, bytes)); }
     L->t = t;
   }
+  if (L->t_total < t || L->allreduce == nullptr) L->t_total = t;
   CUDA_TRY(cudaMemcpy(L->probes, probes_colmajor, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Multi-GPU: the probe columns of the stochastic Lanczos quadrature are sharded over the ranks (each rank holds the whole
+// factor and runs its own columns' PCGs). The only exchanges are one scalar per SLQ iteration (the mean
+// residual norm that decides the common early stop, CG_utils.cpp:175-188) and one scalar at the end (the quadrature sum).
+int gpbdev_vecchia_laplace_set_collective(gpbdev_vecchia_t h, void (*allreduce_sum)(double*, int), int t_total) {
+  if (!h) return fail("gpbdev_vecchia_laplace_set_collective: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (laplace_ensure(h)) return -1;
+  h->lap->allreduce = allreduce_sum;
+  h->lap->t_total = t_total;
   return 0;
 }
 
@@ -857,7 +872,8 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       if (laplace_colsums(h, t, rr.data(), prow)) return -1;
       double mean_norm = 0.;
       for (int c = 0; c < t; ++c) mean_norm += std::sqrt(rr[c]);
-      mean_norm /= t;
+      if (L->allreduce) L->allreduce(&mean_norm, 1);
+      mean_norm /= L->t_total;
       if (!std::isfinite(mean_norm)) { na = true; break; }
       if (mean_norm < cg_delta) early = true;
       if (lap_precond(h, t, L->R, L->Z, L->Y, rz_new.data())) return -1;
@@ -878,7 +894,8 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     if (na) { out[0] = std::nan(""); return 0; }
     double ldet = 0.;
     for (int c = 0; c < t; ++c) ldet += gpl::tridiag_e1_log_e1(Td[c], Ts[c]);
-    ldet = ldet * (double)n / t;
+    if (L->allreduce) L->allreduce(&ldet, 1);
+    ldet = ldet * (double)n / L->t_total;
     // log|Sigma W + I| = log|P^-1 (Sigma^-1 + W)| + log|P| + log|Sigma|   (likelihoods.h:16505-16511)
     if (lap_row_stats(h, L->mode, nullptr, nullptr, nullptr, L->dw, st)) return -1;
     logdet = ldet - sum_log_dinv + st[4];

@@ -66,7 +66,6 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
             "' by the B200 engine (use 'iterative', the reference's default for this model)");
     if (num_re_group > 0 || num_gp != 1 || gp_approx == nullptr || std::string(gp_approx) != "vecchia")
       Fatal("Likelihood '" + likelihood_ + "' is only supported with a single GP and gp_approx = 'vecchia' by the B200 engine");
-    if (GetRuntime().world_size > 1) Fatal("Likelihood '" + likelihood_ + "' is not supported with row-sharded engines yet");
   }
   gp_approx_ = gp_approx == nullptr ? "none" : std::string(gp_approx);
   if (cluster_ids_data != nullptr) {
@@ -146,7 +145,7 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   // ---- device state (+ device neighbour search)
   const Runtime& rt = GetRuntime();
   int64_t rb = 0, re = num_data_;
-  if (rt.world_size > 1) {
+  if (rt.world_size > 1 && gauss_) {  // non-Gaussian: every rank holds the whole factor, the SLQ probe columns are sharded
     const int64_t chunk = (num_data_ + rt.world_size - 1) / rt.world_size;
     rb = std::min<int64_t>(num_data_, chunk * rt.rank);
     re = std::min<int64_t>(num_data_, rb + chunk);
@@ -409,19 +408,29 @@ void REModel::SetIterativeConfig(int cg_max_num_it, int cg_max_num_it_tridiag, d
 void REModel::EnsureProbes() {
   if (probes_t_ == num_rand_vec_trace_ && probes_seed_ == seed_rand_vec_trace_) return;  // reuse_rand_vec_trace
   const int t = num_rand_vec_trace_;
-  std::vector<double> probes((size_t)num_data_ * t);
+  // multi-GPU: rank r owns the probe columns r, r + world, r + 2 world, ... (the columns' generators are independent)
+  const Runtime& rt = GetRuntime();
+  std::vector<int> cols;
+  for (int col = rt.rank; col < t; col += rt.world_size) cols.push_back(col);
+  if (cols.empty()) Fatal("num_rand_vec_trace is smaller than the number of ranks");
+  const int tl = (int)cols.size();
+  std::vector<double> probes((size_t)num_data_ * tl);
   const uint64_t run_id = cg_generator_counter_;
   const uint32_t b32 = static_cast<uint32_t>(seed_rand_vec_trace_);
 #pragma omp parallel for schedule(static) num_threads(16)
-  for (int col = 0; col < t; ++col) {
+  for (int lc = 0; lc < tl; ++lc) {
     std::normal_distribution<double> ndist(0.0, 1.0);
-    std::seed_seq seq{b32, static_cast<uint32_t>(run_id), static_cast<uint32_t>(run_id >> 32), static_cast<uint32_t>(col)};
+    std::seed_seq seq{b32, static_cast<uint32_t>(run_id), static_cast<uint32_t>(run_id >> 32), static_cast<uint32_t>(cols[lc])};
     std::mt19937 gen(seq);
-    double* dst = probes.data() + (size_t)col * num_data_;
+    double* dst = probes.data() + (size_t)lc * num_data_;
     for (int32_t row = 0; row < num_data_; ++row) dst[row] = ndist(gen);
   }
   ++cg_generator_counter_;
-  DevCheck(gpbdev_vecchia_laplace_set_probes(engine_, probes.data(), t));
+  DevCheck(gpbdev_vecchia_laplace_set_probes(engine_, probes.data(), tl));
+  if (rt.world_size > 1) {
+    if (rt.allreduce_sum == nullptr) Fatal("world_size > 1 but no all-reduce callback was registered (GPB200_SetCollective)");
+    DevCheck(gpbdev_vecchia_laplace_set_collective(engine_, rt.allreduce_sum, t));
+  }
   probes_t_ = t;
   probes_seed_ = seed_rand_vec_trace_;
 }

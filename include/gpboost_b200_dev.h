@@ -115,6 +115,8 @@ GPBDEV_EXPORT int gpbdev_vecchia_laplace_set_probes(gpbdev_vecchia_t h, const do
 GPBDEV_EXPORT int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, double range,
                                               const double* fixed_effects_host, const double* cfg, double* out);
 GPBDEV_EXPORT int gpbdev_vecchia_laplace_get_mode(gpbdev_vecchia_t h, double* mode_host);
+/* multi-GPU: this process holds t of the job's t_total probe columns; allreduce_sum sums `count` doubles over the ranks */
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_set_collective(gpbdev_vecchia_t h, void (*allreduce_sum)(double*, int), int t_total);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Exact (dense) Gaussian process, Gaussian likelihood (BASELINE config 1). coords: host n x d row-major in the
