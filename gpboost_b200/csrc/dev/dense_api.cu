@@ -199,6 +199,180 @@ __global__ void dense_backsolve_kernel(const double* __restrict__ A, int ld, int
   for (int c = threadIdx.x; c < n; c += blockDim.x) xs[c] *= scale;
 }
 
+// ---- gradient pieces (REModelTemplate::CalcPsiInv re_model_template.h:6586-6617 + the dense branch of CalcGradPars :2018-2039): W = L^-1 by blocked forward
+// substitution, Psi^-1 = W^T W, then  tr(Psi^-1 dPsi_k)  and  alpha^T dPsi_k alpha  (alpha = Psi^-1 y) as tile reductions with dPsi
+// recomputed from the coordinates. Rows >= n of the factor buffer (response row, padding) are treated as identity rows.
+__device__ __forceinline__ double load_L(const double* __restrict__ A, int ld, int n, int r, int c) {
+  if (r >= n || c >= n) return r == c ? 1. : 0.;
+  return c <= r ? A[(size_t)r * ld + c] : 0.;
+}
+// C[4][4] (thread (ty,tx) of a 16 x 16 layout owns rows 4ty.., cols 4tx..) += As (64 x 64, [r][k]) * Bs (64 x 64, [k][c])
+__device__ __forceinline__ void tile_fma(double (&C)[4][4], const double (*As)[NB + 1], const double (*Bs)[NB + 1], int ty, int tx) {
+#pragma unroll 8
+  for (int k = 0; k < NB; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = As[ty * 4 + u][k]; b[u] = Bs[k][tx * 4 + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) C[u][v] = fma(a[u], b[v], C[u][v]);
+  }
+}
+// W_ii = L_ii^-1 for every diagonal tile (thread c solves column c of the tile by forward substitution)
+__global__ void trinv_diag_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ W) {
+  __shared__ double Ls[NB][NB + 1];
+  const int i = blockIdx.x;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Ls[e / NB][e % NB] = load_L(A, ld, n, i * NB + e / NB, i * NB + e % NB);
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= NB) return;
+  double x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    double s = r == c ? 1. : 0.;
+#pragma unroll
+    for (int t = 0; t < r; ++t) s -= Ls[r][t] * x[t];
+    x[r] = r < c ? 0. : s / Ls[r][r];
+  }
+  double* out = W + (size_t)i * NB * ld + (size_t)i * NB;
+#pragma unroll
+  for (int r = 0; r < NB; ++r) out[(size_t)r * ld + c] = x[r];
+}
+// block row i of W, tiles j < i:  W_ij = -W_ii * sum_{k=j}^{i-1} L_ik W_kj
+__global__ void __launch_bounds__(256) trinv_row_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ W, int i) {
+  extern __shared__ __align__(16) double tsm[];
+  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tsm);
+  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tsm + NB * (NB + 1));
+  const int j = blockIdx.x;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double C[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) C[u][v] = 0.;
+  for (int k = j; k < i; ++k) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+      const int r = e / NB, c = e % NB;
+      As[r][c] = load_L(A, ld, n, i * NB + r, k * NB + c);
+      Bs[r][c] = W[(size_t)(k * NB + r) * ld + (size_t)j * NB + c];
+    }
+    __syncthreads();
+    tile_fma(C, As, Bs, ty, tx);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) As[e / NB][e % NB] = W[(size_t)(i * NB + e / NB) * ld + (size_t)i * NB + e % NB];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) Bs[ty * 4 + u][tx * 4 + v] = C[u][v];
+  __syncthreads();
+  double D[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) D[u][v] = 0.;
+  tile_fma(D, As, Bs, ty, tx);
+  double* out = W + (size_t)i * NB * ld + (size_t)j * NB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) out[(size_t)(ty * 4 + u) * ld + tx * 4 + v] = -D[u][v];
+}
+// P_IJ = sum_{K >= I} W_KI^T W_KJ for the lower tiles I >= J (P = Psi^-1)
+__global__ void __launch_bounds__(256) wtw_kernel(const double* __restrict__ W, int ld, int nt, double* __restrict__ P) {
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  extern __shared__ __align__(16) double tsm[];
+  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tsm);
+  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(tsm + NB * (NB + 1));
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double C[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) C[u][v] = 0.;
+  for (int k = bi; k < nt; ++k) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+      const int r = e / NB, c = e % NB;  // element (r, c) of W_K. : row r of block row K
+      As[c][r] = W[(size_t)(k * NB + r) * ld + (size_t)bi * NB + c];  // transposed: As[row of P tile][k]
+      Bs[r][c] = W[(size_t)(k * NB + r) * ld + (size_t)bj * NB + c];
+    }
+    __syncthreads();
+    tile_fma(C, As, Bs, ty, tx);
+  }
+  double* out = P + (size_t)bi * NB * ld + (size_t)bj * NB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) out[(size_t)(ty * 4 + u) * ld + tx * 4 + v] = C[u][v];
+}
+// per lower tile: 0 sum_{i != j} P_ij G_ij   1 sum_{i != j} alpha_i alpha_j G_ij   2 tr P   (G = dSigma / dlog range, zero diagonal)
+template <int COV>
+__global__ void dense_grad_sums_kernel(const double* __restrict__ coords, int n, int d, double var, double range,
+                                       const double* __restrict__ P, int ld, const double* __restrict__ alpha, double* __restrict__ part) {
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  double s0 = 0., s1 = 0., s2 = 0.;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = bi * NB + e / NB, c = bj * NB + e % NB;
+    if (r >= n || c > r) continue;
+    const double p = P[(size_t)r * ld + c];
+    if (r == c) { s2 += p; continue; }
+    double d2 = 0.;
+    for (int k = 0; k < d; ++k) { const double df = coords[(size_t)r * d + k] - coords[(size_t)c * d + k]; d2 = fma(df, df, d2); }
+    const double dist = d2 * gpb::rsqrt_fast(d2 + 1e-300);
+    double g;
+    gpb::cov_eval<COV, true>(dist, var, range, g);
+    s0 += 2. * p * g;
+    s1 += 2. * alpha[r] * alpha[c] * g;
+  }
+  __shared__ double sh[3][256];
+  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) part[(size_t)blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+// fixed-order sum of the tile partials + alpha^T alpha
+__global__ void dense_grad_final_kernel(const double* __restrict__ part, int nblk, const double* __restrict__ alpha, int n, double* __restrict__ out) {
+  __shared__ double sh[4][256];
+  double a[4] = {0., 0., 0., 0.};
+  const int per = (nblk + 255) / 256;
+  for (int b = threadIdx.x * per; b < min((threadIdx.x + 1) * per, nblk); ++b)
+    for (int q = 0; q < 3; ++q) a[q] += part[(size_t)b * 3 + q];
+  const int pern = (n + 255) / 256;
+  for (int i = threadIdx.x * pern; i < min((threadIdx.x + 1) * pern, n); ++i) a[3] += alpha[i] * alpha[i];
+  for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] = a[q];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+using GradSumsKernel = void (*)(const double*, int, int, double, double, const double*, int, const double*, double*);
+GradSumsKernel pick_grad_sums(int cov) {
+  switch (cov) {
+    case 0: return dense_grad_sums_kernel<0>;
+    case 1: return dense_grad_sums_kernel<1>;
+    case 2: return dense_grad_sums_kernel<2>;
+    default: return dense_grad_sums_kernel<3>;
+  }
+}
+
 using GramKernel = void (*)(const double*, int, int, const double*, double, double, double*, int);
 GramKernel pick_gram(int cov) {
   switch (cov) {
@@ -215,6 +389,8 @@ struct gpbdev_dense {
   int n = 0, d = 0, ld = 0, nt = 0;
   cudaStream_t stream = nullptr;
   double *coords = nullptr, *y = nullptr, *A = nullptr, *out = nullptr, *x = nullptr;
+  double *W = nullptr, *P = nullptr, *gpart = nullptr;  // gradient pass: L^-1, Psi^-1, tile partials (lazy)
+  int last_cov = -1; double last_var = 0., last_range = 0.;
   int* info = nullptr;
   double* out_host = nullptr;
   int64_t launches = 0;
@@ -258,6 +434,7 @@ int gpbdev_dense_free(gpbdev_dense_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->coords); cudaFree(h->y); cudaFree(h->x); cudaFree(h->A); cudaFree(h->out); cudaFree(h->info);
+  cudaFree(h->W); cudaFree(h->P); cudaFree(h->gpart);
   cudaFreeHost(h->out_host);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -307,6 +484,46 @@ int gpbdev_dense_eval(gpbdev_dense_t h, int cov_type, double var, double range, 
   out3[1] = h->out_host[1];
   out3[2] = (double)info;  // non-positive pivots (matrix not positive definite)
   h->factored = true;
+  h->last_cov = cov_type; h->last_var = var; h->last_range = range;
+  return 0;
+}
+
+// Gradient sums at the parameters of the last gpbdev_dense_eval: out4 = {tr(Psi^-1 Sigma), tr(Psi^-1 dSigma/dlog range),
+// alpha^T Sigma alpha, alpha^T dSigma/dlog range alpha} with alpha = Psi^-1 y (transformed scale, Psi = I + Sigma).
+int gpbdev_dense_grad(gpbdev_dense_t h, double* out4) {
+  if (!h || !out4) return dfail("gpbdev_dense_grad: null argument");
+  if (!h->factored) return dfail("gpbdev_dense_grad: call gpbdev_dense_eval first");
+  DCUDA(cudaSetDevice(h->device));
+  const int n = h->n, nt = h->nt, ld = h->ld;
+  const int ntiles = nt * (nt + 1) / 2;
+  if (!h->W) {
+    DCUDA(cudaMalloc(&h->W, sizeof(double) * (size_t)ld * ld));
+    DCUDA(cudaMalloc(&h->P, sizeof(double) * (size_t)ld * ld));
+    DCUDA(cudaMalloc(&h->gpart, sizeof(double) * (size_t)ntiles * 3));
+    const int smem = (int)(sizeof(double) * 2 * NB * (NB + 1));
+    DCUDA(cudaFuncSetAttribute(trinv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DCUDA(cudaFuncSetAttribute(wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  const size_t smem = sizeof(double) * 2 * NB * (NB + 1);
+  const double quad = h->out_host[0];  // y^T Psi^-1 y = alpha^T y
+  dense_backsolve_kernel<<<1, 1024, 0, h->stream>>>(h->A, ld, n, 1.0, h->x);
+  trinv_diag_kernel<<<nt, NB, 0, h->stream>>>(h->A, ld, n, h->W);
+  DCUDA(cudaGetLastError());
+  for (int i = 1; i < nt; ++i) trinv_row_kernel<<<i, 256, smem, h->stream>>>(h->A, ld, n, h->W, i);
+  DCUDA(cudaGetLastError());
+  wtw_kernel<<<ntiles, 256, smem, h->stream>>>(h->W, ld, nt, h->P);
+  pick_grad_sums(h->last_cov)<<<ntiles, 256, 0, h->stream>>>(h->coords, n, h->d, h->last_var, h->last_range, h->P, ld, h->x, h->gpart);
+  dense_grad_final_kernel<<<1, 256, 0, h->stream>>>(h->gpart, ntiles, h->x, n, h->out + 0);
+  DCUDA(cudaGetLastError());
+  h->launches += 4 + nt;
+  DCUDA(cudaMemcpyAsync(h->out_host, h->out, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream));
+  DCUDA(cudaStreamSynchronize(h->stream));
+  const double s_pg = h->out_host[0], s_aga = h->out_host[1], tr_p = h->out_host[2], aa = h->out_host[3];
+  out4[0] = (double)n - tr_p;   // tr(Psi^-1 (Psi - I))
+  out4[1] = s_pg;
+  out4[2] = quad - aa;          // alpha^T (Psi - I) alpha = alpha^T y - alpha^T alpha
+  out4[3] = s_aga;
+  h->out_host[0] = quad;
   return 0;
 }
 

@@ -162,13 +162,21 @@ REModel::~REModel() {
   if (dense_) gpbdev_dense_free(dense_);
 }
 
-void REModel::DensePass(double var, double range) {
+void REModel::DensePass(double var, double range, bool with_grad) {
   double o[3];
   DenseCheck(gpbdev_dense_eval(dense_, cov_id_, var, range, o));
   sums_[GPBDEV_SUM_QUAD] = o[0];    // y' Psi^-1 y = ||L^-1 y||^2 (re_model_template.h:10002)
   sums_[GPBDEV_SUM_LOGDET] = o[1];  // 2 sum log L_ii (:3127)
   sums_[GPBDEV_SUM_NBAD] = o[2];
   ++num_ll_evals_;
+  if (with_grad) {
+    // re_model_template.h:2018-2039: grad_k = -alpha' dPsi_k alpha / (2 sigma^2) + tr(Psi^-1 dPsi_k) / 2, alpha = Psi^-1 y
+    double g[4];
+    DenseCheck(gpbdev_dense_grad(dense_, g));
+    sums_[GPBDEV_SUM_UKU0] = 0.; sums_[GPBDEV_SUM_UKU1] = 0.;
+    sums_[GPBDEV_SUM_TR0] = g[0]; sums_[GPBDEV_SUM_TR1] = g[1];
+    sums_[GPBDEV_SUM_UDU0] = g[2]; sums_[GPBDEV_SUM_UDU1] = g[3];
+  }
 }
 
 // group labels arrive as num_data NUL-terminated strings (c_api.h:1325, ConvertCharToStringGroupLevels); Z is kept as an
@@ -499,7 +507,6 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
   SetY(y_data, fixed_effects);
   num_it_ = max_iter_;
   if (max_iter_ <= 0) return;
-  if (dense_) Fatal("Covariance parameter estimation for the exact (dense) GP is not built on the device yet (likelihood evaluation and Psi^-1 y are); use gp_approx = 'vecchia'");
   const bool reuse_mem = reuse_learning_rates_from_previous_call && called_in_GPBoost_algorithm && cov_pars_estimated_once_;
   // optimisation variables: log of the transformed (variance ratio, range); the error variance is profiled out
   // (optim_utils.h:244-340, re_model_template.h:1082-1084, :2640-2650)
@@ -524,8 +531,10 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
       return cached_f;
     }
     const double var = std::exp(x[0]), range = std::exp(x[1]);
-    const bool with_grad = grad != nullptr || speculative;
-    DevicePass(var, range, with_grad ? GPBDEV_MODE_GRAD : GPBDEV_MODE_NLL);
+    // the dense gradient costs two more n^3/3 passes: no speculative gradient with the first line-search trial
+    const bool with_grad = grad != nullptr || (speculative && !dense_);
+    if (dense_) DensePass(var, range, with_grad);
+    else DevicePass(var, range, with_grad ? GPBDEV_MODE_GRAD : GPBDEV_MODE_NLL);
     sigma2 = sums_[GPBDEV_SUM_QUAD] / num_data_;  // ProfileOutSigma2
     const double f = NegLLFromSums(sigma2);
     have_cached_grad = false;

@@ -85,7 +85,7 @@ class REModel {
   gpbdev_vecchia_t engine_ = nullptr;
   gpbdev_grouped_t grouped_ = nullptr;   // single-level grouped random effect backend
   gpbdev_dense_t dense_ = nullptr;       // exact GP backend, gp_approx = "none" 
-  void DensePass(double var, double range);
+  void DensePass(double var, double range, bool with_grad = false);
   // non-Gaussian likelihood (bernoulli_logit) with a latent Vecchia GP: Laplace approximation on the device
   bool gauss_ = true;
   void EvalLaplace(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects);

@@ -133,6 +133,9 @@ GPBDEV_EXPORT int gpbdev_dense_set_y(gpbdev_dense_t h, const double* y_host);
 GPBDEV_EXPORT int gpbdev_dense_eval(gpbdev_dense_t h, int cov_type, double var, double range, double* out3);
 /* after an eval: Psi^-1 y * scale (host, n doubles) */
 GPBDEV_EXPORT int gpbdev_dense_yaux(gpbdev_dense_t h, double scale, double* yaux_host);
+/* gradient sums at the parameters of the last gpbdev_dense_eval (CalcPsiInv re_model_template.h:6586-6617 + the dense branch of
+ * CalcGradPars :2018-2039): out4 = {tr(Psi^-1 Sigma), tr(Psi^-1 dSigma/dlog range), alpha^T Sigma alpha, alpha^T dSigma/dlog range alpha} */
+GPBDEV_EXPORT int gpbdev_dense_grad(gpbdev_dense_t h, double* out4);
 GPBDEV_EXPORT int64_t gpbdev_dense_launch_count(gpbdev_dense_t h);
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -30,5 +30,18 @@ for spec in cases:
     spec["negll"] = m.neg_log_likelihood(np.array(spec["cov_pars"]), y)
     out["nll"].append(spec)
     print(spec)
+# fits (GPB_OptimCovPar, default optimiser lbfgs): BASELINE configs[0] and two smaller cases
+out["fit"] = []
+for spec in ({"data": "r_test", "cov_function": "exponential", "cov_fct_shape": 0.5},
+             {"data": "synth", "n": 2000, "d": 2, "seed": 1, "cov_function": "matern", "cov_fct_shape": 1.5},
+             {"data": "synth", "n": 777, "d": 3, "seed": 2, "cov_function": "matern", "cov_fct_shape": 2.5},
+             {"data": "synth", "n": 500, "d": 2, "seed": 8, "cov_function": "gaussian", "cov_fct_shape": 0.}):
+    coords, y = datagen.r_test_data() if spec["data"] == "r_test" else datagen.synth(spec["n"], spec["d"], spec["seed"])
+    m = GPModel(gp_coords=coords, cov_function=spec["cov_function"], cov_fct_shape=spec["cov_fct_shape"], gp_approx="none", _lib=ref)
+    m.fit(y)
+    spec = dict(spec)
+    spec.update({"cov_pars": m.get_cov_pars().tolist(), "negll": m.get_current_neg_log_likelihood(), "num_it": m._get_num_optim_iter()})
+    out["fit"].append(spec)
+    print(spec)
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "dense_golden.json"), "w") as f:
     json.dump(out, f, indent=1)

@@ -60,3 +60,45 @@ def test_dense_device_psi_inv_y(product_lib):
     Psi = cp[0] * np.eye(900) + cp[1] * (1 + r * D) * np.exp(-r * D)
     want = np.linalg.solve(Psi, y)
     assert np.abs(g - want).max() <= 1e-9 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+def test_dense_device_fit_matches_reference_golden(dg, product_lib):
+    """GPB_OptimCovPar with gp_approx="none" (BASELINE configs[0]): same optimum as the reference's L-BFGS fit."""
+    from gpboost_b200 import GPModel
+    for spec in dg["fit"]:
+        coords, y = _data(spec)
+        m = GPModel(gp_coords=coords, cov_function=spec["cov_function"], cov_fct_shape=spec["cov_fct_shape"], gp_approx="none")
+        m.fit(y)
+        # both optimisers stop on a 1e-6 relative change of the likelihood: compare the optimum, not the last digits of the path
+        assert abs(m.get_current_neg_log_likelihood() - spec["negll"]) <= 2e-6 * abs(spec["negll"]), (spec, m.get_current_neg_log_likelihood())
+        cp = m.get_cov_pars()
+        assert np.all(np.abs(np.log(cp) - np.log(spec["cov_pars"])) < 5e-2), (spec, cp)
+        assert abs(m._get_num_optim_iter() - spec["num_it"]) <= 3, (spec, m._get_num_optim_iter())
+
+
+@pytest.mark.gpu
+def test_dense_device_gradient_sums(product_lib):
+    """tr(Psi^-1 dPsi_k) and alpha^T dPsi_k alpha from the device (L^-1, Psi^-1 = L^-T L^-1 tiles) against numpy."""
+    import ctypes as C
+    n = 333
+    coords, y = datagen.synth(n, 2, 12)
+    var, rho = 1.7, 0.21
+    r = np.sqrt(3.) / rho
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    h = C.c_void_p()
+    co = np.ascontiguousarray(coords)
+    assert product_lib.gpbdev_dense_create(C.byref(h), 0, n, 2, P(co)) == 0
+    assert product_lib.gpbdev_dense_set_y(h, P(np.ascontiguousarray(y))) == 0
+    o3 = np.zeros(3)
+    assert product_lib.gpbdev_dense_eval(h, 1, C.c_double(var), C.c_double(r), P(o3)) == 0
+    g = np.zeros(4)
+    assert product_lib.gpbdev_dense_grad(h, P(g)) == 0, product_lib.gpbdev_dense_last_error()
+    D = np.sqrt(((coords[:, None, :] - coords[None, :, :]) ** 2).sum(-1))
+    Sig = var * (1 + r * D) * np.exp(-r * D)
+    G = -var * r * r * D * D * np.exp(-r * D)  # d Sigma / d log(range_transformed), cov_fcts.h:1155-1160
+    Pinv = np.linalg.inv(np.eye(n) + Sig)
+    a = Pinv @ y
+    want = np.array([np.sum(Pinv * Sig), np.sum(Pinv * G), a @ Sig @ a, a @ G @ a])
+    assert np.all(np.abs(g - want) <= 1e-9 * (1 + np.abs(want))), (g, want)
+    product_lib.gpbdev_dense_free(h)
