@@ -161,6 +161,22 @@ def time_laplace(n, lib, threads, reps=1, barrier=None):
     return out
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the factor kernel (NLL, n=1e6, one launch) from the committed
+    `ncu --set full` capture summary (profiles/r01_ncu_raw_summary.txt); None when the file is not there."""
+    try:
+        tot, inside = 0.0, False
+        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_raw_summary.txt")):
+            if ln.startswith("=="):
+                inside = "prof_factor" in ln
+            elif inside and ("dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln):
+                val, unit = ln.split("=")[1].split()[:2]
+                tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return tot if tot > 0 else None
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,7 +338,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "kernel": "vecchia_factor_kernel<MATERN15, MODE_NLL, DIM=2>", "kernel_ms": dev_ms,
+                         "traffic": ncu_traffic_bytes() if world == 1 else None, "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_raw_summary.txt)",
+                         "kernel": "vecchia_factor_kernel<MATERN15, MODE_NLL, DIM=2>", "kernel_ms": dev_ms,
                          "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS, "peak_source": peak_src,
                          "note": "this kernel is FP64-pipe bound, not HBM bound (SURVEY §8d, DESIGN.md): see roofline_fp64"},
             "roofline_fp64": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak.value, "unit": "TFLOP/s",
