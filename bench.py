@@ -241,8 +241,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world)
-        from gpboost_b200.parallel import init_collective
-        cb_keep = init_collective(lib, dist, device=torch.device("cuda", local_rank))
+        from gpboost_b200.parallel import init_nccl
+        init_nccl(lib, dist, local_rank)  # NCCL communicator owned by the C++ runtime: device-side all-reduces, no Python in the loop
     assert lib.GPB200_SetDevice(local_rank) == 0
 
     coords, y = make_data(N_OBS)

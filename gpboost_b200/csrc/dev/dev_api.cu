@@ -133,6 +133,8 @@ struct gpb_laplace_state;
 
 struct gpbdev_vecchia {
   gpb_laplace_state* lap = nullptr;  // Laplace-Vecchia buffers (laplace.cuh), lazy
+  gpbdev_allreduce_fn allreduce = nullptr;  // device collective hook (row-sharded engines)
+  void* allreduce_ctx = nullptr;
   int device = 0;
   int64_t n = 0;
   int d = 0, m = 0;
@@ -241,6 +243,9 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)grid * gpb::kWarpsPerBlock, h->sums);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
+  if (h->allreduce && !latent) {  // row shards: the 9 sums are summed over the ranks on this stream (NCCL kernel)
+    if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
+  }
   if (mode == gpb::MODE_STORE) h->factor_stored = true;
   return 0;
 }
@@ -250,6 +255,13 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
 extern "C" {
 
 const char* gpbdev_last_error(void) { return g_last_error.c_str(); }
+
+int gpbdev_vecchia_set_allreduce(gpbdev_vecchia_t h, gpbdev_allreduce_fn fn, void* ctx) {
+  if (!h) return fail("gpbdev_vecchia_set_allreduce: null argument");
+  h->allreduce = fn;
+  h->allreduce_ctx = ctx;
+  return 0;
+}
 
 int gpbdev_device_count(void) {
   int c = 0;
@@ -410,6 +422,7 @@ int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host) {
                                                          h->m, h->row_begin, h->row_end, 1.0);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  if (h->allreduce && h->allreduce(h->allreduce_ctx, h->yaux, h->n, (void*)h->stream)) return fail("gpbdev_vecchia_yaux: device all-reduce failed");
   CUDA_TRY(cudaMemcpyAsync(h->stage_host, h->yaux, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   std::memcpy(yaux_host, h->stage_host, sizeof(double) * h->n);
@@ -425,6 +438,7 @@ int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale
                                                          h->row_begin, h->row_end, scale);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  if (h->allreduce && h->allreduce(h->allreduce_ctx, out_dev, h->n, (void*)h->stream)) return fail("gpbdev_vecchia_yaux_device: device all-reduce failed");
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }

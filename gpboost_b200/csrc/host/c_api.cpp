@@ -8,6 +8,7 @@
 #include <string>
 
 #include "booster.h"
+#include "collective.h"
 #include "dataset.h"
 #include "re_model.h"
 #include "runtime.h"
@@ -284,6 +285,24 @@ int GPB200_SetCollective(int rank, int world_size, void* allreduce_sum) {
   rt.rank = rank;
   rt.world_size = world_size;
   rt.allreduce_sum = reinterpret_cast<gpb200::AllReduceSumFn>(allreduce_sum);
+  API_END();
+}
+
+int GPB200_NcclGetUniqueId(char* id128) {
+  API_BEGIN();
+  gpb200::NcclGetUniqueId(id128);
+  API_END();
+}
+
+int GPB200_NcclInit(int rank, int world_size, const char* id128) {
+  API_BEGIN();
+  gpb200::NcclInit(rank, world_size, id128);
+  API_END();
+}
+
+int GPB200_NcclFinalize(void) {
+  API_BEGIN();
+  gpb200::NcclFinalize();
   API_END();
 }
 

@@ -152,6 +152,11 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   }
   DevCheck(gpbdev_vecchia_create(&engine_, rt.device, num_data_, dim_, num_neighbors_, coords_ordered_.data(), perm_.data(),
                                  nullptr, rb, re));
+  if (rt.world_size > 1 && gauss_ && rt.allreduce_dev != nullptr) {
+    // native collective (GPB200_NcclInit): the engine sums its shard results over the ranks on its own stream
+    DevCheck(gpbdev_vecchia_set_allreduce(engine_, rt.allreduce_dev, rt.allreduce_ctx));
+    device_collective_ = true;
+  }
   estimate_cov_par_index_.assign(num_cov_pars_, 1);
   std::memset(sums_, 0, sizeof(sums_));
 }
@@ -366,7 +371,7 @@ void REModel::SetY(const double* y_data, const double* fixed_effects) {
 void REModel::DevicePass(double var, double range, int mode) {
   DevCheck(gpbdev_vecchia_eval(engine_, cov_id_, var, range, mode, sums_));
   const Runtime& rt = GetRuntime();
-  if (rt.world_size > 1) {
+  if (rt.world_size > 1 && !device_collective_) {
     if (rt.allreduce_sum == nullptr) Fatal("world_size > 1 but no all-reduce callback was registered (GPB200_SetCollective)");
     rt.allreduce_sum(sums_, GPBDEV_NUM_SUMS);
   }
@@ -593,7 +598,7 @@ void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_c
   DevicePass(cov_pars_[1], cov_pars_[2], GPBDEV_MODE_STORE);
   DevCheck(gpbdev_vecchia_yaux(engine_, y));
   const Runtime& rt = GetRuntime();
-  if (rt.world_size > 1) rt.allreduce_sum(y, num_data_);
+  if (rt.world_size > 1 && !device_collective_) rt.allreduce_sum(y, num_data_);
   const double inv_s2 = 1. / cov_pars_[0];
   for (int32_t i = 0; i < num_data_; ++i) y[i] *= inv_s2;
 }

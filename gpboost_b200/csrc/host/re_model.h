@@ -88,6 +88,7 @@ class REModel {
   void DensePass(double var, double range, bool with_grad = false);
   // non-Gaussian likelihood (bernoulli_logit) with a latent Vecchia GP: Laplace approximation on the device
   bool gauss_ = true;
+  bool device_collective_ = false;  // the engine all-reduces its results itself (NCCL on its stream)
   void EvalLaplace(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects);
   void EnsureProbes();
   double TransformRange(double range) const;

@@ -6,12 +6,17 @@
 #ifndef GPB200_RUNTIME_H_
 #define GPB200_RUNTIME_H_
 namespace gpb200 {
+#include <cstdint>
 typedef void (*AllReduceSumFn)(double* buf, int count);
+// in-place sum-all-reduce of a DEVICE buffer, enqueued on `stream` (cudaStream_t); same type as gpbdev_allreduce_fn
+typedef int (*AllReduceDevFn)(void* ctx, double* dev_buf, int64_t count, void* stream);
 struct Runtime {
   int device = 0;
   int rank = 0;
   int world_size = 1;
-  AllReduceSumFn allreduce_sum = nullptr;
+  AllReduceSumFn allreduce_sum = nullptr;   // host buffers: injected (GPB200_SetCollective) or NCCL-backed (GPB200_NcclInit)
+  AllReduceDevFn allreduce_dev = nullptr;   // device buffers: NCCL on the engines' streams (collective.h); null with an injected collective
+  void* allreduce_ctx = nullptr;
 };
 Runtime& GetRuntime();
 }  // namespace gpb200

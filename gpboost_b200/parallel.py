@@ -41,3 +41,22 @@ def init_collective(lib, dist, device=None):
     if rc != 0:
         raise RuntimeError(lib.LGBM_GetLastError().decode())
     return cb
+
+
+def init_nccl(lib, dist, device_index):
+    """Native collective: the C++ runtime opens its own NCCL communicator (csrc/host/collective.cpp) and all-reduces device
+    buffers on the engines' streams. torch.distributed is only the launcher-side channel that broadcasts the 128-byte id."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if lib.GPB200_SetDevice(int(device_index)) != 0:
+        raise RuntimeError(lib.LGBM_GetLastError().decode())
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0 and lib.GPB200_NcclGetUniqueId(buf) != 0:
+        raise RuntimeError(lib.LGBM_GetLastError().decode())
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.to(torch.device("cuda", int(device_index)))
+    dist.broadcast(t, src=0)
+    ident = bytes(t.cpu().numpy().tobytes())
+    if lib.GPB200_NcclInit(rank, world, ctypes.c_char_p(ident)) != 0:
+        raise RuntimeError(lib.LGBM_GetLastError().decode())

@@ -115,6 +115,13 @@ GPB200_EXPORT int GPB200_SetDevice(int device);
 GPB200_EXPORT int GPB200_SetCollective(int rank, int world_size, void* allreduce_sum);
 /* y <- Psi^-1 y / sigma^2 at the current covariance parameters: what the reference's objective obtains from
  * REModel::CalcGradient (regression_objective.hpp:165, re_model.cpp:809); exported for parity tests */
+/* Native collective: NCCL over NVLink driven from the C++ runtime on the engines' own streams (csrc/host/collective.h).
+ * One rank calls GPB200_NcclGetUniqueId and the launcher broadcasts the 128 bytes; every rank then calls GPB200_NcclInit
+ * (after GPB200_SetDevice). Replaces the injected host callback of GPB200_SetCollective; reference analogue: Network::Init
+ * (src/LightGBM/network/network.cpp) behind LGBM_NetworkInit (c_api.h:1294). */
+GPB200_EXPORT int GPB200_NcclGetUniqueId(char* id128);
+GPB200_EXPORT int GPB200_NcclInit(int rank, int world_size, const char* id128);
+GPB200_EXPORT int GPB200_NcclFinalize(void);
 GPB200_EXPORT int GPB200_CalcGradient(REModelHandle handle, double* y_inout);
 /* number of device likelihood passes so far */
 GPB200_EXPORT int GPB200_GetNumLikelihoodEvals(REModelHandle handle, int64_t* out);
