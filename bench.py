@@ -313,6 +313,11 @@ def main():
     if args.laplace_n > 0:
         laplace_res = time_laplace(args.laplace_n, None, ncores, reps=2, barrier=barrier if world > 1 else None)
 
+    # GPBoost iteration (configs[2]/[3] shape): all ranks take part — GP rows and histogram rows are both sharded
+    gb = None
+    if args.boost_n > 0:
+        gb = time_gpboost(args.boost_n, 5, None, ncores)
+
     if rank == 0:
         peaks = {}
         try:
@@ -347,8 +352,7 @@ def main():
                               "flops_per_obs": ALGO_FLOPS_PER_OBS, "peak_source": "measured live: gpbdev_fp64_peak DFMA microbenchmark"},
             "negll": negll_value,
         }
-        if args.boost_n > 0 and world == 1:
-            gb = time_gpboost(args.boost_n, 5, None, ncores)
+        if gb is not None:
             line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "ms_per_iter": gb["sec_per_iter"] * 1e3, "n": args.boost_n,
                                "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
                                "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "

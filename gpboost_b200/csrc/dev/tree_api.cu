@@ -371,11 +371,43 @@ struct gpbdev_tree {
   int last_num_leaves = 0;
   int64_t launches = 0;
   std::vector<uint8_t> bins_rm_host;
+  // data-parallel mode (rows sharded over ranks): histograms of the smaller child and the root gradient sum are
+  // all-reduced on this stream; split decisions are then identical on every rank, the partition stays local
+  gpbdev_allreduce_fn allreduce = nullptr;
+  void* allreduce_ctx = nullptr;
+  int64_t n_global = 0;
 };
+
+namespace {
+__global__ void zero_outside_kernel(double* __restrict__ x, int64_t n, int64_t b, int64_t e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (i < b || i >= e) x[i] = 0.;
+}
+}  // namespace
 
 extern "C" {
 
 const char* gpbdev_tree_last_error(void) { return g_tree_err.c_str(); }
+
+int gpbdev_tree_set_allreduce(gpbdev_tree_t h, gpbdev_allreduce_fn fn, void* ctx, int64_t n_global) {
+  if (!h) return tfail("gpbdev_tree_set_allreduce: null argument");
+  if (fn != nullptr && n_global < h->n) return tfail("gpbdev_tree_set_allreduce: n_global is smaller than the local row count");
+  h->allreduce = fn; h->allreduce_ctx = ctx; h->n_global = fn ? n_global : 0;
+  return 0;
+}
+
+// every rank holds rows [b, e) of a replicated n-vector up to date: make the whole vector current everywhere
+int gpbdev_vec_allgather_rows(gpbdev_tree_t h, double* vec_dev, int64_t n, int64_t b, int64_t e) {
+  if (!h || !vec_dev) return tfail("gpbdev_vec_allgather_rows: null argument");
+  if (!h->allreduce) return tfail("gpbdev_vec_allgather_rows: no collective installed (gpbdev_tree_set_allreduce)");
+  TCUDA(cudaSetDevice(h->device));
+  zero_outside_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(vec_dev, n, b, e);
+  TCUDA(cudaGetLastError());
+  if (h->allreduce(h->allreduce_ctx, vec_dev, n, (void*)h->stream)) return tfail("gpbdev_vec_allgather_rows: device all-reduce failed");
+  TCUDA(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  return 0;
+}
 
 int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major, const int32_t* num_bin,
                        const gpbdev_tree_config* cfg) {
@@ -466,34 +498,55 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
   sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
   sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
+  const bool sharded = h->allreduce != nullptr;
+  const int64_t n_glob = sharded ? h->n_global : n;
+  if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
   TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TCUDA(cudaStreamSynchronize(h->stream));
   h->launches += 3;
-  std::vector<int> leaf_begin(L, 0), leaf_cnt(L, 0), leaf_depth(L, 0), leaf_parent(L, -1), slot_of(L, -1);
+  // leaf_cnt: rows of the leaf on THIS rank (partition, histogram ranges); leaf_cnt_g: rows over all ranks (every decision)
+  std::vector<int> leaf_begin(L, 0), leaf_cnt(L, 0), leaf_cnt_g(L, 0), leaf_depth(L, 0), leaf_parent(L, -1), slot_of(L, -1);
   std::vector<double> leaf_sg(L, 0.), leaf_sh(L, 0.);
   std::vector<SplitOut> best(L);
   for (auto& b : best) { b.gain = -INFINITY; b.feature = -1; }
   std::vector<int> free_slots;
   for (int s = L; s >= 0; --s) free_slots.push_back(s);
   leaf_cnt[0] = (int)n;
+  leaf_cnt_g[0] = (int)n_glob;
   leaf_sg[0] = h->scalar_host[0];
-  leaf_sh[0] = hess_const * (double)n;
-  leaf_value[0] = 0.; leaf_count[0] = (int)n;
+  leaf_sh[0] = hess_const * (double)n_glob;
+  leaf_value[0] = 0.; leaf_count[0] = (int)n_glob;
   int num_leaves = 1, left_leaf = 0, right_leaf = -1;
 
   auto build_hist = [&](int leaf, int slot, int parent_slot_sub) -> int {
     const int64_t cnt = leaf_cnt[leaf];
-    int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
-    const int nchunks = (int)((cnt + rpc - 1) / rpc);
-    dim3 grid(nchunks, Fpad / 32);
-    hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
-                                                       rpc, grad, h->part_g, h->part_c);
-    TCUDA(cudaGetLastError());
-    hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const,
-                                                                      h->hist + (size_t)slot * slot_stride,
-                                                                      parent_slot_sub >= 0 ? h->hist + (size_t)parent_slot_sub * slot_stride : nullptr);
-    TCUDA(cudaGetLastError());
-    h->launches += 2;
+    double* dst = h->hist + (size_t)slot * slot_stride;
+    double* par = parent_slot_sub >= 0 ? h->hist + (size_t)parent_slot_sub * slot_stride : nullptr;
+    if (cnt > 0) {
+      int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
+      const int nchunks = (int)((cnt + rpc - 1) / rpc);
+      dim3 grid(nchunks, Fpad / 32);
+      hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
+                                                         rpc, grad, h->part_g, h->part_c);
+      TCUDA(cudaGetLastError());
+      // single GPU: larger = parent - smaller is fused into the merge of the chunk partials
+      hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,
+                                                                        sharded ? nullptr : par);
+      TCUDA(cudaGetLastError());
+      h->launches += 2;
+    } else {
+      TCUDA(cudaMemsetAsync(dst, 0, sizeof(double) * slot_stride, h->stream));  // this rank holds no row of the leaf
+    }
+    if (sharded) {
+      // data-parallel learner (the reference's DataParallelTreeLearner reduce-scatters the smaller child's histograms,
+      // src/LightGBM/treelearner/data_parallel_tree_learner.cpp:155-175): sum over ranks on this stream, then the subtraction
+      if (h->allreduce(h->allreduce_ctx, dst, (int64_t)slot_stride, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
+      if (par) {
+        hist_subtract_kernel<<<((int)slot_stride + 255) / 256, 256, 0, h->stream>>>(par, dst, (int)slot_stride);
+        TCUDA(cudaGetLastError());
+        h->launches += 1;
+      }
+    }
     return 0;
   };
 
@@ -502,7 +555,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     bool do_find = true;
     if (cfg.max_depth > 0 && leaf_depth[left_leaf] >= cfg.max_depth) do_find = false;
     if (do_find) {
-      const int nl = leaf_cnt[left_leaf], nr = right_leaf >= 0 ? leaf_cnt[right_leaf] : 0;
+      const int nl = leaf_cnt_g[left_leaf], nr = right_leaf >= 0 ? leaf_cnt_g[right_leaf] : 0;
       if (nr < cfg.min_data_in_leaf * 2 && nl < cfg.min_data_in_leaf * 2) do_find = false;
     }
     if (!do_find) {
@@ -511,7 +564,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     } else {
       int smaller, larger = -1, parent_slot = -1;
       if (right_leaf < 0) smaller = left_leaf;
-      else if (leaf_cnt[left_leaf] < leaf_cnt[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
+      else if (leaf_cnt_g[left_leaf] < leaf_cnt_g[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
       else { smaller = right_leaf; larger = left_leaf; }
       if (right_leaf >= 0) parent_slot = slot_of[left_leaf];  // the parent's histograms sit under the left (= parent) id
       const int new_slot = free_slots.back();
@@ -524,9 +577,9 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       if (right_leaf >= 0)
         TCUDA(cudaMemcpyAsync(h->parent_flags, h->splittable + (size_t)left_leaf * F, F, cudaMemcpyDeviceToDevice, h->stream));
       LeafArgs a0, a1;
-      a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = leaf_cnt[smaller];
+      a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = leaf_cnt_g[smaller];
       a0.sum_gradients = leaf_sg[smaller]; a0.sum_hessians = leaf_sh[smaller];
-      a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt[larger] : 0;
+      a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt_g[larger] : 0;
       a1.sum_gradients = larger >= 0 ? leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? leaf_sh[larger] : 0.;
       split_scan_kernel<<<dim3(F, 2), 32, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
                                                           cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
@@ -550,21 +603,36 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     }
     const SplitOut bs = best[best_leaf];
     if (!(bs.gain > 0.0)) break;
-    // ---- DataPartition::Split (stable)
+    // ---- DataPartition::Split (stable) on this rank's rows of the leaf
     const int64_t b = leaf_begin[best_leaf], c = leaf_cnt[best_leaf];
-    const int gridp = (int)std::min<int64_t>((c + 255) / 256, (int64_t)h->num_sms * 8);
-    mark_kernel<<<gridp, 256, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, h->flag);
-    TCUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->flag, h->pos, (int)c, h->stream));
     // With a constant hessian the histogram's hessian entries are exact multiples of it, so the split scan's
     // RoundInt(hess * cnt_factor) counts ARE the partition's counts (the reference overwrites them with the
-    // partition's, serial_tree_learner.cpp:589-593 — same numbers). No device round trip is needed for them.
-    const int nleft = bs.left_count, nright = (int)c - nleft;
-    if (nleft <= 0 || nright <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
-    scatter_kernel<<<gridp, 256, 0, h->stream>>>(h->idx, b, c, h->flag, h->pos, nleft, h->idx_tmp);
-    TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
-    h->launches += 4;
+    // partition's, serial_tree_learner.cpp:589-593 — same numbers). On one GPU no device round trip is needed for them;
+    // with row shards the LOCAL left count comes back from the scan.
+    const int nleft_g = bs.left_count, nright_g = leaf_cnt_g[best_leaf] - nleft_g;
+    if (nleft_g <= 0 || nright_g <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
+    int nleft = nleft_g;
+    if (c > 0) {
+      const int gridp = (int)std::min<int64_t>((c + 255) / 256, (int64_t)h->num_sms * 8);
+      mark_kernel<<<gridp, 256, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, h->flag);
+      TCUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->flag, h->pos, (int)c, h->stream));
+      if (sharded) {
+        int32_t last[2];
+        TCUDA(cudaMemcpyAsync(&last[0], h->pos + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        TCUDA(cudaMemcpyAsync(&last[1], h->flag + (c - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        TCUDA(cudaStreamSynchronize(h->stream));
+        nleft = last[0] + last[1];
+      }
+      scatter_kernel<<<gridp, 256, 0, h->stream>>>(h->idx, b, c, h->flag, h->pos, nleft, h->idx_tmp);
+      TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
+      h->launches += 4;
+    } else {
+      nleft = 0;
+    }
+    const int nright = (int)c - nleft;
     const int new_leaf = num_leaves;
     leaf_cnt[best_leaf] = nleft; leaf_begin[new_leaf] = (int)(b + nleft); leaf_cnt[new_leaf] = nright;
+    leaf_cnt_g[best_leaf] = nleft_g; leaf_cnt_g[new_leaf] = nright_g;
     // ---- Tree::Split (tree.h:533-575)
     const int node = num_leaves - 1;
     const int parent = leaf_parent[best_leaf];
@@ -573,8 +641,8 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     split_gain[node] = (float)(bs.gain + cfg.min_gain_to_split);
     left_child[node] = ~best_leaf; right_child[node] = ~new_leaf;
     leaf_parent[best_leaf] = node; leaf_parent[new_leaf] = node;
-    leaf_value[best_leaf] = std::isnan(bs.left_output) ? 0. : bs.left_output; leaf_count[best_leaf] = nleft;
-    leaf_value[new_leaf] = std::isnan(bs.right_output) ? 0. : bs.right_output; leaf_count[new_leaf] = nright;
+    leaf_value[best_leaf] = std::isnan(bs.left_output) ? 0. : bs.left_output; leaf_count[best_leaf] = nleft_g;
+    leaf_value[new_leaf] = std::isnan(bs.right_output) ? 0. : bs.right_output; leaf_count[new_leaf] = nright_g;
     leaf_depth[new_leaf] = leaf_depth[best_leaf] + 1; leaf_depth[best_leaf]++;
     leaf_sg[best_leaf] = bs.left_sum_gradient; leaf_sh[best_leaf] = bs.left_sum_hessian;
     leaf_sg[new_leaf] = bs.right_sum_gradient; leaf_sh[new_leaf] = bs.right_sum_hessian;

@@ -1,7 +1,9 @@
 #include "booster.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <sstream>
 #include <stdexcept>
 
@@ -80,7 +82,27 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
   if (F <= 0) Fatal("All features are trivial (constant): nothing to learn");
   std::vector<int32_t> num_bin(F);
   for (int k = 0; k < F; ++k) num_bin[k] = train->feature(k).num_bin;
-  TreeCheck(gpbdev_tree_create(&learner_, GetRuntime().device, n_, F, train->bins_feature_major().data(), num_bin.data(), &cfg));
+  const Runtime& rt = GetRuntime();
+  row_begin_ = 0; row_end_ = n_;
+  if (rt.world_size > 1) {
+    if (rt.allreduce_dev == nullptr)
+      Fatal("Boosting over several ranks needs the native collective (GPB200_NcclInit): histograms are all-reduced on the device");
+    const int64_t chunk = (n_ + rt.world_size - 1) / rt.world_size;
+    row_begin_ = std::min<int64_t>(n_, chunk * rt.rank);
+    row_end_ = std::min<int64_t>(n_, row_begin_ + chunk);
+    if (row_end_ <= row_begin_) Fatal("More ranks than training rows");
+    sharded_ = true;
+  }
+  if (!sharded_) {
+    TreeCheck(gpbdev_tree_create(&learner_, rt.device, n_, F, train->bins_feature_major().data(), num_bin.data(), &cfg));
+  } else {  // this rank's rows of the (feature-major) bin matrix; bin boundaries come from the whole data set on every rank
+    const int64_t nl = row_end_ - row_begin_;
+    std::vector<uint8_t> local((size_t)nl * F);
+    const uint8_t* all = train->bins_feature_major().data();
+    for (int f = 0; f < F; ++f) std::memcpy(local.data() + (size_t)f * nl, all + (size_t)f * n_ + row_begin_, (size_t)nl);
+    TreeCheck(gpbdev_tree_create(&learner_, rt.device, nl, F, local.data(), num_bin.data(), &cfg));
+    TreeCheck(gpbdev_tree_set_allreduce(learner_, rt.allreduce_dev, rt.allreduce_ctx, n_));
+  }
   TreeCheck(gpbdev_vec_alloc(learner_, &score_dev_, n_));
   TreeCheck(gpbdev_vec_alloc(learner_, &label_dev_, n_));
   TreeCheck(gpbdev_vec_alloc(learner_, &grad_dev_, n_));
@@ -126,7 +148,7 @@ bool Booster::TrainOneIter() {
   tree->split_feature_inner.assign(L, 0); tree->threshold_bin.assign(L, 0); tree->left_child.assign(L, 0); tree->right_child.assign(L, 0);
   tree->split_gain.assign(L, 0.f); tree->leaf_value.assign(L, 0.); tree->leaf_count.assign(L, 0);
   int nl = 1;
-  TreeCheck(gpbdev_tree_train(learner_, grad_dev_, 1, 1.0, &nl, tree->split_feature_inner.data(), tree->threshold_bin.data(),
+  TreeCheck(gpbdev_tree_train(learner_, grad_dev_ + row_begin_, 1, 1.0, &nl, tree->split_feature_inner.data(), tree->threshold_bin.data(),
                               tree->left_child.data(), tree->right_child.data(), tree->split_gain.data(), tree->leaf_value.data(),
                               tree->leaf_count.data()));
   tree->num_leaves = nl;
@@ -145,7 +167,8 @@ bool Booster::TrainOneIter() {
   }
   for (int i = 0; i < nl; ++i) tree->leaf_value[i] *= learning_rate_;  // Tree::Shrinkage
   tree->shrinkage = learning_rate_;
-  TreeCheck(gpbdev_tree_add_score(learner_, tree->leaf_value.data(), nl, score_dev_, nullptr));  // UpdateScore
+  TreeCheck(gpbdev_tree_add_score(learner_, tree->leaf_value.data(), nl, score_dev_ + row_begin_, nullptr));  // UpdateScore
+  if (sharded_) TreeCheck(gpbdev_vec_allgather_rows(learner_, score_dev_, n_, row_begin_, row_end_));  // scores stay replicated
   if (std::fabs(init_score) > (double)1e-15f) {  // Tree::AddBias (tree.h): stored model only
     for (int i = 0; i < nl; ++i) tree->leaf_value[i] += init_score;
     tree->shrinkage = 1.;

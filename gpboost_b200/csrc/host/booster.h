@@ -60,6 +60,10 @@ class Booster {
   std::vector<std::unique_ptr<Tree>> models_;
   int iter_ = 0;
   bool gradients_ready_ = false;
+  // data-parallel training (native collective, world_size > 1): this rank's learner holds rows [row_begin_, row_end_) of the bins;
+  // scores, labels and gradients stay replicated n-vectors (the GP model needs the whole F - y on every rank)
+  bool sharded_ = false;
+  int64_t row_begin_ = 0, row_end_ = 0;
 };
 
 }  // namespace gpb200

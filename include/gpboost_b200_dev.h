@@ -201,6 +201,12 @@ GPBDEV_EXPORT int gpbdev_vec_download(gpbdev_tree_t h, double* dst_host, const d
 /* out = a - b: the L2 objective's gradient score - label (regression_objective.hpp:158-162) */
 GPBDEV_EXPORT int gpbdev_vec_sub(gpbdev_tree_t h, const double* a_dev, const double* b_dev, double* out_dev, int64_t n);
 GPBDEV_EXPORT int gpbdev_vec_add_const(gpbdev_tree_t h, double* a_dev, double c, int64_t n);
+/* data-parallel mode: this learner holds a contiguous shard of the rows; the root gradient sum and the smaller child's histogram of
+ * every split are summed over the ranks through `fn` on the learner's stream (DataParallelTreeLearner,
+ * src/LightGBM/treelearner/data_parallel_tree_learner.cpp:155-175). n_global = rows over all ranks. */
+GPBDEV_EXPORT int gpbdev_tree_set_allreduce(gpbdev_tree_t h, gpbdev_allreduce_fn fn, void* ctx, int64_t n_global);
+/* replicated n-vector of which this rank keeps rows [b, e) current: bring the whole vector up to date on every rank */
+GPBDEV_EXPORT int gpbdev_vec_allgather_rows(gpbdev_tree_t h, double* vec_dev, int64_t n, int64_t b, int64_t e);
 GPBDEV_EXPORT int gpbdev_tree_sync(gpbdev_tree_t h);
 GPBDEV_EXPORT int64_t gpbdev_tree_launch_count(gpbdev_tree_t h);
 GPBDEV_EXPORT void* gpbdev_tree_stream(gpbdev_tree_t h);
