@@ -294,7 +294,10 @@ __global__ void __launch_bounds__(kBlock) trs_bwd_kernel(const double* __restric
     const int64_t j = n - 1 - jj;
     double acc = R[j * t + u.cc];
     const int e0 = colptr[j], e1 = colptr[j + 1];
-    for (int eb = e0; eb < e1; eb += 32) {
+    // A column's entries are sorted by row. Rows far above j finished long ago, the rows just above j may still be in
+    // flight: batches are taken from the END of the list, so everything that is already there is consumed while the
+    // recent rows complete and only the last batch sits on the dependency chain (early columns have hundreds of entries).
+    for (int eb = e0 + ((e1 - e0 - 1) / 32) * 32; eb >= e0 && e1 > e0; eb -= 32) {
       const int e = eb + u.lane;
       const bool real = e < e1;
       const int32_t pos = real ? csc_pos[e] : 0;
@@ -353,7 +356,17 @@ __global__ void v_trs_bwd_kernel(const double* __restrict__ A, const int32_t* __
     const int e0 = colptr[j], e1 = colptr[j + 1];
     const double rj = r[j];
     double s = 0.;
-    for (int e = e0 + lane; e < e1; e += 32) {
+    int e = e1 - 1 - lane;  // far rows first (long finished), the rows just above j last
+    for (; e - 96 >= e0; e -= 128) {  // four entries per lane in flight
+      int32_t pos[4]; double a[4], v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { pos[q] = csc_pos[e - 32 * q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = A[pos[q]]; v[q] = ld_gpu_nc(y + pos[q] / m); }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += a[q] * (is_sent(v[q]) ? poll(y + pos[q] / m, err) : v[q]);
+    }
+    for (; e >= e0; e -= 32) {
       const int32_t pos = csc_pos[e];
       s += A[pos] * poll(y + pos / m, err);
     }

@@ -11,8 +11,7 @@ gm = GPModel(likelihood="bernoulli_logit", gp_coords=X, gp_approx="vecchia", num
 for rep in range(2):
     t = time.time(); v = gm.neg_log_likelihood(np.array([1.0, 0.05]), y); print(n, time.time() - t, v, gm.laplace_info().tolist(), flush=True)
 PY
-timeout 600 python -m pytest tests/test_laplace_gpu.py -x -q -m gpu 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_laplace_gpu.py -x -q -m gpu 2>&1 | tail -3
 export GPB200_LAPLACE_TRACE=1
-echo "== base"; timeout 300 python /tmp/lap.py 100000 2>&1 | tail -2
-echo "== nofill"; GPB200_LAP_NOFILL=1 timeout 300 python /tmp/lap.py 100000 2>&1 | grep laplace | tail -1
-echo "== 1e6"; timeout 300 python /tmp/lap.py 1000000 2>&1 | tail -2
+timeout 300 python /tmp/lap.py 100000 2>&1 | tail -2 | tee gpurun_out/lap_trace.log
+timeout 300 python /tmp/lap.py 1000000 2>&1 | tail -2 | tee -a gpurun_out/lap_trace.log
