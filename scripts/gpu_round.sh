@@ -1,13 +1,8 @@
 #!/bin/bash
-# One GPU session: parity tests, smoke, bench (both arms), launch list and one full ncu capture of the top kernel.
-set -x
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_info.csv
-nproc > gpurun_out/nproc.txt
-python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:vecchia_factor_kernel -s 3 -c 2 -f -o gpurun_out/prof_factor python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out
+# Round check on the GPU box: GPU parity tests, smoke, both bench arms. Logs -> gpurun_out/
+cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 --laplace-ref-n 100000 2>gpurun_out/bench_ref.err | tail -1 | tee gpurun_out/bench_reference.json
+timeout 900 python bench.py 2>gpurun_out/bench.err | tail -1 | tee gpurun_out/bench.json
+tail -5 gpurun_out/bench.err
