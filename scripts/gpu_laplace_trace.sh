@@ -1,5 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
+cd "$(dirname "$0")/.." && mkdir -p gpurun_out
 cat > /tmp/lap.py <<'PY'
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')

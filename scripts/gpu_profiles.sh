@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list of the bench command + full captures of the Laplace / histogram kernels
-mkdir -p gpurun_out
+cd "$(dirname "$0")/.." && mkdir -p gpurun_out
 cat > /tmp/lap.py <<'PY'
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
