@@ -297,18 +297,19 @@ __global__ void __launch_bounds__(kBlock) trs_bwd_kernel(const double* __restric
     // A column's entries are sorted by row. Rows far above j finished long ago, the rows just above j may still be in
     // flight: batches are taken from the END of the list, so everything that is already there is consumed while the
     // recent rows complete and only the last batch sits on the dependency chain (early columns have hundreds of entries).
-    for (int eb = e0 + ((e1 - e0 - 1) / 32) * 32; eb >= e0 && e1 > e0; eb -= 32) {
-      const int e = eb + u.lane;
-      const bool real = e < e1;
-      const int32_t pos = real ? csc_pos[e] : 0;
-      const double ap = real ? A[pos] : 0.;
-      const int64_t rowp = real ? pos / m : j;  // idle slots: coefficient 0, value never used
-      double v[32];
+    constexpr int kBatch = 16;  // entries resolved together (16 values + coefficients per lane keep two CTAs per SM resident)
+    for (int eb = e0 + ((e1 - e0 - 1) / kBatch) * kBatch; eb >= e0 && e1 > e0; eb -= kBatch) {
+      const int e = eb + (u.lane & (kBatch - 1));
+      const bool real = e < e1 && u.lane < kBatch;
+      const int32_t pos = e < e1 ? csc_pos[e] : 0;
+      const double ap = e < e1 ? A[pos] : 0.;
+      const int64_t rowp = e < e1 ? pos / m : j;  // idle slots: coefficient 0, value never used
+      double v[kBatch];
 #pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] = __ldcg(Y + __shfl_sync(0xffffffffu, rowp, q) * t + u.cc);
-      resolve_deps<32>(v, Y, rowp, real, t, cg0, u.cc, u.lane, err);
+      for (int q = 0; q < kBatch; ++q) v[q] = __ldcg(Y + __shfl_sync(0xffffffffu, rowp, q) * t + u.cc);
+      resolve_deps<kBatch>(v, Y, rowp, real, t, cg0, u.cc, u.lane, err);
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
+      for (int q = 0; q < kBatch; ++q) {
         const double a = __shfl_sync(0xffffffffu, ap, q);
         if (a != 0.) acc += a * v[q];
       }
