@@ -169,6 +169,16 @@ int gpbdev_grouped_set_y(gpbdev_grouped_t h, const double* y_host) {
   return 0;
 }
 
+int gpbdev_grouped_set_y_device(gpbdev_grouped_t h, const double* y_dev) {
+  if (!h || !y_dev) return gfail("gpbdev_grouped_set_y_device: null argument");
+  GCUDA(cudaSetDevice(h->device));
+  GCUDA(cudaMemcpyAsync(h->y, y_dev, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  group_sums_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->y, h->perm, h->offs, h->G, h->s, h->yy);
+  GCUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 int gpbdev_grouped_eval(gpbdev_grouped_t h, double var_ratio, double* out5) {
   if (!h || !out5) return gfail("gpbdev_grouped_eval: null argument");
   if (!(var_ratio > 0.)) return gfail("gpbdev_grouped_eval: the variance ratio must be positive");
@@ -191,6 +201,16 @@ int gpbdev_grouped_yaux(gpbdev_grouped_t h, double var_ratio, double scale, doub
   GCUDA(cudaMemcpyAsync(h->stage, h->yaux, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
   GCUDA(cudaStreamSynchronize(h->stream));
   std::memcpy(yaux_host, h->stage, sizeof(double) * h->n);
+  return 0;
+}
+
+int gpbdev_grouped_yaux_device(gpbdev_grouped_t h, double var_ratio, double scale, double* out_dev) {
+  if (!h || !out_dev) return gfail("gpbdev_grouped_yaux_device: null argument");
+  GCUDA(cudaSetDevice(h->device));
+  group_yaux_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->y, h->perm, h->offs, h->s, h->G, var_ratio, scale, out_dev);
+  GCUDA(cudaGetLastError());
+  h->launches += 1;
+  GCUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

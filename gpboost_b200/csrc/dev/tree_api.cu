@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
 #include <string>
@@ -136,6 +137,87 @@ __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bi
     }
 }
 
+// ---- histogram, multi-warp: one CTA (8 warps) = one row chunk x one 32-feature group. Warp w owns the four features
+// 4w..4w+3 of the group and a private histogram for them (4 x 256 x (f64 + u32) = 12 KB), so the CTA carries the same
+// 96 KB as the single-warp kernel above but with eight read-modify-write chains in flight instead of one, and two CTAs per
+// SM. Rows of the chunk are staged tile by tile (256 rows, one row per thread: row id -> one 32-byte bin sector + one
+// gradient, through registers one tile ahead) into shared memory as eight word columns, so that a warp reads the bins
+// of its four features for eight rows with ONE conflict-free 32-bit access. Lane = (row slot 0..7, feature 0..3): eight
+// rows advance per step. Two lanes of a step can hit the same (feature, bin) counter; match.any finds those groups and
+// the members add in lane (= row) order, one round per member, so the additions on every counter happen in exactly the
+// chunk's row order — the same order as the single-warp kernel and as the reference's per-feature pass — without atomics.
+constexpr int kHistWarps = 8;
+constexpr int kHistTile = 256;
+constexpr int kHist2Smem = kHistWarps * 4 * kBins * 12 + 8 * kHistTile * 4 + kHistTile * 8;
+__global__ void __launch_bounds__(kHistWarps * 32, 2) hist2_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
+                                                                   const int32_t* __restrict__ idx, int64_t begin, int64_t count,
+                                                                   int64_t rows_per_chunk, const double* __restrict__ grad,
+                                                                   double* __restrict__ part_g, uint32_t* __restrict__ part_c) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  double* hg = reinterpret_cast<double*>(sm);                                      // [32 features][256]
+  uint32_t* hc = reinterpret_cast<uint32_t*>(sm + kHistWarps * 4 * kBins * 8);     // [32 features][256]
+  uint32_t* tw = hc + kHistWarps * 4 * kBins;                                      // [8 word columns][256 rows]
+  double* tg = reinterpret_cast<double*>(tw + 8 * kHistTile);                      // [256 rows]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int chunk = blockIdx.x, fg = blockIdx.y;
+  for (int e = tid; e < 32 * kBins; e += kHistWarps * 32) { hg[e] = 0.; hc[e] = 0u; }
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(r0 + rows_per_chunk, count);
+  const bool warp_active = fg * 32 + w * 4 < F;  // padding features: nothing to accumulate
+  const int slot = lane >> 2, fsub = lane & 3;
+  double* myg = hg + (w * 4 + fsub) * kBins;
+  uint32_t* myc = hc + (w * 4 + fsub) * kBins;
+  uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0;
+  double sg = 0.;
+  auto load_row = [&](int64_t j) {
+    if (j < r1) {
+      const int64_t rid = idx ? (int64_t)idx[begin + j] : (begin + j);
+      const uint4* src = reinterpret_cast<const uint4*>(bins + rid * Fpad + fg * 32);
+      s0 = src[0]; s1 = src[1];
+      sg = grad[rid];
+    }
+  };
+  load_row(r0 + tid);
+  for (int64_t t0 = r0; t0 < r1; t0 += kHistTile) {
+    __syncthreads();  // the previous tile has been consumed (first pass: the zero fill is complete)
+    tw[0 * kHistTile + tid] = s0.x; tw[1 * kHistTile + tid] = s0.y; tw[2 * kHistTile + tid] = s0.z; tw[3 * kHistTile + tid] = s0.w;
+    tw[4 * kHistTile + tid] = s1.x; tw[5 * kHistTile + tid] = s1.y; tw[6 * kHistTile + tid] = s1.z; tw[7 * kHistTile + tid] = s1.w;
+    tg[tid] = sg;
+    __syncthreads();
+    load_row(t0 + kHistTile + tid);  // next tile: in flight while this one is accumulated
+    if (!warp_active) continue;
+    const int rows = (int)min((int64_t)kHistTile, r1 - t0);
+    for (int b = 0; b < rows; b += 8) {
+      const int r = b + slot;
+      const bool valid = r < rows;
+      const uint32_t word = tw[w * kHistTile + r];
+      const int bin = (int)((word >> (8 * fsub)) & 0xffu);
+      const double g = tg[r];
+      // lanes with the same feature and bin form a group; an invalid (tail) lane is alone in its group
+      const unsigned key = valid ? (unsigned)(fsub * kBins + bin) : (unsigned)(4 * kBins + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int maxrank = __reduce_max_sync(0xffffffffu, rank);
+      if (maxrank == 0) {
+        if (valid) { myg[bin] += g; myc[bin] += 1u; }
+      } else {
+        for (int rr = 0; rr <= maxrank; ++rr) {
+          if (valid && rank == rr) { myg[bin] += g; myc[bin] += 1u; }
+          __syncwarp();
+        }
+      }
+      __syncwarp();  // the next step's lanes may read counters written by other lanes in this one
+    }
+  }
+  __syncthreads();
+  // partial[chunk][feature][bin], coalesced
+  const int64_t base = ((int64_t)chunk * Fpad + fg * 32) * kBins;
+  for (int e = tid; e < 32 * kBins; e += kHistWarps * 32) {
+    part_g[base + e] = hg[e];
+    part_c[base + e] = hc[e];
+  }
+}
+
 // merge chunk partials in chunk order -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226)
 __global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad,
                                    int F, double hess_const, double* __restrict__ hist, double* __restrict__ parent) {
@@ -144,10 +226,20 @@ __global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint
   double g = 0.;
   uint64_t c = 0;
   const int f = t / kBins, b = t % kBins;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int64_t o = ((int64_t)ch * Fpad + f) * kBins + b;
-    g += part_g[o];
-    c += part_c[o];
+  // chunk order is the summation order; eight chunks' loads are issued together
+  const int64_t cs = (int64_t)Fpad * kBins, o0 = (int64_t)f * kBins + b;
+  int ch = 0;
+  for (; ch + 8 <= nchunks; ch += 8) {
+    double gv[8];
+    uint32_t cv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { gv[u] = part_g[(ch + u) * cs + o0]; cv[u] = part_c[(ch + u) * cs + o0]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { g += gv[u]; c += cv[u]; }
+  }
+  for (; ch < nchunks; ++ch) {
+    g += part_g[ch * cs + o0];
+    c += part_c[ch * cs + o0];
   }
   const double hs = (double)c * hess_const;
   hist[2 * t] = g;
@@ -192,7 +284,11 @@ __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict
   const int nb = num_bin[f];
   if (!skip) {
     const double* src = hist_base + (int64_t)a.hist_slot * slot_stride + (int64_t)f * kBins * 2;
-    for (int t = threadIdx.x; t < nb * 2; t += 32) h[t] = src[t];
+    double v[kBins * 2 / 32];  // all loads of the 4 KB row in flight before the first store
+#pragma unroll
+    for (int u = 0; u < kBins * 2 / 32; ++u) { const int t = threadIdx.x + 32 * u; v[u] = t < nb * 2 ? src[t] : 0.; }
+#pragma unroll
+    for (int u = 0; u < kBins * 2 / 32; ++u) { const int t = threadIdx.x + 32 * u; if (t < nb * 2) h[t] = v[u]; }
   }
   __syncwarp();
   if (skip) {
@@ -212,6 +308,7 @@ __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict
   if (threadIdx.x == 0) {
     double srg = 0., srh = kEps;
     int rc = 0;
+#pragma unroll 8
     for (int t = nb - 1; t >= 1; --t) {
       const double g = h[2 * t], hs = h[2 * t + 1];
       srg += g; srh += hs; rc += (int)(hs * cnt_factor + 0.5f);
@@ -358,6 +455,7 @@ struct gpbdev_tree {
   double* part_g = nullptr;
   uint32_t* part_c = nullptr;
   int max_chunks = 0;
+  int hist_kernel_version = 1;  // 1: single-warp hist_kernel; 2: multi-warp hist2_kernel (GPB200_HIST_KERNEL=2) until its B200 parity run is in profiles/
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -460,6 +558,8 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->leaf_cnt_dev, sizeof(int32_t) * h->L));
   TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
   TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
+  TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHist2Smem));
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 2 ? 2 : 1;
   *out = h;
   return 0;
 }
@@ -526,8 +626,12 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
       const int nchunks = (int)((cnt + rpc - 1) / rpc);
       dim3 grid(nchunks, Fpad / 32);
-      hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
-                                                         rpc, grad, h->part_g, h->part_c);
+      if (h->hist_kernel_version == 2)
+        hist2_kernel<<<grid, kHistWarps * 32, kHist2Smem, h->stream>>>(h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx,
+                                                                       leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c);
+      else
+        hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
+                                                           rpc, grad, h->part_g, h->part_c);
       TCUDA(cudaGetLastError());
       // single GPU: larger = parent - smaller is fused into the merge of the chunk partials
       hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,

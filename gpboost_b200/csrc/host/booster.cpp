@@ -125,10 +125,18 @@ void Booster::Boosting() {
   TreeCheck(gpbdev_vec_sub(learner_, score_dev_, label_dev_, grad_dev_, n_));  // grad = score - label, hessian = 1
   if (re_model_ != nullptr) {
     // Gaussian likelihood: OptimCovPar(grad) then CalcGradient(grad): grad <- Psi^-1 (F - y) / sigma^2
-    TreeCheck(gpbdev_vec_download(learner_, host_buf_.data(), grad_dev_, n_));
-    if (train_gp_model_cov_pars_) re_model_->OptimCovPar(host_buf_.data(), nullptr, true, true);
-    re_model_->CalcGradient(host_buf_.data(), nullptr, true);
-    TreeCheck(gpbdev_vec_upload(learner_, grad_dev_, host_buf_.data(), n_));
+    if (re_model_->DevicePathReady()) {
+      // F - y stays in HBM: the GP engine reads it on its own stream once the learner's stream has produced it, and
+      // writes the gradient back in place (both calls return with their stream synchronised)
+      TreeCheck(gpbdev_tree_sync(learner_));
+      if (train_gp_model_cov_pars_) re_model_->OptimCovParDevice(grad_dev_, true, true);
+      re_model_->CalcGradientDevice(grad_dev_);
+    } else {  // first iteration (initial covariance parameters need the response on the host) / backends without a device entry
+      TreeCheck(gpbdev_vec_download(learner_, host_buf_.data(), grad_dev_, n_));
+      if (train_gp_model_cov_pars_) re_model_->OptimCovPar(host_buf_.data(), nullptr, true, true);
+      re_model_->CalcGradient(host_buf_.data(), nullptr, true);
+      TreeCheck(gpbdev_vec_upload(learner_, grad_dev_, host_buf_.data(), n_));
+    }
   }
   gradients_ready_ = true;
 }

@@ -510,6 +510,29 @@ void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, boo
     if (std::isnan(y_data[i]) || std::isinf(y_data[i])) Fatal("NaN or Inf in response variable / label ");
   InitializeCovParsIfNotDefined(y_data, fixed_effects);
   SetY(y_data, fixed_effects);
+  OptimCovParCore(called_in_GPBoost_algorithm, reuse_learning_rates_from_previous_call);
+}
+
+bool REModel::DevicePathReady() const {
+  // initial covariance parameters come from the sample variance of the response (FindInitCovPar): the first call takes the
+  // host-pointer form; the dense backend and an injected host collective have no device-resident entry
+  const Runtime& rt = GetRuntime();
+  return gauss_ && cov_pars_initialized_ && dense_ == nullptr && !(rt.world_size > 1 && !device_collective_);
+}
+
+void REModel::SetYDevice(const double* y_dev) {
+  if (grouped_) GrpCheck(gpbdev_grouped_set_y_device(grouped_, y_dev));
+  else DevCheck(gpbdev_vecchia_set_y_device(engine_, y_dev));
+}
+
+void REModel::OptimCovParDevice(const double* y_dev, bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call) {
+  if (y_dev == nullptr) Fatal("Check failed: y_data != nullptr");
+  if (!DevicePathReady()) Fatal("OptimCovParDevice: no device-resident path for this model state (use OptimCovPar)");
+  SetYDevice(y_dev);
+  OptimCovParCore(called_in_GPBoost_algorithm, reuse_learning_rates_from_previous_call);
+}
+
+void REModel::OptimCovParCore(bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call) {
   num_it_ = max_iter_;
   if (max_iter_ <= 0) return;
   const bool reuse_mem = reuse_learning_rates_from_previous_call && called_in_GPBoost_algorithm && cov_pars_estimated_once_;
@@ -601,6 +624,20 @@ void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_c
   if (rt.world_size > 1 && !device_collective_) rt.allreduce_sum(y, num_data_);
   const double inv_s2 = 1. / cov_pars_[0];
   for (int32_t i = 0; i < num_data_; ++i) y[i] *= inv_s2;
+}
+
+void REModel::CalcGradientDevice(double* y_dev) {
+  if (!gauss_) Fatal("CalcGradient for likelihood '" + likelihood_ + "' is not built on the device yet");
+  if (y_dev == nullptr) Fatal("Check failed: y != nullptr");
+  if (!DevicePathReady()) Fatal("CalcGradientDevice: no device-resident path for this model state (use CalcGradient)");
+  if (grouped_) {
+    GrpCheck(gpbdev_grouped_set_y_device(grouped_, y_dev));
+    GrpCheck(gpbdev_grouped_yaux_device(grouped_, cov_pars_[1], 1. / cov_pars_[0], y_dev));
+    return;
+  }
+  DevCheck(gpbdev_vecchia_set_y_device(engine_, y_dev));
+  DevicePass(cov_pars_[1], cov_pars_[2], GPBDEV_MODE_STORE);
+  DevCheck(gpbdev_vecchia_yaux_device(engine_, y_dev, 1. / cov_pars_[0]));
 }
 
 void REModel::GetCovPar(double* out, bool calc_std_dev) const {

@@ -48,6 +48,12 @@ class REModel {
   void EvalNegLogLikelihood(const double* y_data, const double* cov_pars, double* negll, const double* fixed_effects);
   // REModel::CalcGradient (re_model.cpp:809): y <- Psi^-1 y / sigma^2 at the current covariance parameters
   void CalcGradient(double* y, const double* fixed_effects, bool calc_cov_factor);
+  // Device-resident forms used by the boosting loop (GBDT::Boosting -> objective -> REModel, gbdt.cpp:194,
+  // regression_objective.hpp:164-165): y_dev is a device pointer to n doubles in original order, complete on the
+  // caller's side (the caller synchronised its stream). No host copy of the response is made.
+  void OptimCovParDevice(const double* y_dev, bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
+  void CalcGradientDevice(double* y_dev);
+  bool DevicePathReady() const;
   // GPB_GetCovPar / GPB_GetInitCovPar (original scale)
   void GetCovPar(double* out, bool calc_std_dev) const;
   void GetInitCovPar(double* out) const;
@@ -68,6 +74,8 @@ class REModel {
   void InitializeCovParsIfNotDefined(const double* y_data, const double* fixed_effects);
   void FindInitCovPar(const double* y_data, const double* fixed_effects, double* init_trans);
   void SetY(const double* y_data, const double* fixed_effects);
+  void SetYDevice(const double* y_dev);
+  void OptimCovParCore(bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
   // one device pass at transformed (var, range); fills sums_
   void DevicePass(double var, double range, int mode);
   double NegLLFromSums(double sigma2) const;

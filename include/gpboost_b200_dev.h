@@ -159,6 +159,11 @@ GPBDEV_EXPORT int gpbdev_grouped_set_y(gpbdev_grouped_t h, const double* y_host)
 GPBDEV_EXPORT int gpbdev_grouped_eval(gpbdev_grouped_t h, double var_ratio, double* out5);
 /* y_aux = Psi^-1 y * scale in original order (CalcYAux single-RE branch) */
 GPBDEV_EXPORT int gpbdev_grouped_yaux(gpbdev_grouped_t h, double var_ratio, double scale, double* yaux_host);
+/* Device-resident forms (the boosting loop keeps F - y and its gradient in HBM): y_dev / out_dev are device pointers to n doubles
+ * in original order. set_y_device is enqueued on the engine's stream (the caller has synchronised the producer);
+ * yaux_device returns after the result is complete. */
+GPBDEV_EXPORT int gpbdev_grouped_set_y_device(gpbdev_grouped_t h, const double* y_dev);
+GPBDEV_EXPORT int gpbdev_grouped_yaux_device(gpbdev_grouped_t h, double var_ratio, double scale, double* out_dev);
 GPBDEV_EXPORT int64_t gpbdev_grouped_launch_count(gpbdev_grouped_t h);
 
 /* ------------------------------------------------------------------------------------------------------------------
