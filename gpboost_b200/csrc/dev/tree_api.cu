@@ -137,99 +137,133 @@ __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bi
     }
 }
 
-// ---- histogram, multi-warp: one CTA (8 warps) = one row chunk x one 32-feature group. Warp w owns the four features
-// 4w..4w+3 of the group and a private histogram for them (4 x 256 x (f64 + u32) = 12 KB), so the CTA carries the same
-// 96 KB as the single-warp kernel above but with eight read-modify-write chains in flight instead of one, and two CTAs per
-// SM. Rows of the chunk are staged tile by tile (256 rows, one row per thread: row id -> one 32-byte bin sector + one
-// gradient, through registers one tile ahead) into shared memory as eight word columns, so that a warp reads the bins
-// of its four features for eight rows with ONE conflict-free 32-bit access. Lane = (row slot 0..7, feature 0..3): eight
-// rows advance per step. Two lanes of a step can hit the same (feature, bin) counter; match.any finds those groups and
-// the members add in lane (= row) order, one round per member, so the additions on every counter happen in exactly the
-// chunk's row order — the same order as the single-warp kernel and as the reference's per-feature pass — without atomics.
-constexpr int kHistWarps = 8;
+// ---- histogram, multi-warp: one CTA = one row chunk x up to 64 features (all of them at F <= 64), one CTA per SM.
+// Warp w owns the four features 4w..4w+3 of the CTA's feature group and a private histogram for them
+// (4 x 256 x (f64 + u32) = 12 KB): thirteen read-modify-write chains per SM at F = 50 instead of the two of the single-warp
+// kernel above. Rows of the chunk are staged tile by tile (256 rows, one row per thread: row id -> the row's bin words +
+// one gradient, through registers one tile ahead) into shared memory as word columns, so that a warp reads the bins of
+// its four features for eight rows with conflict-free 32-bit accesses. Lane = (row slot 0..7, feature 0..3): eight rows
+// advance per step. Two lanes of a step can hit the same (feature, bin) counter: every lane reads the eight bins of its
+// feature from the tile (two broadcast 16-byte loads) and counts the EARLIER slots with its bin (= its rank); lanes add
+// in rank order, one round per rank, so the additions on every counter happen in exactly the chunk's row order — the
+// order of the single-warp kernel and of the reference's per-feature pass — without atomics. (A first version found the
+// groups with match.any: parity was identical but MATCH.ANY costs ~750 cycles on sm_100 and the kernel was no faster than
+// the single-warp one: profiles/r01_hist2_matchany.txt.) The conflict search of step s+1 is issued before the
+// read-modify-write of step s, so its shared-memory latency is off the dependent chain.
 constexpr int kHistTile = 256;
-constexpr int kHist2Smem = kHistWarps * 4 * kBins * 12 + 8 * kHistTile * 4 + kHistTile * 8;
-__global__ void __launch_bounds__(kHistWarps * 32, 2) hist2_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
-                                                                   const int32_t* __restrict__ idx, int64_t begin, int64_t count,
-                                                                   int64_t rows_per_chunk, const double* __restrict__ grad,
-                                                                   double* __restrict__ part_g, uint32_t* __restrict__ part_c) {
+constexpr int kHistMaxWarps = 16;
+static inline int hist2_warps(int F) { return std::max(8, std::min(kHistMaxWarps, (std::min(F, 64) + 3) / 4)); }
+static inline size_t hist2_smem(int nw) { return (size_t)nw * 4 * kBins * 12 + 16 * kHistTile * 4 + kHistTile * 8; }
+__global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
+                                                                      const int32_t* __restrict__ idx, int64_t begin, int64_t count,
+                                                                      int64_t rows_per_chunk, const double* __restrict__ grad,
+                                                                      double* __restrict__ part_g, uint32_t* __restrict__ part_c) {
   extern __shared__ __align__(16) unsigned char sm[];
-  double* hg = reinterpret_cast<double*>(sm);                                      // [32 features][256]
-  uint32_t* hc = reinterpret_cast<uint32_t*>(sm + kHistWarps * 4 * kBins * 8);     // [32 features][256]
-  uint32_t* tw = hc + kHistWarps * 4 * kBins;                                      // [8 word columns][256 rows]
-  double* tg = reinterpret_cast<double*>(tw + 8 * kHistTile);                      // [256 rows]
+  const int nw = blockDim.x >> 5;
+  double* hg = reinterpret_cast<double*>(sm);                            // [nw * 4 features][256]
+  uint32_t* hc = reinterpret_cast<uint32_t*>(sm + (size_t)nw * 4 * kBins * 8);  // [nw * 4 features][256]
+  uint32_t* tw = hc + nw * 4 * kBins;                                    // [16 word columns][256 rows]
+  double* tg = reinterpret_cast<double*>(tw + 16 * kHistTile);           // [256 rows]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int chunk = blockIdx.x, fg = blockIdx.y;
-  for (int e = tid; e < 32 * kBins; e += kHistWarps * 32) { hg[e] = 0.; hc[e] = 0u; }
+  const int chunk = blockIdx.x;
+  const int f0 = blockIdx.y * 64;                 // first feature of this CTA's group
+  const int gwords = min(16, (Fpad - f0) >> 2);   // 32-bit bin words per row in the group (Fpad is a multiple of 32)
+  for (int e = tid; e < nw * 4 * kBins; e += blockDim.x) { hg[e] = 0.; hc[e] = 0u; }
   const int64_t r0 = (int64_t)chunk * rows_per_chunk;
   const int64_t r1 = min(r0 + rows_per_chunk, count);
-  const bool warp_active = fg * 32 + w * 4 < F;  // padding features: nothing to accumulate
-  const int slot = lane >> 2, fsub = lane & 3;
+  const bool warp_active = f0 + w * 4 < F;  // padding features: nothing to accumulate
+  const int slot = lane >> 2, fsub = lane & 3, sh = 8 * fsub;
   double* myg = hg + (w * 4 + fsub) * kBins;
   uint32_t* myc = hc + (w * 4 + fsub) * kBins;
-  uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0;
+  const uint32_t* col = tw + w * kHistTile;  // the word column with this warp's four features
+  uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0, s2 = s0, s3 = s0;
   double sg = 0.;
   auto load_row = [&](int64_t j) {
-    if (j < r1) {
+    if (tid < kHistTile && j < r1) {
       const int64_t rid = idx ? (int64_t)idx[begin + j] : (begin + j);
-      const uint4* src = reinterpret_cast<const uint4*>(bins + rid * Fpad + fg * 32);
+      const uint4* src = reinterpret_cast<const uint4*>(bins + rid * Fpad + f0);
       s0 = src[0]; s1 = src[1];
+      if (gwords > 8) { s2 = src[2]; s3 = src[3]; }
       sg = grad[rid];
     }
+  };
+  // conflict search of the step starting at tile row b: this lane's bin and gradient, and its rank = number of earlier
+  // row slots of the step with the same bin in the same feature
+  auto prep = [&](int b, int& bin, double& g, int& rank) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(col + b);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(col + b + 4);
+    bin = (int)((col[b + slot] >> sh) & 0xffu);
+    g = tg[b + slot];
+    const int b0 = (int)((q0.x >> sh) & 0xffu), b1 = (int)((q0.y >> sh) & 0xffu), b2 = (int)((q0.z >> sh) & 0xffu),
+              b3 = (int)((q0.w >> sh) & 0xffu), b4 = (int)((q1.x >> sh) & 0xffu), b5 = (int)((q1.y >> sh) & 0xffu),
+              b6 = (int)((q1.z >> sh) & 0xffu);
+    rank = (int)(slot > 0 && b0 == bin) + (int)(slot > 1 && b1 == bin) + (int)(slot > 2 && b2 == bin) +
+           (int)(slot > 3 && b3 == bin) + (int)(slot > 4 && b4 == bin) + (int)(slot > 5 && b5 == bin) +
+           (int)(slot > 6 && b6 == bin);
   };
   load_row(r0 + tid);
   for (int64_t t0 = r0; t0 < r1; t0 += kHistTile) {
     __syncthreads();  // the previous tile has been consumed (first pass: the zero fill is complete)
-    tw[0 * kHistTile + tid] = s0.x; tw[1 * kHistTile + tid] = s0.y; tw[2 * kHistTile + tid] = s0.z; tw[3 * kHistTile + tid] = s0.w;
-    tw[4 * kHistTile + tid] = s1.x; tw[5 * kHistTile + tid] = s1.y; tw[6 * kHistTile + tid] = s1.z; tw[7 * kHistTile + tid] = s1.w;
-    tg[tid] = sg;
+    if (tid < kHistTile) {
+      tw[0 * kHistTile + tid] = s0.x; tw[1 * kHistTile + tid] = s0.y; tw[2 * kHistTile + tid] = s0.z; tw[3 * kHistTile + tid] = s0.w;
+      tw[4 * kHistTile + tid] = s1.x; tw[5 * kHistTile + tid] = s1.y; tw[6 * kHistTile + tid] = s1.z; tw[7 * kHistTile + tid] = s1.w;
+      if (gwords > 8) {
+        tw[8 * kHistTile + tid] = s2.x; tw[9 * kHistTile + tid] = s2.y; tw[10 * kHistTile + tid] = s2.z; tw[11 * kHistTile + tid] = s2.w;
+        tw[12 * kHistTile + tid] = s3.x; tw[13 * kHistTile + tid] = s3.y; tw[14 * kHistTile + tid] = s3.z; tw[15 * kHistTile + tid] = s3.w;
+      }
+      tg[tid] = sg;
+    }
     __syncthreads();
     load_row(t0 + kHistTile + tid);  // next tile: in flight while this one is accumulated
     if (!warp_active) continue;
     const int rows = (int)min((int64_t)kHistTile, r1 - t0);
+    int bin, rank, bin_n, rank_n;
+    double g, g_n;
+    prep(0, bin, g, rank);
     for (int b = 0; b < rows; b += 8) {
-      const int r = b + slot;
-      const bool valid = r < rows;
-      const uint32_t word = tw[w * kHistTile + r];
-      const int bin = (int)((word >> (8 * fsub)) & 0xffu);
-      const double g = tg[r];
-      // lanes with the same feature and bin form a group; an invalid (tail) lane is alone in its group
-      const unsigned key = valid ? (unsigned)(fsub * kBins + bin) : (unsigned)(4 * kBins + lane);
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const int maxrank = __reduce_max_sync(0xffffffffu, rank);
-      if (maxrank == 0) {
+      const bool valid = b + slot < rows;
+      prep(b + 8 < kHistTile ? b + 8 : b, bin_n, g_n, rank_n);  // next step (rows past the tile's end are masked by `valid`)
+      if (!__any_sync(0xffffffffu, valid && rank > 0)) {
         if (valid) { myg[bin] += g; myc[bin] += 1u; }
       } else {
+        const int maxrank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
         for (int rr = 0; rr <= maxrank; ++rr) {
           if (valid && rank == rr) { myg[bin] += g; myc[bin] += 1u; }
           __syncwarp();
         }
       }
       __syncwarp();  // the next step's lanes may read counters written by other lanes in this one
+      bin = bin_n; g = g_n; rank = rank_n;
     }
   }
   __syncthreads();
   // partial[chunk][feature][bin], coalesced
-  const int64_t base = ((int64_t)chunk * Fpad + fg * 32) * kBins;
-  for (int e = tid; e < 32 * kBins; e += kHistWarps * 32) {
+  const int nfl = min(nw * 4, Fpad - f0);
+  const int64_t base = ((int64_t)chunk * Fpad + f0) * kBins;
+  for (int e = tid; e < nfl * kBins; e += blockDim.x) {
     part_g[base + e] = hg[e];
     part_c[base + e] = hc[e];
   }
 }
 
-// merge chunk partials in chunk order -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226)
-__global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad,
-                                   int F, double hess_const, double* __restrict__ hist, double* __restrict__ parent) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= F * kBins) return;
-  double g = 0.;
-  uint64_t c = 0;
-  const int f = t / kBins, b = t % kBins;
-  // chunk order is the summation order; eight chunks' loads are issued together
+// merge chunk partials -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226).
+// Block = (feature, 32 bins) x 8 warps; warp s sums a contiguous eighth of the chunks in chunk order, then the eight slice
+// sums are added in slice order: a fixed summation tree (deterministic), 8 x 32 threads per 32 counters in flight.
+constexpr int kReduceSlices = 8;
+__global__ void __launch_bounds__(kReduceSlices * 32) hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c,
+                                                                         int nchunks, int Fpad, int F, double hess_const,
+                                                                         double* __restrict__ hist, double* __restrict__ parent) {
+  __shared__ double sg[kReduceSlices][32];
+  __shared__ unsigned long long sc[kReduceSlices][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int f = blockIdx.x / (kBins / 32), b = (blockIdx.x % (kBins / 32)) * 32 + lane;
+  const int per = (nchunks + kReduceSlices - 1) / kReduceSlices;
+  const int c0 = sl * per, c1 = min(c0 + per, nchunks);
   const int64_t cs = (int64_t)Fpad * kBins, o0 = (int64_t)f * kBins + b;
-  int ch = 0;
-  for (; ch + 8 <= nchunks; ch += 8) {
+  double g = 0.;
+  unsigned long long c = 0;
+  int ch = c0;
+  for (; ch + 8 <= c1; ch += 8) {  // eight chunks' loads are issued together
     double gv[8];
     uint32_t cv[8];
 #pragma unroll
@@ -237,11 +271,18 @@ __global__ void hist_reduce_kernel(const double* __restrict__ part_g, const uint
 #pragma unroll
     for (int u = 0; u < 8; ++u) { g += gv[u]; c += cv[u]; }
   }
-  for (; ch < nchunks; ++ch) {
+  for (; ch < c1; ++ch) {
     g += part_g[ch * cs + o0];
     c += part_c[ch * cs + o0];
   }
+  sg[sl][lane] = g;
+  sc[sl][lane] = c;
+  __syncthreads();
+  if (sl != 0) return;
+#pragma unroll
+  for (int k = 1; k < kReduceSlices; ++k) { g += sg[k][lane]; c += sc[k][lane]; }
   const double hs = (double)c * hess_const;
+  const int t = f * kBins + b;
   hist[2 * t] = g;
   hist[2 * t + 1] = hs;
   if (parent) {  // larger = parent - smaller (feature_histogram.hpp:79-83), in place on the parent's slot
@@ -273,7 +314,7 @@ __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict
   const LeafArgs a = blockIdx.y == 0 ? a0 : a1;
   if (a.leaf < 0) return;
   const int f = blockIdx.x;
-  __shared__ double h[kBins * 2];
+  __shared__ __align__(16) double h[kBins * 2];
   unsigned char* flags = splittable + (int64_t)a.leaf * F;
   SplitOut s;
   s.gain = -INFINITY; s.feature = -1; s.threshold = 0; s.left_count = s.right_count = 0;
@@ -305,14 +346,46 @@ __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict
   const double sum_hessian = a.sum_hessians + 2 * kEps;
   const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
   const double cnt_factor = a.num_data / sum_hessian;
+  // per-bin counts RoundInt(hess * cnt_factor) (feature_histogram.hpp:899) are independent of the scan: all lanes compute
+  // them, then an integer suffix sum (exact in any order) gives the running right-hand count of every threshold
+  {
+    int cl[kBins / 32];  // lane owns bins 8*lane .. 8*lane+7
+    int loc = 0;
+#pragma unroll
+    for (int u = kBins / 32 - 1; u >= 0; --u) {
+      const int t = (kBins / 32) * threadIdx.x + u;
+      const int c = (t >= 1 && t < nb) ? (int)(h[2 * t + 1] * cnt_factor + 0.5f) : 0;
+      loc += c;
+      cl[u] = loc;  // suffix sum inside the lane's block
+    }
+    int above = loc;  // inclusive suffix scan over lanes, then make it exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, above, o);
+      if ((int)threadIdx.x + o < 32) above += v;
+    }
+    above -= loc;
+#pragma unroll
+    for (int u = 0; u < kBins / 32; ++u) rcn[(kBins / 32) * threadIdx.x + u] = cl[u] + above;
+  }
+  // the fp64 running sums follow the reference's order (t = nb-1 .. 1, one addition after the other): lane 0, with the
+  // loads of eight bins issued together ahead of their dependent additions
   if (threadIdx.x == 0) {
     double srg = 0., srh = kEps;
-    int rc = 0;
-#pragma unroll 8
-    for (int t = nb - 1; t >= 1; --t) {
-      const double g = h[2 * t], hs = h[2 * t + 1];
-      srg += g; srh += hs; rc += (int)(hs * cnt_factor + 0.5f);
-      rsg[t] = srg; rsh[t] = srh; rcn[t] = rc;
+    int t = nb - 1;
+    while (t >= 1) {
+      double gg[8], hh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t - u >= 1 ? t - u : 1;
+        const double2 v = *reinterpret_cast<const double2*>(&h[2 * tt]);
+        gg[u] = v.x; hh[u] = v.y;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (t - u >= 1) { srg += gg[u]; srh += hh[u]; rsg[t - u] = srg; rsh[t - u] = srh; }
+      }
+      t -= 8;
     }
   }
   __syncwarp();
@@ -392,6 +465,79 @@ __global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, i
     out[dst] = idx[begin + j];
   }
 }
+// ---- stable partition in two kernels (replaces flag + device-wide scan + scatter). Every CTA owns one contiguous segment
+// of the leaf's rows. part_count_kernel: go-left flags (one byte per row) + lefts per segment. part_scatter_kernel: every
+// CTA sums the segment counts in front of it (<= a few hundred values), then walks its segment tile by tile in row order
+// with ballot / popc ranks, so lefts keep their order at the front and rights theirs behind (data_partition.hpp:101-120).
+constexpr int kPartThreads = 256;
+__global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t* __restrict__ bins, int Fpad, int feature, int threshold,
+                                                                  const int32_t* __restrict__ idx, int64_t begin, int64_t count,
+                                                                  int64_t seg, uint8_t* __restrict__ flag, int32_t* __restrict__ seg_left) {
+  __shared__ int wsum[kPartThreads / 32];
+  const int64_t j0 = (int64_t)blockIdx.x * seg, j1 = min(j0 + seg, count);
+  int c = 0;
+  for (int64_t j = j0 + threadIdx.x; j < j1; j += kPartThreads) {
+    const uint8_t f = bins[(int64_t)idx[begin + j] * Fpad + feature] <= threshold ? 1 : 0;
+    flag[j] = f;
+    c += f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < kPartThreads / 32; ++k) t += wsum[k];
+    seg_left[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(kPartThreads) part_scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, int64_t count, int64_t seg,
+                                                                    const uint8_t* __restrict__ flag, const int32_t* __restrict__ seg_left,
+                                                                    int nseg, int32_t* __restrict__ out, int32_t* __restrict__ nleft_out) {
+  __shared__ int red[2][kPartThreads / 32];
+  __shared__ int woff[kPartThreads / 32];
+  __shared__ int base_s[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // lefts in the segments before this one, and in all segments
+  int before = 0, total = 0;
+  for (int k = threadIdx.x; k < nseg; k += kPartThreads) {
+    const int v = seg_left[k];
+    total += v;
+    if (k < (int)blockIdx.x) before += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+  if (lane == 0) { red[0][wid] = before; red[1][wid] = total; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0, t = 0;
+    for (int k = 0; k < kPartThreads / 32; ++k) { b += red[0][k]; t += red[1][k]; }
+    base_s[0] = b; base_s[1] = t;
+    if (blockIdx.x == 0 && nleft_out) *nleft_out = t;
+  }
+  __syncthreads();
+  int lefts_before = base_s[0];  // lefts in front of the current tile
+  const int nleft = base_s[1];
+  const int64_t j0 = (int64_t)blockIdx.x * seg, j1 = min(j0 + seg, count);
+  for (int64_t t0 = j0; t0 < j1; t0 += kPartThreads) {
+    const int64_t j = t0 + threadIdx.x;
+    const bool in = j < j1;
+    const bool left = in && flag[j] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, left);
+    if (lane == 0) woff[wid] = __popc(bal);
+    __syncthreads();
+    int wbefore = 0, tile_left = 0;
+#pragma unroll
+    for (int k = 0; k < kPartThreads / 32; ++k) { const int v = woff[k]; tile_left += v; if (k < wid) wbefore += v; }
+    if (in) {
+      const int lb = lefts_before + wbefore + __popc(bal & ((1u << lane) - 1u));  // lefts in front of row j
+      const int64_t dst = left ? (int64_t)lb : (int64_t)nleft + (j - lb);
+      out[dst] = idx[begin + j];
+    }
+    lefts_before += tile_left;
+    __syncthreads();  // woff is rewritten by the next tile
+  }
+}
 __global__ void iota_kernel(int32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
 }
@@ -455,6 +601,12 @@ struct gpbdev_tree {
   double* part_g = nullptr;
   uint32_t* part_c = nullptr;
   int max_chunks = 0;
+  uint8_t* flag8 = nullptr;        // n go-left flags of the leaf being split
+  int32_t* seg_left = nullptr;     // lefts per partition segment
+  int32_t* nleft_dev = nullptr;
+  int32_t* nleft_host = nullptr;   // pinned
+  int max_seg = 0;
+  int partition_version = 1;       // 1: flag + CUB scan + scatter; 2: part_count_kernel + part_scatter_kernel (GPB200_PARTITION=2)
   int hist_kernel_version = 1;  // 1: single-warp hist_kernel; 2: multi-warp hist2_kernel (GPB200_HIST_KERNEL=2) until its B200 parity run is in profiles/
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
@@ -558,7 +710,13 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->leaf_cnt_dev, sizeof(int32_t) * h->L));
   TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
   TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
-  TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHist2Smem));
+  TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist2_smem(hist2_warps(F))));
+  h->max_seg = h->num_sms * 4;
+  TCUDA(cudaMalloc(&h->flag8, (size_t)n));
+  TCUDA(cudaMalloc(&h->seg_left, sizeof(int32_t) * h->max_seg));
+  TCUDA(cudaMalloc(&h->nleft_dev, sizeof(int32_t)));
+  TCUDA(cudaMallocHost(&h->nleft_host, sizeof(int32_t)));
+  if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 2 ? 2 : 1;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 2 ? 2 : 1;
   *out = h;
   return 0;
@@ -570,6 +728,7 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
   cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  cudaFree(h->flag8); cudaFree(h->seg_left); cudaFree(h->nleft_dev); cudaFreeHost(h->nleft_host);
   cudaFreeHost(h->split_host); cudaFreeHost(h->scalar_host);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -624,17 +783,22 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     double* par = parent_slot_sub >= 0 ? h->hist + (size_t)parent_slot_sub * slot_stride : nullptr;
     if (cnt > 0) {
       int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
-      const int nchunks = (int)((cnt + rpc - 1) / rpc);
+      int nchunks = (int)((cnt + rpc - 1) / rpc);
       dim3 grid(nchunks, Fpad / 32);
-      if (h->hist_kernel_version == 2)
-        hist2_kernel<<<grid, kHistWarps * 32, kHist2Smem, h->stream>>>(h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx,
-                                                                       leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c);
+      if (h->hist_kernel_version == 2) {
+        // one CTA per SM and chunk; grid.y = groups of 64 features
+        rpc = std::max<int64_t>(256, (cnt + h->num_sms - 1) / h->num_sms);
+        nchunks = (int)((cnt + rpc - 1) / rpc);
+        const int nw = hist2_warps(F);
+        hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
+            h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c);
+      }
       else
         hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
                                                            rpc, grad, h->part_g, h->part_c);
       TCUDA(cudaGetLastError());
       // single GPU: larger = parent - smaller is fused into the merge of the chunk partials
-      hist_reduce_kernel<<<(F * kBins + 255) / 256, 256, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,
+      hist_reduce_kernel<<<F * (kBins / 32), kReduceSlices * 32, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,
                                                                         sharded ? nullptr : par);
       TCUDA(cudaGetLastError());
       h->launches += 2;
@@ -716,7 +880,21 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     const int nleft_g = bs.left_count, nright_g = leaf_cnt_g[best_leaf] - nleft_g;
     if (nleft_g <= 0 || nright_g <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
     int nleft = nleft_g;
-    if (c > 0) {
+    if (c > 0 && h->partition_version == 2) {
+      const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
+      const int nseg = (int)((c + seg - 1) / seg);
+      part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left);
+      part_scatter_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->idx, b, c, seg, h->flag8, h->seg_left, nseg, h->idx_tmp,
+                                                                sharded ? h->nleft_dev : nullptr);
+      TCUDA(cudaGetLastError());
+      TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
+      if (sharded) {  // this rank's share of the left child
+        TCUDA(cudaMemcpyAsync(h->nleft_host, h->nleft_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        TCUDA(cudaStreamSynchronize(h->stream));
+        nleft = *h->nleft_host;
+      }
+      h->launches += 2;
+    } else if (c > 0) {
       const int gridp = (int)std::min<int64_t>((c + 255) / 256, (int64_t)h->num_sms * 8);
       mark_kernel<<<gridp, 256, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, h->flag);
       TCUDA(cub::DeviceScan::ExclusiveSum(h->scan_tmp, h->scan_tmp_bytes, h->flag, h->pos, (int)c, h->stream));
