@@ -139,31 +139,37 @@ __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bi
 
 // ---- histogram, multi-warp: one CTA = one row chunk x up to 64 features (all of them at F <= 64), one CTA per SM.
 // Warp w owns the four features 4w..4w+3 of the CTA's feature group and a private histogram for them
-// (4 x 256 x (f64 + u32) = 12 KB): thirteen read-modify-write chains per SM at F = 50 instead of the two of the single-warp
-// kernel above. Rows of the chunk are staged tile by tile (256 rows, one row per thread: row id -> the row's bin words +
-// one gradient, through registers one tile ahead) into shared memory as word columns, so that a warp reads the bins of
-// its four features for eight rows with conflict-free 32-bit accesses. Lane = (row slot 0..7, feature 0..3): eight rows
-// advance per step. Two lanes of a step can hit the same (feature, bin) counter: every lane reads the eight bins of its
-// feature from the tile (two broadcast 16-byte loads) and counts the EARLIER slots with its bin (= its rank); lanes add
-// in rank order, one round per rank, so the additions on every counter happen in exactly the chunk's row order — the
-// order of the single-warp kernel and of the reference's per-feature pass — without atomics. (A first version found the
-// groups with match.any: parity was identical but MATCH.ANY costs ~750 cycles on sm_100 and the kernel was no faster than
-// the single-warp one: profiles/r01_hist2_matchany.txt.) The conflict search of step s+1 is issued before the
-// read-modify-write of step s, so its shared-memory latency is off the dependent chain.
+// (4 x 256 x (f64 + u32) = 12 KB): thirteen accumulation chains per SM at F = 50 instead of the two of the single-warp
+// kernel above. Rows of the chunk are staged tile by tile (256 rows, one row per thread: row id -> the row's bins + one
+// gradient, through registers one tile ahead) into shared memory TRANSPOSED, tb[feature][row], so that the bins of one
+// feature for eight consecutive rows are one aligned 8-byte word. Lane = (row slot 0..7, feature 0..3): eight rows advance
+// per step, branch-free:
+//   * every lane loads the 8-byte word of its feature and finds the slots holding its own bin with byte-parallel
+//     arithmetic (exact zero-byte test of word ^ bin * 0x01010101);
+//   * the FIRST slot of every (feature, bin) group is the group's leader: it alone touches the counter — one shared-memory
+//     load, its own gradient and then the gradients of the later members in slot order (predicated additions from the
+//     step's eight gradients, which every lane holds in registers), one store, one integer RED for the count.
+// No atomics on the fp64 sums, no votes, no divergence: the additions on a counter follow a fixed schedule (row order
+// inside a step, steps in row order), so the result is deterministic, and a low-cardinality feature (all eight rows in one
+// bin) costs the same as a high-cardinality one. (Two earlier versions: groups found with match.any — MATCH.ANY costs
+// ~750 cycles on sm_100; groups resolved by rank rounds — divergent, and a constant padding feature made its warp 8x slower
+// than the others, which then waited at the tile barrier: profiles/r01_hist2_matchany.txt, r01_hist2_rounds.txt.)
 constexpr int kHistTile = 256;
 constexpr int kHistMaxWarps = 16;
 static inline int hist2_warps(int F) { return std::max(8, std::min(kHistMaxWarps, (std::min(F, 64) + 3) / 4)); }
-static inline size_t hist2_smem(int nw) { return (size_t)nw * 4 * kBins * 12 + 16 * kHistTile * 4 + kHistTile * 8; }
+static inline size_t hist2_smem(int nw) { return (size_t)nw * 4 * kBins * 12 + 64 * kHistTile + kHistTile * 8; }
+// bit 7 of every byte of the result is set iff that byte of x is zero (exact: the 7-bit partial sums cannot carry)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
 __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
                                                                       const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                       int64_t rows_per_chunk, const double* __restrict__ grad,
                                                                       double* __restrict__ part_g, uint32_t* __restrict__ part_c) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int nw = blockDim.x >> 5;
-  double* hg = reinterpret_cast<double*>(sm);                            // [nw * 4 features][256]
+  double* hg = reinterpret_cast<double*>(sm);                                   // [nw * 4 features][256]
   uint32_t* hc = reinterpret_cast<uint32_t*>(sm + (size_t)nw * 4 * kBins * 8);  // [nw * 4 features][256]
-  uint32_t* tw = hc + nw * 4 * kBins;                                    // [16 word columns][256 rows]
-  double* tg = reinterpret_cast<double*>(tw + 16 * kHistTile);           // [256 rows]
+  uint8_t* tb = reinterpret_cast<uint8_t*>(hc + nw * 4 * kBins);                // [64 features][256 rows]
+  double* tg = reinterpret_cast<double*>(tb + 64 * kHistTile);                  // [256 rows]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int chunk = blockIdx.x;
   const int f0 = blockIdx.y * 64;                 // first feature of this CTA's group
@@ -171,11 +177,17 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
   for (int e = tid; e < nw * 4 * kBins; e += blockDim.x) { hg[e] = 0.; hc[e] = 0u; }
   const int64_t r0 = (int64_t)chunk * rows_per_chunk;
   const int64_t r1 = min(r0 + rows_per_chunk, count);
-  const bool warp_active = f0 + w * 4 < F;  // padding features: nothing to accumulate
-  const int slot = lane >> 2, fsub = lane & 3, sh = 8 * fsub;
+  const bool warp_active = f0 + w * 4 < F;  // a warp of padding features has nothing to accumulate
+  const int slot = lane >> 2, fsub = lane & 3;
+  const bool feat_ok = f0 + w * 4 + fsub < F;
   double* myg = hg + (w * 4 + fsub) * kBins;
   uint32_t* myc = hc + (w * 4 + fsub) * kBins;
-  const uint32_t* col = tw + w * kHistTile;  // the word column with this warp's four features
+  const uint8_t* mytb = tb + (w * 4 + fsub) * kHistTile;  // this lane's feature: one byte per tile row
+  // byte masks (bit 7 of a byte = a row slot of the step): slots in front of / behind this lane's slot
+  const unsigned long long all80 = 0x8080808080808080ull;
+  const unsigned long long below64 = slot == 0 ? 0ull : (all80 >> (8 * (8 - slot)));
+  const unsigned long long above64 = slot == 7 ? 0ull : (all80 << (8 * (slot + 1)));
+  const uint32_t blo = (uint32_t)below64, bhi = (uint32_t)(below64 >> 32), alo = (uint32_t)above64, ahi = (uint32_t)(above64 >> 32);
   uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0, s2 = s0, s3 = s0;
   double sg = 0.;
   auto load_row = [&](int64_t j) {
@@ -187,29 +199,21 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
       sg = grad[rid];
     }
   };
-  // conflict search of the step starting at tile row b: this lane's bin and gradient, and its rank = number of earlier
-  // row slots of the step with the same bin in the same feature
-  auto prep = [&](int b, int& bin, double& g, int& rank) {
-    const uint4 q0 = *reinterpret_cast<const uint4*>(col + b);
-    const uint4 q1 = *reinterpret_cast<const uint4*>(col + b + 4);
-    bin = (int)((col[b + slot] >> sh) & 0xffu);
-    g = tg[b + slot];
-    const int b0 = (int)((q0.x >> sh) & 0xffu), b1 = (int)((q0.y >> sh) & 0xffu), b2 = (int)((q0.z >> sh) & 0xffu),
-              b3 = (int)((q0.w >> sh) & 0xffu), b4 = (int)((q1.x >> sh) & 0xffu), b5 = (int)((q1.y >> sh) & 0xffu),
-              b6 = (int)((q1.z >> sh) & 0xffu);
-    rank = (int)(slot > 0 && b0 == bin) + (int)(slot > 1 && b1 == bin) + (int)(slot > 2 && b2 == bin) +
-           (int)(slot > 3 && b3 == bin) + (int)(slot > 4 && b4 == bin) + (int)(slot > 5 && b5 == bin) +
-           (int)(slot > 6 && b6 == bin);
+  auto put_word = [&](int c, uint32_t v) {  // bins 4c..4c+3 of row tid -> tb[4c + k][tid]
+    tb[(4 * c + 0) * kHistTile + tid] = (uint8_t)(v & 0xffu);
+    tb[(4 * c + 1) * kHistTile + tid] = (uint8_t)((v >> 8) & 0xffu);
+    tb[(4 * c + 2) * kHistTile + tid] = (uint8_t)((v >> 16) & 0xffu);
+    tb[(4 * c + 3) * kHistTile + tid] = (uint8_t)(v >> 24);
   };
   load_row(r0 + tid);
   for (int64_t t0 = r0; t0 < r1; t0 += kHistTile) {
     __syncthreads();  // the previous tile has been consumed (first pass: the zero fill is complete)
     if (tid < kHistTile) {
-      tw[0 * kHistTile + tid] = s0.x; tw[1 * kHistTile + tid] = s0.y; tw[2 * kHistTile + tid] = s0.z; tw[3 * kHistTile + tid] = s0.w;
-      tw[4 * kHistTile + tid] = s1.x; tw[5 * kHistTile + tid] = s1.y; tw[6 * kHistTile + tid] = s1.z; tw[7 * kHistTile + tid] = s1.w;
+      put_word(0, s0.x); put_word(1, s0.y); put_word(2, s0.z); put_word(3, s0.w);
+      put_word(4, s1.x); put_word(5, s1.y); put_word(6, s1.z); put_word(7, s1.w);
       if (gwords > 8) {
-        tw[8 * kHistTile + tid] = s2.x; tw[9 * kHistTile + tid] = s2.y; tw[10 * kHistTile + tid] = s2.z; tw[11 * kHistTile + tid] = s2.w;
-        tw[12 * kHistTile + tid] = s3.x; tw[13 * kHistTile + tid] = s3.y; tw[14 * kHistTile + tid] = s3.z; tw[15 * kHistTile + tid] = s3.w;
+        put_word(8, s2.x); put_word(9, s2.y); put_word(10, s2.z); put_word(11, s2.w);
+        put_word(12, s3.x); put_word(13, s3.y); put_word(14, s3.z); put_word(15, s3.w);
       }
       tg[tid] = sg;
     }
@@ -217,23 +221,33 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
     load_row(t0 + kHistTile + tid);  // next tile: in flight while this one is accumulated
     if (!warp_active) continue;
     const int rows = (int)min((int64_t)kHistTile, r1 - t0);
-    int bin, rank, bin_n, rank_n;
-    double g, g_n;
-    prep(0, bin, g, rank);
+#pragma unroll 2
     for (int b = 0; b < rows; b += 8) {
-      const bool valid = b + slot < rows;
-      prep(b + 8 < kHistTile ? b + 8 : b, bin_n, g_n, rank_n);  // next step (rows past the tile's end are masked by `valid`)
-      if (!__any_sync(0xffffffffu, valid && rank > 0)) {
-        if (valid) { myg[bin] += g; myc[bin] += 1u; }
-      } else {
-        const int maxrank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
-        for (int rr = 0; rr <= maxrank; ++rr) {
-          if (valid && rank == rr) { myg[bin] += g; myc[bin] += 1u; }
-          __syncwarp();
-        }
+      // rows b .. b+7 of the tile; nv of them exist
+      const int nv = rows - b;
+      const unsigned long long vm64 = nv >= 8 ? all80 : (all80 >> (8 * (8 - nv)));
+      const uint2 bw = *reinterpret_cast<const uint2*>(mytb + b);  // the 8 bins of my feature
+      const double2 ga = *reinterpret_cast<const double2*>(tg + b), gb = *reinterpret_cast<const double2*>(tg + b + 2),
+                    gc = *reinterpret_cast<const double2*>(tg + b + 4), gd = *reinterpret_cast<const double2*>(tg + b + 6);
+      const double gown = tg[b + slot];
+      const uint32_t mybin = (uint32_t)(((((unsigned long long)bw.y << 32) | bw.x) >> (8 * slot)) & 0xffull);
+      const uint32_t rep = mybin * 0x01010101u;
+      const uint32_t eq_lo = zero_bytes(bw.x ^ rep) & (uint32_t)vm64, eq_hi = zero_bytes(bw.y ^ rep) & (uint32_t)(vm64 >> 32);
+      const bool leader = feat_ok && slot < nv && ((eq_lo & blo) | (eq_hi & bhi)) == 0u;
+      const uint32_t pa_lo = eq_lo & alo, pa_hi = eq_hi & ahi;  // later members of my group
+      if (leader) {
+        double v = myg[mybin] + gown;
+        if (pa_lo & 0x00008000u) v += ga.y;
+        if (pa_lo & 0x00800000u) v += gb.x;
+        if (pa_lo & 0x80000000u) v += gb.y;
+        if (pa_hi & 0x00000080u) v += gc.x;
+        if (pa_hi & 0x00008000u) v += gc.y;
+        if (pa_hi & 0x00800000u) v += gd.x;
+        if (pa_hi & 0x80000000u) v += gd.y;
+        myg[mybin] = v;
+        atomicAdd(&myc[mybin], 1u + (uint32_t)__popc(pa_lo) + (uint32_t)__popc(pa_hi));
       }
-      __syncwarp();  // the next step's lanes may read counters written by other lanes in this one
-      bin = bin_n; g = g_n; rank = rank_n;
+      __syncwarp();  // the next step's leaders may read counters written by other lanes in this one
     }
   }
   __syncthreads();

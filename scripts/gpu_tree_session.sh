@@ -2,7 +2,7 @@
 # GPU session for the tree learner: parity (default + multi-warp histogram kernel + two-kernel partition), timings, ncu of hist2_kernel, launch list.
 cd "$(dirname "$0")/.." && mkdir -p gpurun_out
 timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu_default.log
-GPB200_HIST_KERNEL=2 GPB200_PARTITION=2 timeout 300 python -m pytest tests/test_tree_gpu.py tests/test_grouped.py -x -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu_hist2.log
+GPB200_HIST_KERNEL=2 GPB200_PARTITION=2 timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu_hist2.log
 timeout 300 python scripts/bench_tree.py 1000000 hist1:GPB200_HIST_KERNEL=1 hist2:GPB200_HIST_KERNEL=2 hist2_part2:GPB200_HIST_KERNEL=2,GPB200_PARTITION=2 > gpurun_out/bench_tree.log 2>&1
 GPB200_HIST_KERNEL=2 timeout 240 ncu --set full --clock-control none --import-source on -k regex:hist2_kernel -c 2 -o gpurun_out/hist2 -f \
   python scripts/bench_tree.py 1000000 hist2:GPB200_HIST_KERNEL=2 > gpurun_out/ncu_hist2.log 2>&1
