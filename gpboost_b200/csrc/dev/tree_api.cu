@@ -801,7 +801,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       dim3 grid(nchunks, Fpad / 32);
       if (h->hist_kernel_version == 2) {
         // one CTA per SM and chunk; grid.y = groups of 64 features
-        rpc = std::max<int64_t>(256, (cnt + h->num_sms - 1) / h->num_sms);
+        rpc = std::max<int64_t>(128, ((cnt + h->num_sms - 1) / h->num_sms + 7) / 8 * 8);  // whole 8-row steps per chunk
         nchunks = (int)((cnt + rpc - 1) / rpc);
         const int nw = hist2_warps(F);
         hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
