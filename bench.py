@@ -130,6 +130,34 @@ def time_gpboost(n, iters, lib, threads, F=50):
     return {"sec_per_iter": dt, "first_iter_s": first, "cov_pars": gp.get_cov_pars().tolist()}
 
 
+def time_gpboost_grouped(n, iters, lib, threads, F=50, groups=10000):
+    """BASELINE configs[2]: GPBoost with a single-level grouped random effect (1e4 groups), n x 50 features, 31-leaf trees;
+    one iteration = LGBM_BoosterUpdateOneIter (variance re-fit + Psi^-1(F - y) + one tree). Also times the same data without
+    a random-effects model (tree side alone)."""
+    from gpboost_b200 import GPModel
+    from gpboost_b200.booster import Booster, Dataset
+    rng = np.random.default_rng(1)
+    X = rng.random((n, F))
+    group = rng.integers(0, groups, size=n)
+    y = 2 * np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + rng.standard_normal(groups)[group] + 0.5 * rng.standard_normal(n)
+    params = dict(objective="regression", num_leaves=31, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
+    if lib is not None:
+        params["num_threads"] = threads
+    ds = Dataset(X, y, params=params, _lib=lib)
+    out = {}
+    for key, gp in (("grouped", GPModel(group_data=group, num_parallel_threads=threads, _lib=lib)), ("trees_only", None)):
+        b = Booster(params, ds, gp_model=gp, _lib=lib)
+        t0 = time.perf_counter(); b.update(); first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            b.update()
+        out[key] = {"sec_per_iter": (time.perf_counter() - t0) / iters, "first_iter_s": first}
+        if gp is not None:
+            out[key]["cov_pars"] = gp.get_cov_pars().tolist()
+        del b
+    return out
+
+
 def time_laplace(n, lib, threads, reps=1, barrier=None):
     """BASELINE configs[4]: bernoulli_logit likelihood + latent Vecchia GP (m=30), one Laplace-approximated likelihood
     evaluation = Newton mode finding (VADU-PCG) + log-determinant by stochastic Lanczos quadrature (50 probes), through
@@ -217,6 +245,10 @@ def main():
             "negll": res["negll"]})
         if args.boost_ref_n > 0:
             from gpboost_b200.libpath import load_lib
+            from oracle import ref_lib_path
+            ggr = time_gpboost_grouped(args.boost_ref_n, 3, load_lib(ref_lib_path()), ncores)
+            line["gpboost_grouped"] = {"iters_per_sec": 1.0 / ggr["grouped"]["sec_per_iter"], "ms_per_iter": ggr["grouped"]["sec_per_iter"] * 1e3,
+                                       "trees_only_ms_per_iter": ggr["trees_only"]["sec_per_iter"] * 1e3, "n": args.boost_ref_n}
             from oracle import ref_lib_path
             gb = time_gpboost(args.boost_ref_n, 1, load_lib(ref_lib_path()), ncores)
             line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "n": args.boost_ref_n, "first_iter_s": gb["first_iter_s"],
@@ -318,6 +350,10 @@ def main():
     if args.boost_n > 0:
         gb = time_gpboost(args.boost_n, 5, None, ncores)
 
+    gg = None
+    if args.boost_n > 0 and world == 1:
+        gg = time_gpboost_grouped(args.boost_n, 10, None, ncores)
+
     if rank == 0:
         peaks = {}
         try:
@@ -357,6 +393,12 @@ def main():
                                "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
                                "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "
                                        "parameters re-fitted every iteration (BASELINE metric (i)); host buffers, end to end"}
+        if gg is not None:
+            line["gpboost_grouped"] = {"iters_per_sec": 1.0 / gg["grouped"]["sec_per_iter"], "ms_per_iter": gg["grouped"]["sec_per_iter"] * 1e3,
+                                       "trees_only_ms_per_iter": gg["trees_only"]["sec_per_iter"] * 1e3, "n": args.boost_n,
+                                       "first_iter_s": gg["grouped"]["first_iter_s"], "cov_pars": gg["grouped"]["cov_pars"],
+                                       "note": "LGBM_BoosterUpdateOneIter, single-level grouped random effect (1e4 groups) + 31-leaf trees on "
+                                               "n x 50 features (BASELINE configs[2]); trees_only = the same data without a random-effects model"}
         if laplace_res is not None:
             line["laplace"] = {"evals_per_sec": 1.0 / laplace_res["sec_per_eval"], **laplace_res,
                                "note": "GPB_EvalNegLogLikelihood, bernoulli_logit + latent Vecchia GP m=30 (BASELINE configs[4]); with N GPUs "

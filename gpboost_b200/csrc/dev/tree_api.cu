@@ -62,6 +62,18 @@ struct LeafArgs {
   double sum_gradients, sum_hessians;
 };
 
+// Work description for the device-resident leaf loop (tree_*_kernel below): written by one thread between the data-parallel
+// kernels of a split, read by every CTA of the next kernel in the stream. Kernels that take a `const DevJob*` use their
+// by-value launch parameters when it is null (host-driven loop) and these fields otherwise.
+struct DevJob {
+  int done, error;
+  int do_find;
+  int hist_begin, hist_cnt, hist_use_idx, hist_rpc, hist_nchunks;
+  LeafArgs a0, a1;
+  int parent_row;
+  int part_on, part_begin, part_cnt, part_feature, part_threshold, part_seg, part_nseg;
+};
+
 // ---- histogram: lane = feature, private shared histograms, rows of the chunk in order
 __global__ void __launch_bounds__(32) hist_kernel(const uint8_t* __restrict__ bins, int Fpad, const int32_t* __restrict__ idx,
                                                    int64_t begin, int64_t count, int64_t rows_per_chunk,
@@ -163,7 +175,13 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7f
 __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
                                                                       const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                       int64_t rows_per_chunk, const double* __restrict__ grad,
-                                                                      double* __restrict__ part_g, uint32_t* __restrict__ part_c) {
+                                                                      double* __restrict__ part_g, uint32_t* __restrict__ part_c,
+                                                                      const DevJob* __restrict__ job) {
+  if (job) {  // device-resident leaf loop: the leaf's row range comes from the planner kernel
+    if (job->done || !job->do_find || (int)blockIdx.x >= job->hist_nchunks) return;
+    begin = job->hist_begin; count = job->hist_cnt; rows_per_chunk = job->hist_rpc;
+    if (!job->hist_use_idx) idx = nullptr;
+  }
   extern __shared__ __align__(16) unsigned char sm[];
   const int nw = blockDim.x >> 5;
   double* hg = reinterpret_cast<double*>(sm);                                   // [nw * 4 features][256]
@@ -318,6 +336,113 @@ __device__ __forceinline__ bool split_better(double ga, int fa, double gb, int f
   return fa < fb;
 }
 
+struct ScanScratch {  // per scanning warp
+  double rsg[kBins], rsh[kBins];
+  int rcn[kBins];
+};
+// One warp examines one feature of one leaf: h = the feature's histogram in shared memory (16-byte aligned, 2 * nb doubles).
+// Replays the reference's right-to-left scan (feature_histogram.hpp:858-960, result :1057-1083); writes the feature's
+// candidate to *out and the leaf's "splittable" flag of the feature.
+__device__ __forceinline__ void scan_feature(const double* h, int nb, const LeafArgs& a, int f, int lane, int min_data_in_leaf,
+                                             double min_sum_hessian, double lambda_l2, double min_gain_to_split,
+                                             unsigned char* flags, ScanScratch* scr, SplitOut* out) {
+  double* rsg = scr->rsg;
+  double* rsh = scr->rsh;
+  int* rcn = scr->rcn;
+  SplitOut s;
+  s.gain = -INFINITY; s.feature = -1; s.threshold = 0; s.left_count = s.right_count = 0;
+  s.left_output = s.right_output = 0.;
+  s.left_sum_gradient = s.left_sum_hessian = s.right_sum_gradient = s.right_sum_hessian = 0.;
+  // The reference walks t = nb-1 .. 1 accumulating the right-hand sums in that order and keeps the FIRST strictly larger
+  // gain. Its `continue` / `break` tests are monotone in t (counts and hessian sums only grow), so a threshold is admissible
+  // iff it passes all tests itself: lane 0 reproduces the running sums sequentially (fp64 order matters), then all lanes
+  // evaluate the gains of their thresholds and the warp picks the maximum, ties to the larger t (= the first one met).
+  const double sum_gradient = a.sum_gradients;
+  const double sum_hessian = a.sum_hessians + 2 * kEps;
+  const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
+  const double cnt_factor = a.num_data / sum_hessian;
+  // per-bin counts RoundInt(hess * cnt_factor) (feature_histogram.hpp:899) are independent of the scan: all lanes compute
+  // them, then an integer suffix sum (exact in any order) gives the running right-hand count of every threshold
+  {
+    int cl[kBins / 32];  // lane owns bins 8*lane .. 8*lane+7
+    int loc = 0;
+#pragma unroll
+    for (int u = kBins / 32 - 1; u >= 0; --u) {
+      const int t = (kBins / 32) * lane + u;
+      const int c = (t >= 1 && t < nb) ? (int)(h[2 * t + 1] * cnt_factor + 0.5f) : 0;
+      loc += c;
+      cl[u] = loc;  // suffix sum inside the lane's block
+    }
+    int above = loc;  // inclusive suffix scan over lanes, then make it exclusive
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, above, o);
+      if ((int)lane + o < 32) above += v;
+    }
+    above -= loc;
+#pragma unroll
+    for (int u = 0; u < kBins / 32; ++u) rcn[(kBins / 32) * lane + u] = cl[u] + above;
+  }
+  // the fp64 running sums follow the reference's order (t = nb-1 .. 1, one addition after the other): lane 0, with the
+  // loads of eight bins issued together ahead of their dependent additions
+  if (lane == 0) {
+    double srg = 0., srh = kEps;
+    int t = nb - 1;
+    while (t >= 1) {
+      double gg[8], hh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t - u >= 1 ? t - u : 1;
+        const double2 v = *reinterpret_cast<const double2*>(&h[2 * tt]);
+        gg[u] = v.x; hh[u] = v.y;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (t - u >= 1) { srg += gg[u]; srh += hh[u]; rsg[t - u] = srg; rsh[t - u] = srh; }
+      }
+      t -= 8;
+    }
+  }
+  __syncwarp();
+  double best_gain = -INFINITY;
+  int best_t = -1;
+  for (int t = nb - 1 - (int)lane; t >= 1; t -= 32) {
+    const double srg = rsg[t], srh = rsh[t];
+    const int rc = rcn[t];
+    if (rc < min_data_in_leaf || srh < min_sum_hessian) continue;
+    const int lc = a.num_data - rc;
+    if (lc < min_data_in_leaf) continue;
+    const double slh = sum_hessian - srh;
+    if (slh < min_sum_hessian) continue;
+    const double slg = sum_gradient - srg;
+    const double gain = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
+    if (gain <= min_gain_shift) continue;
+    if (gain > best_gain) { best_gain = gain; best_t = t; }  // this lane visits its t in descending order
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+    const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+    if (og > best_gain || (og == best_gain && ot > best_t)) { best_gain = og; best_t = ot; }
+  }
+  if (lane != 0) return;
+  const bool spl = best_t >= 1;
+  flags[f] = spl ? 1 : 0;
+  if (spl) {
+    const double srg = rsg[best_t], srh = rsh[best_t];
+    const double best_lg = sum_gradient - srg, best_lh = sum_hessian - srh;
+    const int best_lc = a.num_data - rcn[best_t];
+    s.feature = f; s.threshold = best_t - 1;
+    s.left_output = -best_lg / (best_lh + lambda_l2);
+    s.left_count = best_lc;
+    s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
+    s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
+    s.right_count = a.num_data - best_lc;
+    s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
+    s.gain = best_gain - min_gain_shift;
+  }
+  *out = s;
+}
+
 // block (feature f, leaf slot s): the warp stages the 4 KB histogram row in shared memory, lane 0 replays the reference's
 // right-to-left scan (feature_histogram.hpp:858-960, result :1057-1083); per-feature candidates go to cand[s][f]
 __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict__ hist_base, int64_t slot_stride,
@@ -350,96 +475,93 @@ __global__ void __launch_bounds__(32) split_scan_kernel(const double* __restrict
     if (threadIdx.x == 0) { flags[f] = 0; cand[blockIdx.y * F + f] = s; }
     return;
   }
-  // The reference walks t = nb-1 .. 1 accumulating the right-hand sums in that order and keeps the FIRST strictly larger
-  // gain. Its `continue` / `break` tests are monotone in t (counts and hessian sums only grow), so a threshold is admissible
-  // iff it passes all tests itself: lane 0 reproduces the running sums sequentially (fp64 order matters), then all lanes
-  // evaluate the gains of their thresholds and the warp picks the maximum, ties to the larger t (= the first one met).
-  __shared__ double rsg[kBins], rsh[kBins];
-  __shared__ int rcn[kBins];
-  const double sum_gradient = a.sum_gradients;
-  const double sum_hessian = a.sum_hessians + 2 * kEps;
-  const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
-  const double cnt_factor = a.num_data / sum_hessian;
-  // per-bin counts RoundInt(hess * cnt_factor) (feature_histogram.hpp:899) are independent of the scan: all lanes compute
-  // them, then an integer suffix sum (exact in any order) gives the running right-hand count of every threshold
+  __shared__ ScanScratch scr;
+  scan_feature(h, nb, a, f, (int)threadIdx.x, min_data_in_leaf, min_sum_hessian, lambda_l2, min_gain_to_split, flags, &scr,
+               cand + blockIdx.y * F + f);
+}
+
+// ---- merge + subtraction + split scan in one launch (single GPU): block = one feature. 32 warps merge the feature's chunk
+// partials (warp = (slice of the chunks, 32 bins), slices added in slice order), 256 threads write the smaller child's
+// histogram, take larger = parent - smaller in place (feature_histogram.hpp:79-83) and keep both in shared memory, then
+// warp 0 scans the smaller child and warp 1 the larger one straight from there. Replaces hist_reduce_kernel, the snapshot
+// of the parent's flags and split_scan_kernel (two launches, one copy and one histogram round trip through L2 per split).
+constexpr int kFusedSlices = 4;
+__global__ void __launch_bounds__(kFusedSlices * kBins) reduce_scan_kernel(
+    const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad, int F, double hess_const,
+    double* __restrict__ hist_base, int64_t slot_stride, const int32_t* __restrict__ num_bin, LeafArgs a0, LeafArgs a1, int parent_row,
+    int min_data_in_leaf, double min_sum_hessian, double lambda_l2, double min_gain_to_split, unsigned char* __restrict__ splittable,
+    SplitOut* __restrict__ cand, const DevJob* __restrict__ job) {
+  if (job) {
+    if (job->done || !job->do_find) return;
+    nchunks = job->hist_nchunks; a0 = job->a0; a1 = job->a1; parent_row = job->parent_row;
+  }
+  __shared__ __align__(16) double hs[2][kBins * 2];
+  __shared__ double sg[kFusedSlices][kBins];
+  __shared__ unsigned long long sc[kFusedSlices][kBins];
+  __shared__ ScanScratch scr[2];
+  __shared__ int pflag;
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bin = tid & (kBins - 1), sl = tid / kBins;
+  // both children inherit the parent's flag of this feature; the left child overwrites it below (same row)
+  if (tid == 0) pflag = a0.inherit ? (int)splittable[(int64_t)parent_row * F + f] : 1;
   {
-    int cl[kBins / 32];  // lane owns bins 8*lane .. 8*lane+7
-    int loc = 0;
+    const int per = (nchunks + kFusedSlices - 1) / kFusedSlices;
+    const int c0 = sl * per, c1 = min(c0 + per, nchunks);
+    const int64_t cs = (int64_t)Fpad * kBins, o0 = (int64_t)f * kBins + bin;
+    double g = 0.;
+    unsigned long long c = 0;
+    int ch = c0;
+    for (; ch + 8 <= c1; ch += 8) {
+      double gv[8];
+      uint32_t cv[8];
 #pragma unroll
-    for (int u = kBins / 32 - 1; u >= 0; --u) {
-      const int t = (kBins / 32) * threadIdx.x + u;
-      const int c = (t >= 1 && t < nb) ? (int)(h[2 * t + 1] * cnt_factor + 0.5f) : 0;
-      loc += c;
-      cl[u] = loc;  // suffix sum inside the lane's block
+      for (int u = 0; u < 8; ++u) { gv[u] = part_g[(ch + u) * cs + o0]; cv[u] = part_c[(ch + u) * cs + o0]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { g += gv[u]; c += cv[u]; }
     }
-    int above = loc;  // inclusive suffix scan over lanes, then make it exclusive
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_down_sync(0xffffffffu, above, o);
-      if ((int)threadIdx.x + o < 32) above += v;
+    for (; ch < c1; ++ch) {
+      g += part_g[ch * cs + o0];
+      c += part_c[ch * cs + o0];
     }
-    above -= loc;
-#pragma unroll
-    for (int u = 0; u < kBins / 32; ++u) rcn[(kBins / 32) * threadIdx.x + u] = cl[u] + above;
+    sg[sl][bin] = g;
+    sc[sl][bin] = c;
   }
-  // the fp64 running sums follow the reference's order (t = nb-1 .. 1, one addition after the other): lane 0, with the
-  // loads of eight bins issued together ahead of their dependent additions
-  if (threadIdx.x == 0) {
-    double srg = 0., srh = kEps;
-    int t = nb - 1;
-    while (t >= 1) {
-      double gg[8], hh[8];
+  __syncthreads();
+  if (tid < kBins) {
+    double g = sg[0][bin];
+    unsigned long long c = sc[0][bin];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int tt = t - u >= 1 ? t - u : 1;
-        const double2 v = *reinterpret_cast<const double2*>(&h[2 * tt]);
-        gg[u] = v.x; hh[u] = v.y;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (t - u >= 1) { srg += gg[u]; srh += hh[u]; rsg[t - u] = srg; rsh[t - u] = srh; }
-      }
-      t -= 8;
+    for (int k = 1; k < kFusedSlices; ++k) { g += sg[k][bin]; c += sc[k][bin]; }
+    const double hsv = (double)c * hess_const;  // dataset.cpp:1223-1226
+    double* dst = hist_base + (int64_t)a0.hist_slot * slot_stride + ((int64_t)f * kBins + bin) * 2;
+    dst[0] = g; dst[1] = hsv;
+    hs[0][2 * bin] = g; hs[0][2 * bin + 1] = hsv;
+    if (a1.leaf >= 0) {
+      double* par = hist_base + (int64_t)a1.hist_slot * slot_stride + ((int64_t)f * kBins + bin) * 2;
+      const double pg = par[0] - g, ph = par[1] - hsv;
+      par[0] = pg; par[1] = ph;
+      hs[1][2 * bin] = pg; hs[1][2 * bin + 1] = ph;
     }
   }
-  __syncwarp();
-  double best_gain = -INFINITY;
-  int best_t = -1;
-  for (int t = nb - 1 - (int)threadIdx.x; t >= 1; t -= 32) {
-    const double srg = rsg[t], srh = rsh[t];
-    const int rc = rcn[t];
-    if (rc < min_data_in_leaf || srh < min_sum_hessian) continue;
-    const int lc = a.num_data - rc;
-    if (lc < min_data_in_leaf) continue;
-    const double slh = sum_hessian - srh;
-    if (slh < min_sum_hessian) continue;
-    const double slg = sum_gradient - srg;
-    const double gain = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
-    if (gain <= min_gain_shift) continue;
-    if (gain > best_gain) { best_gain = gain; best_t = t; }  // this lane visits its t in descending order
+  __syncthreads();
+  if (warp >= 2) return;
+  const LeafArgs a = warp == 0 ? a0 : a1;
+  if (a.leaf < 0) return;
+  unsigned char* flags = splittable + (int64_t)a.leaf * F;
+  SplitOut* out = cand + warp * F + f;
+  if (a.inherit && !pflag) {  // no admissible threshold in the parent: not examined (serial_tree_learner.cpp:329-336)
+    if (lane == 0) {
+      SplitOut s;
+      s.gain = -INFINITY; s.feature = -1; s.threshold = 0; s.left_count = s.right_count = 0;
+      s.left_output = s.right_output = 0.;
+      s.left_sum_gradient = s.left_sum_hessian = s.right_sum_gradient = s.right_sum_hessian = 0.;
+      flags[f] = 0;
+      *out = s;
+    }
+    return;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
-    const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
-    if (og > best_gain || (og == best_gain && ot > best_t)) { best_gain = og; best_t = ot; }
-  }
-  if (threadIdx.x != 0) return;
-  const bool spl = best_t >= 1;
-  flags[f] = spl ? 1 : 0;
-  if (spl) {
-    const double srg = rsg[best_t], srh = rsh[best_t];
-    const double best_lg = sum_gradient - srg, best_lh = sum_hessian - srh;
-    const int best_lc = a.num_data - rcn[best_t];
-    s.feature = f; s.threshold = best_t - 1;
-    s.left_output = -best_lg / (best_lh + lambda_l2);
-    s.left_count = best_lc;
-    s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
-    s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
-    s.right_count = a.num_data - best_lc;
-    s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
-    s.gain = best_gain - min_gain_shift;
-  }
-  cand[blockIdx.y * F + f] = s;
+  scan_feature(hs[warp], num_bin[f], a, f, lane, min_data_in_leaf, min_sum_hessian, lambda_l2, min_gain_to_split, flags, &scr[warp], out);
 }
 
 // best candidate per leaf with SplitInfo::operator> (gain, then the smaller feature index)
@@ -486,7 +608,12 @@ __global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, i
 constexpr int kPartThreads = 256;
 __global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t* __restrict__ bins, int Fpad, int feature, int threshold,
                                                                   const int32_t* __restrict__ idx, int64_t begin, int64_t count,
-                                                                  int64_t seg, uint8_t* __restrict__ flag, int32_t* __restrict__ seg_left) {
+                                                                  int64_t seg, uint8_t* __restrict__ flag, int32_t* __restrict__ seg_left,
+                                                                  const DevJob* __restrict__ job) {
+  if (job) {
+    if (job->done || !job->part_on || (int)blockIdx.x >= job->part_nseg) return;
+    feature = job->part_feature; threshold = job->part_threshold; begin = job->part_begin; count = job->part_cnt; seg = job->part_seg;
+  }
   __shared__ int wsum[kPartThreads / 32];
   const int64_t j0 = (int64_t)blockIdx.x * seg, j1 = min(j0 + seg, count);
   int c = 0;
@@ -507,7 +634,12 @@ __global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t*
 }
 __global__ void __launch_bounds__(kPartThreads) part_scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, int64_t count, int64_t seg,
                                                                     const uint8_t* __restrict__ flag, const int32_t* __restrict__ seg_left,
-                                                                    int nseg, int32_t* __restrict__ out, int32_t* __restrict__ nleft_out) {
+                                                                    int nseg, int32_t* __restrict__ out, int32_t* __restrict__ nleft_out,
+                                                                    const DevJob* __restrict__ job) {
+  if (job) {
+    if (job->done || !job->part_on || (int)blockIdx.x >= job->part_nseg) return;
+    begin = job->part_begin; count = job->part_cnt; seg = job->part_seg; nseg = job->part_nseg;
+  }
   __shared__ int red[2][kPartThreads / 32];
   __shared__ int woff[kPartThreads / 32];
   __shared__ int base_s[2];
@@ -597,6 +729,133 @@ __global__ void add_const_kernel(double* __restrict__ a, double c, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] += c;
 }
 
+
+// ---- device-resident leaf loop (single GPU): the state SerialTreeLearner::Train keeps on the host (leaf ranges and sums,
+// best split per leaf, the growing tree; serial_tree_learner.cpp:159-209, tree.h:533-575) lives in HBM, one thread advances
+// it between the data-parallel kernels, and the host enqueues the kernels of all num_leaves - 1 splits without reading
+// anything back: one device-to-host copy per TREE instead of one per split.
+constexpr int kMaxLeavesDev = 256;
+struct TreeDevState {
+  DevJob job;
+  int num_leaves, left_leaf, right_leaf, next_slot;
+  int leaf_begin[kMaxLeavesDev], leaf_cnt[kMaxLeavesDev], leaf_depth[kMaxLeavesDev], leaf_parent[kMaxLeavesDev], slot_of[kMaxLeavesDev];
+  double leaf_sg[kMaxLeavesDev], leaf_sh[kMaxLeavesDev];
+  SplitOut best[kMaxLeavesDev];
+  int split_feature[kMaxLeavesDev], threshold_bin[kMaxLeavesDev], left_child[kMaxLeavesDev], right_child[kMaxLeavesDev];
+  float split_gain[kMaxLeavesDev];
+  double leaf_value[kMaxLeavesDev];
+  int leaf_count[kMaxLeavesDev];
+};
+
+// BeforeTrain (leaf_splits.hpp:70-83): all rows in leaf 0
+__global__ void tree_init_kernel(TreeDevState* __restrict__ st, const double* __restrict__ root_sum_gradient, int n, double hess_const, int L) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->job.done = 0; st->job.error = 0; st->job.do_find = 0; st->job.part_on = 0;
+  st->num_leaves = 1; st->left_leaf = 0; st->right_leaf = -1; st->next_slot = 0;
+  for (int l = 0; l < L; ++l) {
+    st->leaf_begin[l] = 0; st->leaf_cnt[l] = 0; st->leaf_depth[l] = 0; st->leaf_parent[l] = -1; st->slot_of[l] = -1;
+    st->leaf_sg[l] = 0.; st->leaf_sh[l] = 0.;
+    st->best[l].gain = -INFINITY; st->best[l].feature = -1;
+    st->split_feature[l] = 0; st->threshold_bin[l] = 0; st->left_child[l] = 0; st->right_child[l] = 0; st->split_gain[l] = 0.f;
+    st->leaf_value[l] = 0.; st->leaf_count[l] = 0;
+  }
+  st->leaf_cnt[0] = n;
+  st->leaf_sg[0] = root_sum_gradient[0];
+  st->leaf_sh[0] = hess_const * (double)n;
+  st->leaf_count[0] = n;
+}
+
+// BeforeFindBestSplit (serial_tree_learner.cpp:283-322): may the two newest leaves be examined, which one gets a histogram pass
+__global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, int min_data_in_leaf, int num_chunk_ctas) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  DevJob& job = st->job;
+  job.do_find = 0;
+  job.part_on = 0;
+  if (job.done) return;
+  const int left_leaf = st->left_leaf, right_leaf = st->right_leaf;
+  bool do_find = true;
+  if (max_depth > 0 && st->leaf_depth[left_leaf] >= max_depth) do_find = false;
+  if (do_find) {
+    const int nl = st->leaf_cnt[left_leaf], nr = right_leaf >= 0 ? st->leaf_cnt[right_leaf] : 0;
+    if (nr < min_data_in_leaf * 2 && nl < min_data_in_leaf * 2) do_find = false;
+  }
+  if (!do_find) {
+    st->best[left_leaf].gain = -INFINITY;
+    if (right_leaf >= 0) st->best[right_leaf].gain = -INFINITY;
+    return;
+  }
+  int smaller, larger = -1, parent_slot = -1;
+  if (right_leaf < 0) smaller = left_leaf;
+  else if (st->leaf_cnt[left_leaf] < st->leaf_cnt[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
+  else { smaller = right_leaf; larger = left_leaf; }
+  if (right_leaf >= 0) parent_slot = st->slot_of[left_leaf];  // the parent's histograms sit under the left (= parent) id
+  const int new_slot = st->next_slot++;
+  if (larger >= 0) st->slot_of[larger] = parent_slot;  // larger = parent - smaller, in place
+  st->slot_of[smaller] = new_slot;
+  LeafArgs a0, a1;
+  a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = st->leaf_cnt[smaller];
+  a0.sum_gradients = st->leaf_sg[smaller]; a0.sum_hessians = st->leaf_sh[smaller];
+  a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? st->leaf_cnt[larger] : 0;
+  a1.sum_gradients = larger >= 0 ? st->leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? st->leaf_sh[larger] : 0.;
+  job.a0 = a0; job.a1 = a1;
+  job.parent_row = left_leaf;
+  const int cnt = st->leaf_cnt[smaller];
+  job.hist_begin = st->leaf_begin[smaller]; job.hist_cnt = cnt; job.hist_use_idx = st->num_leaves > 1 ? 1 : 0;
+  int rpc = ((cnt + num_chunk_ctas - 1) / num_chunk_ctas + 7) / 8 * 8;  // same chunking as the host-driven loop
+  if (rpc < 128) rpc = 128;
+  job.hist_rpc = rpc; job.hist_nchunks = (cnt + rpc - 1) / rpc;
+  job.do_find = 1;
+}
+
+// best leaf (ArrayArgs::ArgMax with SplitInfo::operator>), Tree::Split (tree.h:533-575), the partition job
+__global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ split_dev, double min_gain_to_split, int max_seg) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  DevJob& job = st->job;
+  job.part_on = 0;
+  if (job.done) return;
+  if (job.do_find) {
+    st->best[job.a0.leaf] = split_dev[0];
+    if (job.a1.leaf >= 0) st->best[job.a1.leaf] = split_dev[1];
+  }
+  const int num_leaves = st->num_leaves;
+  int best_leaf = 0;
+  for (int l = 1; l < num_leaves; ++l)
+    if (split_better(st->best[l].gain, st->best[l].feature, st->best[best_leaf].gain, st->best[best_leaf].feature)) best_leaf = l;
+  const SplitOut bs = st->best[best_leaf];
+  if (!(bs.gain > 0.0)) { job.done = 1; return; }
+  const int b = st->leaf_begin[best_leaf], c = st->leaf_cnt[best_leaf];
+  // constant hessian: the scan's RoundInt counts are the partition's counts (see the host-driven loop)
+  const int nleft = bs.left_count, nright = c - nleft;
+  if (nleft <= 0 || nright <= 0) { job.error = 1; job.done = 1; return; }
+  job.part_on = 1; job.part_begin = b; job.part_cnt = c; job.part_feature = bs.feature; job.part_threshold = bs.threshold;
+  int seg = ((c + max_seg - 1) / max_seg + kPartThreads - 1) / kPartThreads * kPartThreads;
+  if (seg < 4 * kPartThreads) seg = 4 * kPartThreads;
+  job.part_seg = seg; job.part_nseg = (c + seg - 1) / seg;
+  const int new_leaf = num_leaves;
+  st->leaf_cnt[best_leaf] = nleft; st->leaf_begin[new_leaf] = b + nleft; st->leaf_cnt[new_leaf] = nright;
+  const int node = num_leaves - 1;
+  const int parent = st->leaf_parent[best_leaf];
+  if (parent >= 0) { if (st->left_child[parent] == ~best_leaf) st->left_child[parent] = node; else st->right_child[parent] = node; }
+  st->split_feature[node] = bs.feature; st->threshold_bin[node] = bs.threshold;
+  st->split_gain[node] = (float)(bs.gain + min_gain_to_split);
+  st->left_child[node] = ~best_leaf; st->right_child[node] = ~new_leaf;
+  st->leaf_parent[best_leaf] = node; st->leaf_parent[new_leaf] = node;
+  st->leaf_value[best_leaf] = isnan(bs.left_output) ? 0. : bs.left_output; st->leaf_count[best_leaf] = nleft;
+  st->leaf_value[new_leaf] = isnan(bs.right_output) ? 0. : bs.right_output; st->leaf_count[new_leaf] = nright;
+  st->leaf_depth[new_leaf] = st->leaf_depth[best_leaf] + 1; st->leaf_depth[best_leaf]++;
+  st->leaf_sg[best_leaf] = bs.left_sum_gradient; st->leaf_sh[best_leaf] = bs.left_sum_hessian;
+  st->leaf_sg[new_leaf] = bs.right_sum_gradient; st->leaf_sh[new_leaf] = bs.right_sum_hessian;
+  st->best[best_leaf].gain = -INFINITY; st->best[best_leaf].feature = -1;
+  st->best[new_leaf].gain = -INFINITY; st->best[new_leaf].feature = -1;
+  st->num_leaves = num_leaves + 1;
+  st->left_leaf = best_leaf; st->right_leaf = new_leaf;
+}
+
+__global__ void part_copyback_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ tmp, const DevJob* __restrict__ job) {
+  if (job->done || !job->part_on) return;
+  const int64_t b = job->part_begin, c = job->part_cnt;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < c; j += (int64_t)gridDim.x * blockDim.x) idx[b + j] = tmp[j];
+}
 }  // namespace
 
 struct gpbdev_tree {
@@ -620,6 +879,10 @@ struct gpbdev_tree {
   int32_t* nleft_dev = nullptr;
   int32_t* nleft_host = nullptr;   // pinned
   int max_seg = 0;
+  int device_loop = 0;             // 1: device-resident leaf loop on one GPU (GPB200_TREE_LOOP=device); needs hist2 + fused scan + partition 2
+  TreeDevState* state_dev = nullptr;
+  TreeDevState* state_host = nullptr;  // pinned
+  int fused_scan = 0;              // 1: reduce_scan_kernel instead of hist_reduce_kernel + split_scan_kernel on one GPU (GPB200_FUSED_SCAN=1)
   int partition_version = 1;       // 1: flag + CUB scan + scatter; 2: part_count_kernel + part_scatter_kernel (GPB200_PARTITION=2)
   int hist_kernel_version = 1;  // 1: single-warp hist_kernel; 2: multi-warp hist2_kernel (GPB200_HIST_KERNEL=2) until its B200 parity run is in profiles/
   double* sum_part = nullptr;
@@ -730,6 +993,10 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->seg_left, sizeof(int32_t) * h->max_seg));
   TCUDA(cudaMalloc(&h->nleft_dev, sizeof(int32_t)));
   TCUDA(cudaMallocHost(&h->nleft_host, sizeof(int32_t)));
+  TCUDA(cudaMalloc(&h->state_dev, sizeof(TreeDevState)));
+  TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
+  if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : 0;
+  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 2 ? 2 : 1;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 2 ? 2 : 1;
   *out = h;
@@ -742,6 +1009,7 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
   cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  cudaFree(h->state_dev); cudaFreeHost(h->state_host);
   cudaFree(h->flag8); cudaFree(h->seg_left); cudaFree(h->nleft_dev); cudaFreeHost(h->nleft_host);
   cudaFreeHost(h->split_host); cudaFreeHost(h->scalar_host);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -751,6 +1019,55 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
 
 int64_t gpbdev_tree_launch_count(gpbdev_tree_t h) { return h ? h->launches : 0; }
 void* gpbdev_tree_stream(gpbdev_tree_t h) { return h ? (void*)h->stream : nullptr; }
+
+// device-resident leaf loop: every kernel of every split is enqueued up front; the planner / selector kernels steer them
+static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double hess_const, int* num_leaves_out, int* split_feature,
+                                  int* threshold_bin, int* left_child, int* right_child, float* split_gain, double* leaf_value,
+                                  int* leaf_count) {
+  const int64_t n = h->n;
+  const int F = h->F, Fpad = h->Fpad, L = h->L;
+  const gpbdev_tree_config& cfg = h->cfg;
+  const size_t slot_stride = (size_t)F * kBins * 2;
+  TreeDevState* st = h->state_dev;
+  const DevJob* job = &st->job;
+  tree_init_kernel<<<1, 32, 0, h->stream>>>(st, h->sum_part + 1023, (int)n, hess_const, L);
+  TCUDA(cudaGetLastError());
+  const int nw = hist2_warps(F);
+  const dim3 hgrid(h->num_sms, (Fpad + 63) / 64);
+  const int cgrid = h->num_sms * 4;
+  for (int split = 0; split < L - 1; ++split) {
+    tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
+    hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+    LeafArgs dummy;
+    dummy.leaf = -1; dummy.hist_slot = 0; dummy.inherit = 0; dummy.num_data = 0; dummy.sum_gradients = 0.; dummy.sum_hessians = 0.;
+    reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
+                                                                 h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
+                                                                 cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                                 h->splittable, h->cand_dev, job);
+    split_argmax_kernel<<<2, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
+    tree_select_kernel<<<1, 32, 0, h->stream>>>(st, h->split_dev, cfg.min_gain_to_split, h->max_seg);
+    part_count_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, 0, 0, h->idx, 0, 0, 0, h->flag8, h->seg_left, job);
+    part_scatter_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->idx, 0, 0, 0, h->flag8, h->seg_left, 0, h->idx_tmp, nullptr, job);
+    part_copyback_kernel<<<cgrid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, job);
+    TCUDA(cudaGetLastError());
+    h->launches += 8;
+  }
+  TCUDA(cudaMemcpyAsync(h->state_host, st, sizeof(TreeDevState), cudaMemcpyDeviceToHost, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  const TreeDevState& r = *h->state_host;
+  if (r.job.error) return tfail("gpbdev_tree_train: inconsistent split counts");
+  const int num_leaves = r.num_leaves;
+  for (int i = 0; i < num_leaves - 1; ++i) {
+    split_feature[i] = r.split_feature[i]; threshold_bin[i] = r.threshold_bin[i]; left_child[i] = r.left_child[i];
+    right_child[i] = r.right_child[i]; split_gain[i] = r.split_gain[i];
+  }
+  for (int i = 0; i < num_leaves; ++i) { leaf_value[i] = r.leaf_value[i]; leaf_count[i] = r.leaf_count[i]; }
+  h->leaf_begin.assign(r.leaf_begin, r.leaf_begin + L);
+  h->leaf_cnt.assign(r.leaf_cnt, r.leaf_cnt + L);
+  h->last_num_leaves = num_leaves;
+  *num_leaves_out = num_leaves;
+  return 0;
+}
 
 int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device, double hess_const, int* num_leaves_out,
                       int* split_feature, int* threshold_bin, int* left_child, int* right_child, float* split_gain,
@@ -773,6 +1090,11 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
   const bool sharded = h->allreduce != nullptr;
   const int64_t n_glob = sharded ? h->n_global : n;
+  if (h->device_loop && !sharded && L <= kMaxLeavesDev) {
+    h->launches += 3;
+    return tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
+                                  leaf_value, leaf_count);
+  }
   if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
   TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TCUDA(cudaStreamSynchronize(h->stream));
@@ -791,7 +1113,8 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   leaf_value[0] = 0.; leaf_count[0] = (int)n_glob;
   int num_leaves = 1, left_leaf = 0, right_leaf = -1;
 
-  auto build_hist = [&](int leaf, int slot, int parent_slot_sub) -> int {
+  // nchunks_out != nullptr: only the chunk partials are produced (the merge is fused into the split scan, reduce_scan_kernel)
+  auto build_hist = [&](int leaf, int slot, int parent_slot_sub, int* nchunks_out) -> int {
     const int64_t cnt = leaf_cnt[leaf];
     double* dst = h->hist + (size_t)slot * slot_stride;
     double* par = parent_slot_sub >= 0 ? h->hist + (size_t)parent_slot_sub * slot_stride : nullptr;
@@ -805,12 +1128,13 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
         nchunks = (int)((cnt + rpc - 1) / rpc);
         const int nw = hist2_warps(F);
         hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
-            h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c);
+            h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
       }
       else
         hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
                                                            rpc, grad, h->part_g, h->part_c);
       TCUDA(cudaGetLastError());
+      if (nchunks_out) { *nchunks_out = nchunks; h->launches += 1; return 0; }
       // single GPU: larger = parent - smaller is fused into the merge of the chunk partials
       hist_reduce_kernel<<<F * (kBins / 32), kReduceSlices * 32, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,
                                                                         sharded ? nullptr : par);
@@ -852,20 +1176,28 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       const int new_slot = free_slots.back();
       free_slots.pop_back();
       // larger = parent - smaller, in place (fused into the merge of the chunk partials): the parent's slot becomes the larger leaf's
-      if (build_hist(smaller, new_slot, larger >= 0 ? parent_slot : -1)) return -1;
+      const bool fused = h->fused_scan && !sharded && leaf_cnt[smaller] > 0;
+      int nchunks_f = 0;
+      if (build_hist(smaller, new_slot, larger >= 0 ? parent_slot : -1, fused ? &nchunks_f : nullptr)) return -1;
       if (larger >= 0) slot_of[larger] = parent_slot;
       slot_of[smaller] = new_slot;
       // both children inherit the parent's flags (the parent's id is the left child's id): snapshot them first
-      if (right_leaf >= 0)
+      if (right_leaf >= 0 && !fused)
         TCUDA(cudaMemcpyAsync(h->parent_flags, h->splittable + (size_t)left_leaf * F, F, cudaMemcpyDeviceToDevice, h->stream));
       LeafArgs a0, a1;
       a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = leaf_cnt_g[smaller];
       a0.sum_gradients = leaf_sg[smaller]; a0.sum_hessians = leaf_sh[smaller];
       a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt_g[larger] : 0;
       a1.sum_gradients = larger >= 0 ? leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? leaf_sh[larger] : 0.;
-      split_scan_kernel<<<dim3(F, 2), 32, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
-                                                          cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
-                                                          h->splittable, h->parent_flags, h->cand_dev);
+      if (fused)
+        reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, nchunks_f, Fpad, F, hess_const, h->hist,
+                                                                     (int64_t)slot_stride, h->num_bin, a0, a1, left_leaf, cfg.min_data_in_leaf,
+                                                                     cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                                     h->splittable, h->cand_dev, nullptr);
+      else
+        split_scan_kernel<<<dim3(F, 2), 32, 0, h->stream>>>(h->hist, (int64_t)slot_stride, h->num_bin, F, a0, a1, cfg.min_data_in_leaf,
+                                                            cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                            h->splittable, h->parent_flags, h->cand_dev);
       TCUDA(cudaGetLastError());
       if (larger < 0) TCUDA(cudaMemsetAsync(h->split_dev + 1, 0, sizeof(SplitOut), h->stream));
       split_argmax_kernel<<<larger >= 0 ? 2 : 1, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
@@ -897,9 +1229,9 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     if (c > 0 && h->partition_version == 2) {
       const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
       const int nseg = (int)((c + seg - 1) / seg);
-      part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left);
+      part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr);
       part_scatter_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->idx, b, c, seg, h->flag8, h->seg_left, nseg, h->idx_tmp,
-                                                                sharded ? h->nleft_dev : nullptr);
+                                                                sharded ? h->nleft_dev : nullptr, nullptr);
       TCUDA(cudaGetLastError());
       TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
       if (sharded) {  // this rank's share of the left child
