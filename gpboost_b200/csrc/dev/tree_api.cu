@@ -879,6 +879,9 @@ struct gpbdev_tree {
   int32_t* nleft_dev = nullptr;
   int32_t* nleft_host = nullptr;   // pinned
   int max_seg = 0;
+  cudaGraphExec_t graph_exec = nullptr;  // GPB200_TREE_LOOP=graph
+  const double* graph_grad = nullptr;
+  double graph_hess = 0.;
   int device_loop = 0;             // 1: device-resident leaf loop on one GPU (GPB200_TREE_LOOP=device); needs hist2 + fused scan + partition 2
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
@@ -995,7 +998,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMallocHost(&h->nleft_host, sizeof(int32_t)));
   TCUDA(cudaMalloc(&h->state_dev, sizeof(TreeDevState)));
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
-  if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : 0;
+  if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "graph" ? 2 : 0);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 2 ? 2 : 1;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 2 ? 2 : 1;
@@ -1009,6 +1012,7 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
   cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   cudaFree(h->state_dev); cudaFreeHost(h->state_host);
   cudaFree(h->flag8); cudaFree(h->seg_left); cudaFree(h->nleft_dev); cudaFreeHost(h->nleft_host);
   cudaFreeHost(h->split_host); cudaFreeHost(h->scalar_host);
@@ -1030,6 +1034,22 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   const size_t slot_stride = (size_t)F * kBins * 2;
   TreeDevState* st = h->state_dev;
   const DevJob* job = &st->job;
+  // GPB200_TREE_LOOP=graph: the whole tree (root sums included) is one CUDA graph, captured once per (gradient buffer,
+  // hessian) and replayed every boosting iteration — one graph launch instead of ~8 launches per split
+  const bool use_graph = h->device_loop == 2;
+  if (use_graph && h->graph_exec && (h->graph_grad != grad || h->graph_hess != hess_const)) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  const bool replay = use_graph && h->graph_exec != nullptr;
+  if (use_graph && !replay) TCUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  if (!replay) {
+  if (use_graph) {  // the eager path ran these before the call
+    iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
+    const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
+    sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
+    sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
+  }
   tree_init_kernel<<<1, 32, 0, h->stream>>>(st, h->sum_part + 1023, (int)n, hess_const, L);
   TCUDA(cudaGetLastError());
   const int nw = hist2_warps(F);
@@ -1050,9 +1070,19 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
     part_scatter_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->idx, 0, 0, 0, h->flag8, h->seg_left, 0, h->idx_tmp, nullptr, job);
     part_copyback_kernel<<<cgrid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, job);
     TCUDA(cudaGetLastError());
-    h->launches += 8;
   }
   TCUDA(cudaMemcpyAsync(h->state_host, st, sizeof(TreeDevState), cudaMemcpyDeviceToHost, h->stream));
+  }  // !replay
+  if (use_graph && !replay) {
+    cudaGraph_t g = nullptr;
+    TCUDA(cudaStreamEndCapture(h->stream, &g));
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { h->graph_exec = nullptr; return tfail(std::string("gpbdev_tree_train: cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+    h->graph_grad = grad; h->graph_hess = hess_const;
+  }
+  if (use_graph) TCUDA(cudaGraphLaunch(h->graph_exec, h->stream));
+  h->launches += 8 * (L - 1) + (use_graph ? 3 : 0);
   TCUDA(cudaStreamSynchronize(h->stream));
   const TreeDevState& r = *h->state_host;
   if (r.job.error) return tfail("gpbdev_tree_train: inconsistent split counts");
@@ -1084,16 +1114,23 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   }
   const size_t slot_stride = (size_t)F * kBins * 2;
   // ---- BeforeTrain: partition = all rows in leaf 0, root sums (leaf_splits.hpp:70-83)
+  const bool sharded = h->allreduce != nullptr;
+  const int64_t n_glob = sharded ? h->n_global : n;
+  if (h->device_loop == 2 && !sharded && L <= kMaxLeavesDev && grad_on_device)  // everything, root sums included, is in the graph
+    return tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
+                                  leaf_value, leaf_count);
   iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
   const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
   sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
   sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
-  const bool sharded = h->allreduce != nullptr;
-  const int64_t n_glob = sharded ? h->n_global : n;
   if (h->device_loop && !sharded && L <= kMaxLeavesDev) {
     h->launches += 3;
-    return tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
-                                  leaf_value, leaf_count);
+    const int keep = h->device_loop;
+    h->device_loop = 1;  // eager enqueue (host gradients are staged per call: no graph)
+    const int rc = tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
+                                          leaf_value, leaf_count);
+    h->device_loop = keep;
+    return rc;
   }
   if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
   TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
