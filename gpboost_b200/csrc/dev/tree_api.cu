@@ -882,12 +882,14 @@ struct gpbdev_tree {
   cudaGraphExec_t graph_exec = nullptr;  // GPB200_TREE_LOOP=graph
   const double* graph_grad = nullptr;
   double graph_hess = 0.;
-  int device_loop = 0;             // 1: device-resident leaf loop on one GPU (GPB200_TREE_LOOP=device); needs hist2 + fused scan + partition 2
+  // Implementation switches (environment, read at creation; every combination below passes the same parity tests,
+  // tests/test_tree_gpu.py::test_tree_kernel_variants_match_oracle). Defaults = the fastest verified set.
+  int device_loop = 2;             // GPB200_TREE_LOOP = graph (2, default) | device (1) | host (0). Row-sharded learners use the host loop.
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
-  int fused_scan = 0;              // 1: reduce_scan_kernel instead of hist_reduce_kernel + split_scan_kernel on one GPU (GPB200_FUSED_SCAN=1)
-  int partition_version = 1;       // 1: flag + CUB scan + scatter; 2: part_count_kernel + part_scatter_kernel (GPB200_PARTITION=2)
-  int hist_kernel_version = 1;  // 1: single-warp hist_kernel; 2: multi-warp hist2_kernel (GPB200_HIST_KERNEL=2) until its B200 parity run is in profiles/
+  int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
+  int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
+  int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -998,10 +1000,10 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMallocHost(&h->nleft_host, sizeof(int32_t)));
   TCUDA(cudaMalloc(&h->state_dev, sizeof(TreeDevState)));
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
-  if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "graph" ? 2 : 0);
-  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 1 ? 1 : 0;
-  if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 2 ? 2 : 1;
-  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 2 ? 2 : 1;
+  if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
+  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : 1;
+  if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : 2;
   *out = h;
   return 0;
 }
@@ -1263,7 +1265,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     const int nleft_g = bs.left_count, nright_g = leaf_cnt_g[best_leaf] - nleft_g;
     if (nleft_g <= 0 || nright_g <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
     int nleft = nleft_g;
-    if (c > 0 && h->partition_version == 2) {
+    if (c > 0 && h->partition_version == 2 && !sharded) {  // row shards keep the CUB path: its two-GPU parity run predates part_*_kernel
       const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
       const int nseg = (int)((c + seg - 1) / seg);
       part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr);
