@@ -278,6 +278,120 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
   }
 }
 
+// hist3_kernel = hist2_kernel with the two shared-memory savings its ncu capture asks for (profiles/r01_ncu_hist2_summary.txt):
+// tile rows padded by 8 bytes (the four 8-byte bin words of a warp fall into different banks: 2 wavefronts instead of 8) and the
+// step's gradients loaded only by leaders whose group has later members. NOT YET RUN ON A B200 (written after the round's
+// GPU budget was spent): opt-in with GPB200_HIST_KERNEL=3, not part of the parity tests until it has passed them once.
+constexpr int kHist3Stride = kHistTile + 8;
+static inline size_t hist3_smem(int nw) { return (size_t)nw * 4 * kBins * 12 + 64 * kHist3Stride + kHistTile * 8; }
+__global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist3_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
+                                                                      const int32_t* __restrict__ idx, int64_t begin, int64_t count,
+                                                                      int64_t rows_per_chunk, const double* __restrict__ grad,
+                                                                      double* __restrict__ part_g, uint32_t* __restrict__ part_c,
+                                                                      const DevJob* __restrict__ job) {
+  if (job) {  // device-resident leaf loop: the leaf's row range comes from the planner kernel
+    if (job->done || !job->do_find || (int)blockIdx.x >= job->hist_nchunks) return;
+    begin = job->hist_begin; count = job->hist_cnt; rows_per_chunk = job->hist_rpc;
+    if (!job->hist_use_idx) idx = nullptr;
+  }
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int nw = blockDim.x >> 5;
+  double* hg = reinterpret_cast<double*>(sm);                                   // [nw * 4 features][256]
+  uint32_t* hc = reinterpret_cast<uint32_t*>(sm + (size_t)nw * 4 * kBins * 8);  // [nw * 4 features][256]
+  uint8_t* tb = reinterpret_cast<uint8_t*>(hc + nw * 4 * kBins);                // [64 features][kHist3Stride]: rows of the four features of a warp in different banks
+  double* tg = reinterpret_cast<double*>(tb + 64 * kHist3Stride);                  // [256 rows]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int chunk = blockIdx.x;
+  const int f0 = blockIdx.y * 64;                 // first feature of this CTA's group
+  const int gwords = min(16, (Fpad - f0) >> 2);   // 32-bit bin words per row in the group (Fpad is a multiple of 32)
+  for (int e = tid; e < nw * 4 * kBins; e += blockDim.x) { hg[e] = 0.; hc[e] = 0u; }
+  const int64_t r0 = (int64_t)chunk * rows_per_chunk;
+  const int64_t r1 = min(r0 + rows_per_chunk, count);
+  const bool warp_active = f0 + w * 4 < F;  // a warp of padding features has nothing to accumulate
+  const int slot = lane >> 2, fsub = lane & 3;
+  const bool feat_ok = f0 + w * 4 + fsub < F;
+  double* myg = hg + (w * 4 + fsub) * kBins;
+  uint32_t* myc = hc + (w * 4 + fsub) * kBins;
+  const uint8_t* mytb = tb + (w * 4 + fsub) * kHist3Stride;  // this lane's feature: one byte per tile row
+  // byte masks (bit 7 of a byte = a row slot of the step): slots in front of / behind this lane's slot
+  const unsigned long long all80 = 0x8080808080808080ull;
+  const unsigned long long below64 = slot == 0 ? 0ull : (all80 >> (8 * (8 - slot)));
+  const unsigned long long above64 = slot == 7 ? 0ull : (all80 << (8 * (slot + 1)));
+  const uint32_t blo = (uint32_t)below64, bhi = (uint32_t)(below64 >> 32), alo = (uint32_t)above64, ahi = (uint32_t)(above64 >> 32);
+  uint4 s0 = make_uint4(0u, 0u, 0u, 0u), s1 = s0, s2 = s0, s3 = s0;
+  double sg = 0.;
+  auto load_row = [&](int64_t j) {
+    if (tid < kHistTile && j < r1) {
+      const int64_t rid = idx ? (int64_t)idx[begin + j] : (begin + j);
+      const uint4* src = reinterpret_cast<const uint4*>(bins + rid * Fpad + f0);
+      s0 = src[0]; s1 = src[1];
+      if (gwords > 8) { s2 = src[2]; s3 = src[3]; }
+      sg = grad[rid];
+    }
+  };
+  auto put_word = [&](int c, uint32_t v) {  // bins 4c..4c+3 of row tid -> tb[4c + k][tid]
+    tb[(4 * c + 0) * kHist3Stride + tid] = (uint8_t)(v & 0xffu);
+    tb[(4 * c + 1) * kHist3Stride + tid] = (uint8_t)((v >> 8) & 0xffu);
+    tb[(4 * c + 2) * kHist3Stride + tid] = (uint8_t)((v >> 16) & 0xffu);
+    tb[(4 * c + 3) * kHist3Stride + tid] = (uint8_t)(v >> 24);
+  };
+  load_row(r0 + tid);
+  for (int64_t t0 = r0; t0 < r1; t0 += kHistTile) {
+    __syncthreads();  // the previous tile has been consumed (first pass: the zero fill is complete)
+    if (tid < kHistTile) {
+      put_word(0, s0.x); put_word(1, s0.y); put_word(2, s0.z); put_word(3, s0.w);
+      put_word(4, s1.x); put_word(5, s1.y); put_word(6, s1.z); put_word(7, s1.w);
+      if (gwords > 8) {
+        put_word(8, s2.x); put_word(9, s2.y); put_word(10, s2.z); put_word(11, s2.w);
+        put_word(12, s3.x); put_word(13, s3.y); put_word(14, s3.z); put_word(15, s3.w);
+      }
+      tg[tid] = sg;
+    }
+    __syncthreads();
+    load_row(t0 + kHistTile + tid);  // next tile: in flight while this one is accumulated
+    if (!warp_active) continue;
+    const int rows = (int)min((int64_t)kHistTile, r1 - t0);
+#pragma unroll 2
+    for (int b = 0; b < rows; b += 8) {
+      // rows b .. b+7 of the tile; nv of them exist
+      const int nv = rows - b;
+      const unsigned long long vm64 = nv >= 8 ? all80 : (all80 >> (8 * (8 - nv)));
+      const uint2 bw = *reinterpret_cast<const uint2*>(mytb + b);  // the 8 bins of my feature
+      const double gown = tg[b + slot];
+      const uint32_t mybin = (uint32_t)(((((unsigned long long)bw.y << 32) | bw.x) >> (8 * slot)) & 0xffull);
+      const uint32_t rep = mybin * 0x01010101u;
+      const uint32_t eq_lo = zero_bytes(bw.x ^ rep) & (uint32_t)vm64, eq_hi = zero_bytes(bw.y ^ rep) & (uint32_t)(vm64 >> 32);
+      const bool leader = feat_ok && slot < nv && ((eq_lo & blo) | (eq_hi & bhi)) == 0u;
+      const uint32_t pa_lo = eq_lo & alo, pa_hi = eq_hi & ahi;  // later members of my group
+      if (leader) {
+        double v = myg[mybin] + gown;
+        if (pa_lo | pa_hi) {  // the group has later members (a minority of the leaders): only they load the step's gradients
+          const double2 ga = *reinterpret_cast<const double2*>(tg + b), gb = *reinterpret_cast<const double2*>(tg + b + 2),
+                        gc = *reinterpret_cast<const double2*>(tg + b + 4), gd = *reinterpret_cast<const double2*>(tg + b + 6);
+          if (pa_lo & 0x00008000u) v += ga.y;
+          if (pa_lo & 0x00800000u) v += gb.x;
+          if (pa_lo & 0x80000000u) v += gb.y;
+          if (pa_hi & 0x00000080u) v += gc.x;
+          if (pa_hi & 0x00008000u) v += gc.y;
+          if (pa_hi & 0x00800000u) v += gd.x;
+          if (pa_hi & 0x80000000u) v += gd.y;
+        }
+        myg[mybin] = v;
+        atomicAdd(&myc[mybin], 1u + (uint32_t)__popc(pa_lo) + (uint32_t)__popc(pa_hi));
+      }
+      __syncwarp();  // the next step's leaders may read counters written by other lanes in this one
+    }
+  }
+  __syncthreads();
+  // partial[chunk][feature][bin], coalesced
+  const int nfl = min(nw * 4, Fpad - f0);
+  const int64_t base = ((int64_t)chunk * Fpad + f0) * kBins;
+  for (int e = tid; e < nfl * kBins; e += blockDim.x) {
+    part_g[base + e] = hg[e];
+    part_c[base + e] = hc[e];
+  }
+}
+
 // merge chunk partials -> hist[slot][f][bin] = (sum grad, count * hess_const)   (dataset.cpp:1223-1226).
 // Block = (feature, 32 bins) x 8 warps; warp s sums a contiguous eighth of the chunks in chunk order, then the eight slice
 // sums are added in slice order: a fixed summation tree (deterministic), 8 x 32 threads per 32 counters in flight.
@@ -889,7 +1003,7 @@ struct gpbdev_tree {
   TreeDevState* state_host = nullptr;  // pinned
   int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
-  int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel
+  int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel | 3: hist3_kernel (unverified)
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -993,6 +1107,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
   TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
   TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist2_smem(hist2_warps(F))));
+  TCUDA(cudaFuncSetAttribute(hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist3_smem(hist2_warps(F))));
   h->max_seg = h->num_sms * 4;
   TCUDA(cudaMalloc(&h->flag8, (size_t)n));
   TCUDA(cudaMalloc(&h->seg_left, sizeof(int32_t) * h->max_seg));
@@ -1003,7 +1118,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : 1;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
-  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : 2;
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 3 ? 3 : 2);
   *out = h;
   return 0;
 }
@@ -1059,7 +1174,10 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   const int cgrid = h->num_sms * 4;
   for (int split = 0; split < L - 1; ++split) {
     tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
-    hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+    if (h->hist_kernel_version == 3)
+      hist3_kernel<<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+    else
+      hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
     LeafArgs dummy;
     dummy.leaf = -1; dummy.hist_slot = 0; dummy.inherit = 0; dummy.num_data = 0; dummy.sum_gradients = 0.; dummy.sum_hessians = 0.;
     reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
@@ -1161,11 +1279,15 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       int64_t rpc = std::max<int64_t>(256, (cnt + h->max_chunks - 1) / h->max_chunks);
       int nchunks = (int)((cnt + rpc - 1) / rpc);
       dim3 grid(nchunks, Fpad / 32);
-      if (h->hist_kernel_version == 2) {
+      if (h->hist_kernel_version >= 2) {
         // one CTA per SM and chunk; grid.y = groups of 64 features
         rpc = std::max<int64_t>(128, ((cnt + h->num_sms - 1) / h->num_sms + 7) / 8 * 8);  // whole 8-row steps per chunk
         nchunks = (int)((cnt + rpc - 1) / rpc);
         const int nw = hist2_warps(F);
+        if (h->hist_kernel_version == 3)
+          hist3_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
+              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
+        else
         hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
             h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
       }
