@@ -299,6 +299,74 @@ int orc_vecchia_factor_latent(const double* coords, int n, int d, int m, const i
 }
 
 /* u = B y  (B = I - A): (B y)_i = y_i - sum_k A[i,k] y[nn[i,k]] */
+/* Latent factor with the derivative w.r.t. the log of the (transformed) range parameter: what CalcCovFactorGradientVecchia
+ * (src/GPBoost/Vecchia_utils.cpp:1620-1652) leaves in B_grad[1] = -Agrad and D_grad[1] for a non-Gaussian likelihood with one GP.
+ * (The marginal-variance derivative is not formed there — exclude_marg_var_grad — because dSigma^-1/dlog(var) = -Sigma^-1.)
+ * The gradient block of the neighbours has a zero diagonal (cov_fcts.h:1179), so the jitter does not enter it. */
+int orc_vecchia_factor_latent_grad(const double* coords, int n, int d, int m, const int32_t* nn, int cov_type,
+                                   const double* pars, double* A, double* Dinv, double* Agrad, double* Dgrad) {
+  const double var = pars[0], range = pars[1];
+  int bad = 0;
+#pragma omp parallel
+  {
+    double* S = (double*)malloc(sizeof(double) * m * m);
+    double* G = (double*)malloc(sizeof(double) * m * m);
+    double* s1 = (double*)malloc(sizeof(double) * m);
+    double* g1 = (double*)malloc(sizeof(double) * m);
+    double* a = (double*)malloc(sizeof(double) * m);
+    double* t1 = (double*)malloc(sizeof(double) * m);
+    double* t2 = (double*)malloc(sizeof(double) * m);
+#pragma omp for schedule(static) reduction(+ : bad)
+    for (int i = 0; i < n; ++i) {
+      const int32_t* nb = nn + (size_t)i * m;
+      int q = 0;
+      while (q < m && nb[q] >= 0) ++q;
+      double Di = var;
+      for (int k = 0; k < m; ++k) { A[(size_t)i * m + k] = 0.; Agrad[(size_t)i * m + k] = 0.; }
+      Dgrad[i] = 0.;
+      if (q > 0) {
+        for (int j = 0; j < q; ++j) {
+          double dist = sqrt(orc_sqdist(coords, n, d, nb[j], i));
+          s1[j] = orc_cov(cov_type, dist, var, range);
+          g1[j] = orc_cov_grad_range(cov_type, dist, var, range, s1[j]);
+          S[j * q + j] = var * (1. + 1e-10);
+          G[j * q + j] = 0.;
+          for (int k = j + 1; k < q; ++k) {
+            double djk = sqrt(orc_sqdist(coords, n, d, nb[j], nb[k]));
+            double c = orc_cov(cov_type, djk, var, range);
+            S[j * q + k] = S[k * q + j] = c;
+            G[j * q + k] = G[k * q + j] = orc_cov_grad_range(cov_type, djk, var, range, c);
+          }
+        }
+        if (orc_chol(S, q) != 0) { ++bad; continue; }
+        memcpy(a, s1, sizeof(double) * q);
+        orc_chol_solve(S, q, a);
+        double dot = 0.;
+        for (int j = 0; j < q; ++j) { A[(size_t)i * m + j] = a[j]; dot += a[j] * s1[j]; }
+        Di -= dot;
+        for (int j = 0; j < q; ++j) {
+          double t = 0.;
+          for (int k = 0; k < q; ++k) t += G[j * q + k] * a[k];
+          t1[j] = g1[j]; t2[j] = t;
+        }
+        orc_chol_solve(S, q, t1);
+        orc_chol_solve(S, q, t2);
+        double d1 = 0., d2 = 0.;
+        for (int j = 0; j < q; ++j) {
+          double ag = t1[j] - t2[j];
+          Agrad[(size_t)i * m + j] = ag;
+          d1 += ag * s1[j]; d2 += a[j] * g1[j];
+        }
+        Dgrad[i] = -(d1 + d2); /* :1650 */
+      }
+      if (!(Di > 0.)) ++bad;
+      Dinv[i] = 1. / Di;
+    }
+    free(S); free(G); free(s1); free(g1); free(a); free(t1); free(t2);
+  }
+  return bad;
+}
+
 void orc_apply_B(int n, int m, const int32_t* nn, const double* A, const double* y, double* u) {
 #pragma omp parallel for schedule(static)
   for (int i = 0; i < n; ++i) {

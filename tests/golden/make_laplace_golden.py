@@ -1,6 +1,7 @@
 """Generates tests/golden/laplace_golden.json with the UNMODIFIED reference library (oracle/_ref) through the shared
 frontend: latent Vecchia GP + bernoulli_logit likelihood, Laplace-approximated negative log-likelihood
-with matrix_inversion_method "cholesky" and "iterative" (VADU preconditioner, 50 SLQ probes, seed 1).
+with matrix_inversion_method "cholesky" and "iterative" (VADU preconditioner, 50 SLQ probes, seed 1), and the gradient of
+both w.r.t. the log covariance parameters (recovered from one gradient-descent step of the reference's optimiser).
 Run in the build container:  python tests/golden/make_laplace_golden.py"""
 import json
 import os
@@ -34,6 +35,24 @@ def case_data(c):
     return datagen.binary_synth(c["n"], c["dseed"], c["offset"])
 
 
+def reference_gradient(c, X, y, off, method):
+    """The reference does not export its gradient, but ONE step of its plain gradient descent on log(cov_pars) does
+    (REModelTemplate::UpdateCovAuxPars, re_model_template.h:8741-8744: cov_pars_new = exp(log(cov_pars) - lr * gradient)):
+    gradient = -log(cov_pars_new / cov_pars) / lr, w.r.t. (log variance, log range) on the original scale. Two learning rates
+    must agree (no step halving, no learning-rate cap involved)."""
+    th0 = np.array(c["cov_pars"], dtype=np.float64)
+    got = []
+    for lr in (1e-4, 5e-5):
+        g = GPModel(likelihood="bernoulli_logit", gp_coords=X, cov_function=c["cov_function"], cov_fct_shape=c["shape"],
+                    gp_approx="vecchia", num_neighbors=c["m"], vecchia_ordering=c["ordering"], seed=c["seed"],
+                    matrix_inversion_method=method, _lib=ref)
+        g.params["use_nesterov_acc"] = False
+        g.fit(y, params=dict(optimizer_cov="gradient_descent", lr_cov=lr, maxit=1, init_cov_pars=th0, delta_rel_conv=1e-30), offset=off)
+        got.append(-np.log(g.get_cov_pars() / th0) / lr)
+    assert np.all(np.abs(got[0] - got[1]) <= 1e-7 * np.abs(got[0])), got
+    return got[0].tolist()
+
+
 if __name__ == "__main__":
     out = {"generator": "tests/golden/make_laplace_golden.py", "cases": []}
     for c in CASES:
@@ -44,6 +63,7 @@ if __name__ == "__main__":
                         gp_approx="vecchia", num_neighbors=c["m"], vecchia_ordering=c["ordering"], seed=c["seed"],
                         matrix_inversion_method=method, _lib=ref)
             rec["negll_" + method] = m.neg_log_likelihood(np.array(c["cov_pars"]), y, fixed_effects=off)
+            rec["grad_" + method] = reference_gradient(c, X, y, off, method)
         print(rec)
         out["cases"].append(rec)
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "laplace_golden.json"), "w") as f:

@@ -54,3 +54,51 @@ def test_golden_iterative(idx):
     r = oracle_negll(c, "iterative")
     # same probe vectors (std::mt19937 + seed_seq + normal_distribution) => deterministic agreement
     assert abs(r["negll"] - c["negll_iterative"]) <= 1e-9 * abs(c["negll_iterative"])
+
+
+def oracle_grad(c, method):
+    X, y, off = data_of(c)
+    vo = ov.VecchiaOracle(X, c["m"], c["cov_function"], c["shape"], c["ordering"], c["seed"])
+    _, pt = ov.transform_cov_pars([1.0] + list(c["cov_pars"]), c["cov_function"], c["shape"])
+    fe = None if off is None else off[vo.perm]
+    return ol.grad_negll(vo.coords, vo.nn, vo.cid, c["cov_pars"][0], pt[1], y[vo.perm], fixed_effects=fe, method=method)
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD)))
+def test_golden_gradient_cholesky(idx):
+    """Gradient w.r.t. (log variance, log range) of the Laplace-approximated likelihood, sparse-Cholesky branch of
+    CalcGradNegMargLikelihoodLaplaceApproxVecchia, against the reference's own gradient (one gradient-descent step)."""
+    c = GOLD[idx]
+    if c.get("n", 100) > 2000:
+        pytest.skip("the oracle inverts Sigma^-1 + W densely")
+    r = oracle_grad(c, "cholesky")
+    g = np.array(c["grad_cholesky"])
+    assert np.all(np.abs(r["grad"] - g) <= 1e-7 * np.abs(g).max()), (r["grad"], g)
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD)))
+def test_golden_gradient_iterative(idx):
+    """Iterative branch: stochastic trace estimates with the SLQ probe vectors and their CG solutions, VADU variance
+    reduction with the optimal c, implicit derivative by PCG — the same probes as the reference => deterministic agreement."""
+    c = GOLD[idx]
+    r = oracle_grad(c, "iterative")
+    g = np.array(c["grad_iterative"])
+    assert np.all(np.abs(r["grad"] - g) <= 1e-6 * np.abs(g).max()), (r["grad"], g)
+
+
+@pytest.mark.parametrize("cov,shape", [("matern", 1.5), ("gaussian", 0.), ("exponential", 0.5)])
+def test_gradient_is_the_derivative_of_the_likelihood(cov, shape):
+    """Central differences of the oracle's own (pinned) likelihood w.r.t. (log variance, log range) against grad_consistent."""
+    X, y, _ = datagen.binary_synth(400, 11, False)
+    vo = ov.VecchiaOracle(X, 10, cov, shape, "random", 1)
+    th = np.array([1.3, 0.12])
+
+    def f(t):
+        _, pt = ov.transform_cov_pars([1.0] + list(t), cov, shape)
+        return ol.negll(vo.coords, vo.nn, vo.cid, t[0], pt[1], y[vo.perm], method="cholesky", delta_conv_mode_finding=1e-13)["negll"]
+    _, pt = ov.transform_cov_pars([1.0] + list(th), cov, shape)
+    g = ol.grad_negll(vo.coords, vo.nn, vo.cid, th[0], pt[1], y[vo.perm], method="cholesky", delta_conv_mode_finding=1e-13)["grad_consistent"]
+    for j in range(2):
+        e = np.zeros(2); e[j] = 1e-5
+        fd = (f(th * np.exp(e)) - f(th * np.exp(-e))) / 2e-5
+        assert abs(fd - g[j]) <= 1e-5 * max(1., abs(g[j])), (cov, j, fd, g[j])
