@@ -101,4 +101,7 @@ def test_gradient_is_the_derivative_of_the_likelihood(cov, shape):
     for j in range(2):
         e = np.zeros(2); e[j] = 1e-5
         fd = (f(th * np.exp(e)) - f(th * np.exp(-e))) / 2e-5
-        assert abs(fd - g[j]) <= 1e-5 * max(1., abs(g[j])), (cov, j, fd, g[j])
+        # Gaussian kernel: the neighbour blocks are nearly singular, and the reference's shortcut dSigma^-1/dlog(var) = -Sigma^-1
+        # ignores the jitter on their diagonal (Vecchia_utils.cpp:1607) — a 1e-5-level effect there, 1e-9 elsewhere
+        tol = 1e-4 if cov == "gaussian" else 1e-6
+        assert abs(fd - g[j]) <= tol * max(1., abs(g[j])), (cov, j, fd, g[j])
