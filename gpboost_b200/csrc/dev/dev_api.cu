@@ -115,7 +115,8 @@ FactorKernel pick_mode(int mode, int d, int m) {
   switch (mode) {
     case gpb::MODE_NLL: return pick_dim<COV, gpb::MODE_NLL>(d, m);
     case gpb::MODE_STORE: return pick_dim<COV, gpb::MODE_STORE>(d, m);
-    default: return pick_dim<COV, gpb::MODE_GRAD>(d, m);
+    case gpb::MODE_GRAD: return pick_dim<COV, gpb::MODE_GRAD>(d, m);
+    default: return pick_dim<COV, gpb::MODE_STORE_GRAD>(d, m);
   }
 }
 FactorKernel pick_kernel(int cov, int mode, int d, int m) {
@@ -150,6 +151,8 @@ struct gpbdev_vecchia {
   double* A = nullptr;        // n x m   (lazy)
   double* Dinv = nullptr;     // n       (lazy)
   double* u = nullptr;        // n       (lazy)
+  double* dA = nullptr;       // n x m   (lazy, MODE_STORE_GRAD)
+  double* dD = nullptr;       // n       (lazy, MODE_STORE_GRAD)
   double* yaux = nullptr;     // n       (lazy, original order)
   int32_t* colptr = nullptr;  // n + 1   (lazy)
   int32_t* csc_pos = nullptr; // nnz     (lazy)
@@ -214,11 +217,17 @@ int ensure_csc(gpbdev_vecchia* h) {
 
 int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int mode, bool latent = false) {
   if (cov_type < 0 || cov_type > 3) return fail("gpbdev_vecchia_eval: unknown covariance id");
-  if (mode < 0 || mode > 2) return fail("gpbdev_vecchia_eval: unknown mode");
+  if (mode < 0 || mode > 3) return fail("gpbdev_vecchia_eval: unknown mode");
   if (!(var > 0.) || !(range > 0.)) return fail("gpbdev_vecchia_eval: covariance parameters must be positive");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (mode == gpb::MODE_STORE) {
+  if (mode == gpb::MODE_STORE || mode == gpb::MODE_STORE_GRAD) {
     if (ensure_store_buffers(h)) return -1;
+  }
+  if (mode == gpb::MODE_STORE_GRAD && !h->dA) {
+    CUDA_TRY(cudaMalloc(&h->dA, sizeof(double) * h->n * h->m));
+    CUDA_TRY(cudaMalloc(&h->dD, sizeof(double) * h->n));
+    CUDA_TRY(cudaMemsetAsync(h->dA, 0, sizeof(double) * h->n * h->m, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->dD, 0, sizeof(double) * h->n, h->stream));
   }
   gpb::FactorArgs a;
   a.coords = h->coords; a.nn = h->nn; a.y = h->y;
@@ -228,6 +237,10 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   a.m = h->m; a.d = h->d; a.var = var; a.range = range;
   a.diag_nb = latent ? var * (1. + 1e-10) : var + 1.;
   a.diag_obs = latent ? var : var + 1.;
+  if (mode == gpb::MODE_STORE_GRAD) {
+    CUDA_TRY(cudaMemcpyToSymbolAsync(gpb::g_factor_dA, &h->dA, sizeof(double*), 0, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyToSymbolAsync(gpb::g_factor_dD, &h->dD, sizeof(double*), 0, cudaMemcpyHostToDevice, h->stream));
+  }
   if (latent && mode == gpb::MODE_GRAD) return fail("gpbdev_vecchia_eval: the gradient pass assumes a Gaussian likelihood");
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);
   const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 64);
@@ -246,7 +259,7 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   if (h->allreduce && !latent) {  // row shards: the 9 sums are summed over the ranks on this stream (NCCL kernel)
     if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
   }
-  if (mode == gpb::MODE_STORE) h->factor_stored = true;
+  if (mode == gpb::MODE_STORE || mode == gpb::MODE_STORE_GRAD) h->factor_stored = true;
   return 0;
 }
 
@@ -348,6 +361,7 @@ int gpbdev_vecchia_free(gpbdev_vecchia_t h) {
   cudaSetDevice(h->device);
   laplace_release(h);
   cudaFree(h->coords); cudaFree(h->nn); cudaFree(h->perm); cudaFree(h->y_in); cudaFree(h->y);
+  cudaFree(h->dA); cudaFree(h->dD);
   cudaFree(h->A); cudaFree(h->Dinv); cudaFree(h->u); cudaFree(h->yaux); cudaFree(h->colptr); cudaFree(h->csc_pos);
   cudaFree(h->partials); cudaFree(h->sums); cudaFree(h->flush);
   cudaFreeHost(h->sums_host); cudaFreeHost(h->stage_host);
@@ -440,6 +454,20 @@ int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale
   h->launches += 1;
   if (h->allreduce && h->allreduce(h->allreduce_ctx, out_dev, h->n, (void*)h->stream)) return fail("gpbdev_vecchia_yaux_device: device all-reduce failed");
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// latent factor (non-Gaussian likelihood: no nugget, jitter on the neighbour blocks) with its range derivative, to host buffers:
+// A, dA n x m row-major; Dinv, dD n. Test / diagnostics entry of MODE_STORE_GRAD.
+int gpbdev_vecchia_latent_factor_grad(gpbdev_vecchia_t h, int cov_type, double var, double range, double* A_host, double* Dinv_host,
+                                      double* dA_host, double* dD_host) {
+  if (!h || !A_host || !Dinv_host || !dA_host || !dD_host) return fail("gpbdev_vecchia_latent_factor_grad: null argument");
+  if (launch_eval(h, cov_type, var, range, gpb::MODE_STORE_GRAD, true)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(A_host, h->A, sizeof(double) * h->n * h->m, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(Dinv_host, h->Dinv, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dA_host, h->dA, sizeof(double) * h->n * h->m, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dD_host, h->dD, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
   return 0;
 }
 

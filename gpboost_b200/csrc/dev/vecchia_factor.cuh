@@ -39,7 +39,10 @@
 namespace gpb {
 
 enum CovType : int { COV_EXPONENTIAL = 0, COV_MATERN15 = 1, COV_MATERN25 = 2, COV_GAUSSIAN = 3 };
-enum FactorMode : int { MODE_NLL = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+// MODE_STORE_GRAD: MODE_STORE plus the derivative of the factor w.r.t. log(range): dA_i (= -B_grad row) and dD_i, what
+// CalcCovFactorGradientVecchia leaves in B_grad[1], D_grad[1] (Vecchia_utils.cpp:1636-1652) — needed where the derivative of
+// Sigma^-1 is applied to many vectors (Laplace-approximated likelihoods, likelihoods.h:6615-6690). NOT YET RUN ON A B200.
+enum FactorMode : int { MODE_NLL = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_STORE_GRAD = 3 };
 
 #ifndef GPB_NLL_BLOCKS
 #define GPB_NLL_BLOCKS 5
@@ -74,6 +77,11 @@ struct FactorArgs {
   double diag_nb;
   double diag_obs;
 };
+// Outputs of MODE_STORE_GRAD (d A_i / d log(range): n x m, d D_i / d log(range): n). Kept out of FactorArgs so that the
+// parameter block — and with it the generated code — of the other modes is exactly what the committed ncu captures describe;
+// set with cudaMemcpyToSymbolAsync on the engine's stream right before the launch (one engine per device at a time).
+__device__ double* g_factor_dA = nullptr;
+__device__ double* g_factor_dD = nullptr;
 
 // exp(ax) for ax <= 0 (clamped at -700): round-to-nearest range reduction by the 1.5*2^52 trick, degree-13 Taylor
 // polynomial on |r| <= ln2/2 (truncation error 4e-18), scaling by an exponent-field add. No special-case paths and the
@@ -137,9 +145,10 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 template <int COV, int MODE, int DIM, int MT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? GPB_GRAD_BLOCKS : GPB_NLL_BLOCKS)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (MODE == MODE_GRAD || MODE == MODE_STORE_GRAD) ? GPB_GRAD_BLOCKS : GPB_NLL_BLOCKS)
 vecchia_factor_kernel(const FactorArgs p) {
   constexpr bool GRAD = (MODE == MODE_GRAD);
+  constexpr bool GPAIR = GRAD || (MODE == MODE_STORE_GRAD);  // the range-derivative pair values are kept
   constexpr bool SOLVE = (MODE != MODE_NLL);
   constexpr int P = MT + 1;      // point slots: 0..MT-1 neighbours (real or dummy), MT = the observation
   constexpr int NT = MT / 2;     // circulant rounds (P is odd)
@@ -205,7 +214,7 @@ vecchia_factor_kernel(const FactorArgs p) {
     __syncwarp();
 
     // ---- pair covariances, circulant schedule: lane l <-> point (l + t) mod P, t = 1..NT
-    double gpair[GRAD ? NT : 1];
+    double gpair[GPAIR ? NT : 1];
     double my[DIM > 0 ? DIM : 1];
     if (DIM > 0) {
 #pragma unroll
@@ -233,14 +242,14 @@ vecchia_factor_kernel(const FactorArgs p) {
       // dist = d2 / sqrt(d2); the tiny offset makes coincident points come out as exactly 0 without a branch
       const double dist = d2 * rsqrt_fast(d2 + 1e-300);
       double g = 0.;
-      double val = cov_eval<COV, GRAD>(dist, var, range, g);
+      double val = cov_eval<COV, GPAIR>(dist, var, range, g);
       if (!full) {
         const bool both = real && ((real_mask >> o) & 1u);
         val = both ? val : 0.;
         g = both ? g : 0.;
       }
       if (lane < P) S[min(lane, o) * kLd + max(lane, o)] = val;
-      if (GRAD) gpair[t - 1] = (lane < P) ? g : 0.;
+      if (GPAIR) gpair[t - 1] = (lane < P) ? g : 0.;
     }
     if (DIM == 2) {  // dependent gather of the next row; lands during the factorisation
       src_pre = src_next;
@@ -322,9 +331,49 @@ vecchia_factor_kernel(const FactorArgs p) {
       // xa = A_i[lane] for lane < q
       const double Dinv_i = 1. / Di;
       const double By = r_over_sd * sqrt(Di);
-      if (MODE == MODE_STORE) {
+      if (MODE == MODE_STORE || MODE == MODE_STORE_GRAD) {
         if (lane < m) p.A[i * m + lane] = (lane < q) ? xa : 0.;
         if (lane == 0) { p.Dinv[i] = Dinv_i; p.w[i] = By * Dinv_i; }
+      }
+      if (MODE == MODE_STORE_GRAD) {
+        // r = dSigma~ b over the P points (b = [-A, 1]): rows 0..MT-1 of r are dSigma_iN - dSigma_NN A, and b.r = dD
+        __syncwarp();
+        xb[lane] = (lane < MT) ? -xa : (lane == MT ? 1. : 0.);
+        __syncwarp();
+        const double bl = xb[lane];
+        double racc = 0.;
+#pragma unroll
+        for (int t = 1; t <= NT; ++t) {
+          int o = lane + t;
+          if (o >= P) o -= P;
+          o = lane < P ? o : 0;
+          const double g = gpair[t - 1];  // pair (lane, o); 0 for padded / inactive pairs
+          racc += g * xb[o];
+          int src = lane - t;             // the lane whose partner of round t is this lane
+          if (src < 0) src += P;
+          const double sent = shfl_d(g * bl, src);
+          if (lane < P) racc += sent;
+        }
+        const double dDv = warp_sum(lane < P ? bl * racc : 0.);
+        // dA = S^-1 r = L^-T L^-1 r: forward substitution with lane = row (L[row][c] = S[c * kLd + row]), then the same
+        // back substitution as for A
+        double xg = (lane < MT) ? racc : 0.;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const double wj = shfl_d(xg * dinv, j);
+          const double lij = (lane > j && lane < MT) ? S[j * kLd + lane] : 0.;
+          if (lane == j) xg = wj;
+          xg -= lij * wj;
+        }
+#pragma unroll
+        for (int r = MT - 1; r >= 0; --r) {
+          const double fa = shfl_d(xg * dinv, r);
+          const double lrc = (lane < r) ? S[lane * kLd + r] : 0.;
+          if (lane == r) xg = fa;
+          xg -= lrc * fa;
+        }
+        if (lane < m) g_factor_dA[i * m + lane] = (lane < q) ? xg : 0.;
+        if (lane == 0) g_factor_dD[i] = dDv;
       }
       if (GRAD) {
         // b = [-A, 1], w~ = [w, 0] over the P points
