@@ -484,6 +484,127 @@ __global__ void scatter_perm_kernel(int64_t n, const double* __restrict__ x, con
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[perm[i]] = x[i];
 }
 
+// ---- gradient of the Laplace-approximated likelihood (likelihoods.h:6521-7044, iterative branch; NOT YET RUN ON A B200) ----
+// T[i,:] = -sum_k dA[i,k] X[nn[i,k],:]  = (B_grad X)[i,:]  (B_grad = -dA has no diagonal); same unit scheme as mv_B_kernel
+__global__ void __launch_bounds__(kBlock) mv_Bg_kernel(const double* __restrict__ dA, const int32_t* __restrict__ nn, int m, int64_t n, int t, int G,
+                                                       const double* __restrict__ X, double* __restrict__ T) {
+  const Unit u = make_unit(t, G);
+  for (int64_t i = u.r0; i < n; i += u.rstep) {
+    int32_t jk = u.lane < m ? nn[i * m + u.lane] : -1;
+    const double ak = jk >= 0 ? dA[i * m + u.lane] : 0.;
+    jk = max(jk, 0);
+    double acc = 0.;
+    double v[kM];
+#pragma unroll
+    for (int k = 0; k < kM; ++k) v[k] = X[(int64_t)__shfl_sync(0xffffffffu, jk, k) * t + u.cc];
+#pragma unroll
+    for (int k = 0; k < kM; ++k) acc -= __shfl_sync(0xffffffffu, ak, k) * v[k];
+    if (u.active) T[i * t + u.c] = acc;
+  }
+}
+// V[j,:] (+)= -sum_{(i,k): nn[i,k]=j} dA[i,k] T[i,:]  = (B_grad^T T)[j,:]; accumulate != 0 adds to what V holds
+__global__ void __launch_bounds__(kBlock) mv_Bgt_kernel(const double* __restrict__ dA, const int32_t* __restrict__ colptr,
+                                                        const int32_t* __restrict__ csc_pos, int m, int64_t n, int t, int G,
+                                                        const double* __restrict__ T, double* __restrict__ V, int accumulate) {
+  const Unit u = make_unit(t, G);
+  for (int64_t j = u.r0; j < n; j += u.rstep) {
+    double acc = accumulate ? V[j * t + u.cc] : 0.;
+    const int e0 = colptr[j], e1 = colptr[j + 1];
+    for (int eb = e0; eb < e1; eb += 32) {
+      const int e = eb + u.lane;
+      const int32_t pos = e < e1 ? csc_pos[e] : 0;
+      const double ap = e < e1 ? dA[pos] : 0.;
+      const int64_t rowp = e < e1 ? pos / m : j;
+      const int cnt = min(32, e1 - eb);
+      for (int q = 0; q < cnt; ++q) acc -= __shfl_sync(0xffffffffu, ap, q) * T[__shfl_sync(0xffffffffu, rowp, q) * t + u.cc];
+    }
+    if (u.active) V[j * t + u.c] = acc;
+  }
+}
+// partial[.][c] = sum_i X[i,c] Y[i,c]
+__global__ void __launch_bounds__(kBlock) coldot_kernel(int64_t n, int t, int G, const double* __restrict__ X, const double* __restrict__ Y,
+                                                        double* __restrict__ partial) {
+  const Unit u = make_unit(t, G);
+  double d = 0.;
+  if (u.active) {
+    for (int64_t i = u.r0; i < n; i += u.rstep) d += X[i * t + u.c] * Y[i * t + u.c];
+    partial[u.pslot * kMaxCols + u.c] = d;
+  }
+}
+// elementwise row scalings of multi-vectors:  out[i,:] = a_i * X[i,:] + b_i * Y[i,:]  with
+//   mode 0: a = Dinv, b = -Dinv * dD          (T3 = D^-1 T2 - D^-1 dD T1,            X = T2, Y = T1)
+//   mode 1: a = Dinv, b = -Dinv * dD + W/Dinv.. see below
+// kept general: a_i = ca[i], b_i = cb[i] are precomputed n-vectors
+__global__ void rowscale2_kernel(int64_t n, int t, const double* __restrict__ ca, const double* __restrict__ X, const double* __restrict__ cb,
+                                 const double* __restrict__ Y, double* __restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n * t; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / t;
+    out[e] = ca[i] * X[e] + cb[i] * Y[e];
+  }
+}
+__global__ void rowscale1_kernel(int64_t n, int t, const double* __restrict__ ca, const double* __restrict__ X, double* __restrict__ out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n * t; e += (int64_t)gridDim.x * blockDim.x) out[e] = ca[e / t] * X[e];
+}
+// coefficient vectors of the range derivative:  c0 = Dinv, c1 = -Dinv dD,  c2 = Dinv + W  (= T3 + W T2 coefficient of T2),
+// c3 = 1 + W / Dinv (coefficient of T1 in T1 + W (B X));  dW = p (1 - p) (1 - 2 p)  (CalcFirstDerivInformationLocPar)
+// per-warp partials: 0 sum Dinv dD   1 sum Dinv / dw   2 sum Dinv^2 dD / dw
+__global__ void grad_coef_kernel(int64_t n, const double* __restrict__ Dinv, const double* __restrict__ dD, const double* __restrict__ W,
+                                 const double* __restrict__ dw, const double* __restrict__ mode, const double* __restrict__ fe,
+                                 double* __restrict__ c1, double* __restrict__ c2, double* __restrict__ c3, double* __restrict__ dWout,
+                                 double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  double s0 = 0., s1 = 0., s2 = 0.;
+  for (int64_t i = gt; i < n; i += nt) {
+    const double di = Dinv[i], dd = dD[i], w = W[i];
+    c1[i] = -di * dd;
+    c2[i] = di + w;
+    c3[i] = 1. + w / di;
+    const double p = sigmoid_stable(mode[i] + (fe ? fe[i] : 0.));
+    dWout[i] = p * (1. - p) * (1. - 2. * p);
+    s0 += di * dd; s1 += di / dw[i]; s2 += di * di * dd / dw[i];
+  }
+  s0 = wsum(s0); s1 = wsum(s1); s2 = wsum(s2);
+  if (lane == 0) {
+    double* o = partial + (size_t)(gt >> 5) * kMaxCols;
+    o[0] = s0; o[1] = s1; o[2] = s2;
+  }
+}
+// d mll / d mode (CalcLogDetStochDerivModeVecchia, VADU branch, + the factor 1/2 of likelihoods.h:6601): one warp per row,
+//   ZA = U dW Z (stochastic tr((Sigma^-1 + W)^-1 dW/db_i)), ZP = T dW T (tr(P^-1 dP/db_i), T = B P^-1 Z),
+//   c = cov(ZA, ZP) / var(ZP) over the probe columns (CalcOptimalCVectorized), out = (mean ZA + c (dW / dw - mean ZP)) / 2
+__global__ void stoch_dmode_kernel(int64_t n, int t, const double* __restrict__ U, const double* __restrict__ Z, const double* __restrict__ T,
+                                   const double* __restrict__ dW, const double* __restrict__ dw, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int kPer = kMaxCols / 32;
+  for (int64_t i = gw; i < n; i += nw) {
+    const double dwi = dW[i];
+    double za[kPer], zp[kPer];
+    double sa = 0., sp = 0.;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int c = q * 32 + lane;
+      if (c < t) {
+        const double tv = T[i * t + c];
+        za[q] = U[i * t + c] * dwi * Z[i * t + c];
+        zp[q] = tv * dwi * tv;
+        sa += za[q]; sp += zp[q];
+      } else { za[q] = 0.; zp[q] = 0.; }
+    }
+    const double ma = wsum(sa) / t, mp = wsum(sp) / t;
+    double cc = 0., cv = 0.;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int c = q * 32 + lane;
+      if (c < t) { const double a = za[q] - ma, b = zp[q] - mp; cc += a * b; cv += b * b; }
+    }
+    cc = wsum(cc) / t; cv = wsum(cv) / t;
+    const double copt = cv == 0. ? 1. : cc / cv;
+    if (lane == 0) out[i] = 0.5 * (ma + copt * (dwi / dw[i]) - copt * mp);
+  }
+}
+
 // e1^T log(T) e1 of a symmetric tridiagonal matrix (LogDetStochTridiag, CG_utils.cpp:1035-1052): implicit-shift QL
 // iteration carrying only the first row of the eigenvector matrix.
 inline double tridiag_e1_log_e1(std::vector<double> d, std::vector<double> e) {
@@ -544,6 +665,11 @@ struct gpb_laplace_state {
   double *r = nullptr, *z = nullptr, *hv = nullptr, *v = nullptr, *tt = nullptr, *yy = nullptr;  // n-vectors of the Newton CG
   double *probes = nullptr;  // n x t column-major (reference layout), ordered rows
   double *R = nullptr, *Z = nullptr, *H = nullptr, *V = nullptr, *T = nullptr, *Y = nullptr;  // n x t row-major
+  // gradient (gpbdev_vecchia_laplace_grad): the SLQ's CG solutions (Sigma^-1 + W)^-1 Z are kept when `keep` is set
+  bool keep = false, fe_set = false, solutions_valid = false;
+  double* U = nullptr;        // n x t
+  int U_t = 0;
+  double *c1 = nullptr, *c2 = nullptr, *c3 = nullptr, *dWv = nullptr;  // n
   double* partial = nullptr;  // nwarps x kMaxCols
   double* colsum = nullptr;   // kMaxCols (device)
   double* colsum_host = nullptr;  // pinned
@@ -557,7 +683,7 @@ void laplace_release(gpbdev_vecchia* h) {
   gpb_laplace_state* L = h->lap;
   if (!L) return;
   double* bufs[] = {L->mode, L->mode_new, L->upd, L->dir, L->rhs, L->W, L->dw, L->fe, L->r, L->z, L->hv, L->v, L->tt, L->yy,
-                    L->probes, L->R, L->Z, L->H, L->V, L->T, L->Y, L->partial, L->colsum};
+                    L->probes, L->R, L->Z, L->H, L->V, L->T, L->Y, L->partial, L->colsum, L->U, L->c1, L->c2, L->c3, L->dWv};
   for (double* b : bufs) cudaFree(b);
   cudaFree(L->err);
   cudaFreeHost(L->colsum_host);
@@ -771,6 +897,8 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     CUDA_TRY(cudaGetLastError());
   }
   const double* fe = fixed_effects_host ? L->fe : nullptr;
+  L->fe_set = fixed_effects_host != nullptr;
+  L->solutions_valid = false;
   CUDA_TRY(cudaMemsetAsync(L->mode, 0, sizeof(double) * n, h->stream));   // InitializeModeAvec (re_model_template.h:3199-3202)
   CUDA_TRY(cudaMemsetAsync(L->upd, 0, sizeof(double) * n, h->stream));
   CUDA_TRY(cudaMemsetAsync(L->err, 0, sizeof(int), h->stream));
@@ -873,6 +1001,12 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     std::vector<std::vector<double>> Td(t), Ts(t);
     if (lap_precond(h, t, L->R, L->Z, L->Y, rz.data())) return -1;
     CUDA_TRY(cudaMemcpyAsync(L->H, L->Z, sizeof(double) * len, cudaMemcpyDeviceToDevice, h->stream));
+    double* Uacc = nullptr;  // solutions U = (Sigma^-1 + W)^-1 Z of the t systems (CG_utils.cpp:171), for the gradient
+    if (L->keep) {
+      if (L->U_t != t) { cudaFree(L->U); L->U = nullptr; CUDA_TRY(cudaMalloc(&L->U, sizeof(double) * len)); L->U_t = t; }
+      CUDA_TRY(cudaMemsetAsync(L->U, 0, sizeof(double) * len, h->stream));
+      Uacc = L->U;
+    }
     int j = 0;
     bool early = false;
     for (j = 0; j < cg_max_tri; ++j) {
@@ -880,7 +1014,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       a_old = a;
       gpl::Coef ac;
       for (int c = 0; c < t; ++c) { a[c] = rz[c] / hvd[c]; ac.v[c] = a[c]; }
-      gpl::axpy_norm_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, ac, L->V, L->R, nullptr, nullptr, L->partial);
+      gpl::axpy_norm_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, ac, L->V, L->R, Uacc ? L->H : nullptr, Uacc, L->partial);
       CUDA_TRY(cudaGetLastError());
       h->launches += 1;
       if (laplace_colsums(h, t, rr.data(), prow)) return -1;
@@ -913,6 +1047,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     // log|Sigma W + I| = log|P^-1 (Sigma^-1 + W)| + log|P| + log|Sigma|   (likelihoods.h:16505-16511)
     if (lap_row_stats(h, L->mode, nullptr, nullptr, nullptr, L->dw, st)) return -1;
     logdet = ldet - sum_log_dinv + st[4];
+    L->solutions_valid = L->keep;
   }
   out[4] = logdet;
   out[0] = -(mll - 0.5 * logdet);
@@ -921,6 +1056,174 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
                  g_trace.t[0], g_trace.c[0], g_trace.t[1], g_trace.c[1], L->t, g_trace.t[2], g_trace.c[2], L->t, g_trace.t[3], g_trace.c[3]);
     for (int i = 0; i < 8; ++i) { g_trace.t[i] = 0.; g_trace.c[i] = 0; }
   }
+  return 0;
+}
+
+// The next evaluation keeps what the gradient needs (the SLQ's CG solutions); costs one more n x t buffer.
+int gpbdev_vecchia_laplace_keep_solutions(gpbdev_vecchia_t h, int keep) {
+  if (!h) return fail("gpbdev_vecchia_laplace_keep_solutions: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (laplace_ensure(h)) return -1;
+  h->lap->keep = keep != 0;
+  return 0;
+}
+
+// Gradient of the Laplace-approximated negative log-likelihood w.r.t. (log variance, log range) at the parameters of the
+// preceding gpbdev_vecchia_laplace_eval (which must have run with keep_solutions): the reference's
+// CalcGradNegMargLikelihoodLaplaceApproxVecchia, iterative branch with the VADU preconditioner (likelihoods.h:6567-6690):
+//   explicit part 1/2 (mode^T dSigma^-1 mode + d log|Sigma W + I|), the log-determinant derivative by stochastic trace
+//   estimation with the SLQ's probe vectors z and solutions (Sigma^-1 + W)^-1 z, variance-reduced with the preconditioner
+//   (CalcLogDetStochDerivCovParVecchia :16706-16781, optimal c CG_utils.cpp:1053-1069), and the implicit part through
+//   d mll / d mode (CalcLogDetStochDerivModeVecchia :16651-16692) and one more PCG solve.
+// dSigma^-1/dlog(var) = -Sigma^-1 (one GP); dSigma^-1/dlog(range) = Bg^T D^-1 B + B^T D^-1 Bg - B^T D^-1 dD D^-1 B with
+// Bg = -dA, dD from the factor kernel's MODE_STORE_GRAD. out[0..1] = gradient on the scale the reference's optimiser uses
+// (log of the ORIGINAL range: factor -1, Gaussian kernel -1/2 as in the reference), out[2] = CG iterations of the implicit solve.
+// NOT YET RUN ON A B200.
+int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, double range, const double* cfg, double* out) {
+  if (!h || !cfg || !out) return fail("gpbdev_vecchia_laplace_grad: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gpb_laplace_state* L = h->lap;
+  if (!L || !L->solutions_valid) return fail("gpbdev_vecchia_laplace_grad: run gpbdev_vecchia_laplace_eval with keep_solutions first");
+  if (L->t != L->t_total) return fail("gpbdev_vecchia_laplace_grad: probe columns sharded over ranks are not supported yet");
+  const int64_t n = h->n;
+  const int t = L->t;
+  const int cg_max = (int)std::min<double>(cfg[3], (double)n);
+  const double cg_delta = cfg[5];
+  if (!L->c1) {
+    double** vecs[] = {&L->c1, &L->c2, &L->c3, &L->dWv};
+    for (double** p : vecs) CUDA_TRY(cudaMalloc(p, sizeof(double) * n));
+  }
+  const double* fe = L->fe_set ? L->fe : nullptr;
+  // factor with its range derivative (A, D^-1 are rewritten with the same values)
+  if (launch_eval(h, cov_type, var, range, gpb::MODE_STORE_GRAD, true)) return -1;
+  const int64_t len = n * t;
+  const int lb = (int)std::min<int64_t>((len + 255) / 256, (int64_t)h->num_sms * 16);
+  const int eb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 16);
+  const int G = lap_groups(t), gridg = lap_grid(L->grid_mv, G), prow = gridg * (gpl::kBlock / 32) / G;
+  const int grid1 = lap_grid(L->grid_mv, 1), prow1 = grid1 * (gpl::kBlock / 32);
+  // coefficient vectors, dW, deterministic sums
+  double sdet[3];
+  gpl::grad_coef_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, h->Dinv, h->dD, L->W, L->dw, L->mode, fe, L->c1, L->c2, L->c3, L->dWv, L->partial);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  if (laplace_colsums(h, 3, sdet, L->grid_mv * (gpl::kBlock / 32))) return -1;
+  // Zp = B^T (sqrt(dw) probes) -> R;  PI_Z = P^-1 Zp -> Z
+  std::vector<double> dots(t), zA(t), zP(t);
+  gpl::scale_transpose_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->probes, L->dw, L->T);
+  gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  CUDA_TRY(cudaMemsetAsync(L->err, 0, sizeof(int), h->stream));
+  if (lap_precond(h, t, L->R, L->Z, L->Y, dots.data())) return -1;
+  // d mll / d mode -> rhs;  x = (Sigma^-1 + W)^-1 rhs -> upd (PCG from zero, Inv_SigmaI_plus_ZtWZ_Vecchia_iterative_given_PC)
+  gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, nullptr, L->Z, L->T);
+  gpl::stoch_dmode_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, t, L->U, L->Z, L->T, L->dWv, L->dw, L->rhs);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  int cg_its = 0;
+  {
+    CUDA_TRY(cudaMemcpyAsync(L->r, L->rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(L->upd, 0, sizeof(double) * n, h->stream));
+    double rz = 0., rz_new = 0., hv = 0., rr = 0.;
+    if (lap_precond(h, 1, L->r, L->z, L->yy, &rz)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(L->hv, L->z, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    for (int j = 0; j < cg_max; ++j) {
+      if (lap_apply_op(h, 1, L->hv, L->v, L->tt, &hv)) return -1;
+      gpl::Coef a; a.v[0] = rz / hv;
+      gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, a, L->v, L->r, L->hv, L->upd, L->partial);
+      CUDA_TRY(cudaGetLastError());
+      h->launches += 1;
+      if (laplace_colsums(h, 1, &rr, L->grid_mv * (gpl::kBlock / 32))) return -1;
+      ++cg_its;
+      const double rn = std::sqrt(rr);
+      if (!std::isfinite(rn)) return fail("gpbdev_vecchia_laplace_grad: NaN or Inf in the conjugate gradient solve");
+      if (rn < cg_delta) break;
+      if (lap_precond(h, 1, L->r, L->z, L->yy, &rz_new)) return -1;
+      gpl::Coef b; b.v[0] = rz_new / rz;
+      rz = rz_new;
+      gpl::h_update_kernel<<<eb, 256, 0, h->stream>>>(n, 1, b, L->z, L->hv);
+      CUDA_TRY(cudaGetLastError());
+      h->launches += 1;
+    }
+  }
+  auto mean = [&](const std::vector<double>& v) { double s = 0.; for (double x : v) s += x; return s / (double)v.size(); };
+  auto optimal_c = [&](const std::vector<double>& za, const std::vector<double>& zb, double tra, double trb) {  // CalcOptimalC
+    double den = 0., num = 0.;
+    for (size_t k = 0; k < zb.size(); ++k) { den += (zb[k] - trb) * (zb[k] - trb); num += (za[k] - tra) * (zb[k] - trb); }
+    den /= (double)zb.size(); num /= (double)zb.size();
+    return den == 0. ? 1. : num / den;
+  };
+  double grad[2];
+  // ---- j = 0, marginal variance: dSigma^-1 = -Sigma^-1
+  double m_v = 0., x_v = 0.;
+  {
+    gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, L->Z, L->T);     // T1 = D^-1 B PI_Z
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->Z, L->V, L->partial);  // V = Sigma^-1 PI_Z
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    if (laplace_colsums(h, t, zP.data(), prow)) return -1;  // PI_Z . V
+    gpl::coldot_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, L->U, L->V, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (laplace_colsums(h, t, zA.data(), prow)) return -1;
+    for (int c = 0; c < t; ++c) { zA[c] = -zA[c]; zP[c] = -zP[c]; }
+    // single vector: Sigma^-1 mode -> v
+    gpl::mv_B_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, 1, 1, h->Dinv, L->mode, L->tt);
+    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->tt, nullptr, L->mode, L->v, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    if (laplace_colsums(h, 1, &m_v, prow1)) return -1;
+    gpl::coldot_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(n, 1, 1, L->upd, L->v, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (laplace_colsums(h, 1, &x_v, prow1)) return -1;
+    const double tr1 = mean(zA), trP = mean(zP);
+    const double c = optimal_c(zA, zP, tr1, trP);
+    const double d = tr1 + (double)n + c * (-sdet[1]) - c * trP;
+    grad[0] = 0.5 * (-m_v + d) + x_v;  // mode^T dSigma^-1 mode = -m_v, implicit term -(x . dSigma^-1 mode) = +x_v
+  }
+  // ---- j = 1, range
+  {
+    // T = D^-1 B PI_Z (still valid), Y = Bg PI_Z, H = D^-1 Y - D^-1 dD T, V = B^T H + Bg^T T
+    gpl::mv_Bg_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->nn, h->m, n, t, G, L->Z, L->Y);
+    gpl::rowscale2_kernel<<<lb, 256, 0, h->stream>>>(n, t, h->Dinv, L->Y, L->c1, L->T, L->H);
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->V, L->partial);
+    gpl::mv_Bgt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, t, G, L->T, L->V, 1);
+    gpl::coldot_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, L->U, L->V, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 5;
+    if (laplace_colsums(h, t, zA.data(), prow)) return -1;
+    // dP = dSigma^-1 + B^T W Bg + Bg^T W B:  R = B^T ((D^-1 + W) Y - D^-1 dD T) + Bg^T ((1 + W / D^-1) T)
+    gpl::rowscale2_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->c2, L->Y, L->c1, L->T, L->H);
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->R, L->partial);
+    gpl::rowscale1_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->c3, L->T, L->H);
+    gpl::mv_Bgt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, t, G, L->H, L->R, 1);
+    gpl::coldot_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, L->Z, L->R, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 5;
+    if (laplace_colsums(h, t, zP.data(), prow)) return -1;
+    // single vector: tt = D^-1 B mode (still valid), yy = Bg mode, z = D^-1 yy - D^-1 dD tt, v = B^T z + Bg^T tt
+    gpl::mv_Bg_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->dA, h->nn, h->m, n, 1, 1, L->mode, L->yy);
+    gpl::rowscale2_kernel<<<eb, 256, 0, h->stream>>>(n, 1, h->Dinv, L->yy, L->c1, L->tt, L->z);
+    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->z, nullptr, L->mode, L->v, L->partial);
+    gpl::mv_Bgt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, 1, 1, L->tt, L->v, 1);
+    gpl::coldot_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(n, 1, 1, L->mode, L->v, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 5;
+    if (laplace_colsums(h, 1, &m_v, prow1)) return -1;
+    gpl::coldot_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(n, 1, 1, L->upd, L->v, L->partial);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (laplace_colsums(h, 1, &x_v, prow1)) return -1;
+    const double tr1 = mean(zA), trP = mean(zP);
+    const double c = optimal_c(zA, zP, tr1, trP);
+    const double d = tr1 + sdet[0] + c * (-sdet[2]) - c * trP;
+    grad[1] = 0.5 * (m_v + d) - x_v;
+  }
+  if (lap_check_err(h)) return -1;
+  out[0] = grad[0];
+  out[1] = grad[1] * (cov_type == gpb::COV_GAUSSIAN ? -0.5 : -1.);
+  out[2] = cg_its;
   return 0;
 }
 

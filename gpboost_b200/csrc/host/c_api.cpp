@@ -325,6 +325,13 @@ int GPB200_GetLaplaceInfo(REModelHandle handle, double* out6) {
   API_END();
 }
 
+int GPB200_EvalLaplaceGradient(REModelHandle handle, const double* y_data, const double* cov_pars, const double* fixed_effects, double* negll,
+                               double* grad2) {
+  API_BEGIN();
+  M(handle)->EvalLaplaceWithGradient(y_data, cov_pars, fixed_effects, negll, grad2);
+  API_END();
+}
+
 int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out) {
   API_BEGIN();
   M(handle)->GetLaplaceMode(mode_out);

@@ -475,6 +475,22 @@ void REModel::EvalLaplace(const double* y_data, const double* cov_pars, double* 
   neg_log_likelihood_ = *negll;
 }
 
+// Laplace-approximated negative log-likelihood AND its gradient w.r.t. (log variance, log range) at cov_pars (original scale):
+// what EvalLLforLBFGSpp / CalcGradPars hand to the optimiser for a non-Gaussian likelihood (re_model_template.h:2055-2100).
+void REModel::EvalLaplaceWithGradient(const double* y_data, const double* cov_pars, const double* fixed_effects, double* negll, double* grad2) {
+  if (gauss_ || engine_ == nullptr) Fatal("EvalLaplaceWithGradient: only for non-Gaussian likelihoods with a Vecchia GP");
+  DevCheck(gpbdev_vecchia_laplace_keep_solutions(engine_, 1));
+  EvalLaplace(y_data, cov_pars, negll, fixed_effects);
+  const double var = cov_pars ? cov_pars[0] : cov_pars_[0];
+  const double range_t = cov_pars ? TransformRange(cov_pars[1]) : cov_pars_[1];
+  const double cfg[8] = {1000., delta_conv_mode_finding_, 20., (double)cg_max_num_it_, (double)cg_max_num_it_tridiag_,
+                         cg_delta_conv_, 1., 1e-4};
+  double out[3] = {0., 0., 0.};
+  DevCheck(gpbdev_vecchia_laplace_grad(engine_, cov_id_, var, range_t, cfg, out));
+  DevCheck(gpbdev_vecchia_laplace_keep_solutions(engine_, 0));
+  grad2[0] = out[0]; grad2[1] = out[1];
+}
+
 void REModel::GetLaplaceMode(double* out) const {
   if (gauss_ || engine_ == nullptr) Fatal("The posterior mode is only available for non-Gaussian likelihoods");
   DevCheck(gpbdev_vecchia_laplace_get_mode(engine_, out));

@@ -108,6 +108,7 @@ class REModel {
  public:
   const double* LaplaceInfo() const { return laplace_out_; }
   void GetLaplaceMode(double* out) const;
+  void EvalLaplaceWithGradient(const double* y_data, const double* cov_pars, const double* fixed_effects, double* negll, double* grad2);
  private:
   int num_groups_ = 0;
   double gsums_[5];

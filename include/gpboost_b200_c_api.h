@@ -130,6 +130,11 @@ GPB200_EXPORT int GPB200_GetNumLikelihoodEvals(REModelHandle handle, int64_t* ou
  * latent process in the original data order (likelihoods.h: mode_, num_it_mode_finding_) */
 GPB200_EXPORT int GPB200_GetLaplaceInfo(REModelHandle handle, double* out6);
 GPB200_EXPORT int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out);
+/* Laplace-approximated negative log-likelihood and its gradient w.r.t. (log variance, log range) on the scale the reference's
+ * optimiser works on (REModelTemplate::CalcGradPars, re_model_template.h:2055-2100 -> likelihoods.h:6521); the reference keeps this
+ * internal to OptimCovPar. Not yet run on a B200 (GPB_OptimCovPar for non-Gaussian likelihoods builds on it). */
+GPB200_EXPORT int GPB200_EvalLaplaceGradient(REModelHandle handle, const double* y_data, const double* cov_pars,
+                                             const double* fixed_effects, double* negll, double* grad2);
 /* the device engine behind a handle (gpbdev_vecchia_t; include/gpboost_b200_dev.h) — bench.py device-only timing */
 GPB200_EXPORT int GPB200_GetDeviceEngine(REModelHandle handle, void** out);
 

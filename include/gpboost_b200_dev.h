@@ -125,6 +125,12 @@ GPBDEV_EXPORT int gpbdev_vecchia_laplace_set_probes(gpbdev_vecchia_t h, const do
 GPBDEV_EXPORT int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, double range,
                                               const double* fixed_effects_host, const double* cfg, double* out);
 GPBDEV_EXPORT int gpbdev_vecchia_laplace_get_mode(gpbdev_vecchia_t h, double* mode_host);
+/* Gradient of the Laplace-approximated negative log-likelihood w.r.t. (log variance, log range) — the covariance-parameter part of
+ * CalcGradNegMargLikelihoodLaplaceApproxVecchia (include/GPBoost/likelihoods.h:6521-7044, iterative branch, VADU). Call
+ * gpbdev_vecchia_laplace_keep_solutions(h, 1), then gpbdev_vecchia_laplace_eval, then this with the same covariance parameters
+ * and cfg. out[0..1] = gradient (scale of the reference's optimiser: log of the original parameters), out[2] = CG iterations. */
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_keep_solutions(gpbdev_vecchia_t h, int keep);
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, double range, const double* cfg, double* out);
 /* multi-GPU: this process holds t of the job's t_total probe columns; allreduce_sum sums `count` doubles over the ranks */
 GPBDEV_EXPORT int gpbdev_vecchia_laplace_set_collective(gpbdev_vecchia_t h, void (*allreduce_sum)(double*, int), int t_total);
 

@@ -124,3 +124,23 @@ def test_latent_factor_range_derivative_matches_oracle(idx):
     assert bad == 0
     for got, want, name in ((A, A0, "A"), (Dinv, Dinv0, "Dinv"), (dA, dA0, "dA"), (dD, dD0, "dD")):
         assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want)), name
+
+
+@UNVERIFIED
+@pytest.mark.parametrize("idx", range(len(GOLD)))
+def test_laplace_gradient_matches_reference_golden(idx):
+    """Gradient of the Laplace-approximated likelihood w.r.t. (log variance, log range), iterative branch with the reference's
+    probe vectors, against the reference's own gradient (recovered from one gradient-descent step; tests/golden)."""
+    import ctypes as C
+    c = GOLD[idx]
+    X, y, off = data_of(c)
+    mdl = product_model(c, X)
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    yy = np.ascontiguousarray(y, dtype=np.float64); cp = np.array(c["cov_pars"], dtype=np.float64)
+    offc = None if off is None else np.ascontiguousarray(off, dtype=np.float64)
+    negll = C.c_double(0.); g = np.zeros(2)
+    rc = mdl._LIB.GPB200_EvalLaplaceGradient(mdl.handle, P(yy), P(cp), None if offc is None else P(offc), C.byref(negll), P(g))
+    assert rc == 0, mdl._LIB.LGBM_GetLastError().decode()
+    assert abs(negll.value - c["negll_iterative"]) <= 1e-6 * abs(c["negll_iterative"])
+    want = np.array(c["grad_iterative"])
+    assert np.all(np.abs(g - want) <= 1e-5 * np.abs(want).max()), (g, want)
