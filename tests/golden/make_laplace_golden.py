@@ -64,6 +64,13 @@ if __name__ == "__main__":
                         matrix_inversion_method=method, _lib=ref)
             rec["negll_" + method] = m.neg_log_likelihood(np.array(c["cov_pars"]), y, fixed_effects=off)
             rec["grad_" + method] = reference_gradient(c, X, y, off, method)
+        if c.get("n", 100) <= 2500:  # GPB_OptimCovPar with the reference's defaults (L-BFGS, iterative method): target of the device fit
+            g = GPModel(likelihood="bernoulli_logit", gp_coords=X, cov_function=c["cov_function"], cov_fct_shape=c["shape"],
+                        gp_approx="vecchia", num_neighbors=c["m"], vecchia_ordering=c["ordering"], seed=c["seed"],
+                        matrix_inversion_method="iterative", _lib=ref)
+            g.fit(y, offset=off)
+            rec["fit_iterative"] = dict(cov_pars=g.get_cov_pars().tolist(), num_it=int(g._get_num_optim_iter()),
+                                        negll=float(g.get_current_neg_log_likelihood()))
         print(rec)
         out["cases"].append(rec)
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "laplace_golden.json"), "w") as f:
