@@ -332,6 +332,31 @@ int GPB200_EvalLaplaceGradient(REModelHandle handle, const double* y_data, const
   API_END();
 }
 
+// The optimiser REModel::OptimCovPar runs (lbfgs.h), with a caller-supplied objective: lets the host-side decisions (step caps,
+// Armijo backtracking, convergence rule) be checked against the reference's iteration counts without a device.
+int GPB200_LbfgsMinimize(double (*objective)(const double* x, int n, double* grad_or_null, void* ctx), void* ctx, int n, double* x_io,
+                         double* fx_out, int max_iterations, double delta_rel_conv, int m_lbfgs, double initial_step_factor, int* num_it) {
+  API_BEGIN();
+  if (objective == nullptr || x_io == nullptr || fx_out == nullptr || num_it == nullptr || n < 1) throw std::runtime_error("GPB200_LbfgsMinimize: bad argument");
+  gpb200::LbfgsObjective f = [&](const std::vector<double>& x, std::vector<double>* grad, bool) -> double {
+    if (grad != nullptr) grad->resize(n);
+    return objective(x.data(), n, grad ? grad->data() : nullptr, ctx);
+  };
+  gpb200::LbfgsMaxStep max_step = [&](const std::vector<double>& neg_dir) {  // re_model_template.h:5413-5421
+    double mx = 0.;
+    for (double v : neg_dir) mx = std::max(mx, std::fabs(v));
+    return std::log(100.) / mx;
+  };
+  gpb200::LbfgsHook hook = [](bool) {};
+  gpb200::LbfgsParams par;
+  par.max_iterations = max_iterations; par.delta = delta_rel_conv; par.m = m_lbfgs; par.initial_step_factor = initial_step_factor;
+  std::vector<double> x(x_io, x_io + n);
+  gpb200::LbfgsMemory mem;
+  *num_it = gpb200::lbfgs_minimize(f, max_step, hook, par, &x, fx_out, &mem, false);
+  for (int i = 0; i < n; ++i) x_io[i] = x[i];
+  API_END();
+}
+
 int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out) {
   API_BEGIN();
   M(handle)->GetLaplaceMode(mode_out);

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -519,14 +520,85 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
 
 void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
                           bool reuse_learning_rates_from_previous_call) {
-  if (!gauss_)
-    Fatal("Covariance parameter estimation for likelihood '" + likelihood_ + "' is not built on the device yet (the Laplace-approximated likelihood and the posterior mode are)");
+  if (!gauss_) {
+    // The fit itself is host logic checked against the reference's fits (tests/test_laplace_oracle_pinned.py drives this L-BFGS
+    // with the oracle's likelihood and gradient: same iteration counts); the device gradient it needs has not run on a B200 yet,
+    // so the entry stays closed unless asked for explicitly.
+    const char* e = std::getenv("GPB200_LAPLACE_FIT");
+    if (e == nullptr || std::string(e) != "1")
+      Fatal("Covariance parameter estimation for likelihood '" + likelihood_ + "' is not enabled yet (the Laplace-approximated likelihood and the posterior mode are; the gradient is awaiting its B200 parity run: GPB200_LAPLACE_FIT=1 opts in)");
+    OptimCovParLaplace(y_data, fixed_effects);
+    return;
+  }
   if (y_data == nullptr) Fatal("Check failed: y_data != nullptr");
   for (int32_t i = 0; i < num_data_; ++i)
     if (std::isnan(y_data[i]) || std::isinf(y_data[i])) Fatal("NaN or Inf in response variable / label ");
   InitializeCovParsIfNotDefined(y_data, fixed_effects);
   SetY(y_data, fixed_effects);
   OptimCovParCore(called_in_GPBoost_algorithm, reuse_learning_rates_from_previous_call);
+}
+
+// GPB_OptimCovPar for a non-Gaussian likelihood with a latent Vecchia GP: L-BFGS on log(cov_pars) (original scale, no nugget),
+// objective = Laplace-approximated negative log-likelihood, gradient = CalcGradNegMargLikelihoodLaplaceApproxVecchia
+// (re_model_template.h:972-1800 with EvalLLforLBFGSpp, optim_utils.h:244-340). Initial values: marginal variance 1, range from the
+// coordinates (FindInitCovPar, re_model_template.h:4901-4925).
+void REModel::OptimCovParLaplace(const double* y_data, const double* fixed_effects) {
+  if (y_data == nullptr) Fatal("Check failed: y_data != nullptr");
+  if (!cov_pars_initialized_) {
+    if (init_cov_pars_provided_) {
+      cov_pars_ = init_cov_pars_;
+    } else {
+      double tmp[3] = {0., 0., 0.};
+      FindInitCovPar(y_data, fixed_effects, tmp);  // tmp[2] = transformed range; the variance part is the Gaussian rule, unused here
+      cov_pars_.assign(2, 0.);
+      cov_pars_[0] = 1.;
+      cov_pars_[1] = tmp[2];
+      init_cov_pars_ = cov_pars_;
+    }
+    cov_pars_initialized_ = true;
+  }
+  num_it_ = max_iter_;
+  if (max_iter_ <= 0) return;
+  double orig[2];
+  TransformBackCovPars(cov_pars_.data(), orig);
+  bool have_cached = false;
+  std::vector<double> cached_x, cached_grad(2, 0.);
+  double cached_f = 0.;
+  LbfgsObjective objective = [&](const std::vector<double>& x, std::vector<double>* grad, bool) -> double {
+    if (grad != nullptr && have_cached && cached_x == x) { *grad = cached_grad; return cached_f; }
+    const double cp[2] = {std::exp(x[0]), std::exp(x[1])};
+    double f = 0.;
+    if (grad != nullptr) {
+      double g[2];
+      EvalLaplaceWithGradient(y_data, cp, fixed_effects, &f, g);
+      grad->assign(g, g + 2);
+      cached_x = x; cached_grad = *grad; cached_f = f; have_cached = true;
+    } else {
+      EvalLaplace(y_data, cp, &f, fixed_effects);
+    }
+    return f;
+  };
+  LbfgsMaxStep max_step = [&](const std::vector<double>& neg_dir) {
+    double mx = 0.;
+    for (double v : neg_dir) mx = std::max(mx, std::fabs(v));
+    return std::log(100.) / mx;
+  };
+  LbfgsHook hook = [](bool) {};
+  LbfgsParams par;
+  par.max_iterations = max_iter_;
+  par.delta = delta_rel_conv_;
+  par.m = m_lbfgs_;
+  par.initial_step_factor = lr_cov_init_;
+  std::vector<double> x = {std::log(orig[0]), std::log(orig[1])};
+  double fx = 0.;
+  LbfgsMemory mem;
+  num_it_ = lbfgs_minimize(objective, max_step, hook, par, &x, &fx, &mem, false);
+  cov_pars_[0] = std::exp(x[0]);
+  cov_pars_[1] = TransformRange(std::exp(x[1]));
+  for (double v : cov_pars_)
+    if (std::isnan(v) || std::isinf(v)) Fatal("NaN or Inf occurred in covariance parameter optimization using 'lbfgs'");
+  neg_log_likelihood_ = fx;
+  cov_pars_estimated_once_ = true;
 }
 
 bool REModel::DevicePathReady() const {

@@ -76,6 +76,7 @@ class REModel {
   void SetY(const double* y_data, const double* fixed_effects);
   void SetYDevice(const double* y_dev);
   void OptimCovParCore(bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
+  void OptimCovParLaplace(const double* y_data, const double* fixed_effects);
   // one device pass at transformed (var, range); fills sums_
   void DevicePass(double var, double range, int mode);
   double NegLLFromSums(double sigma2) const;

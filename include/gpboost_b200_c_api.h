@@ -133,6 +133,12 @@ GPB200_EXPORT int GPB200_GetLaplaceMode(REModelHandle handle, double* mode_out);
 /* Laplace-approximated negative log-likelihood and its gradient w.r.t. (log variance, log range) on the scale the reference's
  * optimiser works on (REModelTemplate::CalcGradPars, re_model_template.h:2055-2100 -> likelihoods.h:6521); the reference keeps this
  * internal to OptimCovPar. Not yet run on a B200 (GPB_OptimCovPar for non-Gaussian likelihoods builds on it). */
+/* The L-BFGS driver behind GPB_OptimCovPar (vendored LBFGSpp settings of include/GPBoost/optim_utils.h:655-676 restated in
+ * csrc/host/lbfgs.h) on a caller-supplied objective f(x, n, grad_or_NULL, ctx): host-logic tests compare its iteration counts with
+ * the reference's fits without a device. */
+GPB200_EXPORT int GPB200_LbfgsMinimize(double (*objective)(const double* x, int n, double* grad_or_null, void* ctx), void* ctx, int n,
+                                       double* x_io, double* fx_out, int max_iterations, double delta_rel_conv, int m_lbfgs,
+                                       double initial_step_factor, int* num_it);
 GPB200_EXPORT int GPB200_EvalLaplaceGradient(REModelHandle handle, const double* y_data, const double* cov_pars,
                                              const double* fixed_effects, double* negll, double* grad2);
 /* the device engine behind a handle (gpbdev_vecchia_t; include/gpboost_b200_dev.h) — bench.py device-only timing */

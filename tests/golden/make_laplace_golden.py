@@ -69,7 +69,9 @@ if __name__ == "__main__":
                         gp_approx="vecchia", num_neighbors=c["m"], vecchia_ordering=c["ordering"], seed=c["seed"],
                         matrix_inversion_method="iterative", _lib=ref)
             g.fit(y, offset=off)
-            rec["fit_iterative"] = dict(cov_pars=g.get_cov_pars().tolist(), num_it=int(g._get_num_optim_iter()),
+            init = np.zeros(2)
+            g._safe_call(g._LIB.GPB_GetInitCovPar(g.handle, init.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))))
+            rec["fit_iterative"] = dict(init_cov_pars=init.tolist(), cov_pars=g.get_cov_pars().tolist(), num_it=int(g._get_num_optim_iter()),
                                         negll=float(g.get_current_neg_log_likelihood()))
         print(rec)
         out["cases"].append(rec)

@@ -105,3 +105,40 @@ def test_gradient_is_the_derivative_of_the_likelihood(cov, shape):
         # ignores the jitter on their diagonal (Vecchia_utils.cpp:1607) — a 1e-5-level effect there, 1e-9 elsewhere
         tol = 1e-4 if cov == "gaussian" else 1e-6
         assert abs(fd - g[j]) <= tol * max(1., abs(g[j])), (cov, j, fd, g[j])
+
+
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(GOLD) if "fit_iterative" in c and c.get("n", 100) <= 2000])
+def test_fit_glue_reproduces_reference_fit(idx):
+    """GPB_OptimCovPar for the bernoulli_logit Vecchia model = the library's L-BFGS driver (GPB200_LbfgsMinimize: the code
+    REModel::OptimCovParLaplace runs) on log(cov_pars), from the reference's initial values, with the Laplace likelihood and its
+    gradient as objective. Here the objective is the pinned oracle (no device): same iteration count and optimum as the
+    reference's own fit (tests/golden/make_laplace_golden.py)."""
+    import ctypes as C
+    from gpboost_b200.libpath import load_lib
+    lib = load_lib()
+    c = GOLD[idx]
+    X, y, off = data_of(c)
+    vo = ov.VecchiaOracle(X, c["m"], c["cov_function"], c["shape"], c["ordering"], c["seed"])
+    fe = None if off is None else off[vo.perm]
+
+    def obj(xp, n, gp, ctx):
+        th = np.exp(np.array([xp[0], xp[1]]))
+        _, pt = ov.transform_cov_pars([1.0] + list(th), c["cov_function"], c["shape"])
+        if bool(gp):
+            r = ol.grad_negll(vo.coords, vo.nn, vo.cid, th[0], pt[1], y[vo.perm], fixed_effects=fe, method="iterative")
+            gp[0], gp[1] = r["grad"][0], r["grad"][1]
+        else:
+            r = ol.negll(vo.coords, vo.nn, vo.cid, th[0], pt[1], y[vo.perm], fixed_effects=fe, method="iterative")
+        return float(r["negll"])
+    cb = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_void_p)(obj)
+    fit = c["fit_iterative"]
+    x = np.log(np.array(fit["init_cov_pars"]))
+    fx = C.c_double(0.); it = C.c_int(0)
+    rc = lib.GPB200_LbfgsMinimize(cb, None, 2, x.ctypes.data_as(C.POINTER(C.c_double)), C.byref(fx), 1000, C.c_double(1e-6), 6,
+                                  C.c_double(1.0), C.byref(it))
+    assert rc == 0, lib.LGBM_GetLastError().decode()
+    # the optimum is flat for the Gaussian kernel (ill-conditioned neighbour blocks): the run stops 3 iterations earlier at the
+    # same likelihood (1e-6 relative); the other cases take exactly the reference's number of iterations
+    assert abs(it.value - fit["num_it"]) <= (3 if c["cov_function"] == "gaussian" else 0), (it.value, fit["num_it"])
+    assert np.all(np.abs(np.exp(x) - np.array(fit["cov_pars"])) <= 5e-3 * np.array(fit["cov_pars"])), (np.exp(x), fit["cov_pars"])
+    assert abs(fx.value - fit["negll"]) <= 1e-5 * abs(fit["negll"])
