@@ -144,3 +144,20 @@ def test_laplace_gradient_matches_reference_golden(idx):
     assert abs(negll.value - c["negll_iterative"]) <= 1e-6 * abs(c["negll_iterative"])
     want = np.array(c["grad_iterative"])
     assert np.all(np.abs(g - want) <= 1e-5 * np.abs(want).max()), (g, want)
+
+
+@UNVERIFIED
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(GOLD) if "fit_iterative" in c])
+def test_laplace_fit_matches_reference_golden(idx, monkeypatch):
+    """GPB_OptimCovPar for the bernoulli_logit Vecchia model on the device against the reference's fit (defaults: L-BFGS,
+    iterative method, 50 probes)."""
+    monkeypatch.setenv("GPB200_LAPLACE_FIT", "1")
+    c = GOLD[idx]
+    X, y, off = data_of(c)
+    mdl = product_model(c, X)
+    mdl.fit(y, offset=off)
+    fit = c["fit_iterative"]
+    cp = mdl.get_cov_pars()
+    assert np.all(np.abs(cp - np.array(fit["cov_pars"])) <= 5e-3 * np.array(fit["cov_pars"])), (cp, fit["cov_pars"])
+    assert abs(mdl._get_num_optim_iter() - fit["num_it"]) <= 3
+    assert abs(mdl.get_current_neg_log_likelihood() - fit["negll"]) <= 1e-5 * abs(fit["negll"])
