@@ -678,6 +678,192 @@ __global__ void __launch_bounds__(kFusedSlices * kBins) reduce_scan_kernel(
   scan_feature(hs[warp], num_bin[f], a, f, lane, min_data_in_leaf, min_sum_hessian, lambda_l2, min_gain_to_split, flags, &scr[warp], out);
 }
 
+// reduce_scan2_kernel = reduce_scan_kernel with the gains of the thresholds evaluated by one thread each (the two fp64 divisions
+// per threshold are paid once instead of eight times per lane; profiles/r01_ncu_split_scan_summary.txt: 28 % of the scan).
+// NOT YET RUN ON A B200: opt-in with GPB200_FUSED_SCAN=2.
+// counts + sequential running sums of one child: the first half of scan_feature
+__device__ __forceinline__ void scan_sums(const double* h, int nb, const LeafArgs& a, int lane, ScanScratch* scr) {
+  double* rsg = scr->rsg;
+  double* rsh = scr->rsh;
+  int* rcn = scr->rcn;
+  const double sum_hessian = a.sum_hessians + 2 * kEps;
+  const double cnt_factor = a.num_data / sum_hessian;
+  {
+    int cl[kBins / 32];
+    int loc = 0;
+#pragma unroll
+    for (int u = kBins / 32 - 1; u >= 0; --u) {
+      const int t = (kBins / 32) * lane + u;
+      const int c = (t >= 1 && t < nb) ? (int)(h[2 * t + 1] * cnt_factor + 0.5f) : 0;
+      loc += c;
+      cl[u] = loc;
+    }
+    int above = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, above, o);
+      if ((int)lane + o < 32) above += v;
+    }
+    above -= loc;
+#pragma unroll
+    for (int u = 0; u < kBins / 32; ++u) rcn[(kBins / 32) * lane + u] = cl[u] + above;
+  }
+  if (lane == 0) {
+    double srg = 0., srh = kEps;
+    int t = nb - 1;
+    while (t >= 1) {
+      double gg[8], hh[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t - u >= 1 ? t - u : 1;
+        const double2 v = *reinterpret_cast<const double2*>(&h[2 * tt]);
+        gg[u] = v.x; hh[u] = v.y;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (t - u >= 1) { srg += gg[u]; srh += hh[u]; rsg[t - u] = srg; rsh[t - u] = srh; }
+      }
+      t -= 8;
+    }
+  }
+  __syncwarp();
+}
+__global__ void __launch_bounds__(kFusedSlices * kBins) reduce_scan2_kernel(
+    const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad, int F, double hess_const,
+    double* __restrict__ hist_base, int64_t slot_stride, const int32_t* __restrict__ num_bin, LeafArgs a0, LeafArgs a1, int parent_row,
+    int min_data_in_leaf, double min_sum_hessian, double lambda_l2, double min_gain_to_split, unsigned char* __restrict__ splittable,
+    SplitOut* __restrict__ cand, const DevJob* __restrict__ job) {
+  if (job) {
+    if (job->done || !job->do_find) return;
+    nchunks = job->hist_nchunks; a0 = job->a0; a1 = job->a1; parent_row = job->parent_row;
+  }
+  __shared__ __align__(16) double hs[2][kBins * 2];
+  __shared__ double sg[kFusedSlices][kBins];
+  __shared__ unsigned long long sc[kFusedSlices][kBins];
+  __shared__ ScanScratch scr[2];
+  __shared__ int pflag;
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bin = tid & (kBins - 1), sl = tid / kBins;
+  // both children inherit the parent's flag of this feature; the left child overwrites it below (same row)
+  if (tid == 0) pflag = a0.inherit ? (int)splittable[(int64_t)parent_row * F + f] : 1;
+  {
+    const int per = (nchunks + kFusedSlices - 1) / kFusedSlices;
+    const int c0 = sl * per, c1 = min(c0 + per, nchunks);
+    const int64_t cs = (int64_t)Fpad * kBins, o0 = (int64_t)f * kBins + bin;
+    double g = 0.;
+    unsigned long long c = 0;
+    int ch = c0;
+    for (; ch + 8 <= c1; ch += 8) {
+      double gv[8];
+      uint32_t cv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { gv[u] = part_g[(ch + u) * cs + o0]; cv[u] = part_c[(ch + u) * cs + o0]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { g += gv[u]; c += cv[u]; }
+    }
+    for (; ch < c1; ++ch) {
+      g += part_g[ch * cs + o0];
+      c += part_c[ch * cs + o0];
+    }
+    sg[sl][bin] = g;
+    sc[sl][bin] = c;
+  }
+  __syncthreads();
+  if (tid < kBins) {
+    double g = sg[0][bin];
+    unsigned long long c = sc[0][bin];
+#pragma unroll
+    for (int k = 1; k < kFusedSlices; ++k) { g += sg[k][bin]; c += sc[k][bin]; }
+    const double hsv = (double)c * hess_const;  // dataset.cpp:1223-1226
+    double* dst = hist_base + (int64_t)a0.hist_slot * slot_stride + ((int64_t)f * kBins + bin) * 2;
+    dst[0] = g; dst[1] = hsv;
+    hs[0][2 * bin] = g; hs[0][2 * bin + 1] = hsv;
+    if (a1.leaf >= 0) {
+      double* par = hist_base + (int64_t)a1.hist_slot * slot_stride + ((int64_t)f * kBins + bin) * 2;
+      const double pg = par[0] - g, ph = par[1] - hsv;
+      par[0] = pg; par[1] = ph;
+      hs[1][2 * bin] = pg; hs[1][2 * bin + 1] = ph;
+    }
+  }
+  __syncthreads();
+  // ---- scan, phase A: per-bin counts and the sequential running sums of both children (warp 0: smaller, warp 1: larger)
+  const int nb = num_bin[f];
+  if (warp < 2) {
+    const LeafArgs a = warp == 0 ? a0 : a1;
+    if (a.leaf >= 0 && !(a.inherit && !pflag)) scan_sums(hs[warp], nb, a, lane, &scr[warp]);
+  }
+  __syncthreads();
+  // ---- phase B: one threshold per thread (two fp64 divisions each, once), arg-max with the reference's tie rule
+  __shared__ double wbest_g[2][kBins / 32];
+  __shared__ int wbest_t[2][kBins / 32];
+  if (tid < 2 * kBins) {
+    const int child = tid / kBins, t = tid & (kBins - 1);
+    const LeafArgs a = child == 0 ? a0 : a1;
+    const bool act = a.leaf >= 0 && !(a.inherit && !pflag);
+    double gain = -INFINITY;
+    int bt = -1;
+    if (act && t >= 1 && t <= nb - 1) {
+      const double sum_gradient = a.sum_gradients;
+      const double sum_hessian = a.sum_hessians + 2 * kEps;
+      const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
+      const double srg = scr[child].rsg[t], srh = scr[child].rsh[t];
+      const int rc = scr[child].rcn[t];
+      const int lc = a.num_data - rc;
+      const double slh = sum_hessian - srh;
+      if (!(rc < min_data_in_leaf || srh < min_sum_hessian || lc < min_data_in_leaf || slh < min_sum_hessian)) {
+        const double slg = sum_gradient - srg;
+        const double gv = (slg * slg) / (slh + lambda_l2) + (srg * srg) / (srh + lambda_l2);
+        if (!(gv <= min_gain_shift)) { gain = gv; bt = t; }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double og = __shfl_xor_sync(0xffffffffu, gain, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      if (og > gain || (og == gain && ot > bt)) { gain = og; bt = ot; }
+    }
+    if (lane == 0) { wbest_g[child][t >> 5] = gain; wbest_t[child][t >> 5] = bt; }
+  }
+  __syncthreads();
+  if (tid != 0 && tid != kBins) return;
+  const int child = tid / kBins;
+  const LeafArgs a = child == 0 ? a0 : a1;
+  if (a.leaf < 0) return;
+  unsigned char* flags = splittable + (int64_t)a.leaf * F;
+  SplitOut s;
+  s.gain = -INFINITY; s.feature = -1; s.threshold = 0; s.left_count = s.right_count = 0;
+  s.left_output = s.right_output = 0.;
+  s.left_sum_gradient = s.left_sum_hessian = s.right_sum_gradient = s.right_sum_hessian = 0.;
+  double best_gain = -INFINITY;
+  int best_t = -1;
+  if (!(a.inherit && !pflag)) {
+    for (int k = 0; k < kBins / 32; ++k) {
+      const double og = wbest_g[child][k];
+      const int ot = wbest_t[child][k];
+      if (og > best_gain || (og == best_gain && ot > best_t)) { best_gain = og; best_t = ot; }
+    }
+  }
+  const bool spl = best_t >= 1;
+  flags[f] = spl ? 1 : 0;
+  if (spl) {
+    const double sum_gradient = a.sum_gradients;
+    const double sum_hessian = a.sum_hessians + 2 * kEps;
+    const double min_gain_shift = (sum_gradient * sum_gradient) / (sum_hessian + lambda_l2) + min_gain_to_split;
+    const double srg = scr[child].rsg[best_t], srh = scr[child].rsh[best_t];
+    const double best_lg = sum_gradient - srg, best_lh = sum_hessian - srh;
+    const int best_lc = a.num_data - scr[child].rcn[best_t];
+    s.feature = f; s.threshold = best_t - 1;
+    s.left_output = -best_lg / (best_lh + lambda_l2);
+    s.left_count = best_lc;
+    s.left_sum_gradient = best_lg; s.left_sum_hessian = best_lh - kEps;
+    s.right_output = -(sum_gradient - best_lg) / (sum_hessian - best_lh + lambda_l2);
+    s.right_count = a.num_data - best_lc;
+    s.right_sum_gradient = sum_gradient - best_lg; s.right_sum_hessian = sum_hessian - best_lh - kEps;
+    s.gain = best_gain - min_gain_shift;
+  }
+  cand[child * F + f] = s;
+}
+
 // best candidate per leaf with SplitInfo::operator> (gain, then the smaller feature index)
 __global__ void split_argmax_kernel(const SplitOut* __restrict__ cand, int F, SplitOut* __restrict__ out) {
   __shared__ SplitOut sh[256];
@@ -1001,7 +1187,7 @@ struct gpbdev_tree {
   int device_loop = 2;             // GPB200_TREE_LOOP = graph (2, default) | device (1) | host (0). Row-sharded learners use the host loop.
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
-  int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
+  int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel | 2: reduce_scan2_kernel (unverified)
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
   int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel | 3: hist3_kernel (unverified)
   double* sum_part = nullptr;
@@ -1116,7 +1302,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->state_dev, sizeof(TreeDevState)));
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
-  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : 1;
+  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 2 ? 2 : 1);
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 3 ? 3 : 2);
   *out = h;
@@ -1180,6 +1366,12 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
       hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
     LeafArgs dummy;
     dummy.leaf = -1; dummy.hist_slot = 0; dummy.inherit = 0; dummy.num_data = 0; dummy.sum_gradients = 0.; dummy.sum_hessians = 0.;
+    if (h->fused_scan == 2)
+      reduce_scan2_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
+                                                                    h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
+                                                                    cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                                    h->splittable, h->cand_dev, job);
+    else
     reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
                                                                  h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
                                                                  cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
@@ -1350,7 +1542,12 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       a0.sum_gradients = leaf_sg[smaller]; a0.sum_hessians = leaf_sh[smaller];
       a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? leaf_cnt_g[larger] : 0;
       a1.sum_gradients = larger >= 0 ? leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? leaf_sh[larger] : 0.;
-      if (fused)
+      if (fused && h->fused_scan == 2)
+        reduce_scan2_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, nchunks_f, Fpad, F, hess_const, h->hist,
+                                                                      (int64_t)slot_stride, h->num_bin, a0, a1, left_leaf, cfg.min_data_in_leaf,
+                                                                      cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
+                                                                      h->splittable, h->cand_dev, nullptr);
+      else if (fused)
         reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, nchunks_f, Fpad, F, hess_const, h->hist,
                                                                      (int64_t)slot_stride, h->num_bin, a0, a1, left_leaf, cfg.min_data_in_leaf,
                                                                      cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,

@@ -13,4 +13,7 @@ GPB200_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests/test_laplace_gpu.py -
 # 4. hist3_kernel (padded tile, on-demand peer gradients): parity through the variant test's cases, then timing against hist2
 GPB200_HIST_KERNEL=3 timeout 300 python -m pytest tests/test_tree_gpu.py tests/test_grouped.py -x -q -m gpu -k "not variants" 2>&1 | tail -6 > gpurun_out/u4_hist3_parity.log
 timeout 300 python scripts/bench_tree.py 1000000 hist2:GPB200_HIST_KERNEL=2 hist3:GPB200_HIST_KERNEL=3 > gpurun_out/u4_hist3_bench.log 2>&1
+# 5. reduce_scan2_kernel (one threshold per thread)
+GPB200_FUSED_SCAN=2 timeout 300 python -m pytest tests/test_tree_gpu.py tests/test_grouped.py -x -q -m gpu -k "not variants" 2>&1 | tail -6 > gpurun_out/u5_scan2_parity.log
+timeout 300 python scripts/bench_tree.py 1000000 scan1:GPB200_FUSED_SCAN=1 scan2:GPB200_FUSED_SCAN=2 scan2_hist3:GPB200_FUSED_SCAN=2,GPB200_HIST_KERNEL=3 > gpurun_out/u5_scan2_bench.log 2>&1
 for f in gpurun_out/u*.log; do echo "== $f"; cat "$f"; done
