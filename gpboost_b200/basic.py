@@ -217,6 +217,28 @@ class GPModel(object):
         self._safe_call(self._LIB.GPB_GetLikelihoodName(self.handle, buf, ctypes.byref(n)))
         return buf.value.decode()
 
+    def predict(self, y, gp_coords_pred, cov_pars, predict_var=False, predict_response=True, vecchia_pred_type=None,
+                num_neighbors_pred=-1):
+        """Predictive mean (and variance) at new locations (GPModel.predict, basic.py:6168-6520 -> GPB_SetPredictionData,
+        GPB_PredictREModel), GP part only. Returns dict(mu, var). The B200 library does not export the prediction entries
+        yet; with `_lib` = the reference library this produces the golden vectors for them."""
+        if not hasattr(self._LIB, "GPB_PredictREModel"):
+            raise GPBoostError("GPB_PredictREModel is not exported by this library (prediction with the GP part: SURVEY §8 f1, not built yet)")
+        y = _as_1d(y, "y", self.num_data)
+        Xp = np.asfortranarray(np.asarray(gp_coords_pred, dtype=np.float64))
+        npred = Xp.shape[0]
+        cp = _as_1d(cov_pars, "cov_pars", self.num_cov_pars)
+        self._safe_call(self._LIB.GPB_SetPredictionData(
+            self.handle, ctypes.c_int32(npred), None, None, None, _dptr(Xp), None, None,
+            c_str(vecchia_pred_type) if vecchia_pred_type else None, ctypes.c_int(num_neighbors_pred), ctypes.c_double(-1.),
+            ctypes.c_int(-1), ctypes.c_int(-1)))
+        out = np.zeros(npred * (2 if predict_var else 1), dtype=np.float64)
+        self._safe_call(self._LIB.GPB_PredictREModel(
+            self.handle, _dptr(y), ctypes.c_int32(npred), _dptr(out), ctypes.c_bool(False), ctypes.c_bool(predict_var),
+            ctypes.c_bool(predict_response), ctypes.c_bool(False), ctypes.c_bool(False), ctypes.c_int(0), ctypes.c_int(0),
+            None, None, None, _dptr(Xp), None, _dptr(cp), None, ctypes.c_bool(True), None, None))
+        return {"mu": out[:npred].copy(), "var": out[npred:].copy() if predict_var else None}
+
     # ---- B200 extensions ------------------------------------------------------------------------
     def response_gradient(self, y):
         """Psi^-1 y / sigma^2 at the current covariance parameters (what the boosting objective consumes)."""
