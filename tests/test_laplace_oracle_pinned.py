@@ -142,3 +142,59 @@ def test_fit_glue_reproduces_reference_fit(idx):
     assert abs(it.value - fit["num_it"]) <= (3 if c["cov_function"] == "gaussian" else 0), (it.value, fit["num_it"])
     assert np.all(np.abs(np.exp(x) - np.array(fit["cov_pars"])) <= 5e-3 * np.array(fit["cov_pars"])), (np.exp(x), fit["cov_pars"])
     assert abs(fx.value - fit["negll"]) <= 1e-5 * abs(fit["negll"])
+
+
+@pytest.mark.parametrize("idx", [1, 4])
+def test_device_gradient_schedule_matches_reference(idx):
+    """The operator schedule of gpbdev_vecchia_laplace_grad (csrc/dev/laplace.cuh) replayed in numpy — the same sequence of
+    products with B, B^T, B_grad, B_grad^T, the same coefficient vectors c1 = -D^-1 dD, c2 = D^-1 + W, c3 = 1 + W / D^-1, the same
+    buffers and signs — on the oracle's factor, mode, probes and CG solutions: it must give the reference's gradient. (The kernels
+    themselves are checked on the GPU; this pins the algebra they are composed with.)"""
+    import scipy.sparse as sp
+    c = GOLD[idx]
+    X, y, off = data_of(c)
+    vo = ov.VecchiaOracle(X, c["m"], c["cov_function"], c["shape"], c["ordering"], c["seed"])
+    _, pt = ov.transform_cov_pars([1.0] + list(c["cov_pars"]), c["cov_function"], c["shape"])
+    fe = None if off is None else off[vo.perm]
+    res = ol.grad_negll(vo.coords, vo.nn, vo.cid, c["cov_pars"][0], pt[1], y[vo.perm], fixed_effects=fe, method="iterative")
+    st = res["_state"]
+    B, Bt, Dinv, W, p_, cfg = st["B"], st["Bt"], st["Dinv"], st["W"], st["p"], st["cfg"]
+    n = y.shape[0]; mode = res["mode"]; U = res["_AinvZ"]; Zp = res["_Zp"]
+    A_, _, dA, dD, bad = ol.factor_latent_grad(vo.coords, vo.nn, vo.cid, c["cov_pars"][0], pt[1])
+    assert bad == 0
+    nn = np.asarray(vo.nn); m = nn.shape[1]
+    rows = np.repeat(np.arange(n), m); mask = nn.ravel() >= 0
+    MA = sp.csr_matrix((A_.ravel()[mask], (rows[mask], nn.ravel()[mask])), shape=(n, n))
+    MdA = sp.csr_matrix((dA.ravel()[mask], (rows[mask], nn.ravel()[mask])), shape=(n, n))
+    mv_B = lambda X_, Ds=None: (X_ - MA @ X_) * (Ds[:, None] if Ds is not None else 1.)   # mv_B_kernel
+    mv_Bt = lambda T_: T_ - MA.T @ T_                                                    # mv_Bt_kernel (W = nullptr)
+    mv_Bg = lambda X_: -(MdA @ X_)                                                       # mv_Bg_kernel
+    mv_Bgt_acc = lambda T_, V_: V_ - MdA.T @ T_                                          # mv_Bgt_kernel (accumulate)
+    dw = Dinv + W
+    c1 = -Dinv * dD; c2 = Dinv + W; c3 = 1. + W / Dinv
+    dWv = p_ * (1 - p_) * (1 - 2 * p_)
+    sdet = [np.sum(Dinv * dD), np.sum(Dinv / dw), np.sum(Dinv ** 2 * dD / dw)]            # grad_coef_kernel
+    Z = ol._vadu_solve(B, Bt, dw, Zp)                                                    # PI_Z
+    T = mv_B(Z)
+    ZA = U * dWv[:, None] * Z; ZP = T * dWv[:, None] * T                                 # stoch_dmode_kernel
+    ma = ZA.mean(1); mp = ZP.mean(1)
+    cc = ((ZA - ma[:, None]) * (ZP - mp[:, None])).mean(1); cv = ((ZP - mp[:, None]) ** 2).mean(1)
+    copt = np.where(cv == 0, 1., cc / np.where(cv == 0, 1., cv))
+    rhs = 0.5 * (ma + copt * (dWv / dw) - copt * mp)
+    x, _ = ol.cg_vadu(B, Bt, Dinv, W, rhs, np.zeros(n), cfg["cg_max_num_it"], cfg["cg_delta_conv"], True)
+    T1 = mv_B(Z, Dinv); V = mv_Bt(T1)                                                    # j = 0
+    zP = -(Z * V).sum(0); zA = -(U * V).sum(0)
+    tt = mv_B(mode[:, None], Dinv); v = mv_Bt(tt)[:, 0]
+    tr1 = zA.mean(); trP = zP.mean(); cq = ol._optimal_c(zA, zP, tr1, trP)
+    g0 = 0.5 * (-(mode @ v) + tr1 + n + cq * (-sdet[1]) - cq * trP) + x @ v
+    Y = mv_Bg(Z)                                                                         # j = 1
+    V = mv_Bgt_acc(T1, mv_Bt(Dinv[:, None] * Y + c1[:, None] * T1))
+    zA = (U * V).sum(0)
+    R = mv_Bgt_acc(c3[:, None] * T1, mv_Bt(c2[:, None] * Y + c1[:, None] * T1))
+    zP = (Z * R).sum(0)
+    yy = mv_Bg(mode[:, None])
+    v = mv_Bgt_acc(tt, mv_Bt(Dinv[:, None] * yy + c1[:, None] * tt))[:, 0]
+    tr1 = zA.mean(); trP = zP.mean(); cq = ol._optimal_c(zA, zP, tr1, trP)
+    g1 = (0.5 * (mode @ v + tr1 + sdet[0] + cq * (-sdet[2]) - cq * trP) - x @ v) * (-0.5 if vo.cid == 3 else -1.)
+    want = np.array(c["grad_iterative"])
+    assert np.all(np.abs(np.array([g0, g1]) - want) <= 1e-6 * np.abs(want).max()), ([g0, g1], want)
