@@ -45,6 +45,7 @@ int CopyString(const std::string& s, char* out_str, int* num_char) {
 extern "C" {
 
 const char* LGBM_GetLastError(void) { return g_last_error; }
+__attribute__((visibility("default"))) void GPB200_SetLastErrorMessage(const char* msg) { SetLastError(msg); }  // for c_api_scope.cpp
 
 int GPB_CreateREModel(int32_t num_data, const int32_t* cluster_ids_data, const char* re_group_data, int32_t num_re_group,
                       const double* re_group_rand_coef_data, const int32_t* ind_effect_group_rand_coef,

@@ -14,6 +14,7 @@
 #ifndef GPBOOST_B200_C_API_H_
 #define GPBOOST_B200_C_API_H_
 #include <stdbool.h>
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -143,6 +144,140 @@ GPB200_EXPORT int GPB200_EvalLaplaceGradient(REModelHandle handle, const double*
                                              const double* fixed_effects, double* negll, double* grad2);
 /* the device engine behind a handle (gpbdev_vecchia_t; include/gpboost_b200_dev.h) — bench.py device-only timing */
 GPB200_EXPORT int GPB200_GetDeviceEngine(REModelHandle handle, void** out);
+
+
+/* ---- Entries of the reference's API outside the hot path --------------------------------------------------
+ * Every GPB_* of include/LightGBM/c_api.h and every LGBM_* that python-package/gpboost/basic.py binds is exported with the
+ * reference's exact signature, so that the reference's bindings load against this library and an unsupported call fails
+ * through the reference's own error channel (-1 + LGBM_GetLastError) instead of a missing symbol. A few have a definite
+ * answer for the models this build carries (no auxiliary likelihood parameters, one model per iteration, the Laplace
+ * iteration counts); the others return -1 with a message naming the entry. Line numbers: include/LightGBM/c_api.h. */
+/* c_api.h:1523 */
+GPB200_EXPORT int GPB_CanCalculateStandardErrorsAuxPars(REModelHandle handle, int* out);
+/* c_api.h:1804 */
+GPB200_EXPORT int GPB_GetAuxPars(REModelHandle handle, double* aux_pars, char* out_str, bool calc_std_dev);
+/* c_api.h:1719 */
+GPB200_EXPORT int GPB_GetCGPreconditionerType(REModelHandle handle, char* out_str, int* num_char);
+/* c_api.h:1556 */
+GPB200_EXPORT int GPB_GetCoef(REModelHandle handle, double* optim_coef, bool calc_std_dev);
+/* c_api.h:1774 */
+GPB200_EXPORT int GPB_GetCovariateData(REModelHandle handle, double* covariate_data);
+/* c_api.h:1824 */
+GPB200_EXPORT int GPB_GetInitAuxPars(REModelHandle handle, double* aux_pars);
+/* c_api.h:1815 */
+GPB200_EXPORT int GPB_GetNumAuxPars(BoosterHandle handle, int* num_aux_pars);
+/* c_api.h:1729 */
+GPB200_EXPORT int GPB_GetNumCGSteps(BoosterHandle handle, int* num_cg_steps);
+/* c_api.h:1738 */
+GPB200_EXPORT int GPB_GetNumCGStepsTridiag(BoosterHandle handle, int* num_cg_steps);
+/* c_api.h:1747 */
+GPB200_EXPORT int GPB_GetNumModeFindingSteps(BoosterHandle handle, int* num_cg_steps);
+/* c_api.h:1783 */
+GPB200_EXPORT int GPB_GetOffsetData(REModelHandle handle, double* fixed_effects);
+/* c_api.h:1708 */
+GPB200_EXPORT int GPB_GetOptimizerCoef(REModelHandle handle, char* out_str, int* num_char);
+/* c_api.h:1765 */
+GPB200_EXPORT int GPB_GetResponseData(REModelHandle handle, double* response_data);
+/* c_api.h:1490 */
+GPB200_EXPORT int GPB_OptimLinRegrCoefCovPar(REModelHandle handle, const double* y_data, const double* covariate_data, int num_covariates, const double* fixed_effects);
+/* c_api.h:1640 */
+GPB200_EXPORT int GPB_PredictREModel(REModelHandle handle, const double* y_data, int32_t num_data_pred, double* out_predict, bool predict_cov_mat, bool predict_var, bool predict_response, bool sample_posterior, bool sample_prior, int num_post_samples, int num_prior_samples, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred, const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred, const double* cov_pars, const double* covariate_data_pred, bool use_saved_data, const double* fixed_effects, const double* fixed_effects_pred);
+/* c_api.h:1672 */
+GPB200_EXPORT int GPB_PredictREModelTrainingDataRandomEffects(REModelHandle handle, const double* cov_pars_pred, const double* y_obs, double* out_predict, const double* fixed_effects, bool calc_var);
+/* c_api.h:1756 */
+GPB200_EXPORT int GPB_SetLikelihood(REModelHandle handle, const char* likelihood);
+/* c_api.h:1792 */
+GPB200_EXPORT int GPB_SetOffsetData(REModelHandle handle, const double* fixed_effects);
+/* c_api.h:1597 */
+GPB200_EXPORT int GPB_SetPredictionData(REModelHandle handle, int32_t num_data_pred, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred, const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred, const double* covariate_data_pred, const char* vecchia_pred_type, int num_neighbors_pred, double cg_delta_conv_pred, int nsim_var_pred, int rank_pred_approx_matrix_lanczos);
+/* c_api.h:497 */
+GPB200_EXPORT int LGBM_BoosterAddValidData(BoosterHandle handle, const DatasetHandle valid_data);
+/* c_api.h:735 */
+GPB200_EXPORT int LGBM_BoosterCalcNumPredict(BoosterHandle handle, int num_row, int predict_type, int start_iteration, int num_iteration, int64_t* out_len);
+/* c_api.h:449 */
+GPB200_EXPORT int LGBM_BoosterCreateFromModelfile(const char* filename, int* out_num_iterations, BoosterHandle* out);
+/* c_api.h:1219 */
+GPB200_EXPORT int LGBM_BoosterDumpModel(BoosterHandle handle, int start_iteration, int num_iteration, int feature_importance_type, int64_t buffer_len, int64_t* out_len, char* out_str);
+/* c_api.h:1263 */
+GPB200_EXPORT int LGBM_BoosterFeatureImportance(BoosterHandle handle, int num_iteration, int importance_type, double* out_results);
+/* c_api.h:850 */
+GPB200_EXPORT int LGBM_BoosterFreePredictSparse(void* indptr, int32_t* indices, void* data, int indptr_type, int data_type);
+/* c_api.h:664 */
+GPB200_EXPORT int LGBM_BoosterGetEval(BoosterHandle handle, int data_idx, int* out_len, double* out_results);
+/* c_api.h:603 */
+GPB200_EXPORT int LGBM_BoosterGetEvalCounts(BoosterHandle handle, int* out_len);
+/* c_api.h:618 */
+GPB200_EXPORT int LGBM_BoosterGetEvalNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs);
+/* c_api.h:637 */
+GPB200_EXPORT int LGBM_BoosterGetFeatureNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs);
+/* c_api.h:1235 */
+GPB200_EXPORT int LGBM_BoosterGetLeafValue(BoosterHandle handle, int tree_idx, int leaf_idx, double* out_val);
+/* c_api.h:416 */
+GPB200_EXPORT int LGBM_BoosterGetLinear(BoosterHandle handle, bool* out);
+/* c_api.h:1283 */
+GPB200_EXPORT int LGBM_BoosterGetLowerBoundValue(BoosterHandle handle, double* out_results);
+/* c_api.h:524 */
+GPB200_EXPORT int LGBM_BoosterGetNumClasses(BoosterHandle handle, int* out_len);
+/* c_api.h:650 */
+GPB200_EXPORT int LGBM_BoosterGetNumFeature(BoosterHandle handle, int* out_len);
+/* c_api.h:1274 */
+GPB200_EXPORT int LGBM_BoosterGetUpperBoundValue(BoosterHandle handle, double* out_results);
+/* c_api.h:460 */
+GPB200_EXPORT int LGBM_BoosterLoadModelFromString(const char* model_str, int* out_num_iterations, BoosterHandle* out);
+/* c_api.h:488 */
+GPB200_EXPORT int LGBM_BoosterMerge(BoosterHandle handle, BoosterHandle other_handle);
+/* c_api.h:585 */
+GPB200_EXPORT int LGBM_BoosterNumModelPerIteration(BoosterHandle handle, int* out_tree_per_iteration);
+/* c_api.h:994 */
+GPB200_EXPORT int LGBM_BoosterPredictForCSC(BoosterHandle handle, const void* col_ptr, int col_ptr_type, const int32_t* indices, const void* data, int data_type, int64_t ncol_ptr, int64_t nelem, int64_t num_row, int predict_type, int start_iteration, int num_iteration, const char* parameter, int64_t* out_len, double* out_result);
+/* c_api.h:778 */
+GPB200_EXPORT int LGBM_BoosterPredictForCSR(BoosterHandle handle, const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type, int64_t nindptr, int64_t nelem, int64_t num_col, int predict_type, int start_iteration, int num_iteration, const char* parameter, int64_t* out_len, double* out_result);
+/* c_api.h:712 */
+GPB200_EXPORT int LGBM_BoosterPredictForFile(BoosterHandle handle, const char* data_filename, int data_has_header, int predict_type, int start_iteration, int num_iteration, const char* parameter, const char* result_filename);
+/* c_api.h:822 */
+GPB200_EXPORT int LGBM_BoosterPredictSparseOutput(BoosterHandle handle, const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type, int64_t nindptr, int64_t nelem, int64_t num_col_or_row, int predict_type, int start_iteration, int num_iteration, const char* parameter, int matrix_type, int64_t* out_len, void** out_indptr, int32_t** out_indices, void** out_data);
+/* c_api.h:544 */
+GPB200_EXPORT int LGBM_BoosterRefit(BoosterHandle handle, const int32_t* leaf_preds, int32_t nrow, int32_t ncol);
+/* c_api.h:515 */
+GPB200_EXPORT int LGBM_BoosterResetParameter(BoosterHandle handle, const char* parameters);
+/* c_api.h:506 */
+GPB200_EXPORT int LGBM_BoosterResetTrainingData(BoosterHandle handle, const DatasetHandle train_data);
+/* c_api.h:568 */
+GPB200_EXPORT int LGBM_BoosterRollbackOneIter(BoosterHandle handle);
+/* c_api.h:1183 */
+GPB200_EXPORT int LGBM_BoosterSaveModel(BoosterHandle handle, int start_iteration, int num_iteration, int feature_importance_type, const char* filename);
+/* c_api.h:478 */
+GPB200_EXPORT int LGBM_BoosterShuffleModels(BoosterHandle handle, int start_iter, int end_iter);
+/* c_api.h:558 */
+GPB200_EXPORT int LGBM_BoosterUpdateOneIterCustom(BoosterHandle handle, const float* grad, const float* hess, int* is_finished);
+/* c_api.h:405 */
+GPB200_EXPORT int LGBM_DatasetAddFeaturesFrom(DatasetHandle target, DatasetHandle source);
+/* c_api.h:212 */
+GPB200_EXPORT int LGBM_DatasetCreateFromCSC(const void* col_ptr, int col_ptr_type, const int32_t* indices, const void* data, int data_type, int64_t ncol_ptr, int64_t nelem, int64_t num_row, const char* parameters, const DatasetHandle reference, DatasetHandle* out);
+/* c_api.h:167 */
+GPB200_EXPORT int LGBM_DatasetCreateFromCSR(const void* indptr, int indptr_type, const int32_t* indices, const void* data, int data_type, int64_t nindptr, int64_t nelem, int64_t num_col, const char* parameters, const DatasetHandle reference, DatasetHandle* out);
+/* c_api.h:73 */
+GPB200_EXPORT int LGBM_DatasetCreateFromFile(const char* filename, const char* parameters, const DatasetHandle reference, DatasetHandle* out);
+/* c_api.h:258 */
+GPB200_EXPORT int LGBM_DatasetCreateFromMats(int32_t nmat, const void** data, int data_type, int32_t* nrow, int32_t ncol, int is_row_major, const char* parameters, const DatasetHandle reference, DatasetHandle* out);
+/* c_api.h:335 */
+GPB200_EXPORT int LGBM_DatasetDumpText(DatasetHandle handle, const char* filename);
+/* c_api.h:306 */
+GPB200_EXPORT int LGBM_DatasetGetFeatureNames(DatasetHandle handle, const int len, int* num_feature_names, const size_t buffer_len, size_t* out_buffer_len, char** feature_names);
+/* c_api.h:366 */
+GPB200_EXPORT int LGBM_DatasetGetField(DatasetHandle handle, const char* field_name, int* out_len, const void** out_ptr, int* out_type);
+/* c_api.h:277 */
+GPB200_EXPORT int LGBM_DatasetGetSubset(const DatasetHandle handle, const int32_t* used_row_indices, int32_t num_used_row_indices, const char* parameters, DatasetHandle* out);
+/* c_api.h:326 */
+GPB200_EXPORT int LGBM_DatasetSaveBinary(DatasetHandle handle, const char* filename);
+/* c_api.h:290 */
+GPB200_EXPORT int LGBM_DatasetSetFeatureNames(DatasetHandle handle, const char** feature_names, int num_feature_names);
+/* c_api.h:378 */
+GPB200_EXPORT int LGBM_DatasetUpdateParamChecking(const char* old_parameters, const char* new_parameters);
+/* c_api.h:1303 */
+GPB200_EXPORT int LGBM_NetworkFree();
+/* c_api.h:1294 */
+GPB200_EXPORT int LGBM_NetworkInit(const char* machines, int local_listen_port, int listen_time_out, int num_machines);
 
 #ifdef __cplusplus
 }
