@@ -47,6 +47,9 @@ class Booster {
  private:
   void Boosting();  // gradients for the next tree (+ covariance-parameter fit when a GP model is attached)
   const Dataset* train_;
+ public:
+  const Dataset* train_data() const { return train_; }
+ private:
   REModel* re_model_;
   Params params_;
   int64_t n_ = 0;

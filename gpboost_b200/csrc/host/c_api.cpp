@@ -2,10 +2,12 @@
 // like the reference's API_BEGIN/API_END (src/LightGBM/c_api.cpp:45-59).
 #include "../../../include/gpboost_b200_c_api.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <exception>
 #include <string>
+#include <vector>
 
 #include "booster.h"
 #include "collective.h"
@@ -45,6 +47,10 @@ int CopyString(const std::string& s, char* out_str, int* num_char) {
 extern "C" {
 
 const char* LGBM_GetLastError(void) { return g_last_error; }
+// c_api.h:61 — the bindings register their logger at load time; this build logs nothing on its own (verbose output of the
+// reference's Log:: is not part of the hot path), the callback is kept for messages raised through it
+static void (*g_log_callback)(const char*) = nullptr;
+int LGBM_RegisterLogCallback(void (*callback)(const char*)) { g_log_callback = callback; return 0; }
 __attribute__((visibility("default"))) void GPB200_SetLastErrorMessage(const char* msg) { SetLastError(msg); }  // for c_api_scope.cpp
 
 int GPB_CreateREModel(int32_t num_data, const int32_t* cluster_ids_data, const char* re_group_data, int32_t num_re_group,
@@ -267,6 +273,105 @@ int LGBM_BoosterSaveModelToString(BoosterHandle handle, int /*start_iteration*/,
   const std::string s = B(handle)->SaveModelToString();
   *out_len = (int64_t)s.size() + 1;
   if (*out_len <= buffer_len) std::memcpy(out_str, s.c_str(), *out_len);
+  API_END();
+}
+
+// ---- host-side entries the reference's Python package calls around the hot path (Dataset.construct, Booster.__init__,
+// Booster.save_model, Booster.predict): python-package/gpboost/basic.py:1816-1836, 2373-2400, 3300-3345, 3530-3560
+int LGBM_DatasetGetField(DatasetHandle handle, const char* field_name, int* out_len, const void** out_ptr, int* out_type) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  auto* ds = reinterpret_cast<gpb200::Dataset*>(handle);
+  const std::string f(field_name);
+  *out_len = 0; *out_ptr = nullptr;
+  if (f == "label" || f == "target") {  // Metadata::label(), float32
+    *out_type = C_API_DTYPE_FLOAT32;
+    if (ds->has_label()) { *out_len = (int)ds->label().size(); *out_ptr = ds->label().data(); }
+  } else if (f == "weight" || f == "weights") {
+    *out_type = C_API_DTYPE_FLOAT32;  // none set
+  } else if (f == "init_score") {
+    *out_type = 1;  // C_API_DTYPE_FLOAT64
+  } else if (f == "group" || f == "query") {
+    *out_type = 2;  // C_API_DTYPE_INT32
+  } else {
+    throw std::runtime_error("Field not found: " + f);
+  }
+  API_END();
+}
+
+int LGBM_DatasetSetFeatureNames(DatasetHandle handle, const char** feature_names, int num_feature_names) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  auto* ds = reinterpret_cast<gpb200::Dataset*>(handle);
+  if (num_feature_names != ds->num_total_features()) throw std::runtime_error("Size of feature_names error");
+  std::vector<std::string> names;
+  for (int i = 0; i < num_feature_names; ++i) names.emplace_back(feature_names[i]);
+  ds->set_feature_names(names);
+  API_END();
+}
+
+namespace {
+std::vector<std::string> FeatureNamesOf(const gpb200::Dataset* ds) {
+  std::vector<std::string> names = ds->feature_names();
+  if (names.empty())
+    for (int i = 0; i < ds->num_total_features(); ++i) names.push_back("Column_" + std::to_string(i));
+  return names;
+}
+void CopyNames(const std::vector<std::string>& names, int len, int* out_len, size_t buffer_len, size_t* out_buffer_len, char** out_strs) {
+  *out_len = (int)names.size();
+  *out_buffer_len = 0;
+  for (size_t i = 0; i < names.size(); ++i) {
+    if ((int)i < len) {
+      std::memcpy(out_strs[i], names[i].c_str(), std::min(names[i].size() + 1, buffer_len));
+      out_strs[i][buffer_len - 1] = '\0';
+    }
+    *out_buffer_len = std::max(names[i].size() + 1, *out_buffer_len);
+  }
+}
+}  // namespace
+
+int LGBM_DatasetGetFeatureNames(DatasetHandle handle, const int len, int* num_feature_names, const size_t buffer_len, size_t* out_buffer_len,
+                                char** feature_names) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  CopyNames(FeatureNamesOf(reinterpret_cast<gpb200::Dataset*>(handle)), len, num_feature_names, buffer_len, out_buffer_len, feature_names);
+  API_END();
+}
+
+int LGBM_BoosterGetFeatureNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs) {
+  API_BEGIN();
+  CopyNames(FeatureNamesOf(B(handle)->train_data()), len, out_len, buffer_len, out_buffer_len, out_strs);
+  API_END();
+}
+
+int LGBM_BoosterGetNumFeature(BoosterHandle handle, int* out_len) {
+  API_BEGIN();
+  *out_len = B(handle)->train_data()->num_total_features();
+  API_END();
+}
+
+int LGBM_BoosterCalcNumPredict(BoosterHandle handle, int num_row, int predict_type, int /*start_iteration*/, int /*num_iteration*/, int64_t* out_len) {
+  API_BEGIN();
+  B(handle);
+  if (predict_type != 0 && predict_type != 1) throw std::runtime_error("Only normal and raw-score predictions are supported by the B200 booster");
+  *out_len = num_row;  // one value per row (regression, one model per iteration)
+  API_END();
+}
+
+int LGBM_BoosterGetEvalNames(BoosterHandle handle, const int /*len*/, int* out_len, const size_t /*buffer_len*/, size_t* out_buffer_len, char** /*out_strs*/) {
+  API_BEGIN();
+  B(handle);
+  *out_len = 0; *out_buffer_len = 0;  // no metric is evaluated by the B200 booster
+  API_END();
+}
+
+int LGBM_BoosterSaveModel(BoosterHandle handle, int /*start_iteration*/, int /*num_iteration*/, int /*feature_importance_type*/, const char* filename) {
+  API_BEGIN();
+  const std::string s = B(handle)->SaveModelToString();
+  FILE* f = std::fopen(filename, "wb");
+  if (f == nullptr) throw std::runtime_error(std::string("Model file ") + filename + " is not available for writes");
+  std::fwrite(s.data(), 1, s.size(), f);
+  std::fclose(f);
   API_END();
 }
 

@@ -165,13 +165,6 @@ int LGBM_BoosterAddValidData(BoosterHandle handle, const DatasetHandle valid_dat
   API_END();
 }
 
-int LGBM_BoosterCalcNumPredict(BoosterHandle handle, int num_row, int predict_type, int start_iteration, int num_iteration, int64_t* out_len) {
-  API_BEGIN();
-  (void)handle; (void)num_row; (void)predict_type; (void)start_iteration; (void)num_iteration; (void)out_len;
-  Unsupported("LGBM_BoosterCalcNumPredict");
-  API_END();
-}
-
 int LGBM_BoosterCreateFromModelfile(const char* filename, int* out_num_iterations, BoosterHandle* out) {
   API_BEGIN();
   (void)filename; (void)out_num_iterations; (void)out;
@@ -213,20 +206,6 @@ int LGBM_BoosterGetEvalCounts(BoosterHandle handle, int* out_len) {
   API_END();
 }
 
-int LGBM_BoosterGetEvalNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs) {
-  API_BEGIN();
-  (void)handle; (void)len; (void)out_len; (void)buffer_len; (void)out_buffer_len; (void)out_strs;
-  Unsupported("LGBM_BoosterGetEvalNames");
-  API_END();
-}
-
-int LGBM_BoosterGetFeatureNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs) {
-  API_BEGIN();
-  (void)handle; (void)len; (void)out_len; (void)buffer_len; (void)out_buffer_len; (void)out_strs;
-  Unsupported("LGBM_BoosterGetFeatureNames");
-  API_END();
-}
-
 int LGBM_BoosterGetLeafValue(BoosterHandle handle, int tree_idx, int leaf_idx, double* out_val) {
   API_BEGIN();
   (void)handle; (void)tree_idx; (void)leaf_idx; (void)out_val;
@@ -251,13 +230,6 @@ int LGBM_BoosterGetLowerBoundValue(BoosterHandle handle, double* out_results) {
 int LGBM_BoosterGetNumClasses(BoosterHandle handle, int* out_len) {
   API_BEGIN();
   (void)handle; *out_len = 1;
-  API_END();
-}
-
-int LGBM_BoosterGetNumFeature(BoosterHandle handle, int* out_len) {
-  API_BEGIN();
-  (void)handle; (void)out_len;
-  Unsupported("LGBM_BoosterGetNumFeature");
   API_END();
 }
 
@@ -344,13 +316,6 @@ int LGBM_BoosterRollbackOneIter(BoosterHandle handle) {
   API_END();
 }
 
-int LGBM_BoosterSaveModel(BoosterHandle handle, int start_iteration, int num_iteration, int feature_importance_type, const char* filename) {
-  API_BEGIN();
-  (void)handle; (void)start_iteration; (void)num_iteration; (void)feature_importance_type; (void)filename;
-  Unsupported("LGBM_BoosterSaveModel");
-  API_END();
-}
-
 int LGBM_BoosterShuffleModels(BoosterHandle handle, int start_iter, int end_iter) {
   API_BEGIN();
   (void)handle; (void)start_iter; (void)end_iter;
@@ -407,20 +372,6 @@ int LGBM_DatasetDumpText(DatasetHandle handle, const char* filename) {
   API_END();
 }
 
-int LGBM_DatasetGetFeatureNames(DatasetHandle handle, const int len, int* num_feature_names, const size_t buffer_len, size_t* out_buffer_len, char** feature_names) {
-  API_BEGIN();
-  (void)handle; (void)len; (void)num_feature_names; (void)buffer_len; (void)out_buffer_len; (void)feature_names;
-  Unsupported("LGBM_DatasetGetFeatureNames");
-  API_END();
-}
-
-int LGBM_DatasetGetField(DatasetHandle handle, const char* field_name, int* out_len, const void** out_ptr, int* out_type) {
-  API_BEGIN();
-  (void)handle; (void)field_name; (void)out_len; (void)out_ptr; (void)out_type;
-  Unsupported("LGBM_DatasetGetField");
-  API_END();
-}
-
 int LGBM_DatasetGetSubset(const DatasetHandle handle, const int32_t* used_row_indices, int32_t num_used_row_indices, const char* parameters, DatasetHandle* out) {
   API_BEGIN();
   (void)handle; (void)used_row_indices; (void)num_used_row_indices; (void)parameters; (void)out;
@@ -432,13 +383,6 @@ int LGBM_DatasetSaveBinary(DatasetHandle handle, const char* filename) {
   API_BEGIN();
   (void)handle; (void)filename;
   Unsupported("LGBM_DatasetSaveBinary");
-  API_END();
-}
-
-int LGBM_DatasetSetFeatureNames(DatasetHandle handle, const char** feature_names, int num_feature_names) {
-  API_BEGIN();
-  (void)handle; (void)feature_names; (void)num_feature_names;
-  Unsupported("LGBM_DatasetSetFeatureNames");
   API_END();
 }
 

@@ -51,6 +51,9 @@ class Dataset {
   const std::vector<float>& label() const { return label_; }
   bool has_label() const { return !label_.empty(); }
   const Params& params() const { return params_; }
+  // feature names (Dataset::set_feature_names / feature_names, include/LightGBM/dataset.h): default "Column_<i>"
+  const std::vector<std::string>& feature_names() const { return feature_names_; }
+  void set_feature_names(const std::vector<std::string>& names) { feature_names_ = names; }
 
  private:
   int32_t num_data_ = 0;
@@ -60,6 +63,7 @@ class Dataset {
   std::vector<int> used_features_;     // inner -> real
   std::vector<uint8_t> bin_data_;
   std::vector<float> label_;
+  std::vector<std::string> feature_names_;
 };
 
 }  // namespace gpb200

@@ -25,6 +25,8 @@ typedef void* REModelHandle;  /* c_api.h:37 */
 
 /* c_api.h:54 */
 GPB200_EXPORT const char* LGBM_GetLastError(void);
+/* c_api.h:61 — called by the bindings when they load the library */
+GPB200_EXPORT int LGBM_RegisterLogCallback(void (*callback)(const char*));
 
 /* c_api.h:1359-1391 — creates the device-resident model: Vecchia ordering (std::shuffle with mt19937(seed)),
  * device neighbour search, coordinates/neighbours uploaded once. */
