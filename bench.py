@@ -108,6 +108,26 @@ def time_reference(n, steps, warmup, threads):
     return {"sec_per_eval": dt, "negll": v, "create_s": t_create}
 
 
+def time_dense(n, lib, threads, reps=5):
+    """BASELINE configs[0]: exact GP (gp_approx="none"), n = 2000, 2-D Matern-1.5: one GPB_EvalNegLogLikelihood = Gram build +
+    dense Cholesky + solves; and one GPB_OptimCovPar (fit)."""
+    from gpboost_b200 import GPModel
+    rng = np.random.default_rng(1)
+    coords = rng.random((n, 2))
+    y = np.sin(5 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.5 * rng.standard_normal(n)
+    mdl = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="none", num_parallel_threads=threads, _lib=lib)
+    cp = np.array([0.25, 1.0, 0.1])
+    v = mdl.neg_log_likelihood(cp, y)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        v = mdl.neg_log_likelihood(cp, y)
+    dt = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    mdl.fit(y)
+    t_fit = time.perf_counter() - t0
+    return {"sec_per_eval": dt, "negll": v, "fit_s": t_fit, "fit_iters": mdl._get_num_optim_iter(), "fit_cov_pars": mdl.get_cov_pars().tolist()}
+
+
 def time_gpboost(n, iters, lib, threads, F=50):
     """One GPBoost iteration = LGBM_BoosterUpdateOneIter with a Vecchia GP (m=30) attached: covariance re-fit (L-BFGS) +
     Psi^-1(F - y) + one 31-leaf tree on n x 50 features (BASELINE configs[3] shape on one GPU, metric (i) of SURVEY §8d)."""
@@ -215,6 +235,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--boost-n", type=int, default=1000000, help="n of the GPBoost-iteration measurement (0 = skip)")
     ap.add_argument("--boost-ref-n", type=int, default=0, help="--impl reference: also time GPBoost iterations at this n (slow)")
+    ap.add_argument("--dense-n", type=int, default=2000, help="n of the exact-GP measurement (BASELINE configs[0]; 0 = skip; --impl reference times it too)")
     ap.add_argument("--laplace-n", type=int, default=100000, help="n of the Laplace-Vecchia (bernoulli_logit) measurement (0 = skip)")
     ap.add_argument("--laplace-ref-n", type=int, default=0, help="--impl reference: also time one Laplace-Vecchia evaluation at this n (slow)")
     args = ap.parse_args()
@@ -253,6 +274,11 @@ def main():
             gb = time_gpboost(args.boost_ref_n, 1, load_lib(ref_lib_path()), ncores)
             line["gpboost"] = {"iters_per_sec": 1.0 / gb["sec_per_iter"], "n": args.boost_ref_n, "first_iter_s": gb["first_iter_s"],
                                "note": "GPBoost Vecchia m=30 + 31-leaf trees on n x 50; sub-problem of n=%d, not scaled" % args.boost_ref_n}
+        if args.dense_n > 0:
+            from gpboost_b200.libpath import load_lib
+            from oracle import ref_lib_path
+            dr = time_dense(args.dense_n, load_lib(ref_lib_path()), ncores, reps=2)
+            line["dense"] = {"evals_per_sec": 1.0 / dr["sec_per_eval"], "n": args.dense_n, **dr}
         if args.laplace_ref_n > 0:
             from gpboost_b200.libpath import load_lib
             from oracle import ref_lib_path
@@ -350,6 +376,12 @@ def main():
     if args.boost_n > 0:
         gb = time_gpboost(args.boost_n, 5, None, ncores)
 
+    dense_res = None
+    if args.dense_n > 0 and world == 1:
+        try:
+            dense_res = time_dense(args.dense_n, None, ncores)
+        except Exception as e:
+            sys.stderr.write("dense measurement failed: %r\n" % (e,))
     gg = None
     if args.boost_n > 0 and world == 1:
         try:
@@ -396,6 +428,9 @@ def main():
                                "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
                                "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "
                                        "parameters re-fitted every iteration (BASELINE metric (i)); host buffers, end to end"}
+        if dense_res is not None:
+            line["dense"] = {"evals_per_sec": 1.0 / dense_res["sec_per_eval"], "n": args.dense_n, **dense_res,
+                             "note": "GPB_EvalNegLogLikelihood / GPB_OptimCovPar, exact GP n x n dense Cholesky on the device (BASELINE configs[0])"}
         if gg is not None:
             line["gpboost_grouped"] = {"iters_per_sec": 1.0 / gg["grouped"]["sec_per_iter"], "ms_per_iter": gg["grouped"]["sec_per_iter"] * 1e3,
                                        "trees_only_ms_per_iter": gg["trees_only"]["sec_per_iter"] * 1e3, "n": args.boost_n,
