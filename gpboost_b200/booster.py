@@ -52,10 +52,17 @@ class Dataset(object):
 
 
 class Booster(object):
-    def __init__(self, params, train_set, gp_model=None, _lib=None):
+    def __init__(self, params=None, train_set=None, gp_model=None, model_str=None, model_file=None, _lib=None):
         self._LIB = load_lib() if _lib is None else _lib
         self.train_set, self.gp_model = train_set, gp_model
         self.handle = ctypes.c_void_p()
+        if model_str is not None or model_file is not None:  # prediction-only booster (Booster(model_file=...), basic.py:2404-2425)
+            n_it = ctypes.c_int(0)
+            if model_str is not None:
+                self._safe_call(self._LIB.LGBM_BoosterLoadModelFromString(c_str(model_str), ctypes.byref(n_it), ctypes.byref(self.handle)))
+            else:
+                self._safe_call(self._LIB.LGBM_BoosterCreateFromModelfile(c_str(model_file), ctypes.byref(n_it), ctypes.byref(self.handle)))
+            return
         params = dict(params or {})
         if gp_model is not None:
             params["has_gp_model"] = True
@@ -91,6 +98,10 @@ class Booster(object):
             self._safe_call(self._LIB.LGBM_BoosterSaveModelToString(self.handle, ctypes.c_int(0), ctypes.c_int(-1), ctypes.c_int(0),
                                                                     ctypes.c_int64(buf_len), ctypes.byref(n), buf))
         return buf.value.decode("utf-8")
+
+    def save_model(self, filename):
+        self._safe_call(self._LIB.LGBM_BoosterSaveModel(self.handle, ctypes.c_int(0), ctypes.c_int(-1), ctypes.c_int(0), c_str(filename)))
+        return self
 
     def inner_predict_train(self):
         """Raw training scores F (Booster.__inner_predict(0), basic.py:3964)."""

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
@@ -109,6 +110,86 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
   host_buf_.resize(n_);
   for (int64_t i = 0; i < n_; ++i) host_buf_[i] = (double)train->label()[i];  // label_t = float (meta.h:49)
   TreeCheck(gpbdev_vec_upload(learner_, label_dev_, host_buf_.data(), n_));
+  // model header: feature names and value ranges (GBDT::SaveModelToString, gbdt_model_text.cpp:330-345; BinMapper::bin_info_string)
+  max_feature_idx_ = train->num_total_features() - 1;
+  feature_names_ = train->feature_names();
+  if (feature_names_.empty())
+    for (int i = 0; i <= max_feature_idx_; ++i) feature_names_.push_back("Column_" + std::to_string(i));
+  feature_infos_ = train->feature_infos();
+}
+
+namespace {
+std::vector<std::string> SplitWs(const std::string& v) {
+  std::vector<std::string> out;
+  std::istringstream is(v);
+  std::string t;
+  while (is >> t) out.push_back(t);
+  return out;
+}
+}  // namespace
+
+Booster::Booster(const std::string& model_str) {
+  std::istringstream in(model_str);
+  std::string line;
+  std::unique_ptr<Tree> cur;
+  bool in_trees = false, seen_end = false;
+  int num_class = -1;
+  auto finish_tree = [&]() {
+    if (!cur) return;
+    const int nl = cur->num_leaves;
+    if ((int)cur->leaf_value.size() != nl) Fatal("Tree model string format error, should contain leaf_value field");
+    if (nl > 1 && ((int)cur->left_child.size() != nl - 1 || (int)cur->right_child.size() != nl - 1 || (int)cur->split_feature.size() != nl - 1 ||
+                   (int)cur->threshold.size() != nl - 1))
+      Fatal("Tree model string format error, should contain left_child, right_child, split_feature and threshold fields");
+    if ((int)cur->leaf_count.size() != nl) cur->leaf_count.assign(nl, 0);
+    if ((int)cur->split_gain.size() != std::max(nl - 1, 0)) cur->split_gain.assign(std::max(nl - 1, 0), 0.f);
+    models_.push_back(std::move(cur));
+  };
+  while (std::getline(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.rfind("Tree=", 0) == 0) { finish_tree(); cur.reset(new Tree()); in_trees = true; continue; }
+    if (line.rfind("end of trees", 0) == 0) { finish_tree(); seen_end = true; break; }
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+    if (!in_trees) {
+      if (k == "num_class") num_class = std::atoi(v.c_str());
+      else if (k == "num_tree_per_iteration") { if (std::atoi(v.c_str()) != 1) Fatal("Only one tree per iteration is supported by the B200 booster"); }
+      else if (k == "max_feature_idx") max_feature_idx_ = std::atoi(v.c_str());
+      else if (k == "feature_names") feature_names_ = SplitWs(v);
+      else if (k == "feature_infos") feature_infos_ = SplitWs(v);
+      else if (k == "objective") {
+        const std::string obj = SplitWs(v).empty() ? std::string() : SplitWs(v)[0];
+        if (obj != "regression" && obj != "regression_l2" && obj != "l2" && obj != "mean_squared_error" && obj != "mse")
+          Fatal("Objective '" + obj + "' is not supported by the B200 booster (hot path: 'regression')");
+      }
+      continue;
+    }
+    Tree& t = *cur;
+    auto ints = [&](std::vector<int>* dst) { dst->clear(); for (const auto& w : SplitWs(v)) dst->push_back(std::atoi(w.c_str())); };
+    auto dbls = [&](std::vector<double>* dst) { dst->clear(); for (const auto& w : SplitWs(v)) dst->push_back(std::strtod(w.c_str(), nullptr)); };
+    if (k == "num_leaves") t.num_leaves = std::atoi(v.c_str());
+    else if (k == "num_cat") { if (std::atoi(v.c_str()) != 0) Fatal("Categorical splits are not supported by the B200 booster"); }
+    else if (k == "split_feature") ints(&t.split_feature);
+    else if (k == "threshold") dbls(&t.threshold);
+    else if (k == "left_child") ints(&t.left_child);
+    else if (k == "right_child") ints(&t.right_child);
+    else if (k == "leaf_value") dbls(&t.leaf_value);
+    else if (k == "leaf_count") ints(&t.leaf_count);
+    else if (k == "split_gain") { t.split_gain.clear(); for (const auto& w : SplitWs(v)) t.split_gain.push_back(std::strtof(w.c_str(), nullptr)); }
+    else if (k == "shrinkage") t.shrinkage = std::strtod(v.c_str(), nullptr);
+    else if (k == "decision_type") {
+      for (const auto& w : SplitWs(v))  // 2 = numerical, default left, MissingType::None (tree.h kDefaultLeftMask); bit 0 = categorical
+        if ((std::atoi(w.c_str()) & 1) != 0) Fatal("Categorical splits are not supported by the B200 booster");
+    } else if (k == "is_linear") { if (std::atoi(v.c_str()) != 0) Fatal("Linear trees are not supported by the B200 booster"); }
+  }
+  if (num_class < 0) Fatal("Model file doesn't specify the number of classes");
+  if (num_class != 1) Fatal("Only num_class = 1 is supported by the B200 booster");
+  if (max_feature_idx_ < 0) Fatal("Model file doesn't specify max_feature_idx");
+  if ((int)feature_names_.size() != max_feature_idx_ + 1) Fatal("Model file doesn't contain feature_names");
+  if ((int)feature_infos_.size() != max_feature_idx_ + 1) Fatal("Model file doesn't contain feature_infos");
+  if (!seen_end) finish_tree();
+  iter_ = (int)models_.size();
 }
 
 Booster::~Booster() {
@@ -142,6 +223,7 @@ void Booster::Boosting() {
 }
 
 bool Booster::TrainOneIter() {
+  if (learner_ == nullptr) Fatal("This Booster was loaded from a model string / file and has no training data (prediction only)");
   double init_score = 0.;
   if (models_.empty() && boost_from_average_) {  // BoostFromAverage (gbdt.cpp:376-408): mean label for L2 (also with a Gaussian GP model)
     double suml = 0.;
@@ -188,10 +270,12 @@ bool Booster::TrainOneIter() {
   return false;
 }
 
-void Booster::GetTrainingScore(double* out) { TreeCheck(gpbdev_vec_download(learner_, out, score_dev_, n_)); }
+void Booster::GetTrainingScore(double* out) {
+  if (learner_ == nullptr) Fatal("This Booster was loaded from a model string / file and has no training data (prediction only)");
+  TreeCheck(gpbdev_vec_download(learner_, out, score_dev_, n_)); }
 
 void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const {
-  if (ncol != train_->num_total_features()) Fatal("The number of features in data is not the same as it was in training data");
+  if (ncol != max_feature_idx_ + 1) Fatal("The number of features in data is not the same as it was in training data");
   std::vector<double> row(ncol);
   for (int64_t i = 0; i < nrow; ++i) {
     for (int j = 0; j < ncol; ++j) {
@@ -206,8 +290,12 @@ void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t nco
 
 std::string Booster::SaveModelToString() const {  // GBDT::SaveModelToString (boosting/gbdt_model_text.cpp), header subset
   std::ostringstream s;
-  s << "tree\nversion=v3\nnum_class=1\nnum_tree_per_iteration=1\nlabel_index=0\nmax_feature_idx=" << train_->num_total_features() - 1
-    << "\nobjective=regression\n\n";
+  s << "tree\nversion=v3\nnum_class=1\nnum_tree_per_iteration=1\nlabel_index=0\nmax_feature_idx=" << max_feature_idx_
+    << "\nobjective=regression\nfeature_names=";
+  for (size_t i = 0; i < feature_names_.size(); ++i) s << (i ? " " : "") << feature_names_[i];
+  s << "\nfeature_infos=";
+  for (size_t i = 0; i < feature_infos_.size(); ++i) s << (i ? " " : "") << feature_infos_[i];
+  s << "\n\n";
   for (size_t i = 0; i < models_.size(); ++i) s << "Tree=" << i << "\n" << models_[i]->ToString() << "\n\n";
   s << "end of trees\n";
   return s.str();

@@ -34,7 +34,13 @@ struct Tree {
 class Booster {
  public:
   Booster(const Dataset* train, const char* parameters, REModel* re_model);
+  // prediction-only booster from a model in the reference's text format (GBDT::LoadModelFromString,
+  // src/LightGBM/boosting/gbdt_model_text.cpp:420-600; Tree::Tree(const char*), src/LightGBM/io/tree.cpp:650-780): no device needed
+  explicit Booster(const std::string& model_str);
   ~Booster();
+  bool can_train() const { return learner_ != nullptr; }
+  int max_feature_idx() const { return max_feature_idx_; }
+  const std::vector<std::string>& feature_names() const { return feature_names_; }
   bool TrainOneIter();  // returns true when training cannot continue (no split), like GBDT::TrainOneIter
   int current_iteration() const { return iter_; }
   int num_models() const { return (int)models_.size(); }
@@ -46,11 +52,11 @@ class Booster {
 
  private:
   void Boosting();  // gradients for the next tree (+ covariance-parameter fit when a GP model is attached)
-  const Dataset* train_;
+  const Dataset* train_ = nullptr;
  public:
   const Dataset* train_data() const { return train_; }
  private:
-  REModel* re_model_;
+  REModel* re_model_ = nullptr;
   Params params_;
   int64_t n_ = 0;
   int num_leaves_ = 31;
@@ -61,6 +67,8 @@ class Booster {
   double *score_dev_ = nullptr, *label_dev_ = nullptr, *grad_dev_ = nullptr;
   std::vector<double> host_buf_;
   std::vector<std::unique_ptr<Tree>> models_;
+  int max_feature_idx_ = -1;
+  std::vector<std::string> feature_names_, feature_infos_;  // model header (gbdt_model_text.cpp:330-345)
   int iter_ = 0;
   bool gradients_ready_ = false;
   // data-parallel training (native collective, world_size > 1): this rank's learner holds rows [row_begin_, row_end_) of the bins;

@@ -340,13 +340,13 @@ int LGBM_DatasetGetFeatureNames(DatasetHandle handle, const int len, int* num_fe
 
 int LGBM_BoosterGetFeatureNames(BoosterHandle handle, const int len, int* out_len, const size_t buffer_len, size_t* out_buffer_len, char** out_strs) {
   API_BEGIN();
-  CopyNames(FeatureNamesOf(B(handle)->train_data()), len, out_len, buffer_len, out_buffer_len, out_strs);
+  CopyNames(B(handle)->feature_names(), len, out_len, buffer_len, out_buffer_len, out_strs);
   API_END();
 }
 
 int LGBM_BoosterGetNumFeature(BoosterHandle handle, int* out_len) {
   API_BEGIN();
-  *out_len = B(handle)->train_data()->num_total_features();
+  *out_len = B(handle)->max_feature_idx() + 1;
   API_END();
 }
 
@@ -362,6 +362,30 @@ int LGBM_BoosterGetEvalNames(BoosterHandle handle, const int /*len*/, int* out_l
   API_BEGIN();
   B(handle);
   *out_len = 0; *out_buffer_len = 0;  // no metric is evaluated by the B200 booster
+  API_END();
+}
+
+int LGBM_BoosterLoadModelFromString(const char* model_str, int* out_num_iterations, BoosterHandle* out) {
+  API_BEGIN();
+  if (model_str == nullptr) throw std::runtime_error("Model string is null");
+  auto* b = new gpb200::Booster(std::string(model_str));
+  *out_num_iterations = b->current_iteration();
+  *out = b;
+  API_END();
+}
+
+int LGBM_BoosterCreateFromModelfile(const char* filename, int* out_num_iterations, BoosterHandle* out) {
+  API_BEGIN();
+  FILE* f = std::fopen(filename, "rb");
+  if (f == nullptr) throw std::runtime_error(std::string("Model file ") + filename + " is not available for reads");
+  std::string s;
+  char buf[65536];
+  size_t k;
+  while ((k = std::fread(buf, 1, sizeof(buf), f)) > 0) s.append(buf, k);
+  std::fclose(f);
+  auto* b = new gpb200::Booster(s);
+  *out_num_iterations = b->current_iteration();
+  *out = b;
   API_END();
 }
 

@@ -165,13 +165,6 @@ int LGBM_BoosterAddValidData(BoosterHandle handle, const DatasetHandle valid_dat
   API_END();
 }
 
-int LGBM_BoosterCreateFromModelfile(const char* filename, int* out_num_iterations, BoosterHandle* out) {
-  API_BEGIN();
-  (void)filename; (void)out_num_iterations; (void)out;
-  Unsupported("LGBM_BoosterCreateFromModelfile");
-  API_END();
-}
-
 int LGBM_BoosterDumpModel(BoosterHandle handle, int start_iteration, int num_iteration, int feature_importance_type, int64_t buffer_len, int64_t* out_len, char* out_str) {
   API_BEGIN();
   (void)handle; (void)start_iteration; (void)num_iteration; (void)feature_importance_type; (void)buffer_len; (void)out_len; (void)out_str;
@@ -237,13 +230,6 @@ int LGBM_BoosterGetUpperBoundValue(BoosterHandle handle, double* out_results) {
   API_BEGIN();
   (void)handle; (void)out_results;
   Unsupported("LGBM_BoosterGetUpperBoundValue");
-  API_END();
-}
-
-int LGBM_BoosterLoadModelFromString(const char* model_str, int* out_num_iterations, BoosterHandle* out) {
-  API_BEGIN();
-  (void)model_str; (void)out_num_iterations; (void)out;
-  Unsupported("LGBM_BoosterLoadModelFromString");
   API_END();
 }
 

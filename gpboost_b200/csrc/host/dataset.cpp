@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <limits>
 #include <set>
 #include <sstream>
@@ -315,6 +316,18 @@ Dataset::Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, in
 void Dataset::SetLabel(const float* label, int n) {
   if (n != num_data_) Fatal("Length of label is not same with #data");
   label_.assign(label, label + n);
+}
+
+std::vector<std::string> Dataset::feature_infos() const {
+  std::vector<std::string> out;
+  for (int j = 0; j < num_total_features_; ++j) {
+    const FeatureBins& fb = bins_[j];
+    if (fb.trivial) { out.push_back("none"); continue; }
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), "[%.17g:%.17g]", fb.min_val, fb.max_val);
+    out.push_back(buf);
+  }
+  return out;
 }
 
 }  // namespace gpb200

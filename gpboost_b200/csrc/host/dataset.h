@@ -54,6 +54,8 @@ class Dataset {
   // feature names (Dataset::set_feature_names / feature_names, include/LightGBM/dataset.h): default "Column_<i>"
   const std::vector<std::string>& feature_names() const { return feature_names_; }
   void set_feature_names(const std::vector<std::string>& names) { feature_names_ = names; }
+  // "[min:max]" per feature, "none" for a trivial one (BinMapper::bin_info_string, include/LightGBM/bin.h:195-215)
+  std::vector<std::string> feature_infos() const;
 
  private:
   int32_t num_data_ = 0;

@@ -1,0 +1,70 @@
+"""Model text I/O of the boosting side (LGBM_BoosterSaveModelToString / SaveModel / LoadModelFromString / CreateFromModelfile /
+PredictForMat; gbdt_model_text.cpp, tree.cpp) — host logic, no device needed, checked against the unmodified reference library:
+  * a model trained by the REFERENCE is loaded by the B200 library: identical raw predictions (host tree traversal);
+  * the B200 library's writer output (of that loaded model) is loaded back by the REFERENCE: identical predictions — the text this
+    build writes carries every field the reference's loader insists on (feature_names, feature_infos, …);
+  * file round trip through LGBM_BoosterSaveModel / LGBM_BoosterCreateFromModelfile."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from gpboost_b200.booster import Booster, Dataset, parse_model_string
+from gpboost_b200.libpath import load_lib
+
+
+@pytest.fixture(scope="module")
+def ref_model(ref_lib):
+    if ref_lib is None:
+        pytest.skip("reference library not built")
+    rng = np.random.default_rng(0)
+    X = rng.random((2000, 6)); X[:, 4] = 3.0  # one constant (trivial) feature
+    X[:, 5] = np.round(X[:, 5] * 4) - 2.        # few distinct values incl. negatives and zero
+    y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.3 * X[:, 5] + 0.1 * rng.standard_normal(2000)
+    params = dict(objective="regression", num_leaves=15, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
+    b = Booster(params, Dataset(X, y, params=params, _lib=ref_lib), _lib=ref_lib)
+    for _ in range(12):
+        b.update()
+    Xt = np.random.default_rng(1).random((500, 6)) * 1.2 - 0.1
+    Xt[:, 5] = np.round(Xt[:, 5] * 4) - 2.
+    return b, b.model_to_string(), Xt
+
+
+def test_reference_model_loads_and_predicts_identically(ref_model, product_lib):
+    b_ref, text, Xt = ref_model
+    ours = Booster(model_str=text, _lib=product_lib)
+    assert ours.current_iteration() == 12
+    assert np.array_equal(ours.predict(Xt), b_ref.predict(Xt))
+
+
+def test_writer_output_is_loadable_by_the_reference(ref_model, product_lib, ref_lib):
+    b_ref, text, Xt = ref_model
+    ours = Booster(model_str=text, _lib=product_lib)
+    text2 = ours.model_to_string()
+    back = Booster(model_str=text2, _lib=ref_lib)  # the reference's loader on OUR text
+    assert np.array_equal(back.predict(Xt), b_ref.predict(Xt))
+    a, b = parse_model_string(text), parse_model_string(text2)
+    assert len(a) == len(b) == 12
+    for ta, tb in zip(a, b):
+        for k in ("split_feature", "left_child", "right_child", "leaf_count"):
+            assert np.array_equal(ta[k], tb[k]), k
+        assert np.array_equal(ta["threshold"], tb["threshold"]) and np.array_equal(ta["leaf_value"], tb["leaf_value"])
+
+
+def test_file_round_trip(ref_model, product_lib):
+    b_ref, text, Xt = ref_model
+    ours = Booster(model_str=text, _lib=product_lib)
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "model.txt")
+        ours.save_model(fn)
+        again = Booster(model_file=fn, _lib=product_lib)
+        assert np.array_equal(again.predict(Xt), b_ref.predict(Xt))
+
+
+def test_load_errors_use_the_error_channel(product_lib):
+    from gpboost_b200.basic import GPBoostError
+    with pytest.raises(GPBoostError):
+        Booster(model_str="tree\nversion=v3\nnum_class=1\n", _lib=product_lib)
+    with pytest.raises(GPBoostError):
+        Booster(model_file="/nonexistent/model.txt", _lib=product_lib)
