@@ -57,3 +57,48 @@ def test_unmodified_reference_package_loads_and_reaches_the_device_entries():
         """ % tmp)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PKG), reason="reference sources not present")
+def test_unmodified_reference_package_predicts_through_the_library(ref_lib):
+    """gpb.Booster(model_str=...) / predict / save_model / Booster(model_file=...) of the unmodified package, bound to THIS library,
+    on a model trained by the reference: predictions equal the reference library's own (host path, no device needed)."""
+    if ref_lib is None:
+        pytest.skip("reference library not built")
+    import numpy as np
+    from gpboost_b200.booster import Booster, Dataset
+    rng = np.random.default_rng(0)
+    X = rng.random((800, 4)); y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.1 * rng.standard_normal(800)
+    params = dict(objective="regression", num_leaves=7, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
+    b = Booster(params, Dataset(X, y, params=params, _lib=ref_lib), _lib=ref_lib)
+    for _ in range(5):
+        b.update()
+    Xt = np.random.default_rng(3).random((50, 4))
+    want = b.predict(Xt)
+    lib = os.path.join(ROOT, "gpboost_b200", "lib_gpboost_b200.so")
+    tmp = tempfile.mkdtemp()
+    pkg = os.path.join(tmp, "gpboost")
+    os.makedirs(pkg)
+    for f in os.listdir(REF_PKG):
+        if f.endswith(".py") or f == "VERSION.txt":
+            os.symlink(os.path.join(REF_PKG, f), os.path.join(pkg, f))
+    os.symlink(lib, os.path.join(pkg, "lib_gpboost.so"))
+    with open(os.path.join(tmp, "model.txt"), "w") as f:
+        f.write(b.model_to_string())
+    np.save(os.path.join(tmp, "Xt.npy"), Xt); np.save(os.path.join(tmp, "want.npy"), want)
+    code = textwrap.dedent("""
+        import os, sys, types
+        sys.modules.setdefault("optuna", types.ModuleType("optuna"))
+        tmp = %r
+        sys.path.insert(0, tmp)
+        import numpy as np
+        import gpboost as gpb
+        Xt = np.load(os.path.join(tmp, "Xt.npy")); want = np.load(os.path.join(tmp, "want.npy"))
+        bst = gpb.Booster(model_str=open(os.path.join(tmp, "model.txt")).read())
+        assert bst.num_trees() == 5 and bst.num_feature() == 4 and bst.feature_name() == ["Column_%%d" %% i for i in range(4)]
+        assert np.array_equal(bst.predict(Xt), want)
+        bst.save_model(os.path.join(tmp, "m2.txt"))
+        assert np.array_equal(gpb.Booster(model_file=os.path.join(tmp, "m2.txt")).predict(Xt), want)
+        """ % tmp)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
