@@ -288,6 +288,26 @@ void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t nco
   }
 }
 
+std::vector<double> Booster::FeatureImportance(int num_iteration, int importance_type) const {
+  int used = (int)models_.size();
+  if (num_iteration > 0) used = std::min(num_iteration, used);
+  if (importance_type != 0 && importance_type != 1) Fatal("Unknown importance type: only support split=0 and gain=1");
+  std::vector<double> imp(max_feature_idx_ + 1, 0.);
+  for (int it = 0; it < used; ++it) {
+    const Tree& t = *models_[it];
+    for (int k = 0; k < t.num_leaves - 1; ++k)
+      if (t.split_gain[k] > 0) imp[t.split_feature[k]] += importance_type == 0 ? 1. : (double)t.split_gain[k];
+  }
+  return imp;
+}
+
+double Booster::LeafValue(int tree_idx, int leaf_idx) const {
+  if (tree_idx < 0 || tree_idx >= (int)models_.size()) Fatal("Check failed: tree_idx < models_.size()");
+  const Tree& t = *models_[tree_idx];
+  if (leaf_idx < 0 || leaf_idx >= t.num_leaves) Fatal("Check failed: leaf_idx < num_leaves");
+  return t.leaf_value[leaf_idx];
+}
+
 std::string Booster::SaveModelToString() const {  // GBDT::SaveModelToString (boosting/gbdt_model_text.cpp), header subset
   std::ostringstream s;
   s << "tree\nversion=v3\nnum_class=1\nnum_tree_per_iteration=1\nlabel_index=0\nmax_feature_idx=" << max_feature_idx_

@@ -48,6 +48,9 @@ class Booster {
   void GetTrainingScore(double* out);
   void Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const;
   std::string SaveModelToString() const;
+  // GBDT::FeatureImportance (gbdt_model_text.cpp:638-674): importance_type 0 = number of splits, 1 = total gain
+  std::vector<double> FeatureImportance(int num_iteration, int importance_type) const;
+  double LeafValue(int tree_idx, int leaf_idx) const;
   gpbdev_tree_t learner() const { return learner_; }
 
  private:

@@ -389,6 +389,19 @@ int LGBM_BoosterCreateFromModelfile(const char* filename, int* out_num_iteration
   API_END();
 }
 
+int LGBM_BoosterFeatureImportance(BoosterHandle handle, int num_iteration, int importance_type, double* out_results) {
+  API_BEGIN();
+  const std::vector<double> imp = B(handle)->FeatureImportance(num_iteration, importance_type);
+  for (size_t i = 0; i < imp.size(); ++i) out_results[i] = imp[i];
+  API_END();
+}
+
+int LGBM_BoosterGetLeafValue(BoosterHandle handle, int tree_idx, int leaf_idx, double* out_val) {
+  API_BEGIN();
+  *out_val = B(handle)->LeafValue(tree_idx, leaf_idx);
+  API_END();
+}
+
 int LGBM_BoosterSaveModel(BoosterHandle handle, int /*start_iteration*/, int /*num_iteration*/, int /*feature_importance_type*/, const char* filename) {
   API_BEGIN();
   const std::string s = B(handle)->SaveModelToString();

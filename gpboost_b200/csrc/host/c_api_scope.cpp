@@ -172,13 +172,6 @@ int LGBM_BoosterDumpModel(BoosterHandle handle, int start_iteration, int num_ite
   API_END();
 }
 
-int LGBM_BoosterFeatureImportance(BoosterHandle handle, int num_iteration, int importance_type, double* out_results) {
-  API_BEGIN();
-  (void)handle; (void)num_iteration; (void)importance_type; (void)out_results;
-  Unsupported("LGBM_BoosterFeatureImportance");
-  API_END();
-}
-
 int LGBM_BoosterFreePredictSparse(void* indptr, int32_t* indices, void* data, int indptr_type, int data_type) {
   API_BEGIN();
   (void)indptr; (void)indices; (void)data; (void)indptr_type; (void)data_type;
@@ -196,13 +189,6 @@ int LGBM_BoosterGetEval(BoosterHandle handle, int data_idx, int* out_len, double
 int LGBM_BoosterGetEvalCounts(BoosterHandle handle, int* out_len) {
   API_BEGIN();
   (void)handle; *out_len = 0;  // no metric is evaluated by the B200 booster
-  API_END();
-}
-
-int LGBM_BoosterGetLeafValue(BoosterHandle handle, int tree_idx, int leaf_idx, double* out_val) {
-  API_BEGIN();
-  (void)handle; (void)tree_idx; (void)leaf_idx; (void)out_val;
-  Unsupported("LGBM_BoosterGetLeafValue");
   API_END();
 }
 

@@ -68,3 +68,19 @@ def test_load_errors_use_the_error_channel(product_lib):
         Booster(model_str="tree\nversion=v3\nnum_class=1\n", _lib=product_lib)
     with pytest.raises(GPBoostError):
         Booster(model_file="/nonexistent/model.txt", _lib=product_lib)
+
+
+def test_feature_importance_and_leaf_values_match_the_reference(ref_model, product_lib, ref_lib):
+    import ctypes as C
+    b_ref, text, _ = ref_model
+    ours = Booster(model_str=text, _lib=product_lib)
+    for typ in (0, 1):
+        for nit in (-1, 5):
+            a = np.zeros(6); b = np.zeros(6)
+            assert product_lib.LGBM_BoosterFeatureImportance(ours.handle, nit, typ, a.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            assert ref_lib.LGBM_BoosterFeatureImportance(b_ref.handle, nit, typ, b.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            assert np.allclose(a, b, rtol=1e-6, atol=0), (typ, nit, a, b)  # gains are printed with 6 significant digits in the text
+    va, vb = C.c_double(0.), C.c_double(0.)
+    assert product_lib.LGBM_BoosterGetLeafValue(ours.handle, 3, 2, C.byref(va)) == 0
+    assert ref_lib.LGBM_BoosterGetLeafValue(b_ref.handle, 3, 2, C.byref(vb)) == 0
+    assert va.value == vb.value
