@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=250000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--boost-n", type=int, default=1000000, help="n of the GPBoost-iteration measurement (0 = skip)")
+    ap.add_argument("--boost-features", type=int, default=50, help="features of the GPBoost-iteration measurements (BASELINE configs[3]: --boost-n 5000000 --boost-features 100 on 8 GPUs)")
     ap.add_argument("--boost-ref-n", type=int, default=0, help="--impl reference: also time GPBoost iterations at this n (slow)")
     ap.add_argument("--dense-n", type=int, default=2000, help="n of the exact-GP measurement (BASELINE configs[0]; 0 = skip; --impl reference times it too)")
     ap.add_argument("--laplace-n", type=int, default=100000, help="n of the Laplace-Vecchia (bernoulli_logit) measurement (0 = skip)")
@@ -374,7 +375,7 @@ def main():
     # GPBoost iteration (configs[2]/[3] shape): all ranks take part — GP rows and histogram rows are both sharded
     gb = None
     if args.boost_n > 0:
-        gb = time_gpboost(args.boost_n, 5, None, ncores)
+        gb = time_gpboost(args.boost_n, 5, None, ncores, F=args.boost_features)
 
     dense_res = None
     if args.dense_n > 0 and world == 1:
@@ -385,7 +386,7 @@ def main():
     gg = None
     if args.boost_n > 0 and world == 1:
         try:
-            gg = time_gpboost_grouped(args.boost_n, 10, None, ncores)
+            gg = time_gpboost_grouped(args.boost_n, 10, None, ncores, F=args.boost_features)
         except Exception as e:  # a secondary measurement must not cost the headline line
             sys.stderr.write("gpboost_grouped measurement failed: %r\n" % (e,))
 
