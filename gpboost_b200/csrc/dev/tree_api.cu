@@ -1188,6 +1188,7 @@ struct gpbdev_tree {
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
   int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel | 2: reduce_scan2_kernel (unverified)
+  int partition_sharded = 1;       // GPB200_PARTITION_SHARDED = 2: part_*_kernel also for row-sharded learners (not yet run on two GPUs)
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
   int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel | 3: hist3_kernel (unverified)
   double* sum_part = nullptr;
@@ -1303,6 +1304,7 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 2 ? 2 : 1);
+  if (const char* e = std::getenv("GPB200_PARTITION_SHARDED")) h->partition_sharded = std::atoi(e) == 2 ? 2 : 1;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 3 ? 3 : 2);
   *out = h;
@@ -1584,7 +1586,8 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     const int nleft_g = bs.left_count, nright_g = leaf_cnt_g[best_leaf] - nleft_g;
     if (nleft_g <= 0 || nright_g <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
     int nleft = nleft_g;
-    if (c > 0 && h->partition_version == 2 && !sharded) {  // row shards keep the CUB path: its two-GPU parity run predates part_*_kernel
+    if (c > 0 && h->partition_version == 2 && (!sharded || h->partition_sharded == 2)) {  // row shards keep the CUB path until part_*_kernel's
+                                                                                          // two-GPU parity run (GPB200_PARTITION_SHARDED=2 opts in)
       const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
       const int nseg = (int)((c + seg - 1) / seg);
       part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr);
