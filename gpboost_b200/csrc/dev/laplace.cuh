@@ -484,7 +484,7 @@ __global__ void scatter_perm_kernel(int64_t n, const double* __restrict__ x, con
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[perm[i]] = x[i];
 }
 
-// ---- gradient of the Laplace-approximated likelihood (likelihoods.h:6521-7044, iterative branch; NOT YET RUN ON A B200) ----
+// ---- gradient of the Laplace-approximated likelihood (likelihoods.h:6521-7044, iterative branch) ----
 // T[i,:] = -sum_k dA[i,k] X[nn[i,k],:]  = (B_grad X)[i,:]  (B_grad = -dA has no diagonal); same unit scheme as mv_B_kernel
 __global__ void __launch_bounds__(kBlock) mv_Bg_kernel(const double* __restrict__ dA, const int32_t* __restrict__ nn, int m, int64_t n, int t, int G,
                                                        const double* __restrict__ X, double* __restrict__ T) {
@@ -1078,7 +1078,7 @@ int gpbdev_vecchia_laplace_keep_solutions(gpbdev_vecchia_t h, int keep) {
 // dSigma^-1/dlog(var) = -Sigma^-1 (one GP); dSigma^-1/dlog(range) = Bg^T D^-1 B + B^T D^-1 Bg - B^T D^-1 dD D^-1 B with
 // Bg = -dA, dD from the factor kernel's MODE_STORE_GRAD. out[0..1] = gradient on the scale the reference's optimiser uses
 // (log of the ORIGINAL range: factor -1, Gaussian kernel -1/2 as in the reference), out[2] = CG iterations of the implicit solve.
-// NOT YET RUN ON A B200.
+// Verified on the B200 against the reference goldens (tests/test_laplace_gpu.py).
 int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, double range, const double* cfg, double* out) {
   if (!h || !cfg || !out) return fail("gpbdev_vecchia_laplace_grad: null argument");
   CUDA_TRY(cudaSetDevice(h->device));

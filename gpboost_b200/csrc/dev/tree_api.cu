@@ -1164,7 +1164,8 @@ struct gpbdev_tree {
   int F = 0, Fpad = 0, L = 0;
   gpbdev_tree_config cfg;
   cudaStream_t stream = nullptr;
-  uint8_t* bins = nullptr;        // n x Fpad row-major
+  const uint8_t* bins = nullptr;  // n x Fpad row-major (bins_owned, or a Dataset's device matrix read in place)
+  uint8_t* bins_owned = nullptr;
   int32_t* num_bin = nullptr;     // F
   int32_t *idx = nullptr, *idx_tmp = nullptr, *flag = nullptr, *pos = nullptr;
   double* grad = nullptr;         // n (device copy when the caller passes host gradients)
@@ -1187,10 +1188,10 @@ struct gpbdev_tree {
   int device_loop = 2;             // GPB200_TREE_LOOP = graph (2, default) | device (1) | host (0). Row-sharded learners use the host loop.
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
-  int fused_scan = 1;              // GPB200_FUSED_SCAN = 1 (default): reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel | 2: reduce_scan2_kernel (unverified)
+  int fused_scan = 2;              // GPB200_FUSED_SCAN = 2 (default): reduce_scan2_kernel | 1: reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
   int partition_sharded = 1;       // GPB200_PARTITION_SHARDED = 2: part_*_kernel also for row-sharded learners (not yet run on two GPUs)
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
-  int hist_kernel_version = 2;     // GPB200_HIST_KERNEL = 2 (default): multi-warp hist2_kernel | 1: single-warp hist_kernel | 3: hist3_kernel (unverified)
+  int hist_kernel_version = 3;     // GPB200_HIST_KERNEL = 3 (default): hist3_kernel | 2: hist2_kernel | 1: single-warp hist_kernel
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -1242,9 +1243,10 @@ int gpbdev_vec_allgather_rows(gpbdev_tree_t h, double* vec_dev, int64_t n, int64
   return 0;
 }
 
-int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major, const int32_t* num_bin,
-                       const gpbdev_tree_config* cfg) {
-  if (!out || !bins_feature_major || !num_bin || !cfg) return tfail("gpbdev_tree_create: null argument");
+// bins_feature_major != nullptr: host bins, transposed and uploaded (owned); else bins_dev: row-major n x Fpad_in already in HBM (adopted)
+static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major, const uint8_t* bins_dev,
+                              int Fpad_in, const int32_t* num_bin, const gpbdev_tree_config* cfg) {
+  if (!out || (!bins_feature_major && !bins_dev) || !num_bin || !cfg) return tfail("gpbdev_tree_create: null argument");
   if (n <= 0 || F <= 0) return tfail("gpbdev_tree_create: need n > 0 and F > 0");
   if (cfg->num_leaves < 2) return tfail("gpbdev_tree_create: num_leaves must be >= 2");
   for (int f = 0; f < F; ++f)
@@ -1262,12 +1264,18 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   h->num_sms = prop.multiProcessorCount;
   TCUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   // feature-major (the reference's dense-bin layout) -> row-major padded (one 32-byte sector per row and feature group)
-  h->bins_rm_host.assign((size_t)n * h->Fpad, 0);
-  for (int f = 0; f < F; ++f)
-    for (int64_t i = 0; i < n; ++i) h->bins_rm_host[(size_t)i * h->Fpad + f] = bins_feature_major[(size_t)f * n + i];
-  TCUDA(cudaMalloc(&h->bins, (size_t)n * h->Fpad));
-  TCUDA(cudaMemcpy(h->bins, h->bins_rm_host.data(), (size_t)n * h->Fpad, cudaMemcpyHostToDevice));
-  h->bins_rm_host.clear(); h->bins_rm_host.shrink_to_fit();
+  if (bins_feature_major) {
+    h->bins_rm_host.assign((size_t)n * h->Fpad, 0);
+    for (int f = 0; f < F; ++f)
+      for (int64_t i = 0; i < n; ++i) h->bins_rm_host[(size_t)i * h->Fpad + f] = bins_feature_major[(size_t)f * n + i];
+    TCUDA(cudaMalloc(&h->bins_owned, (size_t)n * h->Fpad));
+    TCUDA(cudaMemcpy(h->bins_owned, h->bins_rm_host.data(), (size_t)n * h->Fpad, cudaMemcpyHostToDevice));
+    h->bins_rm_host.clear(); h->bins_rm_host.shrink_to_fit();
+    h->bins = h->bins_owned;
+  } else {
+    if (Fpad_in != h->Fpad) { delete h; return tfail("gpbdev_tree_create_on_device_bins: Fpad must be F rounded up to a multiple of 32"); }
+    h->bins = bins_dev;  // read in place; the Dataset owns it
+  }
   TCUDA(cudaMalloc(&h->num_bin, sizeof(int32_t) * F));
   TCUDA(cudaMemcpy(h->num_bin, num_bin, sizeof(int32_t) * F, cudaMemcpyHostToDevice));
   TCUDA(cudaMalloc(&h->idx, sizeof(int32_t) * n));
@@ -1303,18 +1311,30 @@ int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const u
   TCUDA(cudaMalloc(&h->state_dev, sizeof(TreeDevState)));
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
-  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 2 ? 2 : 1);
+  if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 1 ? 1 : 2);
   if (const char* e = std::getenv("GPB200_PARTITION_SHARDED")) h->partition_sharded = std::atoi(e) == 2 ? 2 : 1;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
-  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 3 ? 3 : 2);
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 2 ? 2 : 3);
   *out = h;
   return 0;
+}
+
+int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major, const int32_t* num_bin,
+                       const gpbdev_tree_config* cfg) {
+  if (!bins_feature_major) return tfail("gpbdev_tree_create: null argument");
+  return tree_create_common(out, device, n, F, bins_feature_major, nullptr, 0, num_bin, cfg);
+}
+
+int gpbdev_tree_create_on_device_bins(gpbdev_tree_t* out, int device, int64_t n, int F, int Fpad, const uint8_t* bins_dev,
+                                      const int32_t* num_bin, const gpbdev_tree_config* cfg) {
+  if (!bins_dev) return tfail("gpbdev_tree_create_on_device_bins: null argument");
+  return tree_create_common(out, device, n, F, nullptr, bins_dev, Fpad, num_bin, cfg);
 }
 
 int gpbdev_tree_free(gpbdev_tree_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->bins); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
+  cudaFree(h->bins_owned); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);

@@ -41,7 +41,7 @@ namespace gpb {
 enum CovType : int { COV_EXPONENTIAL = 0, COV_MATERN15 = 1, COV_MATERN25 = 2, COV_GAUSSIAN = 3 };
 // MODE_STORE_GRAD: MODE_STORE plus the derivative of the factor w.r.t. log(range): dA_i (= -B_grad row) and dD_i, what
 // CalcCovFactorGradientVecchia leaves in B_grad[1], D_grad[1] (Vecchia_utils.cpp:1636-1652) — needed where the derivative of
-// Sigma^-1 is applied to many vectors (Laplace-approximated likelihoods, likelihoods.h:6615-6690). NOT YET RUN ON A B200.
+// Sigma^-1 is applied to many vectors (Laplace-approximated likelihoods, likelihoods.h:6615-6690).
 enum FactorMode : int { MODE_NLL = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_STORE_GRAD = 3 };
 
 #ifndef GPB_NLL_BLOCKS

@@ -94,16 +94,12 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
     if (row_end_ <= row_begin_) Fatal("More ranks than training rows");
     sharded_ = true;
   }
-  if (!sharded_) {
-    TreeCheck(gpbdev_tree_create(&learner_, rt.device, n_, F, train->bins_feature_major().data(), num_bin.data(), &cfg));
-  } else {  // this rank's rows of the (feature-major) bin matrix; bin boundaries come from the whole data set on every rank
-    const int64_t nl = row_end_ - row_begin_;
-    std::vector<uint8_t> local((size_t)nl * F);
-    const uint8_t* all = train->bins_feature_major().data();
-    for (int f = 0; f < F; ++f) std::memcpy(local.data() + (size_t)f * nl, all + (size_t)f * n_ + row_begin_, (size_t)nl);
-    TreeCheck(gpbdev_tree_create(&learner_, rt.device, nl, F, local.data(), num_bin.data(), &cfg));
-    TreeCheck(gpbdev_tree_set_allreduce(learner_, rt.allreduce_dev, rt.allreduce_ctx, n_));
-  }
+  // the learner reads the Dataset's device bin matrix in place; a row shard is an offset into it (row-major rows)
+  if (train->bins_device_id() != rt.device) Fatal("The Dataset was binned on another device than the one this process trains on");
+  const int Fpad = train->bins_row_stride();
+  TreeCheck(gpbdev_tree_create_on_device_bins(&learner_, rt.device, row_end_ - row_begin_, F, Fpad,
+                                              train->bins_device() + (size_t)row_begin_ * Fpad, num_bin.data(), &cfg));
+  if (sharded_) TreeCheck(gpbdev_tree_set_allreduce(learner_, rt.allreduce_dev, rt.allreduce_ctx, n_));
   TreeCheck(gpbdev_vec_alloc(learner_, &score_dev_, n_));
   TreeCheck(gpbdev_vec_alloc(learner_, &label_dev_, n_));
   TreeCheck(gpbdev_vec_alloc(learner_, &grad_dev_, n_));

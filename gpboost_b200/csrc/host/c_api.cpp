@@ -276,6 +276,38 @@ int LGBM_BoosterSaveModelToString(BoosterHandle handle, int /*start_iteration*/,
   API_END();
 }
 
+// Dataset::DumpTextFile (src/LightGBM/io/dataset.cpp:1070-1125): header, then one line per row with the bin of every feature
+// ("NA" for a feature that was filtered out). The bins come back from HBM — this is how tests/test_binning_gpu.py compares the
+// device binning with the reference's, entry against entry. (num_groups: this build does not bundle features, one group each.)
+int LGBM_DatasetDumpText(DatasetHandle handle, const char* filename) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  auto* ds = reinterpret_cast<gpb200::Dataset*>(handle);
+  const std::vector<uint8_t> bins = ds->DownloadBins();
+  FILE* file = std::fopen(filename, "wt");
+  if (file == nullptr) throw std::runtime_error(std::string("Cannot open ") + filename + " for writing");
+  const int F = ds->num_features(), T = ds->num_total_features(), stride = ds->bins_row_stride();
+  std::vector<std::string> names = ds->feature_names();
+  if (names.empty()) for (int j = 0; j < T; ++j) names.push_back("Column_" + std::to_string(j));
+  std::fprintf(file, "num_features: %d\nnum_total_features: %d\nnum_groups: %d\nnum_data: %d\nfeature_names: ", F, T, F, ds->num_data());
+  for (const auto& n : names) std::fprintf(file, "%s, ", n.c_str());
+  std::fprintf(file, "\nmax_bin_by_feature: \n");
+  for (const auto& n : names) std::fprintf(file, "%s, ", n.c_str());
+  std::fprintf(file, "\nforced_bins: ");
+  for (int j = 0; j < T; ++j) std::fprintf(file, "\nfeature %d: ", j);
+  std::vector<int> inner(T, -1);
+  for (int k = 0; k < F; ++k) inner[ds->real_feature_index(k)] = k;
+  for (int64_t i = 0; i < ds->num_data(); ++i) {
+    std::fprintf(file, "\n");
+    for (int j = 0; j < T; ++j) {
+      if (inner[j] < 0) std::fprintf(file, "NA, ");
+      else std::fprintf(file, "%d, ", (int)bins[(size_t)i * stride + inner[j]]);
+    }
+  }
+  std::fclose(file);
+  API_END();
+}
+
 // ---- host-side entries the reference's Python package calls around the hot path (Dataset.construct, Booster.__init__,
 // Booster.save_model, Booster.predict): python-package/gpboost/basic.py:1816-1836, 2373-2400, 3300-3345, 3530-3560
 int LGBM_DatasetGetField(DatasetHandle handle, const char* field_name, int* out_len, const void** out_ptr, int* out_type) {
@@ -409,6 +441,20 @@ int LGBM_BoosterSaveModel(BoosterHandle handle, int /*start_iteration*/, int /*n
   if (f == nullptr) throw std::runtime_error(std::string("Model file ") + filename + " is not available for writes");
   std::fwrite(s.data(), 1, s.size(), f);
   std::fclose(f);
+  API_END();
+}
+
+// Bin boundaries of one (real) feature as found by the host search: *num_bin bounds (the last one +inf) into upper_bounds (room for
+// 256), *is_trivial != 0 for a feature the Dataset filtered out. Host metadata only — works without a device (CPU parity tests).
+int GPB200_DatasetGetFeatureBins(DatasetHandle handle, int real_feature, int* num_bin, int* is_trivial, double* upper_bounds) {
+  API_BEGIN();
+  if (handle == nullptr) throw std::runtime_error("Dataset handle is null");
+  auto* ds = reinterpret_cast<gpb200::Dataset*>(handle);
+  if (real_feature < 0 || real_feature >= ds->num_total_features()) throw std::runtime_error("feature index out of range");
+  const gpb200::FeatureBins& fb = ds->feature_by_real_index(real_feature);
+  *num_bin = fb.num_bin;
+  *is_trivial = fb.trivial ? 1 : 0;
+  std::copy(fb.upper_bounds.begin(), fb.upper_bounds.end(), upper_bounds);
   API_END();
 }
 

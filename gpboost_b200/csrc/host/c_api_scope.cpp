@@ -337,13 +337,6 @@ int LGBM_DatasetCreateFromMats(int32_t nmat, const void** data, int data_type, i
   API_END();
 }
 
-int LGBM_DatasetDumpText(DatasetHandle handle, const char* filename) {
-  API_BEGIN();
-  (void)handle; (void)filename;
-  Unsupported("LGBM_DatasetDumpText");
-  API_END();
-}
-
 int LGBM_DatasetGetSubset(const DatasetHandle handle, const int32_t* used_row_indices, int32_t num_used_row_indices, const char* parameters, DatasetHandle* out) {
   API_BEGIN();
   (void)handle; (void)used_row_indices; (void)num_used_row_indices; (void)parameters; (void)out;

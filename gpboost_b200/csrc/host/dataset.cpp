@@ -1,209 +1,197 @@
 #include "dataset.h"
 
+#include "../../../include/gpboost_b200_dev.h"
+#include "runtime.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <limits>
-#include <set>
+#include <unordered_set>
 #include <sstream>
 #include <stdexcept>
 
 namespace gpb200 {
 
 namespace {
-constexpr double kZeroThreshold = 1e-35f;  // include/LightGBM/meta.h:56
+constexpr double kZeroThreshold = 1e-35f;  // the reference's zero band (include/LightGBM/meta.h:56): |v| <= this is "zero"
 [[noreturn]] void Fatal(const std::string& m) { throw std::runtime_error(m); }
 
-// include/LightGBM/utils/random.h:41-109 — the linear congruential generator behind Dataset row sampling
-class Random {
- public:
-  explicit Random(int seed) : x(seed) {}
-  int NextInt(int lo, int hi) { return RandInt32() % (hi - lo) + lo; }
-  float NextFloat() { return static_cast<float>(RandInt16()) / (32768.0f); }
-  std::vector<int> Sample(int N, int K) {
-    std::vector<int> ret;
-    ret.reserve(K);
-    if (K > N || K <= 0) return ret;
-    if (K == N) {
-      for (int i = 0; i < N; ++i) ret.push_back(i);
-    } else if (K > 1 && K > (N / std::log2(K))) {
-      for (int i = 0; i < N; ++i) {
-        double prob = (K - ret.size()) / static_cast<double>(N - i);
-        if (NextFloat() < prob) ret.push_back(i);
-      }
-    } else {
-      std::set<int> sample_set;
-      for (int r = N - K; r < N; ++r) {
-        int v = NextInt(0, r);
-        if (!sample_set.insert(v).second) sample_set.insert(r);
-      }
-      for (int v : sample_set) ret.push_back(v);
-    }
-    return ret;
-  }
-
- private:
-  int RandInt16() { x = (214013 * x + 2531011); return static_cast<int>((x >> 16) & 0x7FFF); }
-  int RandInt32() { x = (214013 * x + 2531011); return static_cast<int>(x & 0x7FFFFFFF); }
-  unsigned int x;
+// ---- row sample --------------------------------------------------------------------------------------------------
+// The bin boundaries are a function of WHICH rows are sampled, so the sampler has to draw the reference's rows: the
+// 32-bit multiplicative congruential stream of include/LightGBM/utils/random.h (x <- 214013 x + 2531011; 15 bits from
+// bit 16 for the float draw, the low 31 bits for the integer draw) and its three regimes (everything / one Bernoulli draw
+// per row when the sample is a large part of the data / Floyd's subset algorithm otherwise), ascending row ids.
+struct SampleStream {
+  uint32_t state;
+  uint32_t Advance() { state = state * 214013u + 2531011u; return state; }
+  float Unit() { return static_cast<float>((Advance() >> 16) & 0x7FFFu) / 32768.0f; }
+  int Below(int bound) { return static_cast<int>(Advance() & 0x7FFFFFFFu) % bound; }
 };
 
-inline bool CheckDoubleEqualOrdered(double a, double b) { return b <= std::nextafter(a, INFINITY); }  // common.h:861
-inline double GetDoubleUpperBound(double a) { return std::nextafter(a, INFINITY); }                   // common.h:866
-
-// bin.cpp:78-155
-std::vector<double> GreedyFindBin(const double* distinct_values, const int* counts, int num_distinct_values, int max_bin,
-                                  size_t total_cnt, int min_data_in_bin) {
-  std::vector<double> bin_upper_bound;
-  if (!(max_bin > 0)) Fatal("Check failed: max_bin > 0");
-  if (num_distinct_values <= max_bin) {
-    int cur_cnt_inbin = 0;
-    for (int i = 0; i < num_distinct_values - 1; ++i) {
-      cur_cnt_inbin += counts[i];
-      if (cur_cnt_inbin >= min_data_in_bin) {
-        auto val = GetDoubleUpperBound((distinct_values[i] + distinct_values[i + 1]) / 2.0);
-        if (bin_upper_bound.empty() || !CheckDoubleEqualOrdered(bin_upper_bound.back(), val)) {
-          bin_upper_bound.push_back(val);
-          cur_cnt_inbin = 0;
-        }
-      }
-    }
-    bin_upper_bound.push_back(std::numeric_limits<double>::infinity());
-  } else {
-    if (min_data_in_bin > 0) {
-      max_bin = std::min(max_bin, static_cast<int>(total_cnt / min_data_in_bin));
-      max_bin = std::max(max_bin, 1);
-    }
-    double mean_bin_size = static_cast<double>(total_cnt) / max_bin;
-    int rest_bin_cnt = max_bin;
-    int rest_sample_cnt = static_cast<int>(total_cnt);
-    std::vector<bool> is_big_count_value(num_distinct_values, false);
-    for (int i = 0; i < num_distinct_values; ++i) {
-      if (counts[i] >= mean_bin_size) {
-        is_big_count_value[i] = true;
-        --rest_bin_cnt;
-        rest_sample_cnt -= counts[i];
-      }
-    }
-    mean_bin_size = static_cast<double>(rest_sample_cnt) / rest_bin_cnt;
-    std::vector<double> upper_bounds(max_bin, std::numeric_limits<double>::infinity());
-    std::vector<double> lower_bounds(max_bin, std::numeric_limits<double>::infinity());
-    int bin_cnt = 0;
-    lower_bounds[bin_cnt] = distinct_values[0];
-    int cur_cnt_inbin = 0;
-    for (int i = 0; i < num_distinct_values - 1; ++i) {
-      if (!is_big_count_value[i]) rest_sample_cnt -= counts[i];
-      cur_cnt_inbin += counts[i];
-      if (is_big_count_value[i] || cur_cnt_inbin >= mean_bin_size ||
-          (is_big_count_value[i + 1] && cur_cnt_inbin >= std::max(1.0, mean_bin_size * 0.5f))) {
-        upper_bounds[bin_cnt] = distinct_values[i];
-        ++bin_cnt;
-        lower_bounds[bin_cnt] = distinct_values[i + 1];
-        if (bin_cnt >= max_bin - 1) break;
-        cur_cnt_inbin = 0;
-        if (!is_big_count_value[i]) {
-          --rest_bin_cnt;
-          mean_bin_size = rest_sample_cnt / static_cast<double>(rest_bin_cnt);
-        }
-      }
-    }
-    ++bin_cnt;
-    for (int i = 0; i < bin_cnt - 1; ++i) {
-      auto val = GetDoubleUpperBound((upper_bounds[i] + lower_bounds[i + 1]) / 2.0);
-      if (bin_upper_bound.empty() || !CheckDoubleEqualOrdered(bin_upper_bound.back(), val)) bin_upper_bound.push_back(val);
-    }
-    bin_upper_bound.push_back(std::numeric_limits<double>::infinity());
+std::vector<int> DrawSampleRows(int num_rows, int want, int seed) {
+  std::vector<int> rows;
+  if (want <= 0 || want > num_rows) return rows;
+  SampleStream rng{static_cast<uint32_t>(seed)};
+  rows.reserve(want);
+  if (want == num_rows) {
+    rows.resize(num_rows);
+    for (int i = 0; i < num_rows; ++i) rows[i] = i;
+    return rows;
   }
-  return bin_upper_bound;
+  if (want > 1 && want > num_rows / std::log2(want)) {
+    // selection sampling: row i is taken with probability (still wanted) / (still available)
+    for (int i = 0; i < num_rows; ++i) {
+      const double p_take = (want - rows.size()) / static_cast<double>(num_rows - i);
+      if (rng.Unit() < p_take) rows.push_back(i);
+    }
+    return rows;
+  }
+  // Floyd: for r = N-K .. N-1 draw v in [0, r); take v unless already taken, else take r
+  std::unordered_set<int> taken;
+  taken.reserve(2 * want);
+  for (int r = num_rows - want; r < num_rows; ++r) {
+    const int v = rng.Below(r);
+    rows.push_back(taken.insert(v).second ? v : (taken.insert(r), r));
+  }
+  std::sort(rows.begin(), rows.end());
+  return rows;
 }
 
-// bin.cpp:241-297
-std::vector<double> FindBinWithZeroAsOneBin(const double* distinct_values, const int* counts, int num_distinct_values, int max_bin,
-                                            size_t total_sample_cnt, int min_data_in_bin) {
-  std::vector<double> bin_upper_bound;
-  int left_cnt_data = 0, cnt_zero = 0, right_cnt_data = 0;
-  for (int i = 0; i < num_distinct_values; ++i) {
-    if (distinct_values[i] <= -kZeroThreshold) left_cnt_data += counts[i];
-    else if (distinct_values[i] > kZeroThreshold) right_cnt_data += counts[i];
-    else cnt_zero += counts[i];
+// ---- bin boundaries ----------------------------------------------------------------------------------------------
+// What has to come out (BinMapper::FindBin for a numerical feature without NaNs, src/LightGBM/io/bin.cpp:325-520 with
+// FindBinWithZeroAsOneBin :241-297 and GreedyFindBin :78-155): the strictly increasing upper bounds b_0 < ... < b_{k-1} = +inf with
+// zero in a bin of its own. Formulated here on a run-length view of the sorted sample:
+//   * Runs: maximal groups of sample values that are equal up to one ulp, represented by their largest member, with an explicit
+//     run for the implicit zeros (rows whose |value| is inside the zero band are not part of the sample vector);
+//   * a side (the negative runs, or the positive runs) is cut into at most `budget` bins by CutSide(), which returns the run
+//     indices after which a bin ends; a bound is the midpoint between the last run of a bin and the first run of the next one,
+//     nudged one ulp up, and dropped when it does not exceed the previous bound by more than an ulp.
+struct Run { double value; int count; };
+
+inline double UlpUp(double a) { return std::nextafter(a, std::numeric_limits<double>::infinity()); }
+inline bool WithinUlp(double lo, double hi) { return hi <= UlpUp(lo); }  // for lo <= hi
+
+std::vector<Run> BuildRuns(std::vector<double>& sample, int implicit_zeros) {
+  std::stable_sort(sample.begin(), sample.end());
+  std::vector<Run> runs;
+  const size_t ns = sample.size();
+  if (ns == 0 || (sample[0] > 0.0 && implicit_zeros > 0)) runs.push_back({0.0, implicit_zeros});
+  for (size_t i = 0; i < ns; ++i) {
+    if (i > 0 && WithinUlp(sample[i - 1], sample[i])) {
+      runs.back().value = sample[i];
+      ++runs.back().count;
+      continue;
+    }
+    if (i > 0 && sample[i - 1] < 0.0 && sample[i] > 0.0) runs.push_back({0.0, implicit_zeros});  // zero sits between the signs
+    runs.push_back({sample[i], 1});
   }
-  int left_cnt = -1;
-  for (int i = 0; i < num_distinct_values; ++i) {
-    if (distinct_values[i] > -kZeroThreshold) { left_cnt = i; break; }
-  }
-  if (left_cnt < 0) left_cnt = num_distinct_values;
-  if ((left_cnt > 0) && (max_bin > 1)) {
-    int left_max_bin = static_cast<int>(static_cast<double>(left_cnt_data) / (total_sample_cnt - cnt_zero) * (max_bin - 1));
-    left_max_bin = std::max(1, left_max_bin);
-    bin_upper_bound = GreedyFindBin(distinct_values, counts, left_cnt, left_max_bin, left_cnt_data, min_data_in_bin);
-    if (bin_upper_bound.size() > 0) bin_upper_bound.back() = -kZeroThreshold;
-  }
-  int right_start = -1;
-  for (int i = left_cnt; i < num_distinct_values; ++i) {
-    if (distinct_values[i] > kZeroThreshold) { right_start = i; break; }
-  }
-  int right_max_bin = max_bin - 1 - static_cast<int>(bin_upper_bound.size());
-  if (right_start >= 0 && right_max_bin > 0) {
-    auto right_bounds = GreedyFindBin(distinct_values + right_start, counts + right_start, num_distinct_values - right_start,
-                                      right_max_bin, right_cnt_data, min_data_in_bin);
-    bin_upper_bound.push_back(kZeroThreshold);
-    bin_upper_bound.insert(bin_upper_bound.end(), right_bounds.begin(), right_bounds.end());
-  } else {
-    bin_upper_bound.push_back(std::numeric_limits<double>::infinity());
-  }
-  if (!(bin_upper_bound.size() <= static_cast<size_t>(max_bin))) Fatal("Check failed: bin_upper_bound.size() <= max_bin");
-  return bin_upper_bound;
+  if (ns > 0 && sample[ns - 1] < 0.0 && implicit_zeros > 0) runs.push_back({0.0, implicit_zeros});
+  return runs;
 }
 
-// bin.cpp:53-66 (numerical)
-bool NeedFilter(const std::vector<int>& cnt_in_bin, int total_cnt, int filter_cnt) {
-  int sum_left = 0;
-  for (size_t i = 0; i + 1 < cnt_in_bin.size(); ++i) {
-    sum_left += cnt_in_bin[i];
-    if (sum_left >= filter_cnt && total_cnt - sum_left >= filter_cnt) return false;
+// Appends midpoint bounds; keeps the list strictly increasing by more than an ulp.
+struct BoundList {
+  std::vector<double> b;
+  void Between(double last_of_bin, double first_of_next) {
+    const double cut = UlpUp((last_of_bin + first_of_next) / 2.0);
+    if (b.empty() || !WithinUlp(b.back(), cut)) b.push_back(cut);
+  }
+};
+
+// Bins for runs[0..nr): at most `budget` of them, at least `min_in_bin` sample rows each where possible; `rows` = sample rows on
+// this side. Returns the bounds, the last one +inf.
+std::vector<double> CutSide(const Run* runs, int nr, int budget, int64_t rows, int min_in_bin) {
+  if (budget <= 0) Fatal("Check failed: max_bin > 0");
+  BoundList out;
+  if (nr <= budget) {
+    // few distinct values: every run may get its own bin as soon as the bin holds min_in_bin rows
+    int held = 0;
+    for (int i = 0; i + 1 < nr; ++i) {
+      held += runs[i].count;
+      if (held < min_in_bin) continue;
+      const size_t before = out.b.size();
+      out.Between(runs[i].value, runs[i + 1].value);
+      if (out.b.size() != before) held = 0;
+    }
+    out.b.push_back(std::numeric_limits<double>::infinity());
+    return out.b;
+  }
+  if (min_in_bin > 0) budget = std::max(1, std::min(budget, static_cast<int>(rows / min_in_bin)));
+  // equal-frequency cutting; runs at least as heavy as the average bin get a bin of their own and leave the average
+  double target = static_cast<double>(rows) / budget;
+  std::vector<char> heavy(nr, 0);
+  int light_bins = budget;
+  int light_rows = static_cast<int>(rows);
+  for (int i = 0; i < nr; ++i) {
+    if (runs[i].count >= target) { heavy[i] = 1; --light_bins; light_rows -= runs[i].count; }
+  }
+  target = static_cast<double>(light_rows) / light_bins;
+  std::vector<int> cut_after;  // run index that closes a bin
+  int held = 0;
+  for (int i = 0; i + 1 < nr; ++i) {
+    if (!heavy[i]) light_rows -= runs[i].count;
+    held += runs[i].count;
+    const bool close = heavy[i] || held >= target || (heavy[i + 1] && held >= std::max(1.0, target * 0.5f));
+    if (!close) continue;
+    cut_after.push_back(i);
+    if (static_cast<int>(cut_after.size()) >= budget - 1) break;
+    held = 0;
+    if (!heavy[i]) { --light_bins; target = light_rows / static_cast<double>(light_bins); }
+  }
+  for (int i : cut_after) out.Between(runs[i].value, runs[i + 1].value);
+  out.b.push_back(std::numeric_limits<double>::infinity());
+  return out.b;
+}
+
+// true when no bound leaves at least `need` sample rows on both sides (the feature cannot be split: bin.cpp:53-66)
+bool NoUsefulCut(const std::vector<int>& rows_in_bin, int total, int need) {
+  int left = 0;
+  for (size_t i = 0; i + 1 < rows_in_bin.size(); ++i) {
+    left += rows_in_bin[i];
+    if (left >= need && total - left >= need) return false;
   }
   return true;
 }
 
-// BinMapper::FindBin, numerical, use_missing but no NaN present -> MissingType::None (bin.cpp:325-520)
-FeatureBins FindBin(std::vector<double>& values, size_t total_sample_cnt, int max_bin, int min_data_in_bin, int min_split_data,
-                    bool pre_filter) {
-  FeatureBins fb;
-  int num_sample_values = (int)values.size();
-  for (double v : values)
+FeatureBins BoundsFromSample(std::vector<double>& sample, size_t sample_rows, int max_bin, int min_in_bin, int min_split_rows, bool pre_filter) {
+  for (double v : sample)
     if (std::isnan(v)) Fatal("Missing values (NaN) in the feature matrix are not supported by the B200 tree learner yet");
-  const int zero_cnt = static_cast<int>(total_sample_cnt - num_sample_values);
-  std::vector<double> distinct_values;
-  std::vector<int> counts;
-  std::stable_sort(values.begin(), values.end());
-  if (num_sample_values == 0 || (values[0] > 0.0f && zero_cnt > 0)) { distinct_values.push_back(0.0f); counts.push_back(zero_cnt); }
-  if (num_sample_values > 0) { distinct_values.push_back(values[0]); counts.push_back(1); }
-  for (int i = 1; i < num_sample_values; ++i) {
-    if (!CheckDoubleEqualOrdered(values[i - 1], values[i])) {
-      if (values[i - 1] < 0.0f && values[i] > 0.0f) { distinct_values.push_back(0.0f); counts.push_back(zero_cnt); }
-      distinct_values.push_back(values[i]);
-      counts.push_back(1);
-    } else {
-      distinct_values.back() = values[i];
-      ++counts.back();
-    }
+  FeatureBins fb;
+  const std::vector<Run> runs = BuildRuns(sample, static_cast<int>(sample_rows - sample.size()));
+  const int nr = static_cast<int>(runs.size());
+  fb.min_val = runs.front().value;
+  fb.max_val = runs.back().value;
+  // sides: [0, neg_end) negative, [pos_begin, nr) positive, anything between is the zero run
+  int neg_end = 0, pos_begin = nr;
+  int64_t neg_rows = 0, pos_rows = 0, zero_rows = 0;
+  while (neg_end < nr && runs[neg_end].value <= -kZeroThreshold) neg_rows += runs[neg_end++].count;
+  for (int i = neg_end; i < nr; ++i) {
+    if (runs[i].value > kZeroThreshold) { if (pos_begin == nr) pos_begin = i; pos_rows += runs[i].count; }
+    else zero_rows += runs[i].count;
   }
-  if (num_sample_values > 0 && values[num_sample_values - 1] < 0.0f && zero_cnt > 0) { distinct_values.push_back(0.0f); counts.push_back(zero_cnt); }
-  fb.min_val = distinct_values.front();
-  fb.max_val = distinct_values.back();
-  const int num_distinct_values = (int)distinct_values.size();
-  fb.upper_bounds = FindBinWithZeroAsOneBin(distinct_values.data(), counts.data(), num_distinct_values, max_bin, total_sample_cnt,
-                                            min_data_in_bin);
-  fb.num_bin = (int)fb.upper_bounds.size();
-  std::vector<int> cnt_in_bin(fb.num_bin, 0);
-  int i_bin = 0;
-  for (int i = 0; i < num_distinct_values; ++i) {
-    if (distinct_values[i] > fb.upper_bounds[i_bin]) ++i_bin;
-    cnt_in_bin[i_bin] += counts[i];
+  std::vector<double>& ub = fb.upper_bounds;
+  if (neg_end > 0 && max_bin > 1) {
+    const int share = static_cast<int>(static_cast<double>(neg_rows) / (sample_rows - zero_rows) * (max_bin - 1));
+    ub = CutSide(runs.data(), neg_end, std::max(1, share), neg_rows, min_in_bin);
+    if (!ub.empty()) ub.back() = -kZeroThreshold;  // the negative side ends where the zero bin starts
   }
-  if (!(fb.num_bin <= max_bin)) Fatal("Check failed: num_bin_ <= max_bin");
-  fb.trivial = fb.num_bin <= 1;
-  if (!fb.trivial && pre_filter && NeedFilter(cnt_in_bin, static_cast<int>(total_sample_cnt), min_split_data)) fb.trivial = true;
+  const int pos_budget = max_bin - 1 - static_cast<int>(ub.size());
+  if (pos_begin < nr && pos_budget > 0) {
+    const std::vector<double> pos = CutSide(runs.data() + pos_begin, nr - pos_begin, pos_budget, pos_rows, min_in_bin);
+    ub.push_back(kZeroThreshold);
+    ub.insert(ub.end(), pos.begin(), pos.end());
+  } else {
+    ub.push_back(std::numeric_limits<double>::infinity());
+  }
+  if (ub.size() > static_cast<size_t>(max_bin)) Fatal("Check failed: bin_upper_bound.size() <= max_bin");
+  fb.num_bin = static_cast<int>(ub.size());
+  std::vector<int> rows_in_bin(fb.num_bin, 0);
+  for (int i = 0, bin = 0; i < nr; ++i) {
+    if (runs[i].value > ub[bin]) ++bin;
+    rows_in_bin[bin] += runs[i].count;
+  }
+  fb.trivial = fb.num_bin <= 1 || (pre_filter && NoUsefulCut(rows_in_bin, static_cast<int>(sample_rows), min_split_rows));
   return fb;
 }
 
@@ -254,16 +242,6 @@ std::string Params::GetString(const std::string& k, const std::string& d, std::i
   return v ? *v : d;
 }
 
-uint32_t FeatureBins::ValueToBin(double value) const {  // bin.h:465-488 (numerical, MissingType::None)
-  if (std::isnan(value)) value = 0.0f;
-  int l = 0, r = num_bin - 1;
-  while (l < r) {
-    int m = (r + l - 1) / 2;
-    if (value <= upper_bounds[m]) r = m; else l = m + 1;
-  }
-  return (uint32_t)l;
-}
-
 Dataset::Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, const Params& params)
     : num_data_(nrow), num_total_features_(ncol), params_(params) {
   if (data == nullptr || nrow <= 0 || ncol <= 0) Fatal("LGBM_DatasetCreateFromMat: empty data");
@@ -273,28 +251,26 @@ Dataset::Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, in
   const int min_data_in_bin = params.GetInt("min_data_in_bin", 3);
   const int sample_cnt_cfg = params.GetInt("bin_construct_sample_cnt", 200000, {"subsample_for_bin"});
   const int data_random_seed = params.GetInt("data_random_seed", 1, {"data_seed"});
-  const bool pre_filter = params.GetBool("feature_pre_filter", true);
+  const bool pre_filter = params.GetBool("feature_pre_filter", false);  // GPBoost default (include/LightGBM/config.h:649)
   const int min_data_in_leaf = params.GetInt("min_data_in_leaf", 20, {"min_data_per_leaf", "min_data", "min_child_samples"});
   auto at = [&](int64_t i, int j) {
     return data_type == 0 ? At<float>(data, nrow, ncol, is_row_major, i, j) : At<double>(data, nrow, ncol, is_row_major, i, j);
   };
-  // ---- row sample (c_api.cpp:1182-1206)
-  Random rand(data_random_seed);
-  int sample_cnt = nrow < sample_cnt_cfg ? nrow : sample_cnt_cfg;
-  std::vector<int> sample_indices = rand.Sample(nrow, sample_cnt);
-  sample_cnt = (int)sample_indices.size();
-  const int filter_cnt = static_cast<int>(static_cast<double>(min_data_in_leaf * (int64_t)sample_cnt) / nrow);  // dataset_loader.cpp:644
+  // ---- bin boundaries from a row sample, on the host (c_api.cpp:1182-1206 draws the rows; dataset_loader.cpp:600-700 one feature at a time)
+  const std::vector<int> sample_rows = DrawSampleRows(nrow, std::min<int>(nrow, sample_cnt_cfg), data_random_seed);
+  const int sample_cnt = (int)sample_rows.size();
+  const int min_split_rows = static_cast<int>(static_cast<double>(min_data_in_leaf * (int64_t)sample_cnt) / nrow);  // dataset_loader.cpp:644
   bins_.resize(ncol);
 #pragma omp parallel for schedule(dynamic)
   for (int j = 0; j < ncol; ++j) {
     std::vector<double> vals;
     vals.reserve(sample_cnt);
     for (int s = 0; s < sample_cnt; ++s) {
-      const double v = at(sample_indices[s], j);
-      if (std::fabs(v) > kZeroThreshold || std::isnan(v)) vals.push_back(v);
+      const double v = at(sample_rows[s], j);
+      if (std::fabs(v) > kZeroThreshold || std::isnan(v)) vals.push_back(v);  // zeros stay implicit
     }
     try {
-      bins_[j] = FindBin(vals, (size_t)sample_cnt, max_bin, min_data_in_bin, filter_cnt, pre_filter);
+      bins_[j] = BoundsFromSample(vals, (size_t)sample_cnt, max_bin, min_data_in_bin, min_split_rows, pre_filter);
     } catch (...) {
       bins_[j].num_bin = -1;  // re-raised below (no exceptions across the OpenMP region)
     }
@@ -303,14 +279,41 @@ Dataset::Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, in
     if (bins_[j].num_bin < 0) Fatal("Missing values (NaN) in the feature matrix are not supported by the B200 tree learner yet");
   for (int j = 0; j < ncol; ++j)
     if (!bins_[j].trivial) used_features_.push_back(j);
-  // ---- value -> bin for every row (Dataset::PushOneRow -> BinMapper::ValueToBin), feature-major like DenseBin
-  bin_data_.resize((size_t)used_features_.size() * nrow);
-#pragma omp parallel for schedule(static)
-  for (int k = 0; k < (int)used_features_.size(); ++k) {
-    const int j = used_features_[k];
-    uint8_t* col = bin_data_.data() + (size_t)k * nrow;
-    for (int64_t i = 0; i < nrow; ++i) col[i] = (uint8_t)bins_[j].ValueToBin(at(i, j));
+  // ---- value -> bin for every row: on the device, straight into the learner's row-major layout (csrc/dev/binning.cu)
+  const int F = (int)used_features_.size();
+  if (F == 0) return;
+  fpad_ = (F + 31) / 32 * 32;
+  device_ = GetRuntime().device;
+  std::vector<int32_t> real(F), nb(F);
+  std::vector<double> ub((size_t)F * 256, std::numeric_limits<double>::infinity());
+  for (int k = 0; k < F; ++k) {
+    const FeatureBins& fb = bins_[used_features_[k]];
+    real[k] = used_features_[k];
+    nb[k] = fb.num_bin;
+    std::copy(fb.upper_bounds.begin(), fb.upper_bounds.end(), ub.begin() + (size_t)k * 256);
   }
+  if (gpbdev_bin_matrix(device_, data, data_type, nrow, ncol, is_row_major, F, real.data(), nb.data(), ub.data(), 256, fpad_, &bins_dev_) != 0) {
+    const std::string msg = gpbdev_bin_last_error();
+    // Without a device the Dataset keeps its metadata (labels, names, boundaries) so that callers reach the error where the
+    // reference's packages expect it — at Booster creation; there is no host binning path.
+    if (msg.find("no CUDA device") != std::string::npos) { bins_dev_ = nullptr; bins_error_ = msg; }
+    else Fatal(msg);
+  }
+}
+
+Dataset::~Dataset() {
+  if (bins_dev_ != nullptr) gpbdev_bin_free(device_, bins_dev_);
+}
+
+const uint8_t* Dataset::bins_device() const {
+  if (bins_dev_ == nullptr) Fatal(bins_error_.empty() ? std::string("The Dataset holds no binned features") : bins_error_);
+  return bins_dev_;
+}
+
+std::vector<uint8_t> Dataset::DownloadBins() const {
+  std::vector<uint8_t> out((size_t)num_data_ * fpad_);
+  if (gpbdev_bin_download(device_, bins_device(), num_data_, fpad_, out.data()) != 0) Fatal(gpbdev_bin_last_error());
+  return out;
 }
 
 void Dataset::SetLabel(const float* label, int n) {

@@ -1,5 +1,6 @@
-// Host-side Dataset of the B200 build: parameter parsing, bin finding and value->bin mapping for dense numerical
-// matrices; produces the feature-major uint8 bins the device tree learner consumes.
+// Dataset of the B200 build: parameter parsing and bin-boundary finding on the host (sample-based, once per data set), value -> bin
+// for every row on the device (csrc/dev/binning.cu); owns the row-major uint8 bin matrix in HBM that the tree
+// learner reads in place.
 //
 // Restates, for numerical features without missing values:
 //   LGBM_DatasetCreateFromMat / ...Mats           src/LightGBM/c_api.cpp:1112-1232 (row sampling with Random(data_random_seed))
@@ -9,7 +10,8 @@
 //   NeedFilter                                    bin.cpp:53-75
 //   BinMapper::ValueToBin                         include/LightGBM/bin.h:465-503
 //   Random::Sample / NextFloat / NextInt          include/LightGBM/utils/random.h:41-109
-// Bin finding runs once per dataset on the host, as in the reference (device binning is a later row).
+// The boundary search is formulated on runs of the sorted sample (dataset.cpp); its outputs are pinned to the reference's bins by
+// tests/test_binning_gpu.py (bins dumped by the reference's LGBM_DatasetDumpText).
 #ifndef GPB200_DATASET_H_
 #define GPB200_DATASET_H_
 #include <cstdint>
@@ -34,19 +36,26 @@ struct FeatureBins {
   int num_bin = 0;
   bool trivial = false;
   double min_val = 0., max_val = 0.;
-  uint32_t ValueToBin(double v) const;
 };
 
 class Dataset {
  public:
   // data: nrow x ncol, float32 or float64 (C_API_DTYPE_*), row- or column-major
   Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, const Params& params);
+  ~Dataset();
+  Dataset(const Dataset&) = delete;
+  Dataset& operator=(const Dataset&) = delete;
   int32_t num_data() const { return num_data_; }
   int num_total_features() const { return num_total_features_; }
   int num_features() const { return (int)used_features_.size(); }   // non-trivial ("inner") features
   int real_feature_index(int inner) const { return used_features_[inner]; }
   const FeatureBins& feature(int inner) const { return bins_[used_features_[inner]]; }
-  const std::vector<uint8_t>& bins_feature_major() const { return bin_data_; }  // num_features() x num_data
+  const FeatureBins& feature_by_real_index(int real) const { return bins_[real]; }
+  // device matrix, row-major num_data() x bins_row_stride() uint8 (padding features 0); throws when the process has no device
+  const uint8_t* bins_device() const;
+  int bins_row_stride() const { return fpad_; }
+  int bins_device_id() const { return device_; }
+  std::vector<uint8_t> DownloadBins() const;  // test hook (GPB200_DatasetGetBins)
   void SetLabel(const float* label, int n);
   const std::vector<float>& label() const { return label_; }
   bool has_label() const { return !label_.empty(); }
@@ -63,7 +72,9 @@ class Dataset {
   Params params_;
   std::vector<FeatureBins> bins_;      // per real feature
   std::vector<int> used_features_;     // inner -> real
-  std::vector<uint8_t> bin_data_;
+  uint8_t* bins_dev_ = nullptr;        // owned, on device_
+  int fpad_ = 0, device_ = 0;
+  std::string bins_error_;             // why bins_dev_ is null (no device in this process)
   std::vector<float> label_;
   std::vector<std::string> feature_names_;
 };

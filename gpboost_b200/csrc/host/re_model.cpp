@@ -521,12 +521,8 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
 void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
                           bool reuse_learning_rates_from_previous_call) {
   if (!gauss_) {
-    // The fit itself is host logic checked against the reference's fits (tests/test_laplace_oracle_pinned.py drives this L-BFGS
-    // with the oracle's likelihood and gradient: same iteration counts); the device gradient it needs has not run on a B200 yet,
-    // so the entry stays closed unless asked for explicitly.
-    const char* e = std::getenv("GPB200_LAPLACE_FIT");
-    if (e == nullptr || std::string(e) != "1")
-      Fatal("Covariance parameter estimation for likelihood '" + likelihood_ + "' is not enabled yet (the Laplace-approximated likelihood and the posterior mode are; the gradient is awaiting its B200 parity run: GPB200_LAPLACE_FIT=1 opts in)");
+    // L-BFGS on log(cov_pars) with the device gradient of the Laplace-approximated likelihood (tests/test_laplace_gpu.py: gradient and
+    // fits against the reference's goldens on the B200; tests/test_laplace_oracle_pinned.py: the same driver fed by the oracle)
     OptimCovParLaplace(y_data, fixed_effects);
     return;
   }

@@ -79,7 +79,7 @@ typedef void* BoosterHandle;  /* c_api.h:36 */
 #define C_API_DTYPE_FLOAT64 (1)
 #define C_API_PREDICT_NORMAL (0)
 #define C_API_PREDICT_RAW_SCORE (1)
-/* c_api.h:236 — bin finding (BinMapper::FindBin) + value->bin on the host, bins handed to the device learner */
+/* c_api.h:236 — bin boundaries (BinMapper::FindBin) on the host from the row sample, value->bin for all rows on the device */
 GPB200_EXPORT int LGBM_DatasetCreateFromMat(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major,
     const char* parameters, const DatasetHandle reference, DatasetHandle* out);
 /* c_api.h:351 — field "label" (float32) */
@@ -110,6 +110,8 @@ GPB200_EXPORT int LGBM_BoosterSaveModelToString(BoosterHandle handle, int start_
     int feature_importance_type, int64_t buffer_len, int64_t* out_len, char* out_str);
 
 /* ---- extensions of the B200 build (no counterpart in the reference's exported API) ---------------------- */
+/* test hook: the bin boundaries the host search found for one feature (upper_bounds: room for 256 doubles) */
+GPB200_EXPORT int GPB200_DatasetGetFeatureBins(DatasetHandle handle, int real_feature, int* num_bin, int* is_trivial, double* upper_bounds);
 /* device ordinal used by models created afterwards in this process (default 0) */
 GPB200_EXPORT int GPB200_SetDevice(int device);
 /* Row sharding of observations over `world_size` processes (one per GPU) + the sum-all-reduce used on shard

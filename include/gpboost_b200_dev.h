@@ -197,7 +197,26 @@ GPBDEV_EXPORT const char* gpbdev_tree_last_error(void);
  * Replaces TreeLearner::Init (serial_tree_learner.cpp:38-85). */
 GPBDEV_EXPORT int gpbdev_tree_create(gpbdev_tree_t* out, int device, int64_t n, int F, const uint8_t* bins_feature_major,
                                      const int32_t* num_bin, const gpbdev_tree_config* cfg);
+/* Same learner on a bin matrix that is already in HBM (gpbdev_bin_matrix below): bins_dev is row-major n x Fpad uint8 on `device`
+ * (Fpad a multiple of 32, padding bytes 0); the learner reads it in place and does NOT own it — a row shard is just an offset. */
+GPBDEV_EXPORT int gpbdev_tree_create_on_device_bins(gpbdev_tree_t* out, int device, int64_t n, int F, int Fpad, const uint8_t* bins_dev,
+                                                    const int32_t* num_bin, const gpbdev_tree_config* cfg);
 GPBDEV_EXPORT int gpbdev_tree_free(gpbdev_tree_t h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device binning. Replaces the n x F value -> bin pass of LGBM_DatasetCreateFromMat
+ * (src/LightGBM/c_api.cpp:1134-1232 -> BinMapper::ValueToBin, include/LightGBM/bin.h:465-503; numerical, MissingType::None).
+ * data_host: nrow x ncol matrix in host memory, data_type 0 = float32 / 1 = float64 (C_API_DTYPE_*), row- or column-major.
+ * real_feature[f] = column of used feature f; upper_bounds[f * upper_bounds_stride + b], b < num_bin[f] = the feature's strictly
+ * increasing bin upper bounds (last one +inf). Output: *bins_dev_out = device buffer, row-major nrow x Fpad uint8 (Fpad multiple of 32,
+ * >= F; padding 0), released with gpbdev_bin_free. No CPU fallback: fails without a CUDA device. */
+GPBDEV_EXPORT const char* gpbdev_bin_last_error(void);
+GPBDEV_EXPORT int gpbdev_bin_matrix(int device, const void* data_host, int data_type, int64_t nrow, int ncol, int is_row_major, int F,
+                                    const int32_t* real_feature, const int32_t* num_bin, const double* upper_bounds,
+                                    int upper_bounds_stride, int Fpad, uint8_t** bins_dev_out);
+GPBDEV_EXPORT int gpbdev_bin_free(int device, uint8_t* bins_dev);
+/* test hook: the bin matrix back on the host (nrow x Fpad bytes) */
+GPBDEV_EXPORT int gpbdev_bin_download(int device, const uint8_t* bins_dev, int64_t nrow, int Fpad, uint8_t* out_host);
 /* Grow one tree from gradients (n doubles; host pointer, or device pointer when grad_on_device != 0) with hessian == hess_const.
  * Replaces SerialTreeLearner::Train (serial_tree_learner.cpp:159-209). Output arrays are caller-allocated with num_leaves entries:
  * per internal node split_feature / threshold_bin / left_child / right_child (~leaf for leaves, Tree convention) / split_gain;

@@ -96,16 +96,11 @@ def test_large_n_self_consistency():
     assert 1 <= info[1] <= 20 and info[3] >= 2
 
 
-# ---- paths written after the round's GPU budget was spent: they run only on request until they have passed once on a B200
-UNVERIFIED = pytest.mark.skipif(os.environ.get("GPB200_RUN_UNVERIFIED") != "1",
-                                reason="not yet run on a B200 (set GPB200_RUN_UNVERIFIED=1)")
-
-
-@UNVERIFIED
 @pytest.mark.parametrize("idx", range(len(GOLD)))
 def test_latent_factor_range_derivative_matches_oracle(idx):
     """MODE_STORE_GRAD of the factor kernel: A, D^-1 and their derivatives w.r.t. log(range) of the latent factor
-    (B_grad[1], D_grad[1] of CalcCovFactorGradientVecchia) against the oracle's restatement, <= 1e-9 relative."""
+    (B_grad[1], D_grad[1] of CalcCovFactorGradientVecchia) against the oracle's restatement, <= 1e-8 of the largest entry (the
+    north_star's fp64 tolerance; the latent blocks carry no nugget, so two fp64 evaluation orders differ by ~2e-9 there)."""
     import ctypes as C
     c = GOLD[idx]
     X, y, off = data_of(c)
@@ -123,10 +118,9 @@ def test_latent_factor_range_derivative_matches_oracle(idx):
     A0, Dinv0, dA0, dD0, bad = ol.factor_latent_grad(vo.coords, vo.nn, vo.cid, c["cov_pars"][0], pt[1])
     assert bad == 0
     for got, want, name in ((A, A0, "A"), (Dinv, Dinv0, "Dinv"), (dA, dA0, "dA"), (dD, dD0, "dD")):
-        assert np.max(np.abs(got - want)) <= 1e-9 * np.max(np.abs(want)), name
+        assert np.max(np.abs(got - want)) <= 1e-8 * np.max(np.abs(want)), name
 
 
-@UNVERIFIED
 @pytest.mark.parametrize("idx", range(len(GOLD)))
 def test_laplace_gradient_matches_reference_golden(idx):
     """Gradient of the Laplace-approximated likelihood w.r.t. (log variance, log range), iterative branch with the reference's
@@ -146,12 +140,10 @@ def test_laplace_gradient_matches_reference_golden(idx):
     assert np.all(np.abs(g - want) <= 1e-5 * np.abs(want).max()), (g, want)
 
 
-@UNVERIFIED
 @pytest.mark.parametrize("idx", [i for i, c in enumerate(GOLD) if "fit_iterative" in c])
-def test_laplace_fit_matches_reference_golden(idx, monkeypatch):
+def test_laplace_fit_matches_reference_golden(idx):
     """GPB_OptimCovPar for the bernoulli_logit Vecchia model on the device against the reference's fit (defaults: L-BFGS,
     iterative method, 50 probes)."""
-    monkeypatch.setenv("GPB200_LAPLACE_FIT", "1")
     c = GOLD[idx]
     X, y, off = data_of(c)
     mdl = product_model(c, X)
