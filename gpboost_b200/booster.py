@@ -86,16 +86,16 @@ class Booster(object):
         self._safe_call(self._LIB.LGBM_BoosterGetCurrentIteration(self.handle, ctypes.byref(it)))
         return it.value
 
-    def model_to_string(self):
+    def model_to_string(self, start_iteration=0, num_iteration=-1):
         n = ctypes.c_int64(0)
         buf_len = 1 << 20
         buf = ctypes.create_string_buffer(buf_len)
-        self._safe_call(self._LIB.LGBM_BoosterSaveModelToString(self.handle, ctypes.c_int(0), ctypes.c_int(-1), ctypes.c_int(0),
+        self._safe_call(self._LIB.LGBM_BoosterSaveModelToString(self.handle, ctypes.c_int(start_iteration), ctypes.c_int(num_iteration), ctypes.c_int(0),
                                                                 ctypes.c_int64(buf_len), ctypes.byref(n), buf))
         if n.value > buf_len:
             buf_len = n.value
             buf = ctypes.create_string_buffer(buf_len)
-            self._safe_call(self._LIB.LGBM_BoosterSaveModelToString(self.handle, ctypes.c_int(0), ctypes.c_int(-1), ctypes.c_int(0),
+            self._safe_call(self._LIB.LGBM_BoosterSaveModelToString(self.handle, ctypes.c_int(start_iteration), ctypes.c_int(num_iteration), ctypes.c_int(0),
                                                                     ctypes.c_int64(buf_len), ctypes.byref(n), buf))
         return buf.value.decode("utf-8")
 
@@ -111,14 +111,14 @@ class Booster(object):
         self._safe_call(self._LIB.LGBM_BoosterGetPredict(self.handle, ctypes.c_int(0), ctypes.byref(n), _dptr(out)))
         return out
 
-    def predict(self, data, raw_score=True):
+    def predict(self, data, raw_score=True, start_iteration=0, num_iteration=-1):
         data = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
         n = ctypes.c_int64(0)
         out = np.empty(data.shape[0], dtype=np.float64)
         self._safe_call(self._LIB.LGBM_BoosterPredictForMat(
             self.handle, data.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(C_API_DTYPE_FLOAT64), ctypes.c_int32(data.shape[0]),
             ctypes.c_int32(data.shape[1]), ctypes.c_int(1), ctypes.c_int(C_API_PREDICT_RAW_SCORE if raw_score else C_API_PREDICT_NORMAL),
-            ctypes.c_int(0), ctypes.c_int(-1), c_str(""), ctypes.byref(n), _dptr(out)))
+            ctypes.c_int(start_iteration), ctypes.c_int(num_iteration), c_str(""), ctypes.byref(n), _dptr(out)))
         return out
 
     def __del__(self):

@@ -24,13 +24,19 @@ std::string Num(double v) {
 }
 }  // namespace
 
-double Tree::Predict(const double* row) const {  // Tree::Predict / NumericalDecision (tree.h:577-640), MissingType::None
+double Tree::Predict(const double* row) const {  // Tree::Predict / NumericalDecision (tree.h:329-347): all three missing types
   if (num_leaves <= 1) return leaf_value[0];
+  constexpr double kZero = 1e-35f;
   int node = 0;
   while (node >= 0) {
     double fval = row[split_feature[node]];
-    if (std::isnan(fval)) fval = 0.0;
-    node = fval <= threshold[node] ? left_child[node] : right_child[node];
+    const int dt = decision_type.empty() ? 2 : decision_type[node];
+    const int missing = (dt >> 2) & 3;  // 0 None, 1 Zero, 2 NaN
+    if (std::isnan(fval) && missing != 2) fval = 0.0;
+    if ((missing == 1 && fval >= -kZero && fval <= kZero) || (missing == 2 && std::isnan(fval)))
+      node = (dt & 2) ? left_child[node] : right_child[node];
+    else
+      node = fval <= threshold[node] ? left_child[node] : right_child[node];
   }
   return leaf_value[~node];
 }
@@ -43,7 +49,7 @@ std::string Tree::ToString() const {  // Tree::ToString (io/tree.cpp:333-400), f
   arr_i("split_feature", split_feature, num_leaves - 1);
   s << "split_gain="; for (int i = 0; i < num_leaves - 1; ++i) s << (i ? " " : "") << Num(split_gain[i]); s << "\n";
   arr_d("threshold", threshold, num_leaves - 1);
-  s << "decision_type="; for (int i = 0; i < num_leaves - 1; ++i) s << (i ? " " : "") << 2; s << "\n";
+  s << "decision_type="; for (int i = 0; i < num_leaves - 1; ++i) s << (i ? " " : "") << (decision_type.empty() ? 2 : decision_type[i]); s << "\n";
   arr_i("left_child", left_child, num_leaves - 1);
   arr_i("right_child", right_child, num_leaves - 1);
   arr_d("leaf_value", leaf_value, num_leaves);
@@ -67,9 +73,7 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
   learning_rate_ = params_.GetDouble("learning_rate", 0.1, {"shrinkage_rate", "eta"});
   boost_from_average_ = params_.GetBool("boost_from_average", true);
   train_gp_model_cov_pars_ = params_.GetBool("train_gp_model_cov_pars", true);
-  for (const char* k : {"bagging_fraction", "feature_fraction", "feature_fraction_bynode"})
-    if (params_.GetDouble(k, 1.0) < 1.0) Fatal(std::string(k) + " < 1 is not supported by the B200 booster yet");
-  if (params_.GetDouble("lambda_l1", 0., {"reg_alpha"}) > 0.) Fatal("lambda_l1 > 0 is not supported by the B200 booster yet");
+  params_.RejectUnsupported("Booster");
   if (params_.GetBool("leaves_newton_update", false) || params_.GetBool("line_search_step_length", false))
     Fatal("leaves_newton_update / line_search_step_length are not supported by the B200 booster yet");
   gpbdev_tree_config cfg;
@@ -137,6 +141,18 @@ Booster::Booster(const std::string& model_str) {
     if (nl > 1 && ((int)cur->left_child.size() != nl - 1 || (int)cur->right_child.size() != nl - 1 || (int)cur->split_feature.size() != nl - 1 ||
                    (int)cur->threshold.size() != nl - 1))
       Fatal("Tree model string format error, should contain left_child, right_child, split_feature and threshold fields");
+    if (nl < 1) Fatal("Tree model string format error: num_leaves must be >= 1");
+    if (!cur->decision_type.empty() && (int)cur->decision_type.size() != nl - 1) Fatal("Tree model string format error: decision_type has the wrong length");
+    // value ranges: a corrupt model must end in LGBM_GetLastError, not in an out-of-bounds read or an endless walk. Children of node i are
+    // leaves (~leaf in [0, nl)) or internal nodes with a LARGER index (Tree::Split appends nodes), so every walk terminates.
+    for (int i = 0; i < nl - 1; ++i) {
+      if (cur->split_feature[i] < 0 || (max_feature_idx_ >= 0 && cur->split_feature[i] > max_feature_idx_))
+        Fatal("Tree model string format error: split_feature out of range");
+      for (int c : {cur->left_child[i], cur->right_child[i]}) {
+        const bool ok = c >= 0 ? (c > i && c < nl - 1) : (~c < nl);
+        if (!ok) Fatal("Tree model string format error: child index out of range");
+      }
+    }
     if ((int)cur->leaf_count.size() != nl) cur->leaf_count.assign(nl, 0);
     if ((int)cur->split_gain.size() != std::max(nl - 1, 0)) cur->split_gain.assign(std::max(nl - 1, 0), 0.f);
     models_.push_back(std::move(cur));
@@ -175,8 +191,9 @@ Booster::Booster(const std::string& model_str) {
     else if (k == "split_gain") { t.split_gain.clear(); for (const auto& w : SplitWs(v)) t.split_gain.push_back(std::strtof(w.c_str(), nullptr)); }
     else if (k == "shrinkage") t.shrinkage = std::strtod(v.c_str(), nullptr);
     else if (k == "decision_type") {
-      for (const auto& w : SplitWs(v))  // 2 = numerical, default left, MissingType::None (tree.h kDefaultLeftMask); bit 0 = categorical
-        if ((std::atoi(w.c_str()) & 1) != 0) Fatal("Categorical splits are not supported by the B200 booster");
+      ints(&t.decision_type);  // bit 0 categorical, bit 1 default left, bits 2-3 missing type (tree.h:20-21, :270)
+      for (int dt : t.decision_type)
+        if ((dt & 1) != 0) Fatal("Categorical splits are not supported by the B200 booster");
     } else if (k == "is_linear") { if (std::atoi(v.c_str()) != 0) Fatal("Linear trees are not supported by the B200 booster"); }
   }
   if (num_class < 0) Fatal("Model file doesn't specify the number of classes");
@@ -270,8 +287,19 @@ void Booster::GetTrainingScore(double* out) {
   if (learner_ == nullptr) Fatal("This Booster was loaded from a model string / file and has no training data (prediction only)");
   TreeCheck(gpbdev_vec_download(learner_, out, score_dev_, n_)); }
 
-void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const {
+void Booster::IterationRange(int start_iteration, int num_iteration, int* first, int* count) const {  // gbdt.cpp PredictRaw clamping
+  const int total = (int)models_.size();
+  const int b = std::max(0, std::min(start_iteration, total));
+  int c = total - b;
+  if (num_iteration > 0) c = std::min(num_iteration, c);
+  *first = b; *count = c;
+}
+
+void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out, int start_iteration,
+                      int num_iteration) const {
   if (ncol != max_feature_idx_ + 1) Fatal("The number of features in data is not the same as it was in training data");
+  int first, count;
+  IterationRange(start_iteration, num_iteration, &first, &count);
   std::vector<double> row(ncol);
   for (int64_t i = 0; i < nrow; ++i) {
     for (int j = 0; j < ncol; ++j) {
@@ -279,7 +307,7 @@ void Booster::Predict(const void* data, int data_type, int32_t nrow, int32_t nco
       row[j] = data_type == 0 ? (double)static_cast<const float*>(data)[o] : static_cast<const double*>(data)[o];
     }
     double s = 0.;
-    for (const auto& t : models_) s += t->Predict(row.data());
+    for (int k = first; k < first + count; ++k) s += models_[k]->Predict(row.data());
     out[i] = s;
   }
 }
@@ -304,7 +332,7 @@ double Booster::LeafValue(int tree_idx, int leaf_idx) const {
   return t.leaf_value[leaf_idx];
 }
 
-std::string Booster::SaveModelToString() const {  // GBDT::SaveModelToString (boosting/gbdt_model_text.cpp), header subset
+std::string Booster::SaveModelToString(int start_iteration, int num_iteration) const {  // GBDT::SaveModelToString (gbdt_model_text.cpp:311-400)
   std::ostringstream s;
   s << "tree\nversion=v3\nnum_class=1\nnum_tree_per_iteration=1\nlabel_index=0\nmax_feature_idx=" << max_feature_idx_
     << "\nobjective=regression\nfeature_names=";
@@ -312,7 +340,9 @@ std::string Booster::SaveModelToString() const {  // GBDT::SaveModelToString (bo
   s << "\nfeature_infos=";
   for (size_t i = 0; i < feature_infos_.size(); ++i) s << (i ? " " : "") << feature_infos_[i];
   s << "\n\n";
-  for (size_t i = 0; i < models_.size(); ++i) s << "Tree=" << i << "\n" << models_[i]->ToString() << "\n\n";
+  int first, count;
+  IterationRange(start_iteration, num_iteration, &first, &count);
+  for (int i = 0; i < count; ++i) s << "Tree=" << i << "\n" << models_[first + i]->ToString() << "\n\n";
   s << "end of trees\n";
   return s.str();
 }

@@ -23,6 +23,7 @@ struct Tree {
   std::vector<int> threshold_bin;
   std::vector<double> threshold;        // bin upper bound (Dataset::RealThreshold)
   std::vector<int> left_child, right_child;
+  std::vector<int> decision_type;       // per internal node (tree.h:20-21, :270): bit 1 default-left, bits 2-3 missing type; empty = all 2
   std::vector<float> split_gain;
   std::vector<double> leaf_value;
   std::vector<int> leaf_count;
@@ -46,8 +47,12 @@ class Booster {
   int num_models() const { return (int)models_.size(); }
   int64_t num_data() const { return n_; }
   void GetTrainingScore(double* out);
-  void Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out) const;
-  std::string SaveModelToString() const;
+  // trees [first, first + count) of the ensemble, clamped like GBDT::PredictRaw / SaveModelToString (start_iteration, num_iteration
+  // of the C API; num_iteration <= 0: all remaining)
+  void IterationRange(int start_iteration, int num_iteration, int* first, int* count) const;
+  void Predict(const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major, double* out, int start_iteration = 0,
+               int num_iteration = -1) const;
+  std::string SaveModelToString(int start_iteration = 0, int num_iteration = -1) const;
   // GBDT::FeatureImportance (gbdt_model_text.cpp:638-674): importance_type 0 = number of splits, 1 = total gain
   std::vector<double> FeatureImportance(int num_iteration, int importance_type) const;
   double LeafValue(int tree_idx, int leaf_idx) const;

@@ -257,20 +257,20 @@ int LGBM_BoosterGetPredict(BoosterHandle handle, int data_idx, int64_t* out_len,
 }
 
 int LGBM_BoosterPredictForMat(BoosterHandle handle, const void* data, int data_type, int32_t nrow, int32_t ncol, int is_row_major,
-                              int predict_type, int /*start_iteration*/, int /*num_iteration*/, const char* /*parameter*/,
+                              int predict_type, int start_iteration, int num_iteration, const char* /*parameter*/,
                               int64_t* out_len, double* out_result) {
   API_BEGIN();
   if (predict_type != C_API_PREDICT_NORMAL && predict_type != C_API_PREDICT_RAW_SCORE)
     throw std::runtime_error("Only normal / raw-score prediction is supported by the B200 build");
-  B(handle)->Predict(data, data_type, nrow, ncol, is_row_major, out_result);
+  B(handle)->Predict(data, data_type, nrow, ncol, is_row_major, out_result, start_iteration, num_iteration);
   *out_len = nrow;
   API_END();
 }
 
-int LGBM_BoosterSaveModelToString(BoosterHandle handle, int /*start_iteration*/, int /*num_iteration*/, int /*feature_importance_type*/,
+int LGBM_BoosterSaveModelToString(BoosterHandle handle, int start_iteration, int num_iteration, int /*feature_importance_type*/,
                                   int64_t buffer_len, int64_t* out_len, char* out_str) {
   API_BEGIN();
-  const std::string s = B(handle)->SaveModelToString();
+  const std::string s = B(handle)->SaveModelToString(start_iteration, num_iteration);
   *out_len = (int64_t)s.size() + 1;
   if (*out_len <= buffer_len) std::memcpy(out_str, s.c_str(), *out_len);
   API_END();
@@ -353,7 +353,7 @@ void CopyNames(const std::vector<std::string>& names, int len, int* out_len, siz
   *out_len = (int)names.size();
   *out_buffer_len = 0;
   for (size_t i = 0; i < names.size(); ++i) {
-    if ((int)i < len) {
+    if ((int)i < len && buffer_len > 0) {
       std::memcpy(out_strs[i], names[i].c_str(), std::min(names[i].size() + 1, buffer_len));
       out_strs[i][buffer_len - 1] = '\0';
     }
@@ -434,9 +434,9 @@ int LGBM_BoosterGetLeafValue(BoosterHandle handle, int tree_idx, int leaf_idx, d
   API_END();
 }
 
-int LGBM_BoosterSaveModel(BoosterHandle handle, int /*start_iteration*/, int /*num_iteration*/, int /*feature_importance_type*/, const char* filename) {
+int LGBM_BoosterSaveModel(BoosterHandle handle, int start_iteration, int num_iteration, int /*feature_importance_type*/, const char* filename) {
   API_BEGIN();
-  const std::string s = B(handle)->SaveModelToString();
+  const std::string s = B(handle)->SaveModelToString(start_iteration, num_iteration);
   FILE* f = std::fopen(filename, "wb");
   if (f == nullptr) throw std::runtime_error(std::string("Model file ") + filename + " is not available for writes");
   std::fwrite(s.data(), 1, s.size(), f);

@@ -203,6 +203,39 @@ inline double At(const void* data, int32_t nrow, int32_t ncol, int is_row_major,
 
 }  // namespace
 
+// Aliases of the parameters this build reads or has to refuse (the reference resolves them in Config::alias_table,
+// src/LightGBM/io/config_auto.cpp:11-170, before anything else looks at a key): alias -> canonical name.
+static const std::map<std::string, std::string>& AliasTable() {
+  static const std::map<std::string, std::string> t = {
+      {"objective_type", "objective"}, {"app", "objective"}, {"application", "objective"}, {"likelihood", "objective"},
+      {"shrinkage_rate", "learning_rate"}, {"eta", "learning_rate"},
+      {"num_leaf", "num_leaves"}, {"max_leaves", "num_leaves"}, {"max_leaf", "num_leaves"},
+      {"tree", "tree_learner"}, {"tree_type", "tree_learner"}, {"tree_learner_type", "tree_learner"},
+      {"boosting_type", "boosting"}, {"boost", "boosting"},
+      {"min_data_per_leaf", "min_data_in_leaf"}, {"min_data", "min_data_in_leaf"}, {"min_child_samples", "min_data_in_leaf"},
+      {"min_sum_hessian_per_leaf", "min_sum_hessian_in_leaf"}, {"min_sum_hessian", "min_sum_hessian_in_leaf"},
+      {"min_hessian", "min_sum_hessian_in_leaf"}, {"min_child_weight", "min_sum_hessian_in_leaf"},
+      {"sub_row", "bagging_fraction"}, {"subsample", "bagging_fraction"}, {"bagging", "bagging_fraction"},
+      {"pos_sub_row", "pos_bagging_fraction"}, {"pos_subsample", "pos_bagging_fraction"}, {"pos_bagging", "pos_bagging_fraction"},
+      {"neg_sub_row", "neg_bagging_fraction"}, {"neg_subsample", "neg_bagging_fraction"}, {"neg_bagging", "neg_bagging_fraction"},
+      {"subsample_freq", "bagging_freq"},
+      {"sub_feature", "feature_fraction"}, {"colsample_bytree", "feature_fraction"},
+      {"sub_feature_bynode", "feature_fraction_bynode"}, {"colsample_bynode", "feature_fraction_bynode"},
+      {"max_tree_output", "max_delta_step"}, {"max_leaf_output", "max_delta_step"},
+      {"reg_alpha", "lambda_l1"}, {"reg_lambda", "lambda_l2"}, {"lambda", "lambda_l2"},
+      {"min_split_gain", "min_gain_to_split"},
+      {"mc", "monotone_constraints"}, {"monotone_constraint", "monotone_constraints"},
+      {"feature_contrib", "feature_contri"}, {"fc", "feature_contri"}, {"fp", "feature_contri"}, {"feature_penalty", "feature_contri"},
+      {"fs", "forcedsplits_filename"}, {"forced_splits_filename", "forcedsplits_filename"}, {"forced_splits_file", "forcedsplits_filename"},
+      {"forced_splits", "forcedsplits_filename"},
+      {"verbose", "verbosity"},
+      {"subsample_for_bin", "bin_construct_sample_cnt"}, {"data_seed", "data_random_seed"},
+      {"cat_feature", "categorical_feature"}, {"categorical_column", "categorical_feature"}, {"cat_column", "categorical_feature"},
+      {"num_classes", "num_class"}, {"unbalance", "is_unbalance"}, {"unbalanced_sets", "is_unbalance"},
+  };
+  return t;
+}
+
 Params Params::Parse(const char* s) {
   Params p;
   if (!s) return p;
@@ -211,10 +244,41 @@ Params Params::Parse(const char* s) {
   while (is >> tok) {
     auto eq = tok.find('=');
     if (eq == std::string::npos) continue;
-    p.kv[tok.substr(0, eq)] = tok.substr(eq + 1);
+    std::string key = tok.substr(0, eq);
+    auto al = AliasTable().find(key);
+    if (al != AliasTable().end()) key = al->second;
+    p.kv[key] = tok.substr(eq + 1);
   }
   return p;
 }
+
+// Parameters that change the model in the reference but that this build does not implement: refuse them instead of training a
+// different model silently. Keys are canonical (Parse resolves aliases). A value equal to the reference's default passes.
+void Params::RejectUnsupported(const char* where) const {
+  auto bad = [&](const std::string& k, const std::string& why) {
+    Fatal(std::string(where) + ": parameter '" + k + "=" + kv.at(k) + "' is not supported by the B200 build (" + why + ")");
+  };
+  auto has = [&](const char* k) { return kv.find(k) != kv.end() && !kv.at(k).empty(); };
+  auto num = [&](const char* k, double d) { return has(k) ? std::stod(kv.at(k)) : d; };
+  auto flag = [&](const char* k) { return has(k) && GetBool(k, false); };
+  auto nonempty_list = [&](const char* k) { return has(k) && kv.at(k) != "\"\"" && kv.at(k) != "''" && kv.at(k) != "none" && kv.at(k) != "None"; };
+  if (has("boosting") && kv.at("boosting") != "gbdt" && kv.at("boosting") != "gbrt") bad("boosting", "only gbdt");
+  if (has("tree_learner") && kv.at("tree_learner") != "serial" && kv.at("tree_learner") != "data" && kv.at("tree_learner") != "data_parallel")
+    bad("tree_learner", "serial, or data-parallel through GPB200_NcclInit");
+  for (const char* k : {"bagging_fraction", "pos_bagging_fraction", "neg_bagging_fraction", "feature_fraction", "feature_fraction_bynode"})
+    if (num(k, 1.0) < 1.0) bad(k, "row / feature sampling is not implemented");
+  for (const char* k : {"lambda_l1", "max_delta_step", "path_smooth", "linear_lambda", "cegb_penalty_split", "monotone_penalty"})
+    if (num(k, 0.0) > 0.0) bad(k, "not implemented");
+  for (const char* k : {"extra_trees", "linear_tree", "use_nesterov_acc", "zero_as_missing", "is_unbalance", "use_quantized_grad"})
+    if (flag(k)) bad(k, "not implemented");
+  for (const char* k : {"monotone_constraints", "categorical_feature", "max_bin_by_feature", "interaction_constraints", "feature_contri",
+                        "forcedsplits_filename", "forcedbins_filename", "cegb_penalty_feature_lazy", "cegb_penalty_feature_coupled"})
+    if (nonempty_list(k)) bad(k, "not implemented");
+  if (has("num_class") && std::stoi(kv.at("num_class")) != 1) bad("num_class", "single-output regression only");
+  if (has("device_type") && kv.at("device_type") != "cuda" && kv.at("device_type") != "gpu" && kv.at("device_type") != "cpu")
+    bad("device_type", "unknown device");
+}
+
 static const std::string* Find(const std::map<std::string, std::string>& kv, const std::string& k, std::initializer_list<const char*> al) {
   auto it = kv.find(k);
   if (it != kv.end()) return &it->second;
@@ -246,6 +310,7 @@ Dataset::Dataset(const void* data, int data_type, int32_t nrow, int32_t ncol, in
     : num_data_(nrow), num_total_features_(ncol), params_(params) {
   if (data == nullptr || nrow <= 0 || ncol <= 0) Fatal("LGBM_DatasetCreateFromMat: empty data");
   if (data_type != 0 && data_type != 1) Fatal("Unknown data type in LGBM_DatasetCreateFromMat (float32 / float64 supported)");
+  params.RejectUnsupported("Dataset");
   const int max_bin = params.GetInt("max_bin", 255);
   if (max_bin < 2 || max_bin > 255) Fatal("max_bin must be in [2, 255] for the B200 tree learner (uint8 bins)");
   const int min_data_in_bin = params.GetInt("min_data_in_bin", 3);

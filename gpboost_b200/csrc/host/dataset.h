@@ -24,7 +24,8 @@ namespace gpb200 {
 // key=value parameters ("parameters" strings of the LGBM_* API; Config::Str2Map, src/LightGBM/io/config.cpp)
 struct Params {
   std::map<std::string, std::string> kv;
-  static Params Parse(const char* s);
+  static Params Parse(const char* s);  // keys are stored under their canonical names (aliases resolved)
+  void RejectUnsupported(const char* where) const;  // throws for result-changing parameters this build does not implement
   int GetInt(const std::string& k, int dflt, std::initializer_list<const char*> aliases = {}) const;
   double GetDouble(const std::string& k, double dflt, std::initializer_list<const char*> aliases = {}) const;
   bool GetBool(const std::string& k, bool dflt, std::initializer_list<const char*> aliases = {}) const;

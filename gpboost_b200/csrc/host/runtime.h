@@ -5,8 +5,8 @@
 // that sums a small fp64 buffer over all ranks (torch.distributed over NCCL/NVLink in bench.py, gloo in CPU tests).
 #ifndef GPB200_RUNTIME_H_
 #define GPB200_RUNTIME_H_
-namespace gpb200 {
 #include <cstdint>
+namespace gpb200 {
 typedef void (*AllReduceSumFn)(double* buf, int count);
 // in-place sum-all-reduce of a DEVICE buffer, enqueued on `stream` (cudaStream_t); same type as gpbdev_allreduce_fn
 typedef int (*AllReduceDevFn)(void* ctx, double* dev_buf, int64_t count, void* stream);
