@@ -152,6 +152,20 @@ int GPB_GetOptimizerCovPars(REModelHandle handle, char* out_str, int* num_char) 
   API_END();
 }
 
+// defaults of the reference for the models this build covers: coefficients "wls" (Gaussian) / "lbfgs" (InitializeOptimSettings,
+// re_model_template.h:8280-8288); CG preconditioner "vadu" for a non-Gaussian Vecchia model, unset otherwise (:7128-7142)
+int GPB_GetOptimizerCoef(REModelHandle handle, char* out_str, int* num_char) {
+  API_BEGIN();
+  CopyString(M(handle)->LikelihoodName() == "gaussian" ? "wls" : "lbfgs", out_str, num_char);
+  API_END();
+}
+
+int GPB_GetCGPreconditionerType(REModelHandle handle, char* out_str, int* num_char) {
+  API_BEGIN();
+  CopyString(M(handle)->LikelihoodName() == "gaussian" ? "" : "vadu", out_str, num_char);
+  API_END();
+}
+
 int GPB_CanCalculateStandardErrorsCovPars(REModelHandle handle, int* out) {
   API_BEGIN();
   M(handle);

@@ -44,13 +44,6 @@ int GPB_GetAuxPars(REModelHandle handle, double* aux_pars, char* out_str, bool c
   API_END();
 }
 
-int GPB_GetCGPreconditionerType(REModelHandle handle, char* out_str, int* num_char) {
-  API_BEGIN();
-  (void)handle; (void)out_str; (void)num_char;
-  Unsupported("GPB_GetCGPreconditionerType");
-  API_END();
-}
-
 int GPB_GetCoef(REModelHandle handle, double* optim_coef, bool calc_std_dev) {
   API_BEGIN();
   (void)handle; (void)optim_coef; (void)calc_std_dev;
@@ -99,13 +92,6 @@ int GPB_GetOffsetData(REModelHandle handle, double* fixed_effects) {
   API_BEGIN();
   (void)handle; (void)fixed_effects;
   Unsupported("GPB_GetOffsetData");
-  API_END();
-}
-
-int GPB_GetOptimizerCoef(REModelHandle handle, char* out_str, int* num_char) {
-  API_BEGIN();
-  (void)handle; (void)out_str; (void)num_char;
-  Unsupported("GPB_GetOptimizerCoef");
   API_END();
 }
 
