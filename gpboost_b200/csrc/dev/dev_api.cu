@@ -14,6 +14,7 @@
 
 #include "knn.cuh"
 #include "vecchia_factor.cuh"
+#include "vecchia_big.cuh"
 
 namespace {
 
@@ -125,6 +126,25 @@ FactorKernel pick_kernel(int cov, int mode, int d, int m) {
     case gpb::COV_MATERN15: return pick_mode<gpb::COV_MATERN15>(mode, d, m);
     case gpb::COV_MATERN25: return pick_mode<gpb::COV_MATERN25>(mode, d, m);
     default: return pick_mode<gpb::COV_GAUSSIAN>(mode, d, m);
+  }
+}
+
+using BigKernel = void (*)(const gpb::BigArgs);
+template <int COV>
+BigKernel pick_big_mode(int mode) {
+  switch (mode) {
+    case gpb::BIG_NLL: return gpb::vecchia_big_kernel<COV, gpb::BIG_NLL>;
+    case gpb::BIG_STORE: return gpb::vecchia_big_kernel<COV, gpb::BIG_STORE>;
+    case gpb::BIG_GRAD: return gpb::vecchia_big_kernel<COV, gpb::BIG_GRAD>;
+    default: return gpb::vecchia_big_kernel<COV, gpb::BIG_PRED>;
+  }
+}
+BigKernel pick_big_kernel(int cov, int mode) {
+  switch (cov) {
+    case gpb::COV_EXPONENTIAL: return pick_big_mode<gpb::COV_EXPONENTIAL>(mode);
+    case gpb::COV_MATERN15: return pick_big_mode<gpb::COV_MATERN15>(mode);
+    case gpb::COV_MATERN25: return pick_big_mode<gpb::COV_MATERN25>(mode);
+    default: return pick_big_mode<gpb::COV_GAUSSIAN>(mode);
   }
 }
 
@@ -242,6 +262,31 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
     CUDA_TRY(cudaMemcpyToSymbolAsync(gpb::g_factor_dD, &h->dD, sizeof(double*), 0, cudaMemcpyHostToDevice, h->stream));
   }
   if (latent && mode == gpb::MODE_GRAD) return fail("gpbdev_vecchia_eval: the gradient pass assumes a Gaussian likelihood");
+  if (h->m > gpb::kMaxNeighbors) {  // 30 < num_neighbors <= 60: shared-memory kernel (vecchia_big.cuh), same sums and factor layout
+    if (mode == gpb::MODE_STORE_GRAD) return fail("gpbdev_vecchia_eval: the factor derivative (non-Gaussian likelihoods) supports num_neighbors <= 30");
+    gpb::BigArgs b;
+    b.coords = h->coords; b.y = h->y; b.nn = h->nn; b.qcoords = nullptr;
+    b.A = h->A; b.Dinv = h->Dinv; b.w = h->u; b.pred_mean = nullptr; b.pred_var = nullptr; b.partials = h->partials;
+    b.row_begin = h->row_begin; b.row_end = h->row_end; b.m = h->m; b.d = h->d;
+    b.var = var; b.range = range; b.diag_nb = a.diag_nb; b.diag_obs = a.diag_obs;
+    const int bmode = mode == gpb::MODE_NLL ? gpb::BIG_NLL : (mode == gpb::MODE_STORE ? gpb::BIG_STORE : gpb::BIG_GRAD);
+    const int warps = bmode == gpb::BIG_GRAD ? 2 : 4;
+    BigKernel bk = pick_big_kernel(cov_type, bmode);
+    const size_t bsmem = gpb::big_smem_bytes(bmode, warps, h->d);
+    CUDA_TRY(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int grid = std::min(h->num_sms, (int)((h->grid_cap * gpb::kWarpsPerBlock) / warps));  // one CTA per SM; partials has grid_cap * 4 rows
+    grid = std::max(grid, 1);
+    bk<<<grid, warps * 32, bsmem, h->stream>>>(b);
+    CUDA_TRY(cudaGetLastError());
+    reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)grid * warps, h->sums);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    if (h->allreduce && !latent) {
+      if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
+    }
+    if (mode == gpb::MODE_STORE) h->factor_stored = true;
+    return 0;
+  }
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);
   const size_t smem = sizeof(double) * gpb::kWarpsPerBlock * (32 * gpb::kLd + 32 * h->d + 64);
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -286,8 +331,8 @@ int gpbdev_vecchia_create(gpbdev_vecchia_t* out, int device, int64_t n, int d, i
                           const int32_t* perm, const int32_t* nn, int64_t row_begin, int64_t row_end) {
   if (!out || !coords_ordered || !perm) return fail("gpbdev_vecchia_create: null argument");
   if (n <= 0 || d <= 0 || d > 16) return fail("gpbdev_vecchia_create: need n > 0 and 1 <= dim <= 16");
-  if (m < 1 || m > gpb::kMaxNeighbors)
-    return fail("gpbdev_vecchia_create: num_neighbors must be in [1, " + std::to_string(gpb::kMaxNeighbors) +
+  if (m < 1 || m > gpb::kBigMaxNeighbors)
+    return fail("gpbdev_vecchia_create: num_neighbors must be in [1, " + std::to_string(gpb::kBigMaxNeighbors) +
                 "] for the B200 Vecchia engine");
   if ((int64_t)n * m >= (int64_t)2147483647) return fail("gpbdev_vecchia_create: n * num_neighbors exceeds int32 positions");
   if (row_begin < 0 || row_end > n || row_begin > row_end) return fail("gpbdev_vecchia_create: bad row shard");
@@ -459,6 +504,84 @@ int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale
 
 // latent factor (non-Gaussian likelihood: no nugget, jitter on the neighbour blocks) with its range derivative, to host buffers:
 // A, dA n x m row-major; Dinv, dD n. Test / diagnostics entry of MODE_STORE_GRAD.
+// Vecchia prediction at new locations, observed data ordered first, neighbours among the observed points only
+// (CalcPredVecchiaObservedFirstOrder, CondObsOnly = true: src/GPBoost/Vecchia_utils.cpp:1701-2100). Uses the responses of the last
+// gpbdev_vecchia_set_y*. coords_pred_host: np x d row-major. Outputs (host, np each): mean = A_p y_N(p), var = D_p on the
+// transformed scale (the caller multiplies by sigma^2 and adds the nugget when the response is predicted).
+int gpbdev_vecchia_predict(gpbdev_vecchia_t h, int cov_type, double var, double range, const double* coords_pred_host, int64_t np,
+                           int num_neighbors_pred, double* mean_out_host, double* var_out_host) {
+  if (!h || !coords_pred_host || !mean_out_host || !var_out_host) return fail("gpbdev_vecchia_predict: null argument");
+  if (np <= 0) return fail("gpbdev_vecchia_predict: no prediction points");
+  if (cov_type < 0 || cov_type > 3) return fail("gpbdev_vecchia_predict: unknown covariance id");
+  if (!(var > 0.) || !(range > 0.)) return fail("gpbdev_vecchia_predict: covariance parameters must be positive");
+  if (h->row_begin != 0 || h->row_end != h->n) return fail("gpbdev_vecchia_predict: prediction needs the whole model on this device (row-sharded engine)");
+  const int64_t n = h->n;
+  const int d = h->d;
+  int mp = (int)std::min<int64_t>(num_neighbors_pred, n);  // Vecchia_utils.cpp:752-755
+  if (mp < 1 || mp > gpb::kBigMaxNeighbors)
+    return fail("gpbdev_vecchia_predict: num_neighbors_pred must be in [1, " + std::to_string(gpb::kBigMaxNeighbors) + "] for the B200 Vecchia engine");
+  if ((n + np) >= (int64_t)2147483647 || np * (int64_t)mp >= (int64_t)2147483647) return fail("gpbdev_vecchia_predict: too many points for int32 indices");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const int64_t na = n + np;
+  // all points = observed (Vecchia order) followed by the prediction points; ranks in the sorted coordinate sums decide distance ties
+  std::vector<double> call((size_t)na * d);
+  CUDA_TRY(cudaMemcpy(call.data(), h->coords, sizeof(double) * n * d, cudaMemcpyDeviceToHost));
+  std::memcpy(call.data() + (size_t)n * d, coords_pred_host, sizeof(double) * np * d);
+  std::vector<double> csum((size_t)na);
+  for (int64_t i = 0; i < na; ++i) {
+    double sacc = 0.;
+    for (int k = 0; k < d; ++k) sacc += call[(size_t)i * d + k];
+    csum[(size_t)i] = sacc;
+  }
+  std::vector<int> sort_sum((size_t)na);
+  std::iota(sort_sum.begin(), sort_sum.end(), 0);
+  std::sort(sort_sum.begin(), sort_sum.end(), [&csum](int i1, int i2) { return csum[i1] < csum[i2]; });
+  std::vector<int32_t> pos((size_t)na);
+  for (int64_t r = 0; r < na; ++r) pos[(size_t)sort_sum[(size_t)r]] = (int32_t)r;
+  double *call_dev = nullptr, *csum_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr;
+  int32_t *pos_dev = nullptr, *sort_dev = nullptr, *nnp = nullptr;
+  auto release = [&]() { cudaFree(call_dev); cudaFree(csum_dev); cudaFree(mean_dev); cudaFree(var_dev); cudaFree(pos_dev); cudaFree(sort_dev); cudaFree(nnp); };
+  cudaError_t e = cudaMalloc(&call_dev, sizeof(double) * na * d);
+  if (e == cudaSuccess) e = cudaMalloc(&csum_dev, sizeof(double) * na);
+  if (e == cudaSuccess) e = cudaMalloc(&pos_dev, sizeof(int32_t) * na);
+  if (e == cudaSuccess) e = cudaMalloc(&sort_dev, sizeof(int32_t) * na);
+  if (e == cudaSuccess) e = cudaMalloc(&nnp, sizeof(int32_t) * np * mp);
+  if (e == cudaSuccess) e = cudaMalloc(&mean_dev, sizeof(double) * np);
+  if (e == cudaSuccess) e = cudaMalloc(&var_dev, sizeof(double) * np);
+  if (e == cudaSuccess) e = cudaMemcpy(call_dev, call.data(), sizeof(double) * na * d, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(csum_dev, csum.data(), sizeof(double) * na, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pos_dev, pos.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sort_dev, sort_sum.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { release(); return fail(std::string("gpbdev_vecchia_predict: ") + cudaGetErrorString(e)); }
+  std::string err;
+  int replayed = 0;
+  const int nl = gpb::knn_vecchia_device(call_dev, call.data(), na, d, mp, pos_dev, sort_dev, csum_dev, nnp, h->stream, h->num_sms, &replayed, &err,
+                                         /*q_begin=*/n, /*end_search_at=*/n - 1);
+  if (nl < 0) { release(); return fail("gpbdev_vecchia_predict: device neighbour search failed: " + err); }
+  h->launches += nl;
+  gpb::BigArgs b;
+  b.coords = h->coords; b.y = h->y; b.nn = nnp; b.qcoords = call_dev + (size_t)n * d;
+  b.A = nullptr; b.Dinv = nullptr; b.w = nullptr; b.pred_mean = mean_dev; b.pred_var = var_dev; b.partials = nullptr;
+  b.row_begin = 0; b.row_end = np; b.m = mp; b.d = d;
+  b.var = var; b.range = range; b.diag_nb = var + 1.; b.diag_obs = var;  // Vecchia_utils.cpp:1940-1952 (nugget on the neighbour block), :1925-1931
+  BigKernel bk = pick_big_kernel(cov_type, gpb::BIG_PRED);
+  const size_t bsmem = gpb::big_smem_bytes(gpb::BIG_PRED, 4, d);
+  e = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+  if (e == cudaSuccess) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->num_sms, (np + 3) / 4));
+    bk<<<grid, 128, bsmem, h->stream>>>(b);
+    e = cudaGetLastError();
+    h->launches += 1;
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(mean_out_host, mean_dev, sizeof(double) * np, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(var_out_host, var_dev, sizeof(double) * np, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  release();
+  if (e != cudaSuccess) return fail(std::string("gpbdev_vecchia_predict: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 int gpbdev_vecchia_latent_factor_grad(gpbdev_vecchia_t h, int cov_type, double var, double range, double* A_host, double* Dinv_host,
                                       double* dA_host, double* dD_host) {
   if (!h || !A_host || !Dinv_host || !dA_host || !dD_host) return fail("gpbdev_vecchia_latent_factor_grad: null argument");

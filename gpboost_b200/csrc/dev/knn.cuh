@@ -50,16 +50,57 @@ __device__ __forceinline__ bool knn_before(double sa, int ra, double sb, int rb)
   return sa < sb || (sa == sb && ra < rb);
 }
 
-// one entry per lane, ascending over lanes; insert (s, r, id) if it sorts before the entry of lane m-1
-__device__ __forceinline__ void knn_insert(double& ks, int& kr, int& ki, double s, int r, int id, int lane, int m) {
-  const unsigned before = __ballot_sync(0xffffffffu, knn_before(ks, kr, s, r) || (ks == s && kr == r));
-  const int posn = __popc(before);  // entries are sorted: the first posn lanes stay
+// Running top-m of a query, m <= 32 * KS: KS entries per lane, entry (slot, lane) holds position slot * 32 + lane of the list,
+// ascending by (sed, rank). KS = 1 is the Vecchia search (m <= 30 neighbours ... 32), KS = 2 serves up to 64 (prediction uses
+// 2 m neighbours, re_model_template.h:299; models with 30 < num_neighbors <= 60).
+template <int KS>
+struct KnnTop {
+  double s[KS];
+  int r[KS];
+  int id[KS];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { s[k] = INFINITY; r[k] = 0x7fffffff; id[k] = -1; }
+  }
+  // entry at list position p (warp-uniform p)
+  __device__ __forceinline__ double s_at(int p) const {
+    double v = 0.;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { const double t = __shfl_sync(0xffffffffu, s[k], p & 31); if ((p >> 5) == k) v = t; }
+    return v;
+  }
+  __device__ __forceinline__ int r_at(int p) const {
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) { const int t = __shfl_sync(0xffffffffu, r[k], p & 31); if ((p >> 5) == k) v = t; }
+    return v;
+  }
+};
+
+// insert (cs, cr, cid) if it sorts before the entry at position m-1
+template <int KS>
+__device__ __forceinline__ void knn_insert(KnnTop<KS>& t, double cs, int cr, int cid, int lane, int m) {
+  int posn = 0;  // entries that stay in front of the candidate (the list is sorted: they form a prefix)
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    posn += __popc(__ballot_sync(0xffffffffu, knn_before(t.s[k], t.r[k], cs, cr) || (t.s[k] == cs && t.r[k] == cr)));
   if (posn >= m) return;
-  const double us = __shfl_up_sync(0xffffffffu, ks, 1);
-  const int ur = __shfl_up_sync(0xffffffffu, kr, 1);
-  const int ui = __shfl_up_sync(0xffffffffu, ki, 1);
-  if (lane > posn) { ks = us; kr = ur; ki = ui; }
-  else if (lane == posn) { ks = s; kr = r; ki = id; }
+  // shift positions > posn up by one (the last entry of slot k-1 moves into lane 0 of slot k), then place the candidate
+#pragma unroll
+  for (int k = KS - 1; k >= 0; --k) {
+    double us = __shfl_up_sync(0xffffffffu, t.s[k], 1);
+    int ur = __shfl_up_sync(0xffffffffu, t.r[k], 1);
+    int ui = __shfl_up_sync(0xffffffffu, t.id[k], 1);
+    if (k > 0) {
+      const double ps = __shfl_sync(0xffffffffu, t.s[k - 1], 31);
+      const int pr = __shfl_sync(0xffffffffu, t.r[k - 1], 31);
+      const int pi = __shfl_sync(0xffffffffu, t.id[k - 1], 31);
+      if (lane == 0) { us = ps; ur = pr; ui = pi; }
+    }
+    const int p = k * 32 + lane;
+    if (p > posn) { t.s[k] = us; t.r[k] = ur; t.id[k] = ui; }
+    else if (p == posn) { t.s[k] = cs; t.r[k] = cr; t.id[k] = cid; }
+  }
 }
 
 __device__ __forceinline__ int knn_rank(int pj, int pi) {
@@ -68,10 +109,10 @@ __device__ __forceinline__ int knn_rank(int pj, int pi) {
 }
 
 // offer one candidate per lane (valid flag), serialised through the warp in lane order
-__device__ __forceinline__ void knn_offer(double& ks, int& kr, int& ki, bool valid, double s, int r, int id, int lane, int m) {
-  // threshold = entry of lane m-1
-  double ts = __shfl_sync(0xffffffffu, ks, m - 1);
-  int tr = __shfl_sync(0xffffffffu, kr, m - 1);
+template <int KS>
+__device__ __forceinline__ void knn_offer(KnnTop<KS>& t, bool valid, double s, int r, int id, int lane, int m) {
+  const double ts = t.s_at(m - 1);  // threshold = entry at position m-1
+  const int tr = t.r_at(m - 1);
   unsigned mask = __ballot_sync(0xffffffffu, valid && knn_before(s, r, ts, tr));
   while (mask) {
     const int src = __ffs(mask) - 1;
@@ -79,7 +120,7 @@ __device__ __forceinline__ void knn_offer(double& ks, int& kr, int& ki, bool val
     const double cs = __shfl_sync(0xffffffffu, s, src);
     const int cr = __shfl_sync(0xffffffffu, r, src);
     const int ci = __shfl_sync(0xffffffffu, id, src);
-    knn_insert(ks, kr, ki, cs, cr, ci, lane, m);
+    knn_insert<KS>(t, cs, cr, ci, lane, m);
   }
 }
 
@@ -88,15 +129,22 @@ __device__ __forceinline__ void knn_offer(double& ks, int& kr, int& ki, bool val
 // floating point it can when the comparison is decided by rounding (equidistant points on lattices). If every
 // neighbour found here satisfies smd <= d * T_final the reference provably visited all of them and the results are
 // identical; otherwise the query is queued for knn_walk_kernel, which replays the reference's walk exactly.
-__device__ __forceinline__ void knn_finish(int64_t i, int lane, int m, int d, double ks, int ki, const double* __restrict__ csum,
-                                           int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
-  if (lane < m) nn[i * m + lane] = ki;
-  const double tfin = __shfl_sync(0xffffffffu, ks, m - 1);
+template <int KS>
+__device__ __forceinline__ void knn_finish(int64_t i, int lane, int m, int d, const KnnTop<KS>& t, const double* __restrict__ csum,
+                                           int32_t* __restrict__ nn_row, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
+  const double tfin = t.s_at(m - 1);
   bool risky = false;
-  if (lane < m && ki >= 0) {
-    const double dd = __dsub_rn(csum[ki], csum[i]);
-    const double smd = __dmul_rn(dd, dd);
-    risky = smd > __dmul_rn((double)d, tfin);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const int p = k * 32 + lane;
+    if (p < m) {
+      nn_row[p] = t.id[k];
+      if (t.id[k] >= 0) {
+        const double dd = __dsub_rn(csum[t.id[k]], csum[i]);
+        const double smd = __dmul_rn(dd, dd);
+        risky = risky || smd > __dmul_rn((double)d, tfin);
+      }
+    }
   }
   const unsigned any = __ballot_sync(0xffffffffu, risky);
   if (any && lane == 0) flagged[atomicAdd(nflag, 1)] = (int32_t)i;
@@ -105,18 +153,21 @@ __device__ __forceinline__ void knn_finish(int64_t i, int lane, int m, int d, do
 // Exact replay of find_nearest_neighbors_fast_internal (Vecchia_utils.cpp:1029-1093) for the queued queries:
 // one thread per query walks the sorted coordinate sums down/up alternately with the reference's pruning rule,
 // strict-'<' replacement and stable insertion (utils.h:250-262).
+// Candidates of query i are the points c < i with c <= end_search_at (training: end_search_at = n - 1; prediction points are
+// appended behind the observed ones and search the observed ones only, Vecchia_utils.cpp:1784-1800). nn row of query i = i - row0.
+template <int KS>
 __global__ void knn_walk_kernel(const double* __restrict__ coords, const double* __restrict__ csum,
                                 const int32_t* __restrict__ sort_sum, const int32_t* __restrict__ pos, int64_t n, int d, int m,
+                                int64_t end_search_at, int64_t row0,
                                 const int32_t* __restrict__ flagged, const int* __restrict__ nflag, int32_t* __restrict__ nn) {
   const int nf = *nflag;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const int64_t i = flagged[f];
-    double sq[32];
-    int id[32];
+    double sq[32 * KS];
+    int id[32 * KS];
     for (int j = 0; j < m; ++j) { sq[j] = INFINITY; id[j] = -1; }
     bool down = true, up = true;
     int64_t up_i = pos[i], down_i = pos[i];
-    const int64_t end_search_at = n - 2;
     while (up || down) {
       if (down_i == 0) down = false;
       if (up_i == n - 1) up = false;
@@ -145,7 +196,7 @@ __global__ void knn_walk_kernel(const double* __restrict__ coords, const double*
         }
       }
     }
-    for (int j = 0; j < m; ++j) nn[i * m + j] = id[j];
+    for (int j = 0; j < m; ++j) nn[(i - row0) * m + j] = id[j];
   }
 }
 
@@ -173,43 +224,49 @@ __global__ void knn_cell_start_kernel(const uint32_t* __restrict__ sorted_cell, 
   }
 }
 
-// queries i in [q_begin, q_end): brute force over all j < i (early points) — warp per query
+// queries i in [q_begin, q_end): brute force over all j < min(i, end_search_at + 1) — warp per query
+template <int KS>
 __global__ void knn_brute_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos,
-                                 const double* __restrict__ csum, int d, int m, int64_t q_begin, int64_t q_end,
-                                 int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
+                                 const double* __restrict__ csum, int d, int m, int64_t q_begin, int64_t q_end, int64_t end_search_at,
+                                 int64_t row0, int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = q_begin + warp; i < q_end; i += nwarps) {
-    if (i <= m) {  // Vecchia_utils.cpp:788-813: all predecessors, in index order
-      if (lane < m) nn[i * m + lane] = lane < i ? lane : -1;
+    const int64_t ncand = min(i, end_search_at + 1);
+    int32_t* row = nn + (i - row0) * m;
+    if (ncand <= m) {  // Vecchia_utils.cpp:788-813: all predecessors, in index order
+      for (int p = lane; p < m; p += 32) row[p] = p < ncand ? p : -1;
       continue;
     }
-    double ks = INFINITY; int kr = 0x7fffffff, ki = -1;
+    KnnTop<KS> top; top.init();
     const int pi = pos[i];
-    for (int64_t j0 = 0; j0 < i; j0 += 32) {
+    for (int64_t j0 = 0; j0 < ncand; j0 += 32) {
       const int64_t j = j0 + lane;
-      const bool valid = j < i;
+      const bool valid = j < ncand;
       double s = 0.; int r = 0;
       if (valid) { s = knn_sqdist(coords + j * d, coords + i * d, d); r = knn_rank(pos[j], pi); }
-      knn_offer(ks, kr, ki, valid, s, r, (int)j, lane, m);
+      knn_offer<KS>(top, valid, s, r, (int)j, lane, m);
     }
-    knn_finish(i, lane, m, d, ks, ki, csum, nn, flagged, nflag);
+    knn_finish<KS>(i, lane, m, d, top, csum, row, flagged, nflag);
   }
 }
 
 // queries i in [q_begin, n): cell-list search — warp per query, DIM in {1,2,3}
+template <int KS>
 __global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t* __restrict__ pos,
                                 const double* __restrict__ csum, const int32_t* __restrict__ cell_start,
                                 const int32_t* __restrict__ sorted_idx, KnnGrid gr, int m, int64_t q_begin, int64_t n,
+                                int64_t end_search_at, int64_t row0,
                                 int32_t* __restrict__ nn, int32_t* __restrict__ flagged, int* __restrict__ nflag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int d = gr.dim;
   for (int64_t i = q_begin + warp; i < n; i += nwarps) {
-    double ks = INFINITY; int kr = 0x7fffffff, ki = -1;
+    KnnTop<KS> top; top.init();
     const int pi = pos[i];
+    const int64_t id_end = min(i, end_search_at + 1);  // candidates: ids below this
     int qc[3] = {0, 0, 0};
     for (int k = 0; k < d; ++k) {
       int ck = (int)floor((coords[i * d + k] - gr.lo[k]) * gr.inv_h[k]);
@@ -252,7 +309,7 @@ __global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t
           double s = 0.; int rk = 0; int id = -1;
           if (pb < pe) {
             id = sorted_idx[pb];
-            if (id < i) {
+            if (id < id_end) {
               valid = true;
               s = knn_sqdist(coords + (int64_t)id * d, coords + i * d, d);
               rk = knn_rank(pos[id], pi);
@@ -261,22 +318,28 @@ __global__ void knn_grid_kernel(const double* __restrict__ coords, const int32_t
               pb = pe;
             }
           }
-          knn_offer(ks, kr, ki, valid, s, rk, id, lane, m);
+          knn_offer<KS>(top, valid, s, rk, id, lane, m);
         }
       }
       // every unscanned point is farther than r*hmin in some coordinate (safety margin for the cell rounding)
-      const double ts = __shfl_sync(0xffffffffu, ks, m - 1);
+      const double ts = top.s_at(m - 1);
       const double reach = (double)r * gr.hmin * (1. - 1e-9);
       if (ts < reach * reach) break;
     }
-    knn_finish(i, lane, m, d, ks, ki, csum, nn, flagged, nflag);
+    knn_finish<KS>(i, lane, m, d, top, csum, nn + (i - row0) * m, flagged, nflag);
   }
 }
 
-// Returns the number of kernels launched, or -1 with *err set. coords: device n x d row-major (Vecchia order).
-inline int knn_vecchia_device(const double* coords_dev, const double* coords_host, int64_t n, int d, int m,
-                              const int32_t* pos_dev, const int32_t* sort_sum_dev, const double* csum_dev, int32_t* nn_dev,
-                              cudaStream_t stream, int num_sms, int* num_replayed, std::string* err) {
+// Returns the number of kernels launched, or -1 with *err set. coords: device n x d row-major (Vecchia order; prediction: the
+// observed points followed by the prediction points). Queries are the points [q_begin, n); the candidates of query i are the
+// points below min(i, end_search_at + 1); nn_dev holds the rows of the queries only (row of query i = i - q_begin).
+// Training: q_begin = 0, end_search_at = n - 2. KS = entries per lane of the running top-m (m <= 32 KS).
+template <int KS>
+inline int knn_vecchia_device_ks(const double* coords_dev, const double* coords_host, int64_t n, int d, int m,
+                                 const int32_t* pos_dev, const int32_t* sort_sum_dev, const double* csum_dev, int32_t* nn_dev,
+                                 cudaStream_t stream, int num_sms, int* num_replayed, std::string* err, int64_t q_begin,
+                                 int64_t end_search_at) {
+  const int64_t row0 = q_begin;
   auto ck = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e); return false; }
     return true;
@@ -288,7 +351,7 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
       !ck(cudaMemsetAsync(nflag, 0, sizeof(int), stream), "memset")) return -1;
   auto finish = [&](bool ok) -> int {
     if (ok) {
-      knn_walk_kernel<<<num_sms * 4, 128, 0, stream>>>(coords_dev, csum_dev, sort_sum_dev, pos_dev, n, d, m, flagged, nflag, nn_dev);
+      knn_walk_kernel<KS><<<num_sms * 4, 128, 0, stream>>>(coords_dev, csum_dev, sort_sum_dev, pos_dev, n, d, m, end_search_at, row0, flagged, nflag, nn_dev);
       ok = ck(cudaGetLastError(), "knn_walk_kernel");
       ++launches;
       int nf = 0;
@@ -299,10 +362,14 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
     cudaFree(flagged); cudaFree(nflag);
     return ok ? launches : -1;
   };
-  const int64_t brute_end = std::min<int64_t>(n, d <= 3 ? 4096 : n);
-  {
-    const int blocks = (int)std::min<int64_t>((brute_end + 7) / 8, (int64_t)num_sms * 8);
-    knn_brute_kernel<<<std::max(blocks, 1), 256, 0, stream>>>(coords_dev, pos_dev, csum_dev, d, m, 0, brute_end, nn_dev, flagged, nflag);
+  // queries with few candidates (the first points of the ordering; every query when there are few observed points, or in more
+  // than three dimensions) are done by brute force
+  int64_t brute_end = std::min<int64_t>(n, d <= 3 ? 4096 : n);
+  if (end_search_at + 1 <= 4096) brute_end = n;
+  if (brute_end > q_begin) {
+    const int blocks = (int)std::min<int64_t>((brute_end - q_begin + 7) / 8, (int64_t)num_sms * 8);
+    knn_brute_kernel<KS><<<std::max(blocks, 1), 256, 0, stream>>>(coords_dev, pos_dev, csum_dev, d, m, q_begin, brute_end, end_search_at, row0,
+                                                                  nn_dev, flagged, nflag);
     if (!ck(cudaGetLastError(), "knn_brute_kernel")) return finish(false);
     ++launches;
   }
@@ -362,7 +429,8 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
     ++launches;
   }
   if (ok) {
-    knn_grid_kernel<<<num_sms * 16, 128, 0, stream>>>(coords_dev, pos_dev, csum_dev, cell_start, idx_sorted, gr, m, brute_end, n, nn_dev, flagged, nflag);
+    knn_grid_kernel<KS><<<num_sms * 16, 128, 0, stream>>>(coords_dev, pos_dev, csum_dev, cell_start, idx_sorted, gr, m, std::max(brute_end, q_begin), n,
+                                                          end_search_at, row0, nn_dev, flagged, nflag);
     ok = ck(cudaGetLastError(), "knn_grid_kernel");
     ++launches;
   }
@@ -370,6 +438,18 @@ inline int knn_vecchia_device(const double* coords_dev, const double* coords_hos
   const int rc = finish(ok);
   cudaFree(cell); cudaFree(cell_sorted); cudaFree(idx); cudaFree(idx_sorted); cudaFree(cell_start); cudaFree(tmp);
   return rc;
+}
+
+inline int knn_vecchia_device(const double* coords_dev, const double* coords_host, int64_t n, int d, int m,
+                              const int32_t* pos_dev, const int32_t* sort_sum_dev, const double* csum_dev, int32_t* nn_dev,
+                              cudaStream_t stream, int num_sms, int* num_replayed, std::string* err, int64_t q_begin = 0,
+                              int64_t end_search_at = -1) {
+  if (end_search_at < 0) end_search_at = n - 2;
+  if (m <= 32)
+    return knn_vecchia_device_ks<1>(coords_dev, coords_host, n, d, m, pos_dev, sort_sum_dev, csum_dev, nn_dev, stream, num_sms, num_replayed, err,
+                                    q_begin, end_search_at);
+  return knn_vecchia_device_ks<2>(coords_dev, coords_host, n, d, m, pos_dev, sort_sum_dev, csum_dev, nn_dev, stream, num_sms, num_replayed, err,
+                                  q_begin, end_search_at);
 }
 
 }  // namespace gpb

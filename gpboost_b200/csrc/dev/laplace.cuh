@@ -695,6 +695,7 @@ void laplace_release(gpbdev_vecchia* h) {
 int laplace_ensure(gpbdev_vecchia* h) {
   if (h->lap) return 0;
   if (h->row_begin != 0 || h->row_end != h->n) return fail("Laplace-Vecchia: row-sharded engines are not supported yet");
+  if (h->m > gpl::kM) return fail("Laplace-Vecchia: num_neighbors must be <= 30 for non-Gaussian likelihoods in the B200 engine");
   int coop = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
   if (!coop) return fail("Laplace-Vecchia: the device does not support cooperative launches");

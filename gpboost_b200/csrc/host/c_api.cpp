@@ -166,6 +166,35 @@ int GPB_GetCGPreconditionerType(REModelHandle handle, char* out_str, int* num_ch
   API_END();
 }
 
+// c_api.h:1601 / :1640 — prediction with the GP part: Gaussian Vecchia model, the reference's default prediction type
+int GPB_SetPredictionData(REModelHandle handle, int32_t num_data_pred, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred,
+                          const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred,
+                          const double* covariate_data_pred, const char* vecchia_pred_type, int num_neighbors_pred, double /*cg_delta_conv_pred*/,
+                          int /*nsim_var_pred*/, int /*rank_pred_approx_matrix_lanczos*/) {
+  API_BEGIN();
+  if (cluster_ids_data_pred != nullptr || re_group_data_pred != nullptr || re_group_rand_coef_data_pred != nullptr ||
+      gp_rand_coef_data_pred != nullptr || covariate_data_pred != nullptr)
+    throw std::runtime_error("GPB_SetPredictionData: only GP coordinates are supported as prediction data by the B200 build");
+  M(handle)->SetPredictionData(num_data_pred, gp_coords_data_pred, vecchia_pred_type, num_neighbors_pred);
+  API_END();
+}
+
+int GPB_PredictREModel(REModelHandle handle, const double* y_data, int32_t num_data_pred, double* out_predict, bool predict_cov_mat,
+                       bool predict_var, bool predict_response, bool sample_posterior, bool sample_prior, int /*num_post_samples*/,
+                       int /*num_prior_samples*/, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred,
+                       const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred,
+                       const double* cov_pars, const double* covariate_data_pred, bool use_saved_data, const double* fixed_effects,
+                       const double* /*fixed_effects_pred*/) {
+  API_BEGIN();
+  if (sample_posterior || sample_prior) throw std::runtime_error("GPB_PredictREModel: posterior / prior sampling is not supported by the B200 build");
+  if (cluster_ids_data_pred != nullptr || re_group_data_pred != nullptr || re_group_rand_coef_data_pred != nullptr ||
+      gp_rand_coef_data_pred != nullptr || covariate_data_pred != nullptr)
+    throw std::runtime_error("GPB_PredictREModel: only GP coordinates are supported as prediction data by the B200 build");
+  M(handle)->Predict(y_data, num_data_pred, out_predict, predict_cov_mat, predict_var, predict_response, gp_coords_data_pred, cov_pars,
+                     use_saved_data, fixed_effects);
+  API_END();
+}
+
 int GPB_CanCalculateStandardErrorsCovPars(REModelHandle handle, int* out) {
   API_BEGIN();
   M(handle);

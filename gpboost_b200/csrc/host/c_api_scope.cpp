@@ -109,13 +109,6 @@ int GPB_OptimLinRegrCoefCovPar(REModelHandle handle, const double* y_data, const
   API_END();
 }
 
-int GPB_PredictREModel(REModelHandle handle, const double* y_data, int32_t num_data_pred, double* out_predict, bool predict_cov_mat, bool predict_var, bool predict_response, bool sample_posterior, bool sample_prior, int num_post_samples, int num_prior_samples, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred, const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred, const double* cov_pars, const double* covariate_data_pred, bool use_saved_data, const double* fixed_effects, const double* fixed_effects_pred) {
-  API_BEGIN();
-  (void)handle; (void)y_data; (void)num_data_pred; (void)out_predict; (void)predict_cov_mat; (void)predict_var; (void)predict_response; (void)sample_posterior; (void)sample_prior; (void)num_post_samples; (void)num_prior_samples; (void)cluster_ids_data_pred; (void)re_group_data_pred; (void)re_group_rand_coef_data_pred; (void)gp_coords_data_pred; (void)gp_rand_coef_data_pred; (void)cov_pars; (void)covariate_data_pred; (void)use_saved_data; (void)fixed_effects; (void)fixed_effects_pred;
-  Unsupported("GPB_PredictREModel");
-  API_END();
-}
-
 int GPB_PredictREModelTrainingDataRandomEffects(REModelHandle handle, const double* cov_pars_pred, const double* y_obs, double* out_predict, const double* fixed_effects, bool calc_var) {
   API_BEGIN();
   (void)handle; (void)cov_pars_pred; (void)y_obs; (void)out_predict; (void)fixed_effects; (void)calc_var;
@@ -134,13 +127,6 @@ int GPB_SetOffsetData(REModelHandle handle, const double* fixed_effects) {
   API_BEGIN();
   (void)handle; (void)fixed_effects;
   Unsupported("GPB_SetOffsetData");
-  API_END();
-}
-
-int GPB_SetPredictionData(REModelHandle handle, int32_t num_data_pred, const int32_t* cluster_ids_data_pred, const char* re_group_data_pred, const double* re_group_rand_coef_data_pred, double* gp_coords_data_pred, const double* gp_rand_coef_data_pred, const double* covariate_data_pred, const char* vecchia_pred_type, int num_neighbors_pred, double cg_delta_conv_pred, int nsim_var_pred, int rank_pred_approx_matrix_lanczos) {
-  API_BEGIN();
-  (void)handle; (void)num_data_pred; (void)cluster_ids_data_pred; (void)re_group_data_pred; (void)re_group_rand_coef_data_pred; (void)gp_coords_data_pred; (void)gp_rand_coef_data_pred; (void)covariate_data_pred; (void)vecchia_pred_type; (void)num_neighbors_pred; (void)cg_delta_conv_pred; (void)nsim_var_pred; (void)rank_pred_approx_matrix_lanczos;
-  Unsupported("GPB_SetPredictionData");
   API_END();
 }
 

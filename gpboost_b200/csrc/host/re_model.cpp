@@ -126,6 +126,7 @@ REModel::REModel(int32_t num_data, const int32_t* cluster_ids_data, const char* 
   if (gp_approx_ != "vecchia")
     Fatal("GP approximation '" + gp_approx_ + "' is currently not supported by the B200 engine (hot path: 'vecchia', 'none')");
   num_neighbors_ = num_neighbors > 0 ? num_neighbors : 20;  // re_model_template.h:288-294
+  num_neighbors_pred_ = 2 * num_neighbors_;                  // re_model_template.h:299
   vecchia_ordering_ = vecchia_ordering == nullptr ? "none" : std::string(vecchia_ordering);
   if (vecchia_ordering_ != "none" && vecchia_ordering_ != "random")
     Fatal("Ordering of type '" + vecchia_ordering_ + "' is not supported for the Veccia approximation ");
@@ -358,6 +359,7 @@ void REModel::InitializeCovParsIfNotDefined(const double* y_data, const double* 
 }
 
 void REModel::SetY(const double* y_data, const double* fixed_effects) {
+  y_has_been_set_ = true;
   const double* src = y_data;
   if (fixed_effects != nullptr) {  // y - fixed_effects (re_model_template.h:2907-2917)
     work_.resize(num_data_);
@@ -518,6 +520,66 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
   neg_log_likelihood_ = *negll;
 }
 
+void REModel::SetPredictionData(int32_t num_data_pred, const double* gp_coords_data_pred, const char* vecchia_pred_type, int num_neighbors_pred) {
+  if (engine_ == nullptr) Fatal("Prediction data can only be set for a Vecchia GP model in the B200 build");
+  if (vecchia_pred_type != nullptr && vecchia_pred_type[0] != '\0') {
+    const std::string t(vecchia_pred_type);
+    if (gauss_ && t != "order_obs_first_cond_obs_only")
+      Fatal("Prediction type '" + t + "' is not supported by the B200 engine (supported: 'order_obs_first_cond_obs_only', the reference's default)");
+    if (!gauss_) Fatal("Prediction is not supported for likelihood '" + likelihood_ + "' by the B200 engine yet");
+  }
+  if (num_neighbors_pred > 0) num_neighbors_pred_ = num_neighbors_pred;
+  if (gp_coords_data_pred != nullptr) {
+    if (!(num_data_pred > 0)) Fatal("Check failed: num_data_pred > 0");
+    coords_pred_saved_.resize((size_t)num_data_pred * dim_);
+    for (int32_t i = 0; i < num_data_pred; ++i)
+      for (int k = 0; k < dim_; ++k) coords_pred_saved_[(size_t)i * dim_ + k] = gp_coords_data_pred[(size_t)k * num_data_pred + i];
+    num_data_pred_saved_ = num_data_pred;
+  }
+}
+
+void REModel::Predict(const double* y_obs, int32_t num_data_pred, double* out_predict, bool predict_cov_mat, bool predict_var,
+                      bool predict_response, const double* gp_coords_data_pred, const double* cov_pars_pred, bool use_saved_data,
+                      const double* fixed_effects) {
+  if (engine_ == nullptr) Fatal("GPB_PredictREModel: only the Vecchia GP model predicts on the device in the B200 build (grouped / exact models: not yet)");
+  if (!gauss_) Fatal("Prediction is not supported for likelihood '" + likelihood_ + "' by the B200 engine yet");
+  if (predict_cov_mat) Fatal("Predictive covariance matrices are not supported by the B200 engine (predict_var gives the variances)");
+  if (out_predict == nullptr) Fatal("Check failed: out_predict != nullptr");
+  double trans[3] = {0., 0., 1.};
+  if (cov_pars_pred != nullptr) {
+    for (int i = 0; i < num_cov_pars_; ++i)
+      if (!(cov_pars_pred[i] > 0.)) Fatal("Covariance parameters must be positive");
+    TransformCovPars(cov_pars_pred, trans);
+  } else {
+    if (!cov_pars_initialized_) Fatal("Covariance parameters have not been estimated or are not given.");  // re_model.cpp:1119-1121
+    for (int i = 0; i < num_cov_pars_; ++i) trans[i] = cov_pars_[i];
+  }
+  const double* cp = nullptr;
+  std::vector<double> rowmajor;
+  if (use_saved_data) {
+    if (num_data_pred_saved_ <= 0) Fatal("No data has been set for making predictions. Call set_prediction_data first");
+    if (num_data_pred != num_data_pred_saved_) Fatal("Check failed: num_data_pred == num_data_pred_ (saved prediction data)");
+    cp = coords_pred_saved_.data();
+  } else {
+    if (gp_coords_data_pred == nullptr) Fatal("Check failed: gp_coords_data_pred != nullptr");
+    if (!(num_data_pred > 0)) Fatal("Check failed: num_data_pred > 0");
+    rowmajor.resize((size_t)num_data_pred * dim_);
+    for (int32_t i = 0; i < num_data_pred; ++i)
+      for (int k = 0; k < dim_; ++k) rowmajor[(size_t)i * dim_ + k] = gp_coords_data_pred[(size_t)k * num_data_pred + i];
+    cp = rowmajor.data();
+  }
+  (void)fixed_effects;  // ignored for Gaussian data (c_api.h:1640 ff.)
+  if (y_obs != nullptr) SetY(y_obs, nullptr);
+  else if (!y_has_been_set_) Fatal("Response variable data is not available for making predictions (pass y or fit the model first)");
+  std::vector<double> dvar((size_t)num_data_pred);
+  DevCheck(gpbdev_vecchia_predict(engine_, cov_id_, trans[1], trans[2], cp, num_data_pred, num_neighbors_pred_, out_predict, dvar.data()));
+  if (predict_var) {
+    // back to the original scale (re_model_template.h:3427 ff.): sigma^2 D_p, plus the error variance when the response is predicted
+    const double add = predict_response ? 1. : 0.;
+    for (int32_t i = 0; i < num_data_pred; ++i) out_predict[(size_t)num_data_pred + i] = trans[0] * (dvar[(size_t)i] + add);
+  }
+}
+
 void REModel::OptimCovPar(const double* y_data, const double* fixed_effects, bool called_in_GPBoost_algorithm,
                           bool reuse_learning_rates_from_previous_call) {
   if (!gauss_) {
@@ -605,6 +667,7 @@ bool REModel::DevicePathReady() const {
 }
 
 void REModel::SetYDevice(const double* y_dev) {
+  y_has_been_set_ = true;
   if (grouped_) GrpCheck(gpbdev_grouped_set_y_device(grouped_, y_dev));
   else DevCheck(gpbdev_vecchia_set_y_device(engine_, y_dev));
 }

@@ -54,6 +54,13 @@ class REModel {
   void OptimCovParDevice(const double* y_dev, bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
   void CalcGradientDevice(double* y_dev);
   bool DevicePathReady() const;
+  // GPB_SetPredictionData (c_api.h:1601-1613): prediction locations / neighbour count kept for later Predict calls
+  void SetPredictionData(int32_t num_data_pred, const double* gp_coords_data_pred, const char* vecchia_pred_type, int num_neighbors_pred);
+  // REModel::Predict (re_model.cpp:1081-1215) for the Gaussian Vecchia model: out_predict = mean (num_data_pred),
+  // followed by the predictive variances when predict_var. gp_coords_data_pred column-major like every matrix of the API.
+  void Predict(const double* y_obs, int32_t num_data_pred, double* out_predict, bool predict_cov_mat, bool predict_var,
+               bool predict_response, const double* gp_coords_data_pred, const double* cov_pars_pred, bool use_saved_data,
+               const double* fixed_effects);
   // GPB_GetCovPar / GPB_GetInitCovPar (original scale)
   void GetCovPar(double* out, bool calc_std_dev) const;
   void GetInitCovPar(double* out) const;
@@ -84,6 +91,10 @@ class REModel {
   int32_t num_data_ = 0;
   int dim_ = 0;
   int num_neighbors_ = 20;
+  int num_neighbors_pred_ = 40;          // 2 x num_neighbors (re_model_template.h:299)
+  std::vector<double> coords_pred_saved_;  // np x d row-major (GPB_SetPredictionData)
+  int32_t num_data_pred_saved_ = 0;
+  bool y_has_been_set_ = false;
   int cov_id_ = 0;
   std::string cov_fct_, gp_approx_, vecchia_ordering_, likelihood_;
   double shape_ = 0.;

@@ -41,10 +41,11 @@ def make_engine(lib, coords, m, ordering="random", seed=1):
 
 
 # ---------------------------------------------------------------------------------------- neighbours
-@pytest.mark.parametrize("n,d,m", [(300, 2, 10), (5000, 2, 30), (20000, 2, 20), (6000, 3, 15), (4000, 1, 8), (1200, 5, 12), (40, 2, 30)])
+@pytest.mark.parametrize("n,d,m", [(300, 2, 10), (5000, 2, 30), (20000, 2, 20), (6000, 3, 15), (4000, 1, 8), (1200, 5, 12), (40, 2, 30),
+                                   (9000, 2, 60), (5000, 3, 45), (50, 2, 60)])
 def test_neighbours_bit_exact_random_coords(lib, n, d, m):
     coords, _ = datagen.synth(n, d, 9)
-    m = min(m, n - 1, 30)
+    m = min(m, n - 1, 60)
     h, perm, co = make_engine(lib, coords, m)
     nn = np.empty((n, m), dtype=np.int32)
     chk(lib, lib.gpbdev_vecchia_get_nn(h, P(nn, C.c_int32)))
@@ -52,7 +53,7 @@ def test_neighbours_bit_exact_random_coords(lib, n, d, m):
     lib.gpbdev_vecchia_free(h)
 
 
-@pytest.mark.parametrize("k,m,ordering", [(30, 12, "random"), (40, 8, "none"), (25, 30, "random")])
+@pytest.mark.parametrize("k,m,ordering", [(30, 12, "random"), (40, 8, "none"), (25, 30, "random"), (30, 48, "random")])
 def test_neighbours_bit_exact_on_lattice_with_distance_ties(lib, k, m, ordering):
     coords = datagen.lattice(k)
     h, perm, co = make_engine(lib, coords, m, ordering, seed=2)
@@ -75,7 +76,7 @@ def test_neighbours_duplicates_and_clusters(lib):
 
 # ---------------------------------------------------------------------------------------- factor / sums
 @pytest.mark.parametrize("cov,shape", [("exponential", 0.5), ("matern", 1.5), ("matern", 2.5), ("gaussian", 0.)])
-@pytest.mark.parametrize("n,d,m", [(700, 2, 30), (3000, 2, 17), (2500, 3, 9), (35, 2, 30)])
+@pytest.mark.parametrize("n,d,m", [(700, 2, 30), (3000, 2, 17), (2500, 3, 9), (35, 2, 30), (1500, 2, 60), (900, 3, 40), (45, 2, 60)])
 def test_factor_sums_and_gradient_match_oracle(lib, cov, shape, n, d, m):
     coords, y = datagen.synth(n, d, 13)
     m = min(m, n - 1)
