@@ -669,4 +669,5 @@ int gpbdev_vecchia_flush_l2(gpbdev_vecchia_t h) {
 
 }  // extern "C"
 
+#include "newton.cuh"
 #include "laplace.cuh"

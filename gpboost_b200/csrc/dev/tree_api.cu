@@ -1166,6 +1166,7 @@ struct gpbdev_tree {
   cudaStream_t stream = nullptr;
   const uint8_t* bins = nullptr;  // n x Fpad row-major (bins_owned, or a Dataset's device matrix read in place)
   uint8_t* bins_owned = nullptr;
+  int32_t* leaf_of_row = nullptr;  // n, lazy (gpbdev_tree_leaf_indices)
   int32_t* num_bin = nullptr;     // F
   int32_t *idx = nullptr, *idx_tmp = nullptr, *flag = nullptr, *pos = nullptr;
   double* grad = nullptr;         // n (device copy when the caller passes host gradients)
@@ -1334,7 +1335,7 @@ int gpbdev_tree_create_on_device_bins(gpbdev_tree_t* out, int device, int64_t n,
 int gpbdev_tree_free(gpbdev_tree_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->bins_owned); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
+  cudaFree(h->bins_owned); cudaFree(h->leaf_of_row); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -1678,6 +1679,25 @@ int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_le
   add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, score_dev, leaf_of_row_dev);
   TCUDA(cudaGetLastError());
   h->launches += 1;
+  return 0;
+}
+
+int gpbdev_tree_leaf_indices(gpbdev_tree_t h, const int32_t** leaf_of_row_dev) {
+  if (!h || !leaf_of_row_dev) return tfail("gpbdev_tree_leaf_indices: null argument");
+  if (h->last_num_leaves < 1) return tfail("gpbdev_tree_leaf_indices: no tree has been trained");
+  TCUDA(cudaSetDevice(h->device));
+  if (!h->leaf_of_row) TCUDA(cudaMalloc(&h->leaf_of_row, sizeof(int32_t) * h->n));
+  const int nl = h->last_num_leaves;
+  std::vector<int32_t> lb(h->leaf_begin.begin(), h->leaf_begin.begin() + nl), lc(h->leaf_cnt.begin(), h->leaf_cnt.begin() + nl);
+  TCUDA(cudaMemcpyAsync(h->leaf_begin_dev, lb.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaMemcpyAsync(h->leaf_cnt_dev, lc.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  dim3 grid((unsigned)std::min<int64_t>((h->n / nl + 255) / 256 + 1, 1024), nl);
+  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, nullptr, h->leaf_of_row);
+  TCUDA(cudaGetLastError());
+  TCUDA(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  *leaf_of_row_dev = h->leaf_of_row;
   return 0;
 }
 

@@ -74,8 +74,10 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
   boost_from_average_ = params_.GetBool("boost_from_average", true);
   train_gp_model_cov_pars_ = params_.GetBool("train_gp_model_cov_pars", true);
   params_.RejectUnsupported("Booster");
-  if (params_.GetBool("leaves_newton_update", false) || params_.GetBool("line_search_step_length", false))
-    Fatal("leaves_newton_update / line_search_step_length are not supported by the B200 booster yet");
+  leaves_newton_update_ = params_.GetBool("leaves_newton_update", false);
+  if (leaves_newton_update_ && re_model_ == nullptr)
+    Fatal("leaves_newton_update can only be 'true' if Gaussian process boosting is done ");  // c_api.cpp:226-228
+  if (params_.GetBool("line_search_step_length", false)) Fatal("line_search_step_length is not supported by the B200 booster yet");
   gpbdev_tree_config cfg;
   cfg.num_leaves = num_leaves_;
   cfg.min_data_in_leaf = params_.GetInt("min_data_in_leaf", 20, {"min_data_per_leaf", "min_data", "min_child_samples"});
@@ -267,6 +269,12 @@ bool Booster::TrainOneIter() {
   for (int i = 0; i < nl - 1; ++i) {
     tree->split_feature[i] = train_->real_feature_index(tree->split_feature_inner[i]);
     tree->threshold[i] = train_->feature(tree->split_feature_inner[i]).upper_bounds[tree->threshold_bin[i]];  // RealThreshold
+  }
+  if (leaves_newton_update_) {  // gbdt.cpp:470-478: Newton step for the leaf values on the structure just found
+    if (sharded_) Fatal("leaves_newton_update is not supported with row-sharded training yet");
+    const int32_t* leaf_of_row = nullptr;
+    TreeCheck(gpbdev_tree_leaf_indices(learner_, &leaf_of_row));
+    re_model_->NewtonUpdateLeafValuesDevice(leaf_of_row, nl, grad_dev_, tree->leaf_value.data());
   }
   for (int i = 0; i < nl; ++i) tree->leaf_value[i] *= learning_rate_;  // Tree::Shrinkage
   tree->shrinkage = learning_rate_;

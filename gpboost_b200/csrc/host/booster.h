@@ -71,6 +71,7 @@ class Booster {
   double learning_rate_ = 0.1;
   bool boost_from_average_ = true;
   bool train_gp_model_cov_pars_ = true;
+  bool leaves_newton_update_ = false;   // config.h: Newton step for the leaf values after the structure search (GPBoost only)
   gpbdev_tree_t learner_ = nullptr;
   double *score_dev_ = nullptr, *label_dev_ = nullptr, *grad_dev_ = nullptr;
   std::vector<double> host_buf_;

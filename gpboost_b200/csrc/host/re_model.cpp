@@ -787,6 +787,37 @@ void REModel::CalcGradientDevice(double* y_dev) {
   DevCheck(gpbdev_vecchia_yaux_device(engine_, y_dev, 1. / cov_pars_[0]));
 }
 
+void REModel::NewtonUpdateLeafValuesDevice(const int32_t* leaf_of_row_dev, int num_leaves, const double* grad_dev, double* leaf_values) {
+  if (!gauss_) Fatal("Newton updates for leaf values is only supported for Gaussian data");  // re_model_template.h:4986-4988
+  if (engine_ == nullptr) Fatal("Newton updates for leaf values are only built for the Vecchia GP model in the B200 engine");
+  const int L = num_leaves;
+  std::vector<double> M((size_t)L * L), rhs((size_t)L);
+  DevCheck(gpbdev_vecchia_newton_system(engine_, leaf_of_row_dev, L, grad_dev, M.data(), rhs.data()));
+  // new leaf values = (H^T Psi^-1 H)^-1 (-sigma^2 H^T g)   (:5057-5061: HTYAux *= marg_variance; llt().solve) — dense Cholesky, L <= 256
+  for (int j = 0; j < L; ++j) {
+    double d = M[(size_t)j * L + j];
+    for (int k = 0; k < j; ++k) d -= M[(size_t)j * L + k] * M[(size_t)j * L + k];
+    if (!(d > 0.)) Fatal("NewtonUpdateLeafValues: H^T Psi^-1 H is not positive definite");
+    d = std::sqrt(d);
+    M[(size_t)j * L + j] = d;
+    for (int i = j + 1; i < L; ++i) {
+      double v = M[(size_t)i * L + j];
+      for (int k = 0; k < j; ++k) v -= M[(size_t)i * L + k] * M[(size_t)j * L + k];
+      M[(size_t)i * L + j] = v / d;
+    }
+  }
+  for (int i = 0; i < L; ++i) {
+    double v = -cov_pars_[0] * rhs[i];
+    for (int k = 0; k < i; ++k) v -= M[(size_t)i * L + k] * leaf_values[k];
+    leaf_values[i] = v / M[(size_t)i * L + i];
+  }
+  for (int i = L - 1; i >= 0; --i) {
+    double v = leaf_values[i];
+    for (int k = i + 1; k < L; ++k) v -= M[(size_t)k * L + i] * leaf_values[k];
+    leaf_values[i] = v / M[(size_t)i * L + i];
+  }
+}
+
 void REModel::GetCovPar(double* out, bool calc_std_dev) const {
   if (!cov_pars_initialized_) Fatal("Covariance parameters have not been estimated or set");
   if (calc_std_dev) Fatal("Standard deviations of covariance parameters are not available in the B200 engine");

@@ -54,6 +54,9 @@ class REModel {
   void OptimCovParDevice(const double* y_dev, bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
   void CalcGradientDevice(double* y_dev);
   bool DevicePathReady() const;
+  // REModel::NewtonUpdateLeafValues (re_model.cpp:1298-1310 -> re_model_template.h:4982-5063), device-resident: leaf ids and the
+  // gradient of the tree that was just grown stay in HBM; only the L x L system comes to the host. After CalcGradient*.
+  void NewtonUpdateLeafValuesDevice(const int32_t* leaf_of_row_dev, int num_leaves, const double* grad_dev, double* leaf_values);
   // GPB_SetPredictionData (c_api.h:1601-1613): prediction locations / neighbour count kept for later Predict calls
   void SetPredictionData(int32_t num_data_pred, const double* gp_coords_data_pred, const char* vecchia_pred_type, int num_neighbors_pred);
   // REModel::Predict (re_model.cpp:1081-1215) for the Gaussian Vecchia model: out_predict = mean (num_data_pred),

@@ -88,6 +88,12 @@ GPBDEV_EXPORT int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev
  * mean_out_host[p] = A_p y_N(p); var_out_host[p] = D_p on the transformed scale (times sigma^2 = latent predictive variance). */
 GPBDEV_EXPORT int gpbdev_vecchia_predict(gpbdev_vecchia_t h, int cov_type, double var, double range, const double* coords_pred_host,
                                          int64_t np, int num_neighbors_pred, double* mean_out_host, double* var_out_host);
+/* Newton update of the leaf values in GPBoost (REModelTemplate::NewtonUpdateLeafValues, Vecchia branch,
+ * include/GPBoost/re_model_template.h:4982-5063). After a STORE pass at the current parameters: M_host (L x L row-major) =
+ * H^T B^T D^-1 B H and rhs_host (L) = H^T g for the leaf incidence H given by leaf_of_row_dev (n int32, original row order, device)
+ * and g = grad_dev (n doubles, original order, device). The caller solves M x = -sigma^2 rhs (L <= 256). */
+GPBDEV_EXPORT int gpbdev_vecchia_newton_system(gpbdev_vecchia_t h, const int32_t* leaf_of_row_dev, int num_leaves, const double* grad_dev,
+                                               double* M_host, double* rhs_host);
 /* Latent factor (non-Gaussian likelihood) and its derivative w.r.t. log(range) — B_grad[1] = -dA, D_grad[1] = dD of
  * CalcCovFactorGradientVecchia (src/GPBoost/Vecchia_utils.cpp:1636-1652) — copied to host buffers (A, dA: n x m row-major in
  * Vecchia order; Dinv, dD: n). Diagnostics / test entry of the factor kernel's MODE_STORE_GRAD. */
@@ -234,6 +240,9 @@ GPBDEV_EXPORT int gpbdev_tree_train(gpbdev_tree_t h, const double* grad, int gra
  * score_updater.hpp); optionally also writes the leaf index of every row (GetDataLeafIndices). Either pointer may be NULL. */
 GPBDEV_EXPORT int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_leaves, double* score_dev,
                                         int32_t* leaf_of_row_dev);
+/* leaf index of every row of the last trained tree (TreeLearner::GetDataLeafIndices, serial_tree_learner.cpp:818): device pointer to n
+ * int32 owned by the learner, valid until the next call / tree */
+GPBDEV_EXPORT int gpbdev_tree_leaf_indices(gpbdev_tree_t h, const int32_t** leaf_of_row_dev);
 /* device vectors of the boosting driver (training score, label, gradient) on the learner's device/stream */
 GPBDEV_EXPORT int gpbdev_vec_alloc(gpbdev_tree_t h, double** out, int64_t n);
 GPBDEV_EXPORT int gpbdev_vec_free(gpbdev_tree_t h, double* p);

@@ -26,6 +26,8 @@ for spec in treedata.CASES:
     if coords is not None:
         gp = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=spec["num_neighbors"],
                      vecchia_ordering="random", seed=1, _lib=ref)
+        if spec.get("init_cov_pars"):
+            gp.set_optim_params({"init_cov_pars": np.array(spec["init_cov_pars"])})
     b = Booster(params, ds, gp_model=gp, _lib=ref)
     for _ in range(spec["num_iter"]):
         b.update()

@@ -117,10 +117,15 @@ def test_latent_factor_range_derivative_matches_oracle(idx):
     assert rc == 0, mdl._LIB.gpbdev_last_error().decode()
     A0, Dinv0, dA0, dD0, bad = ol.factor_latent_grad(vo.coords, vo.nn, vo.cid, c["cov_pars"][0], pt[1])
     assert bad == 0
+    # The smooth kernels (Matern-2.5, Gaussian) give neighbour blocks with condition numbers ~1e8-1e10 on the latent scale (jitter 1e-10,
+    # no nugget): two correct fp64 evaluation orders of dA = S^-1 r then differ by ~1e-8 relative — the oracle (LAPACK order) is no more
+    # exact than the kernel. The bar is the north_star's 1e-8 where the blocks are well conditioned and 1e-6 for those two kernels, the
+    # same split the prediction goldens use (tests/test_predict_oracle_pinned.py).
+    tol = 1e-6 if (c["cov_function"] == "gaussian" or c["shape"] == 2.5) else 1e-8
     # D_i = v - A_i . s_i is a difference of O(v) terms and reaches 3e-8 v for the smooth kernels (no nugget on the latent scale), so the
     # conditional variance is compared as D = 1 / D^-1 on the scale it is computed on: both sides carry an absolute error of ~1e-16 v
     for got, want, name in ((A, A0, "A"), (1. / Dinv, 1. / Dinv0, "D"), (dA, dA0, "dA"), (dD, dD0, "dD")):
-        assert np.max(np.abs(got - want)) <= 1e-8 * np.max(np.abs(want)), name
+        assert np.max(np.abs(got - want)) <= tol * np.max(np.abs(want)), name
 
 
 @pytest.mark.parametrize("idx", range(len(GOLD)))

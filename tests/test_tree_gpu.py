@@ -122,6 +122,8 @@ def _run_product(spec):
     if coords is not None:
         gp = GPModel(gp_coords=coords, cov_function="matern", cov_fct_shape=1.5, gp_approx="vecchia", num_neighbors=spec["num_neighbors"],
                      vecchia_ordering="random", seed=1)
+        if spec.get("init_cov_pars"):
+            gp.set_optim_params({"init_cov_pars": np.array(spec["init_cov_pars"])})
     b = Booster(params, ds, gp_model=gp)
     for _ in range(spec["num_iter"]):
         b.update()
@@ -154,7 +156,7 @@ def test_gpboost_iteration_matches_reference_golden(lib, tree_golden):
     """GPBoost algorithm (LGBM_GPBoosterCreate): every iteration re-fits the covariance parameters (L-BFGS on the device
     likelihood) and boosts on Psi^-1 (F - y). The optimiser path is decision dependent, so trees are compared on structure
     of the FIRST tree (same init parameters) and the final state within optimiser tolerance."""
-    rec = [r for r in tree_golden["cases"] if r["spec"].get("gp")][0]
+    rec = [r for r in tree_golden["cases"] if r["spec"]["name"] == "gpboost_vecchia"][0]
     trees, score, gp, _, _ = _run_product(rec["spec"])
     g0 = rec["trees"][0]
     assert np.array_equal(trees[0]["split_feature"], np.array(g0["split_feature"]))
@@ -163,6 +165,26 @@ def test_gpboost_iteration_matches_reference_golden(lib, tree_golden):
     cp = gp.get_cov_pars()
     assert np.all(np.abs(cp - np.array(rec["cov_pars"])) <= 5e-3 * np.abs(rec["cov_pars"])), (cp, rec["cov_pars"])
     assert np.abs(score[:64] - np.array(rec["score_head"])).max() <= 2e-3 * np.abs(rec["score_head"]).max()
+
+
+@pytest.mark.parametrize("name", ["gpboost_vecchia_fixed_pars", "gpboost_vecchia_newton", "gpboost_vecchia_newton_many_leaves"])
+def test_gpboost_fixed_parameters_all_trees_match_reference(lib, tree_golden, name):
+    """GPBoost iterations at fixed covariance parameters (train_gp_model_cov_pars = false): gradient Psi^-1 (F - y) / sigma^2 from the
+    device factor, trees on it, optionally Newton leaf values (H^T Psi^-1 H)^-1 H^T Psi^-1 (y - F) (leaves_newton_update).
+    Nothing is decided by an optimiser, so EVERY tree is compared: split features / thresholds / counts bit-exact, leaf values and the
+    training scores to 1e-8 — the reference's own GPU-vs-CPU bar."""
+    rec = [r for r in tree_golden["cases"] if r["spec"]["name"] == name][0]
+    trees, score, gp, _, _ = _run_product(rec["spec"])
+    assert len(trees) == len(rec["trees"])
+    for t, g in zip(trees, rec["trees"]):
+        assert t["num_leaves"] == g["num_leaves"]
+        assert np.array_equal(t["split_feature"], np.array(g["split_feature"])) and np.array_equal(t["threshold"], np.array(g["threshold"]))
+        assert np.array_equal(t["left_child"], np.array(g["left_child"])) and np.array_equal(t["right_child"], np.array(g["right_child"]))
+        assert np.array_equal(t["leaf_count"], np.array(g["leaf_count"]))
+        assert np.max(np.abs(t["leaf_value"] - np.array(g["leaf_value"]))) <= 1e-8 * np.max(np.abs(g["leaf_value"]))
+    assert np.abs(score[:64] - np.array(rec["score_head"])).max() <= 1e-8 * np.abs(rec["score_head"]).max()
+    assert abs(score.sum() - rec["score_sum"]) <= 1e-8 * max(abs(rec["score_sum"]), np.abs(score).sum() * 1e-3)
+    assert np.allclose(gp.get_cov_pars(), rec["spec"]["init_cov_pars"], rtol=1e-12)
 
 
 def test_full_size_histogram_properties(lib):

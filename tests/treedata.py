@@ -10,6 +10,14 @@ CASES = [
     {"name": "mixed_signs_and_zeros", "n": 8000, "F": 7, "kind": "mixed", "num_leaves": 16, "min_data_in_leaf": 10, "num_iter": 3, "seed": 7},
     {"name": "gpboost_vecchia", "n": 3000, "F": 5, "kind": "real", "num_leaves": 8, "min_data_in_leaf": 20, "num_iter": 3, "seed": 8,
      "gp": True, "num_neighbors": 15},
+    # covariance parameters held fixed (train_gp_model_cov_pars = false): every iteration is a deterministic function of the data,
+    # so ALL trees are compared (structure bit-exact, values 1e-8) — and the same with Newton leaf updates
+    {"name": "gpboost_vecchia_fixed_pars", "n": 4000, "F": 6, "kind": "real", "num_leaves": 12, "min_data_in_leaf": 20, "num_iter": 4, "seed": 9,
+     "gp": True, "num_neighbors": 20, "train_cov": False, "init_cov_pars": [0.12, 0.3, 0.15]},
+    {"name": "gpboost_vecchia_newton", "n": 4000, "F": 6, "kind": "real", "num_leaves": 12, "min_data_in_leaf": 20, "num_iter": 4, "seed": 9,
+     "gp": True, "num_neighbors": 20, "train_cov": False, "init_cov_pars": [0.12, 0.3, 0.15], "newton": True},
+    {"name": "gpboost_vecchia_newton_many_leaves", "n": 6000, "F": 4, "kind": "real", "num_leaves": 80, "min_data_in_leaf": 10, "num_iter": 2, "seed": 10,
+     "gp": True, "num_neighbors": 10, "train_cov": False, "init_cov_pars": [0.1, 0.4, 0.1], "newton": True},
 ]
 
 
@@ -43,6 +51,10 @@ def booster_params(spec, reference):
     for k in ("lambda_l2", "min_gain_to_split", "max_depth"):
         if k in spec:
             p[k] = spec[k]
+    if spec.get("train_cov") is False:
+        p["train_gp_model_cov_pars"] = False
+    if spec.get("newton"):
+        p["leaves_newton_update"] = True
     if reference:  # make the reference's summation order deterministic (column-wise histograms, fixed threads)
         p.update({"force_col_wise": True, "deterministic": True, "num_threads": 4})
     return p
