@@ -398,7 +398,12 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist3_kernel(const uint
 constexpr int kReduceSlices = 8;
 __global__ void __launch_bounds__(kReduceSlices * 32) hist_reduce_kernel(const double* __restrict__ part_g, const uint32_t* __restrict__ part_c,
                                                                          int nchunks, int Fpad, int F, double hess_const,
-                                                                         double* __restrict__ hist, double* __restrict__ parent) {
+                                                                         double* __restrict__ hist, double* __restrict__ parent,
+                                                                         const DevJob* __restrict__ job) {
+  if (job) {  // device-resident leaf loop of a data-parallel learner: local chunk partials -> the staging histogram that is all-reduced
+    if (job->done || !job->do_find) return;
+    nchunks = job->hist_nchunks;
+  }
   __shared__ double sg[kReduceSlices][32];
   __shared__ unsigned long long sc[kReduceSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -728,15 +733,18 @@ __device__ __forceinline__ void scan_sums(const double* h, int nb, const LeafArg
   }
   __syncwarp();
 }
+// stage != nullptr (data-parallel learner): the smaller child's histogram has already been merged and summed over the ranks
+// (hist_reduce_kernel -> all-reduce); it is taken from there instead of from the chunk partials.
 __global__ void __launch_bounds__(kFusedSlices * kBins) reduce_scan2_kernel(
     const double* __restrict__ part_g, const uint32_t* __restrict__ part_c, int nchunks, int Fpad, int F, double hess_const,
     double* __restrict__ hist_base, int64_t slot_stride, const int32_t* __restrict__ num_bin, LeafArgs a0, LeafArgs a1, int parent_row,
     int min_data_in_leaf, double min_sum_hessian, double lambda_l2, double min_gain_to_split, unsigned char* __restrict__ splittable,
-    SplitOut* __restrict__ cand, const DevJob* __restrict__ job) {
+    SplitOut* __restrict__ cand, const DevJob* __restrict__ job, const double* __restrict__ stage) {
   if (job) {
     if (job->done || !job->do_find) return;
     nchunks = job->hist_nchunks; a0 = job->a0; a1 = job->a1; parent_row = job->parent_row;
   }
+  if (stage) nchunks = 0;
   __shared__ __align__(16) double hs[2][kBins * 2];
   __shared__ double sg[kFusedSlices][kBins];
   __shared__ unsigned long long sc[kFusedSlices][kBins];
@@ -775,7 +783,8 @@ __global__ void __launch_bounds__(kFusedSlices * kBins) reduce_scan2_kernel(
     unsigned long long c = sc[0][bin];
 #pragma unroll
     for (int k = 1; k < kFusedSlices; ++k) { g += sg[k][bin]; c += sc[k][bin]; }
-    const double hsv = (double)c * hess_const;  // dataset.cpp:1223-1226
+    double hsv = (double)c * hess_const;  // dataset.cpp:1223-1226
+    if (stage) { g = stage[((int64_t)f * kBins + bin) * 2]; hsv = stage[((int64_t)f * kBins + bin) * 2 + 1]; }
     double* dst = hist_base + (int64_t)a0.hist_slot * slot_stride + ((int64_t)f * kBins + bin) * 2;
     dst[0] = g; dst[1] = hsv;
     hs[0][2 * bin] = g; hs[0][2 * bin + 1] = hsv;
@@ -1038,7 +1047,9 @@ constexpr int kMaxLeavesDev = 256;
 struct TreeDevState {
   DevJob job;
   int num_leaves, left_leaf, right_leaf, next_slot;
-  int leaf_begin[kMaxLeavesDev], leaf_cnt[kMaxLeavesDev], leaf_depth[kMaxLeavesDev], leaf_parent[kMaxLeavesDev], slot_of[kMaxLeavesDev];
+  // leaf_begin / leaf_cnt: this rank's rows of the leaf (partition and histogram ranges); leaf_cnt_g: rows over all ranks — every
+  // decision uses the global counts so that all ranks of a data-parallel learner grow the same tree (equal on one GPU)
+  int leaf_begin[kMaxLeavesDev], leaf_cnt[kMaxLeavesDev], leaf_cnt_g[kMaxLeavesDev], leaf_depth[kMaxLeavesDev], leaf_parent[kMaxLeavesDev], slot_of[kMaxLeavesDev];
   double leaf_sg[kMaxLeavesDev], leaf_sh[kMaxLeavesDev];
   SplitOut best[kMaxLeavesDev];
   int split_feature[kMaxLeavesDev], threshold_bin[kMaxLeavesDev], left_child[kMaxLeavesDev], right_child[kMaxLeavesDev];
@@ -1048,21 +1059,22 @@ struct TreeDevState {
 };
 
 // BeforeTrain (leaf_splits.hpp:70-83): all rows in leaf 0
-__global__ void tree_init_kernel(TreeDevState* __restrict__ st, const double* __restrict__ root_sum_gradient, int n, double hess_const, int L) {
+__global__ void tree_init_kernel(TreeDevState* __restrict__ st, const double* __restrict__ root_sum_gradient, int n, int n_global, double hess_const, int L) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->job.done = 0; st->job.error = 0; st->job.do_find = 0; st->job.part_on = 0;
   st->num_leaves = 1; st->left_leaf = 0; st->right_leaf = -1; st->next_slot = 0;
   for (int l = 0; l < L; ++l) {
-    st->leaf_begin[l] = 0; st->leaf_cnt[l] = 0; st->leaf_depth[l] = 0; st->leaf_parent[l] = -1; st->slot_of[l] = -1;
+    st->leaf_begin[l] = 0; st->leaf_cnt[l] = 0; st->leaf_cnt_g[l] = 0; st->leaf_depth[l] = 0; st->leaf_parent[l] = -1; st->slot_of[l] = -1;
     st->leaf_sg[l] = 0.; st->leaf_sh[l] = 0.;
     st->best[l].gain = -INFINITY; st->best[l].feature = -1;
     st->split_feature[l] = 0; st->threshold_bin[l] = 0; st->left_child[l] = 0; st->right_child[l] = 0; st->split_gain[l] = 0.f;
     st->leaf_value[l] = 0.; st->leaf_count[l] = 0;
   }
   st->leaf_cnt[0] = n;
+  st->leaf_cnt_g[0] = n_global;
   st->leaf_sg[0] = root_sum_gradient[0];
-  st->leaf_sh[0] = hess_const * (double)n;
-  st->leaf_count[0] = n;
+  st->leaf_sh[0] = hess_const * (double)n_global;
+  st->leaf_count[0] = n_global;
 }
 
 // BeforeFindBestSplit (serial_tree_learner.cpp:283-322): may the two newest leaves be examined, which one gets a histogram pass
@@ -1076,7 +1088,7 @@ __global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, i
   bool do_find = true;
   if (max_depth > 0 && st->leaf_depth[left_leaf] >= max_depth) do_find = false;
   if (do_find) {
-    const int nl = st->leaf_cnt[left_leaf], nr = right_leaf >= 0 ? st->leaf_cnt[right_leaf] : 0;
+    const int nl = st->leaf_cnt_g[left_leaf], nr = right_leaf >= 0 ? st->leaf_cnt_g[right_leaf] : 0;
     if (nr < min_data_in_leaf * 2 && nl < min_data_in_leaf * 2) do_find = false;
   }
   if (!do_find) {
@@ -1086,16 +1098,16 @@ __global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, i
   }
   int smaller, larger = -1, parent_slot = -1;
   if (right_leaf < 0) smaller = left_leaf;
-  else if (st->leaf_cnt[left_leaf] < st->leaf_cnt[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
+  else if (st->leaf_cnt_g[left_leaf] < st->leaf_cnt_g[right_leaf]) { smaller = left_leaf; larger = right_leaf; }
   else { smaller = right_leaf; larger = left_leaf; }
   if (right_leaf >= 0) parent_slot = st->slot_of[left_leaf];  // the parent's histograms sit under the left (= parent) id
   const int new_slot = st->next_slot++;
   if (larger >= 0) st->slot_of[larger] = parent_slot;  // larger = parent - smaller, in place
   st->slot_of[smaller] = new_slot;
   LeafArgs a0, a1;
-  a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = st->leaf_cnt[smaller];
+  a0.leaf = smaller; a0.hist_slot = new_slot; a0.inherit = right_leaf >= 0 ? 1 : 0; a0.num_data = st->leaf_cnt_g[smaller];
   a0.sum_gradients = st->leaf_sg[smaller]; a0.sum_hessians = st->leaf_sh[smaller];
-  a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? st->leaf_cnt[larger] : 0;
+  a1.leaf = larger; a1.hist_slot = larger >= 0 ? parent_slot : 0; a1.inherit = 1; a1.num_data = larger >= 0 ? st->leaf_cnt_g[larger] : 0;
   a1.sum_gradients = larger >= 0 ? st->leaf_sg[larger] : 0.; a1.sum_hessians = larger >= 0 ? st->leaf_sh[larger] : 0.;
   job.a0 = a0; job.a1 = a1;
   job.parent_row = left_leaf;
@@ -1108,7 +1120,9 @@ __global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, i
 }
 
 // best leaf (ArrayArgs::ArgMax with SplitInfo::operator>), Tree::Split (tree.h:533-575), the partition job
-__global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ split_dev, double min_gain_to_split, int max_seg) {
+// sharded != 0: the children's LOCAL row ranges are not known before the partition ran (tree_local_ranges_kernel sets them)
+__global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ split_dev, double min_gain_to_split, int max_seg,
+                                   int sharded) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   DevJob& job = st->job;
   job.part_on = 0;
@@ -1125,14 +1139,15 @@ __global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut
   if (!(bs.gain > 0.0)) { job.done = 1; return; }
   const int b = st->leaf_begin[best_leaf], c = st->leaf_cnt[best_leaf];
   // constant hessian: the scan's RoundInt counts are the partition's counts (see the host-driven loop)
-  const int nleft = bs.left_count, nright = c - nleft;
+  const int nleft = bs.left_count, nright = st->leaf_cnt_g[best_leaf] - nleft;
   if (nleft <= 0 || nright <= 0) { job.error = 1; job.done = 1; return; }
   job.part_on = 1; job.part_begin = b; job.part_cnt = c; job.part_feature = bs.feature; job.part_threshold = bs.threshold;
   int seg = ((c + max_seg - 1) / max_seg + kPartThreads - 1) / kPartThreads * kPartThreads;
   if (seg < 4 * kPartThreads) seg = 4 * kPartThreads;
   job.part_seg = seg; job.part_nseg = (c + seg - 1) / seg;
   const int new_leaf = num_leaves;
-  st->leaf_cnt[best_leaf] = nleft; st->leaf_begin[new_leaf] = b + nleft; st->leaf_cnt[new_leaf] = nright;
+  st->leaf_cnt_g[best_leaf] = nleft; st->leaf_cnt_g[new_leaf] = nright;
+  if (!sharded) { st->leaf_cnt[best_leaf] = nleft; st->leaf_begin[new_leaf] = b + nleft; st->leaf_cnt[new_leaf] = nright; }
   const int node = num_leaves - 1;
   const int parent = st->leaf_parent[best_leaf];
   if (parent >= 0) { if (st->left_child[parent] == ~best_leaf) st->left_child[parent] = node; else st->right_child[parent] = node; }
@@ -1151,6 +1166,19 @@ __global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut
   st->left_leaf = best_leaf; st->right_leaf = new_leaf;
 }
 
+// data-parallel learner: after the local partition, the children's ranges on THIS rank (lefts counted by part_count_kernel)
+__global__ void tree_local_ranges_kernel(TreeDevState* __restrict__ st, const int32_t* __restrict__ seg_left) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const DevJob& job = st->job;
+  if (job.done || !job.part_on) return;
+  int nl = 0;
+  for (int k = 0; k < job.part_nseg; ++k) nl += seg_left[k];
+  const int best_leaf = st->left_leaf, new_leaf = st->right_leaf;
+  st->leaf_cnt[best_leaf] = nl;
+  st->leaf_begin[new_leaf] = job.part_begin + nl;
+  st->leaf_cnt[new_leaf] = job.part_cnt - nl;
+}
+
 __global__ void part_copyback_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ tmp, const DevJob* __restrict__ job) {
   if (job->done || !job->part_on) return;
   const int64_t b = job->part_begin, c = job->part_cnt;
@@ -1167,6 +1195,7 @@ struct gpbdev_tree {
   const uint8_t* bins = nullptr;  // n x Fpad row-major (bins_owned, or a Dataset's device matrix read in place)
   uint8_t* bins_owned = nullptr;
   int32_t* leaf_of_row = nullptr;  // n, lazy (gpbdev_tree_leaf_indices)
+  double* stage = nullptr;         // F x 256 x 2: the smaller child's merged histogram on its way through the all-reduce (data-parallel)
   int32_t* num_bin = nullptr;     // F
   int32_t *idx = nullptr, *idx_tmp = nullptr, *flag = nullptr, *pos = nullptr;
   double* grad = nullptr;         // n (device copy when the caller passes host gradients)
@@ -1190,7 +1219,8 @@ struct gpbdev_tree {
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
   int fused_scan = 2;              // GPB200_FUSED_SCAN = 2 (default): reduce_scan2_kernel | 1: reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
-  int partition_sharded = 1;       // GPB200_PARTITION_SHARDED = 2: part_*_kernel also for row-sharded learners (not yet run on two GPUs)
+  int sharded_host_loop = 0;       // GPB200_SHARDED_LOOP = host: data-parallel learners use the host-driven leaf loop (one blocking all-reduce and one
+                                   // D2H per split, CUB partition) instead of the device-resident / graph loop with in-stream all-reduces
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
   int hist_kernel_version = 3;     // GPB200_HIST_KERNEL = 3 (default): hist3_kernel | 2: hist2_kernel | 1: single-warp hist_kernel
   double* sum_part = nullptr;
@@ -1313,7 +1343,7 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 1 ? 1 : 2);
-  if (const char* e = std::getenv("GPB200_PARTITION_SHARDED")) h->partition_sharded = std::atoi(e) == 2 ? 2 : 1;
+  if (const char* e = std::getenv("GPB200_SHARDED_LOOP")) h->sharded_host_loop = std::string(e) == "host" ? 1 : 0;
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 2 ? 2 : 3);
   *out = h;
@@ -1335,7 +1365,7 @@ int gpbdev_tree_create_on_device_bins(gpbdev_tree_t* out, int device, int64_t n,
 int gpbdev_tree_free(gpbdev_tree_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->bins_owned); cudaFree(h->leaf_of_row); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
+  cudaFree(h->bins_owned); cudaFree(h->leaf_of_row); cudaFree(h->stage); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
   cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
@@ -1368,20 +1398,31 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
     h->graph_exec = nullptr;
   }
   const bool replay = use_graph && h->graph_exec != nullptr;
+  // data-parallel learner (row shards over ranks): the same enqueued sequence with three additions — the root gradient sum and the
+  // smaller child's merged histogram are summed over the ranks ON THIS STREAM (NCCL kernels, captured into the graph like everything
+  // else; DataParallelTreeLearner, data_parallel_tree_learner.cpp:155-175, :244), and the children's local row ranges are set after
+  // the local partition. Every rank replays the same number of collectives whatever the tree does (finished trees skip the work,
+  // not the exchange). The whole 2 F x 256 block is all-reduced and scanned on every rank: at F = 50..100 it is a 0.2..0.4 MB
+  // message, latency-bound on NVSwitch — a reduce-scatter by feature block (the reference's choice for Ethernet clusters) would add
+  // a second latency-bound collective per split for the best-split exchange and scan no faster (one CTA per feature either way).
+  const bool sharded = h->allreduce != nullptr;
+  const int n_glob = sharded ? (int)h->n_global : (int)n;
+  if (sharded && !h->stage) TCUDA(cudaMalloc(&h->stage, sizeof(double) * slot_stride));
   if (use_graph && !replay) TCUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  bool coll_failed = false;
   if (!replay) {
   if (use_graph) {  // the eager path ran these before the call
     iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
     const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
     sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
     sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
+    if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) coll_failed = true;
   }
-  tree_init_kernel<<<1, 32, 0, h->stream>>>(st, h->sum_part + 1023, (int)n, hess_const, L);
-  TCUDA(cudaGetLastError());
+  tree_init_kernel<<<1, 32, 0, h->stream>>>(st, h->sum_part + 1023, (int)n, n_glob, hess_const, L);
   const int nw = hist2_warps(F);
   const dim3 hgrid(h->num_sms, (Fpad + 63) / 64);
   const int cgrid = h->num_sms * 4;
-  for (int split = 0; split < L - 1; ++split) {
+  for (int split = 0; split < L - 1 && !coll_failed; ++split) {
     tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
     if (h->hist_kernel_version == 3)
       hist3_kernel<<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
@@ -1389,35 +1430,42 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
       hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
     LeafArgs dummy;
     dummy.leaf = -1; dummy.hist_slot = 0; dummy.inherit = 0; dummy.num_data = 0; dummy.sum_gradients = 0.; dummy.sum_hessians = 0.;
-    if (h->fused_scan == 2)
+    if (sharded) {
+      hist_reduce_kernel<<<F * (kBins / 32), kReduceSlices * 32, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->stage, nullptr, job);
+      if (h->allreduce(h->allreduce_ctx, h->stage, (int64_t)slot_stride, (void*)h->stream)) { coll_failed = true; break; }
+    }
+    if (h->fused_scan == 2 || sharded)
       reduce_scan2_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
                                                                     h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
                                                                     cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
-                                                                    h->splittable, h->cand_dev, job);
+                                                                    h->splittable, h->cand_dev, job, sharded ? h->stage : nullptr);
     else
     reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, 0, Fpad, F, hess_const, h->hist, (int64_t)slot_stride,
                                                                  h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
                                                                  cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
                                                                  h->splittable, h->cand_dev, job);
     split_argmax_kernel<<<2, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
-    tree_select_kernel<<<1, 32, 0, h->stream>>>(st, h->split_dev, cfg.min_gain_to_split, h->max_seg);
+    tree_select_kernel<<<1, 32, 0, h->stream>>>(st, h->split_dev, cfg.min_gain_to_split, h->max_seg, sharded ? 1 : 0);
     part_count_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, 0, 0, h->idx, 0, 0, 0, h->flag8, h->seg_left, job);
     part_scatter_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->idx, 0, 0, 0, h->flag8, h->seg_left, 0, h->idx_tmp, nullptr, job);
     part_copyback_kernel<<<cgrid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, job);
-    TCUDA(cudaGetLastError());
+    if (sharded) tree_local_ranges_kernel<<<1, 32, 0, h->stream>>>(st, h->seg_left);
   }
   TCUDA(cudaMemcpyAsync(h->state_host, st, sizeof(TreeDevState), cudaMemcpyDeviceToHost, h->stream));
   }  // !replay
   if (use_graph && !replay) {
     cudaGraph_t g = nullptr;
     TCUDA(cudaStreamEndCapture(h->stream, &g));
+    if (coll_failed) { if (g) cudaGraphDestroy(g); return tfail("gpbdev_tree_train: device all-reduce failed"); }
     const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
     cudaGraphDestroy(g);
     if (ie != cudaSuccess) { h->graph_exec = nullptr; return tfail(std::string("gpbdev_tree_train: cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
     h->graph_grad = grad; h->graph_hess = hess_const;
   }
+  if (!use_graph && coll_failed) return tfail("gpbdev_tree_train: device all-reduce failed");
+  if (!replay) TCUDA(cudaGetLastError());
   if (use_graph) TCUDA(cudaGraphLaunch(h->graph_exec, h->stream));
-  h->launches += 8 * (L - 1) + (use_graph ? 3 : 0);
+  h->launches += (sharded ? 11 : 8) * (L - 1) + (use_graph ? (sharded ? 4 : 3) : 0);
   TCUDA(cudaStreamSynchronize(h->stream));
   const TreeDevState& r = *h->state_host;
   if (r.job.error) return tfail("gpbdev_tree_train: inconsistent split counts");
@@ -1451,14 +1499,16 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   // ---- BeforeTrain: partition = all rows in leaf 0, root sums (leaf_splits.hpp:70-83)
   const bool sharded = h->allreduce != nullptr;
   const int64_t n_glob = sharded ? h->n_global : n;
-  if (h->device_loop == 2 && !sharded && L <= kMaxLeavesDev && grad_on_device)  // everything, root sums included, is in the graph
+  const bool dev_loop_sharded = !sharded || !h->sharded_host_loop;
+  if (h->device_loop == 2 && dev_loop_sharded && L <= kMaxLeavesDev && grad_on_device)  // everything, root sums included, is in the graph
     return tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
                                   leaf_value, leaf_count);
   iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
   const int nb1 = (int)std::min<int64_t>(1024, (n + 4095) / 4096);
   sum_stage1_kernel<<<nb1, 256, 0, h->stream>>>(grad, n, h->sum_part);
   sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
-  if (h->device_loop && !sharded && L <= kMaxLeavesDev) {
+  if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
+  if (h->device_loop && dev_loop_sharded && L <= kMaxLeavesDev) {
     h->launches += 3;
     const int keep = h->device_loop;
     h->device_loop = 1;  // eager enqueue (host gradients are staged per call: no graph)
@@ -1467,7 +1517,6 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     h->device_loop = keep;
     return rc;
   }
-  if (sharded && h->allreduce(h->allreduce_ctx, h->sum_part + 1023, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
   TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TCUDA(cudaStreamSynchronize(h->stream));
   h->launches += 3;
@@ -1513,7 +1562,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
       if (nchunks_out) { *nchunks_out = nchunks; h->launches += 1; return 0; }
       // single GPU: larger = parent - smaller is fused into the merge of the chunk partials
       hist_reduce_kernel<<<F * (kBins / 32), kReduceSlices * 32, 0, h->stream>>>(h->part_g, h->part_c, nchunks, Fpad, F, hess_const, dst,
-                                                                        sharded ? nullptr : par);
+                                                                        sharded ? nullptr : par, nullptr);
       TCUDA(cudaGetLastError());
       h->launches += 2;
     } else {
@@ -1569,7 +1618,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
         reduce_scan2_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, nchunks_f, Fpad, F, hess_const, h->hist,
                                                                       (int64_t)slot_stride, h->num_bin, a0, a1, left_leaf, cfg.min_data_in_leaf,
                                                                       cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
-                                                                      h->splittable, h->cand_dev, nullptr);
+                                                                      h->splittable, h->cand_dev, nullptr, nullptr);
       else if (fused)
         reduce_scan_kernel<<<F, kFusedSlices * kBins, 0, h->stream>>>(h->part_g, h->part_c, nchunks_f, Fpad, F, hess_const, h->hist,
                                                                      (int64_t)slot_stride, h->num_bin, a0, a1, left_leaf, cfg.min_data_in_leaf,
@@ -1607,8 +1656,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     const int nleft_g = bs.left_count, nright_g = leaf_cnt_g[best_leaf] - nleft_g;
     if (nleft_g <= 0 || nright_g <= 0) return tfail("gpbdev_tree_train: inconsistent split counts");
     int nleft = nleft_g;
-    if (c > 0 && h->partition_version == 2 && (!sharded || h->partition_sharded == 2)) {  // row shards keep the CUB path until part_*_kernel's
-                                                                                          // two-GPU parity run (GPB200_PARTITION_SHARDED=2 opts in)
+    if (c > 0 && h->partition_version == 2 && !sharded) {  // the host loop of a data-parallel learner keeps the CUB path
       const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
       const int nseg = (int)((c + seg - 1) / seg);
       part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr);

@@ -517,7 +517,9 @@ void REModel::EvalNegLogLikelihood(const double* y_data, const double* cov_pars,
   else if (dense_) DensePass(trans[1], trans[2]);
   else DevicePass(trans[1], trans[2], GPBDEV_MODE_NLL);
   *negll = NegLLFromSums(trans[0]);
-  neg_log_likelihood_ = *negll;
+  // Gaussian data: the value goes to the caller only; GPB_GetCurrentNegLogLikelihood keeps reporting the last optimisation's value
+  // (the reference passes `negll` by reference here and stores neg_log_likelihood_ in CalcCovFactorOrModeAndNegLL, i.e. during fits:
+  // re_model.cpp:752-794, re_model_template.h:2832-2851)
 }
 
 void REModel::SetPredictionData(int32_t num_data_pred, const double* gp_coords_data_pred, const char* vecchia_pred_type, int num_neighbors_pred) {
