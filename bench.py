@@ -125,17 +125,24 @@ def time_dense(n, lib, threads, reps=5):
     t0 = time.perf_counter()
     mdl.fit(y)
     t_fit = time.perf_counter() - t0
-    return {"sec_per_eval": dt, "negll": v, "fit_s": t_fit, "fit_iters": mdl._get_num_optim_iter(), "fit_cov_pars": mdl.get_cov_pars().tolist()}
+    res = {"sec_per_eval": dt, "negll": v, "fit_s": t_fit, "fit_iters": mdl._get_num_optim_iter(), "fit_cov_pars": mdl.get_cov_pars().tolist()}
+    if lib is None:
+        flops = n ** 3 / 3.0 + 30.0 * n * n  # Cholesky n^3/3 + Gram build (~30 flop per entry incl. exp)
+        res["roofline"] = {"bound": "fp64_tensor", "achieved": flops / dt / 1e12, "unit": "TFLOP/s", "flops": flops,
+                           "note": "whole GPB_EvalNegLogLikelihood call (Gram + blocked Cholesky with DMMA trailing updates + solves), wall clock; at "
+                                   "n = 2000 the 32 panel steps are launch-latency bound, not tensor bound"}
+    return res
 
 
-def time_gpboost(n, iters, lib, threads, F=50):
+def time_gpboost(n, iters, lib, threads, F=50, f32=False):
     """One GPBoost iteration = LGBM_BoosterUpdateOneIter with a Vecchia GP (m=30) attached: covariance re-fit (L-BFGS) +
     Psi^-1(F - y) + one 31-leaf tree on n x 50 features (BASELINE configs[3] shape on one GPU, metric (i) of SURVEY §8d)."""
     from gpboost_b200 import GPModel
     from gpboost_b200.booster import Booster, Dataset
     rng = np.random.default_rng(1)
-    coords = rng.random((n, 2)); X = rng.random((n, F))
-    y = 2 * np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + np.sin(5 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.5 * rng.standard_normal(n)
+    coords = rng.random((n, 2))
+    X = rng.random((n, F), dtype=np.float32) if f32 else rng.random((n, F))  # float32 features halve the host memory of configs[3]
+    y = 2 * np.sin(3 * X[:, 0]) + X[:, 1].astype(np.float64) ** 2 + np.sin(5 * coords[:, 0]) * np.cos(4 * coords[:, 1]) + 0.5 * rng.standard_normal(n)
     params = dict(objective="regression", num_leaves=31, min_data_in_leaf=20, learning_rate=0.1, max_bin=255, verbose=-1)
     if lib is not None:
         params["num_threads"] = threads
@@ -147,7 +154,33 @@ def time_gpboost(n, iters, lib, threads, F=50):
     for _ in range(iters):
         b.update()
     dt = (time.perf_counter() - t0) / iters
-    return {"sec_per_iter": dt, "first_iter_s": first, "cov_pars": gp.get_cov_pars().tolist()}
+    out = {"sec_per_iter": dt, "first_iter_s": first, "cov_pars": gp.get_cov_pars().tolist()}
+    if lib is None:
+        out["hist_roofline"] = hist_roofline(b)
+    return out
+
+
+def hist_roofline(booster):
+    """Roofline of the tree side's dominant kernel: the root-pass histogram kernel timed alone with CUDA events (L2 flushed before every
+    launch). Algorithmic bytes per row: the row's bins (Fpad) + its gradient (8)."""
+    ms, row_bytes, rows = C.c_float(0), C.c_int(0), C.c_int64(0)
+    L = booster._LIB
+    if L.GPB200_BoosterTimeRootHistogram(booster.handle, 10, C.byref(ms), C.byref(row_bytes), C.byref(rows)) != 0:
+        return {"error": L.LGBM_GetLastError().decode()}
+    hbm_peak, src = measured_hbm_peak()
+    ach = rows.value * row_bytes.value / (ms.value * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "hist3_kernel<plain counters> (root pass, all rows of this rank)", "kernel_ms": ms.value,
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "algorithmic_bytes_per_row": row_bytes.value, "rows": rows.value, "peak_source": src,
+            "note": "shared-memory (LSU) bound: one read-modify-write per (row, feature) on private fp64 histograms"}
+
+
+def measured_hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s"
 
 
 def time_gpboost_grouped(n, iters, lib, threads, F=50, groups=10000):
@@ -174,6 +207,8 @@ def time_gpboost_grouped(n, iters, lib, threads, F=50, groups=10000):
         out[key] = {"sec_per_iter": (time.perf_counter() - t0) / iters, "first_iter_s": first}
         if gp is not None:
             out[key]["cov_pars"] = gp.get_cov_pars().tolist()
+        elif lib is None:
+            out[key]["hist_roofline"] = hist_roofline(b)
         del b
     return out
 
@@ -206,6 +241,34 @@ def time_laplace(n, lib, threads, reps=1, barrier=None):
     if lib is None:
         info = gp.laplace_info()
         out.update({"newton_it": int(info[1]), "cg_it": int(info[2]), "slq_it": int(info[3])})
+        # roofline of the dominant kernels: one operator and one preconditioner application on the probe block, CUDA events.
+        # Compulsory bytes per row: two passes over B (coefficients 8 B + indices 4 B per entry, m+1 entries) + four
+        # t-column vector rows read or written.
+        L = gp._LIB
+        eng = gp.device_engine()
+        t_cols = 50 // max(1, int(os.environ.get("WORLD_SIZE", "1")))
+        hbm_peak, src = measured_hbm_peak()
+        roof = {}
+        for label, tc in (("probe_block", None), ("newton_vector", 1)):
+            ms = (C.c_float * 2)()
+            tcols = tc if tc is not None else -1
+            # the probe count of this rank is whatever set_probes received; ask with t = 1 first, then the block size
+            rc = -1
+            for cand in ([1] if tc == 1 else [t_cols, t_cols + 1, 50]):
+                rc = L.gpbdev_vecchia_laplace_time_ops(eng, cand, 5, ms)
+                if rc == 0:
+                    tcols = cand
+                    break
+            if rc != 0:
+                continue
+            algo = n * (2 * 12 * (M_NEIGH + 1) + 4 * 8 * tcols)
+            for k, nm in ((0, "operator"), (1, "preconditioner")):
+                ach = algo / (ms[k] * 1e-3) / 1e9
+                roof["%s_%s" % (label, nm)] = {"bound": "hbm", "kernel_ms": ms[k], "t": tcols, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                               "frac": ach / hbm_peak, "algorithmic_bytes": algo, "peak_source": src}
+        roof["note"] = ("operator = mv_B + mv_Bt kernels, preconditioner = the two sparse triangular solves; every row gathers m neighbour rows, "
+                        "so DRAM/L2 traffic is up to (m+1)/2 times the compulsory bytes when the block does not fit L2; t = 1 is latency bound")
+        out["roofline"] = roof
     return out
 
 
@@ -237,6 +300,7 @@ def main():
     ap.add_argument("--boost-features", type=int, default=50, help="features of the GPBoost-iteration measurements (BASELINE configs[3]: --boost-n 5000000 --boost-features 100 on 8 GPUs)")
     ap.add_argument("--boost-ref-n", type=int, default=100000, help="--impl reference: n of the GPBoost-Vecchia iteration sub-problem (0 = skip)")
     ap.add_argument("--grouped-ref-n", type=int, default=1000000, help="--impl reference: n of the grouped-RE GPBoost iterations (configs[2] is cheap on the CPU: full size; 0 = skip)")
+    ap.add_argument("--config3", default="auto", choices=["auto", "on", "off"], help="BASELINE configs[3] (n=5e6 x 100 features, Vecchia m=30 + trees): auto = when launched on 8 GPUs")
     ap.add_argument("--dense-n", type=int, default=2000, help="n of the exact-GP measurement (BASELINE configs[0]; 0 = skip; --impl reference times it too)")
     ap.add_argument("--laplace-n", type=int, default=1000000, help="n of the Laplace-Vecchia (bernoulli_logit) measurement, BASELINE configs[4] (0 = skip)")
     ap.add_argument("--laplace-ref-n", type=int, default=100000, help="--impl reference: n of the Laplace-Vecchia evaluation sub-problem (0 = skip)")
@@ -388,6 +452,13 @@ def main():
     gb = None
     if args.boost_n > 0:
         gb = time_gpboost(args.boost_n, 5, None, ncores, F=args.boost_features)
+    # BASELINE configs[3]: n = 5e6, 100 features, Vecchia m = 30 + trees, row-sharded over 8 GPUs — run when the job has 8 ranks
+    gb3 = None
+    if (args.config3 == "auto" and world == 8) or args.config3 == "on":
+        try:
+            gb3 = time_gpboost(5000000, 3, None, ncores, F=100, f32=True)
+        except Exception as e:
+            sys.stderr.write("configs[3] measurement failed: %r\n" % (e,))
 
     dense_res = None
     if args.dense_n > 0 and world == 1:
@@ -441,6 +512,13 @@ def main():
                                "first_iter_s": gb["first_iter_s"], "cov_pars": gb["cov_pars"],
                                "note": "LGBM_BoosterUpdateOneIter, GPBoost Vecchia m=30 + 31-leaf trees on n x 50 features, covariance "
                                        "parameters re-fitted every iteration (BASELINE metric (i)); host buffers, end to end"}
+        if gb is not None and "hist_roofline" in gb:
+            line["gpboost"]["roofline"] = gb["hist_roofline"]
+        if gb3 is not None:
+            line["gpboost_config3"] = {"iters_per_sec": 1.0 / gb3["sec_per_iter"], "ms_per_iter": gb3["sec_per_iter"] * 1e3, "n": 5000000, "features": 100,
+                                       "first_iter_s": gb3["first_iter_s"], "cov_pars": gb3["cov_pars"], "roofline": gb3.get("hist_roofline"),
+                                       "note": "BASELINE configs[3]: LGBM_BoosterUpdateOneIter, Vecchia m=30 + 31-leaf trees, n=5e6 x 100 float32 features, GP rows "
+                                               "and histogram rows sharded over the ranks"}
         if dense_res is not None:
             line["dense"] = {"evals_per_sec": 1.0 / dense_res["sec_per_eval"], "n": args.dense_n, **dense_res,
                              "note": "GPB_EvalNegLogLikelihood / GPB_OptimCovPar, exact GP n x n dense Cholesky on the device (BASELINE configs[0])"}
@@ -448,6 +526,7 @@ def main():
             line["gpboost_grouped"] = {"iters_per_sec": 1.0 / gg["grouped"]["sec_per_iter"], "ms_per_iter": gg["grouped"]["sec_per_iter"] * 1e3,
                                        "trees_only_ms_per_iter": gg["trees_only"]["sec_per_iter"] * 1e3, "n": args.boost_n,
                                        "first_iter_s": gg["grouped"]["first_iter_s"], "cov_pars": gg["grouped"]["cov_pars"],
+                                       "roofline": gg["trees_only"].get("hist_roofline"),
                                        "note": "LGBM_BoosterUpdateOneIter, single-level grouped random effect (1e4 groups) + 31-leaf trees on "
                                                "n x 50 features (BASELINE configs[2]); trees_only = the same data without a random-effects model"}
         if laplace_res is not None:

@@ -19,13 +19,16 @@ def param_dict_to_str(params):
 class Dataset(object):
     def __init__(self, data, label=None, params=None, _lib=None):
         self._LIB = load_lib() if _lib is None else _lib
-        data = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
+        data = np.asarray(data)
+        # float32 matrices are passed as they are (C_API_DTYPE_FLOAT32), like the reference's package (basic.py: __init_from_np2d)
+        dt = np.float32 if data.dtype == np.float32 else np.float64
+        data = np.ascontiguousarray(data, dtype=dt)
         if data.ndim != 2:
             raise ValueError("'data' needs to be a 2-D array")
         self.num_data, self.num_feature = data.shape
         self.handle = ctypes.c_void_p()
         self._safe_call(self._LIB.LGBM_DatasetCreateFromMat(
-            data.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(C_API_DTYPE_FLOAT64), ctypes.c_int32(self.num_data),
+            data.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(C_API_DTYPE_FLOAT32 if dt == np.float32 else C_API_DTYPE_FLOAT64), ctypes.c_int32(self.num_data),
             ctypes.c_int32(self.num_feature), ctypes.c_int(1), c_str(param_dict_to_str(params)), None, ctypes.byref(self.handle)))
         if label is not None:
             self.set_label(label)

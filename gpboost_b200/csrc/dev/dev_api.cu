@@ -176,6 +176,8 @@ struct gpbdev_vecchia {
   double* yaux = nullptr;     // n       (lazy, original order)
   int32_t* colptr = nullptr;  // n + 1   (lazy)
   int32_t* csc_pos = nullptr; // nnz     (lazy)
+  int32_t* csc_row = nullptr; // nnz     (lazy, Laplace): row of every CSC entry (= csc_pos / m)
+  double* A_csc = nullptr;    // nnz     (lazy, Laplace): A in CSC order, refreshed after every latent factorisation
   double* partials = nullptr;
   double* sums = nullptr;     // kNumAcc (device)
   double* sums_host = nullptr;  // pinned
@@ -408,6 +410,7 @@ int gpbdev_vecchia_free(gpbdev_vecchia_t h) {
   cudaFree(h->coords); cudaFree(h->nn); cudaFree(h->perm); cudaFree(h->y_in); cudaFree(h->y);
   cudaFree(h->dA); cudaFree(h->dD);
   cudaFree(h->A); cudaFree(h->Dinv); cudaFree(h->u); cudaFree(h->yaux); cudaFree(h->colptr); cudaFree(h->csc_pos);
+  cudaFree(h->csc_row); cudaFree(h->A_csc);
   cudaFree(h->partials); cudaFree(h->sums); cudaFree(h->flush);
   cudaFreeHost(h->sums_host); cudaFreeHost(h->stage_host);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -117,10 +117,15 @@ __device__ __forceinline__ Unit make_unit(int t, int G) {
 }
 
 // T[i,:] = s_i * (X[i,:] - sum_k A[i,k] X[nn[i,k],:]),  s_i = Dinv[i] (or 1 when Dinv == nullptr)
+// `order` (optional): rows are taken in this order instead of by index — a space-filling-curve order of the locations, so that
+// the rows in flight across the grid at any moment are spatial neighbours and share their (spatially near) gathered rows in L2; the
+// multi-vector itself stays in Vecchia order, only the time at which a row is processed changes.
 __global__ void __launch_bounds__(kBlock) mv_B_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t, int G,
-                                                      const double* __restrict__ Dinv, const double* __restrict__ X, double* __restrict__ T) {
+                                                      const double* __restrict__ Dinv, const double* __restrict__ X, double* __restrict__ T,
+                                                      const int32_t* __restrict__ order) {
   const Unit u = make_unit(t, G);
-  for (int64_t i = u.r0; i < n; i += u.rstep) {
+  for (int64_t p = u.r0; p < n; p += u.rstep) {
+    const int64_t i = order ? (int64_t)order[p] : p;
     int32_t jk = u.lane < m ? nn[i * m + u.lane] : -1;
     const double ak = jk >= 0 ? A[i * m + u.lane] : 0.;
     jk = max(jk, 0);
@@ -154,10 +159,12 @@ __global__ void v_mv_B_kernel(const double* __restrict__ A, const int32_t* __res
 __global__ void __launch_bounds__(kBlock) mv_Bt_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr,
                                                        const int32_t* __restrict__ csc_pos, int m, int64_t n, int t, int G,
                                                        const double* __restrict__ T, const double* __restrict__ W,
-                                                       const double* __restrict__ X, double* __restrict__ V, double* __restrict__ partial) {
+                                                       const double* __restrict__ X, double* __restrict__ V, double* __restrict__ partial,
+                                                       const int32_t* __restrict__ order) {
   const Unit u = make_unit(t, G);
   double dot = 0.;
-  for (int64_t j = u.r0; j < n; j += u.rstep) {
+  for (int64_t p = u.r0; p < n; p += u.rstep) {
+    const int64_t j = order ? (int64_t)order[p] : p;
     double acc = T[j * t + u.cc];
     const double xj = X[j * t + u.cc];
     const int e0 = colptr[j], e1 = colptr[j + 1];
@@ -184,8 +191,8 @@ __global__ void __launch_bounds__(kBlock) mv_Bt_kernel(const double* __restrict_
   if (u.active) partial[u.pslot * kMaxCols + u.c] = dot;
 }
 
-__global__ void v_mv_Bt_kernel(const double* __restrict__ A, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_pos,
-                               int m, int64_t n, const double* __restrict__ T, const double* __restrict__ W,
+__global__ void v_mv_Bt_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
+                               int64_t n, const double* __restrict__ T, const double* __restrict__ W,
                                const double* __restrict__ x, double* __restrict__ V, double* __restrict__ partial) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -193,10 +200,7 @@ __global__ void v_mv_Bt_kernel(const double* __restrict__ A, const int32_t* __re
   for (int64_t j = gw; j < n; j += nw) {
     const int e0 = colptr[j], e1 = colptr[j + 1];
     double s = 0.;
-    for (int e = e0 + lane; e < e1; e += 32) {
-      const int32_t pos = csc_pos[e];
-      s += A[pos] * T[pos / m];
-    }
+    for (int e = e0 + lane; e < e1; e += 32) s += A_csc[e] * T[csc_row[e]];  // coefficients and rows stream, T is gathered (L2)
     s = wsum(s);
     if (lane == 0) {
       const double xj = x[j];
@@ -223,6 +227,23 @@ __global__ void axpy_norm_kernel(int64_t n, int t, int G, Coef a, const double* 
     }
     partial[u.pslot * kMaxCols + u.c] = rr;
   }
+}
+
+// single-vector form of axpy_norm_kernel (the lane = column layout leaves 31 of 32 lanes idle at t = 1): r -= a v, u += a h,
+// per-warp partial of sum r^2 in row 0 of the warp's partial slot; grid-stride with a fixed assignment, so deterministic
+__global__ void v_axpy_norm_kernel(int64_t n, double a, const double* __restrict__ v, double* __restrict__ r, const double* __restrict__ hh,
+                                   double* __restrict__ u, double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  double rr = 0.;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ri = r[i] - v[i] * a;
+    r[i] = ri;
+    rr += ri * ri;
+    if (u) u[i] += hh[i] * a;
+  }
+  rr = wsum(rr);
+  if (lane == 0) partial[(size_t)gw * kMaxCols] = rr;
 }
 
 // H = Z + H * b[c]
@@ -405,6 +426,199 @@ __global__ void v_trs_fwd_kernel(const double* __restrict__ A, const int32_t* __
     }
   }
   if (lane == 0) partial[(size_t)gw * kMaxCols] = dot;
+}
+
+// ---- single-vector solves, second generation: head in shared memory + sub-warp tail ---------------------------------
+// The dependency DAG of B is deep where it is thin: at n = 1e6, m = 30 (random ordering) 310 of the 517 levels lie in the first
+// 16 384 rows. Polled through L2 every level costs microseconds (a store that has to become visible on the other die, a back-off
+// period, a load), through shared memory a few hundred cycles. So the first K rows — the HEAD — are solved by ONE CTA that keeps
+// its K unknowns in shared memory (same value-is-the-flag protocol, volatile shared loads), and the remaining rows — the TAIL,
+// ~200 levels — by the persistent grid with FOUR rows per warp (eight lanes per row, four dependencies per lane), which
+// quadruples the rows in flight. Head kernels take a column of an n x t row-major multi-vector (blockIdx.x = column), t = 1 here.
+constexpr int kHeadRows = 16384;
+constexpr int kHeadThreads = 1024;
+
+__device__ __forceinline__ double poll_shared(volatile double* p, int* err) {
+  double v = *p;
+  int spins = 0;
+  while (is_sent(v)) {
+    if (++spins > kSpinLimit) { atomicExch(err, 1); return 0.; }
+    v = *p;
+  }
+  return v;
+}
+
+// rows [0, K): z_i = y_i / dw_i + sum_k A[i,k] z[nn[i,k]]; warp per row, rows taken in order by the CTA's warps
+__global__ void __launch_bounds__(kHeadThreads) trs_head_fwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int K,
+                                                                   int t, const double* __restrict__ dw, const double* __restrict__ Y,
+                                                                   const double* __restrict__ R, double* Z, double* __restrict__ partial_row,
+                                                                   int* err) {
+  extern __shared__ double xs_raw[];
+  volatile double* xs = xs_raw;
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double sent = __longlong_as_double((long long)kSentinel);
+  for (int e = threadIdx.x; e < K; e += blockDim.x) xs_raw[e] = sent;
+  __syncthreads();
+  double dot = 0.;
+  int32_t jn = -1; double an = 0., yn = 0., rn = 0.;
+  if (w < K) {
+    if (lane < m) { jn = nn[(int64_t)w * m + lane]; an = A[(int64_t)w * m + lane]; }
+    yn = Y[(int64_t)w * t + c] / dw[w]; rn = R[(int64_t)w * t + c];
+  }
+  for (int i = w; i < K; i += nw) {
+    const int32_t j = jn; const double a = an, yi = yn, ri = rn;
+    const int ni = i + nw;
+    if (ni < K) {  // next row's pattern and right-hand side: in flight while this row waits
+      jn = lane < m ? nn[(int64_t)ni * m + lane] : -1;
+      an = lane < m ? A[(int64_t)ni * m + lane] : 0.;
+      yn = Y[(int64_t)ni * t + c] / dw[ni]; rn = R[(int64_t)ni * t + c];
+    }
+    double s = 0.;
+    if (j >= 0) s = a * poll_shared(xs + j, err);
+    s = wsum(s);
+    if (lane == 0) {
+      const double zi = yi + s;
+      xs[i] = zi;
+      Z[(int64_t)i * t + c] = zi;
+      dot += ri * zi;
+    }
+  }
+  // block sum of the per-warp dots, fixed order
+  __shared__ double wd[kHeadThreads / 32];
+  if (lane == 0) wd[w] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sacc = 0.;
+    for (int k = 0; k < nw; ++k) sacc += wd[k];
+    partial_row[c] = sacc;
+  }
+}
+
+// tail rows [row0, n): eight lanes per row, four dependencies per lane; dependencies in the head are final (the head kernel ran first)
+__global__ void v_trs_fwd_tail_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int64_t row0,
+                                      const double* __restrict__ dw, const double* __restrict__ y, const double* __restrict__ r,
+                                      double* z, double* __restrict__ partial, int* err) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+  const unsigned smask = 0xffu << (sub * 8);
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // subgroups of one warp take rows nw apart: neighbouring rows (the likeliest dependencies) sit in different warps
+  double dot = 0.;
+  for (int64_t i = row0 + sub * nw + gw; i < n; i += 4 * nw) {
+    int32_t j[4]; double a[4], v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = sl + 8 * q;
+      j[q] = k < m ? nn[i * m + k] : -1;
+      a[q] = (k < m && j[q] >= 0) ? A[i * m + k] : 0.;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = j[q] >= 0 ? ld_gpu_nc(z + j[q]) : 0.;
+    double s = 0.;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j[q] >= 0) { if (is_sent(v[q])) v[q] = poll(z + j[q], err); s += a[q] * v[q]; }
+    }
+    s += __shfl_xor_sync(smask, s, 4);
+    s += __shfl_xor_sync(smask, s, 2);
+    s += __shfl_xor_sync(smask, s, 1);
+    if (sl == 0) {
+      const double zi = y[i] / dw[i] + s;
+      st_gpu(z + i, zi);
+      dot += r[i] * zi;
+    }
+  }
+  // the four subgroup dots of the warp in subgroup order
+  double d1 = __shfl_sync(0xffffffffu, dot, 8), d2 = __shfl_sync(0xffffffffu, dot, 16), d3 = __shfl_sync(0xffffffffu, dot, 24);
+  if (lane == 0) partial[(size_t)gw * kMaxCols] = ((dot + d1) + d2) + d3;
+}
+
+// backward solve y = B^-T r, tail rows j = n-1 .. row0 (all their dependents are tail rows): eight lanes per column
+__global__ void v_trs_bwd_tail_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
+                                      int64_t n, int64_t row0, const double* __restrict__ r, double* y, int* err) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
+  const unsigned smask = 0xffu << (sub * 8);
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t jj = sub * nw + gw; jj < n - row0; jj += 4 * nw) {
+    const int64_t j = n - 1 - jj;
+    const int e0 = colptr[j], e1 = colptr[j + 1];
+    double s = 0.;
+    // far rows (finished long ago) first, the rows just above j last; four entries per lane in flight
+    int e = e1 - 1 - sl;
+    for (; e - 24 >= e0; e -= 32) {
+      int32_t row[4]; double a[4], v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { row[q] = csc_row[e - 8 * q]; a[q] = A_csc[e - 8 * q]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = ld_gpu_nc(y + row[q]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += a[q] * (is_sent(v[q]) ? poll(y + row[q], err) : v[q]);
+    }
+    for (; e >= e0; e -= 8) s += A_csc[e] * poll(y + csc_row[e], err);
+    s += __shfl_xor_sync(smask, s, 4);
+    s += __shfl_xor_sync(smask, s, 2);
+    s += __shfl_xor_sync(smask, s, 1);
+    if (sl == 0) st_gpu(y + j, r[j] + s);
+  }
+}
+
+// first entry of column j (entries sorted by row) whose row is >= K
+__device__ __forceinline__ int col_split(const int32_t* __restrict__ csc_row, int e0, int e1, int K) {
+  int lo = e0, hi = e1;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (csc_row[mid] < K) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// head columns j < K, contributions of the (finished) tail rows: Yacc[j,c] = R[j,c] + sum_{entries with row >= K} A Y[row,c]; warp per (j, c)
+__global__ void trs_head_bwd_gather_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
+                                           int K, int t, const double* __restrict__ R, double* Y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = gw; u < (int64_t)K * t; u += nw) {
+    const int j = (int)(u / t), c = (int)(u % t);
+    const int e1 = colptr[j + 1];
+    const int es = col_split(csc_row, colptr[j], e1, K);
+    double s = 0.;
+    for (int e = es + lane; e < e1; e += 32) s += A_csc[e] * Y[(int64_t)csc_row[e] * t + c];
+    s = wsum(s);
+    if (lane == 0) Y[(int64_t)j * t + c] = R[(int64_t)j * t + c] + s;
+  }
+}
+
+// head columns j = K-1 .. 0 from shared memory: y_j = Yacc_j + sum_{entries with row < K} A y_row; one CTA per column of the multi-vector
+__global__ void __launch_bounds__(kHeadThreads) trs_head_bwd_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr,
+                                                                   const int32_t* __restrict__ csc_row, int K, int t, double* Y, int* err) {
+  extern __shared__ double xs_raw[];
+  volatile double* xs = xs_raw;
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double sent = __longlong_as_double((long long)kSentinel);
+  for (int e = threadIdx.x; e < K; e += blockDim.x) xs_raw[e] = sent;
+  __syncthreads();
+  for (int jj = w; jj < K; jj += nw) {
+    const int j = K - 1 - jj;
+    const int e0 = colptr[j];
+    const int es = col_split(csc_row, e0, colptr[j + 1], K);  // head entries: [e0, es)
+    const double acc = Y[(int64_t)j * t + c];
+    double s = 0.;
+    // far rows first (the rows just above j finish last)
+    for (int e = es - 1 - lane; e >= e0; e -= 32) s += A_csc[e] * poll_shared(xs + csc_row[e], err);
+    s = wsum(s);
+    if (lane == 0) {
+      const double yj = acc + s;
+      xs[j] = yj;
+      Y[(int64_t)j * t + c] = yj;
+    }
+  }
+}
+
+__global__ void csc_gather_kernel(const double* __restrict__ A, const int32_t* __restrict__ csc_pos, int m, int64_t cnt,
+                                  double* __restrict__ A_csc, int32_t* __restrict__ csc_row) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t pos = csc_pos[e];
+    A_csc[e] = A[pos];
+    csc_row[e] = pos / m;
+  }
 }
 
 // ---- bernoulli_logit pieces (DF_utils.h:37-60, likelihoods.h:11401, 12477, 13307) ----------------------------
@@ -660,6 +874,10 @@ struct gpb_laplace_state {
   int grid = 0;           // persistent cooperative grid (blocks): what is co-resident for the polling kernels
   int grid_mv = 0;        // grid of the ordinary (non-polling) row kernels
   int grid_v = 0;         // cooperative grid of the single-vector polling kernels (few registers: more resident warps)
+  int grid_v2 = 0;        // cooperative grid of the second-generation tail kernels
+  int32_t* order = nullptr;  // n: processing order of the order-free row kernels (Morton order of the locations); null = by index
+  int trs_variant = 1;    // GPB200_TRS_VARIANT = 1 (default): shared-memory head + sub-warp tail | 0: first generation
+  int head_rows = gpl::kHeadRows;  // GPB200_TRS_HEAD_ROWS (<= 16384): rows solved in shared memory (tests shrink it to exercise the tail on small models)
   int nwarps = 0;
   double *mode = nullptr, *mode_new = nullptr, *upd = nullptr, *dir = nullptr, *rhs = nullptr, *W = nullptr, *dw = nullptr, *fe = nullptr;
   double *r = nullptr, *z = nullptr, *hv = nullptr, *v = nullptr, *tt = nullptr, *yy = nullptr;  // n-vectors of the Newton CG
@@ -686,6 +904,7 @@ void laplace_release(gpbdev_vecchia* h) {
                     L->probes, L->R, L->Z, L->H, L->V, L->T, L->Y, L->partial, L->colsum, L->U, L->c1, L->c2, L->c3, L->dWv};
   for (double* b : bufs) cudaFree(b);
   cudaFree(L->err);
+  cudaFree(L->order);
   cudaFreeHost(L->colsum_host);
   cudaFreeHost(L->stage);
   delete L;
@@ -714,7 +933,21 @@ int laplace_ensure(gpbdev_vecchia* h) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v, gpl::v_trs_bwd_kernel, gpl::kBlock, 0));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v2, gpl::v_trs_fwd_kernel, gpl::kBlock, 0));
   L->grid_v = std::max(1, std::min(std::min(per_v, per_v2), 4)) * h->num_sms;
-  L->nwarps = std::max(std::max(L->grid, L->grid_mv), L->grid_v) * (gpl::kBlock / 32);
+  int per_t = 0, per_t2 = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_t, gpl::v_trs_bwd_tail_kernel, gpl::kBlock, 0));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_t2, gpl::v_trs_fwd_tail_kernel, gpl::kBlock, 0));
+  int cap_v2 = 6;
+  if (const char* e = std::getenv("GPB200_TRS_CTAS_PER_SM")) cap_v2 = std::max(1, std::atoi(e));
+  L->grid_v2 = std::max(1, std::min(std::min(per_t, per_t2), cap_v2)) * h->num_sms;
+  if (const char* e = std::getenv("GPB200_TRS_VARIANT")) L->trs_variant = std::atoi(e) == 0 ? 0 : 1;
+  if (const char* e = std::getenv("GPB200_TRS_HEAD_ROWS")) L->head_rows = std::max(1, std::min(gpl::kHeadRows, std::atoi(e)));
+  if (const char* e = std::getenv("GPB200_TRS_SLEEP_NS")) {
+    const int ns = std::max(0, std::atoi(e));
+    CUDA_TRY(cudaMemcpyToSymbol(gpl::g_sleep_ns, &ns, sizeof(int)));
+  }
+  CUDA_TRY(cudaFuncSetAttribute(gpl::trs_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * gpl::kHeadRows)));
+  CUDA_TRY(cudaFuncSetAttribute(gpl::trs_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * gpl::kHeadRows)));
+  L->nwarps = std::max(std::max(std::max(L->grid, L->grid_mv), L->grid_v), L->grid_v2) * (gpl::kBlock / 32) + 1;
   double** vecs[] = {&L->mode, &L->mode_new, &L->upd, &L->dir, &L->rhs, &L->W, &L->dw, &L->fe, &L->r, &L->z, &L->hv, &L->v, &L->tt, &L->yy};
   for (double** p : vecs) {
     CUDA_TRY(cudaMalloc(p, sizeof(double) * n));
@@ -727,6 +960,34 @@ int laplace_ensure(gpbdev_vecchia* h) {
   CUDA_TRY(cudaMalloc(&L->err, sizeof(int)));
   CUDA_TRY(cudaMemsetAsync(L->err, 0, sizeof(int), h->stream));
   CUDA_TRY(cudaMallocHost(&L->stage, sizeof(double) * n));
+  // processing order of mv_B / mv_Bt: Morton (Z-order) curve over the bounding box of the locations (d = 2: 2 x 16 bits, d = 3: 3 x 10 bits)
+  const char* oe = std::getenv("GPB200_LAPLACE_ORDER");
+  if ((h->d == 2 || h->d == 3) && !(oe && std::string(oe) == "index")) {
+    const int d = h->d;
+    std::vector<double> c((size_t)n * d);
+    CUDA_TRY(cudaMemcpy(c.data(), h->coords, sizeof(double) * n * d, cudaMemcpyDeviceToHost));
+    double lo[3] = {c[0], c[1], d > 2 ? c[2] : 0.}, hi[3] = {c[0], c[1], d > 2 ? c[2] : 0.};
+    for (int64_t i = 0; i < n; ++i)
+      for (int k = 0; k < d; ++k) { lo[k] = std::min(lo[k], c[(size_t)i * d + k]); hi[k] = std::max(hi[k], c[(size_t)i * d + k]); }
+    const int bits = d == 2 ? 16 : 10;
+    std::vector<std::pair<uint32_t, int32_t>> key((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t code = 0;
+      uint32_t q[3] = {0, 0, 0};
+      for (int k = 0; k < d; ++k) {
+        const double w = hi[k] > lo[k] ? (c[(size_t)i * d + k] - lo[k]) / (hi[k] - lo[k]) : 0.;
+        q[k] = (uint32_t)std::min<double>((double)((1u << bits) - 1), w * (double)(1u << bits));
+      }
+      for (int b = bits - 1; b >= 0; --b)
+        for (int k = 0; k < d; ++k) code = (code << 1) | ((q[k] >> b) & 1u);
+      key[(size_t)i] = std::make_pair(code, (int32_t)i);
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int32_t> ord((size_t)n);
+    for (int64_t p = 0; p < n; ++p) ord[(size_t)p] = key[(size_t)p].second;
+    CUDA_TRY(cudaMalloc(&L->order, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMemcpy(L->order, ord.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -767,6 +1028,24 @@ struct LapScope {
   ~LapScope() { g_trace.t[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_trace.c[id]; }
 };
 
+// Coefficients in CSC order: the B^T products and the backward solves walk columns, and A[csc_pos[e]] is a random 8-byte read
+// (one 32-byte sector each) where A_csc[e] streams. Rebuilt after every latent factorisation (one gather over nnz entries).
+int lap_refresh_csc_coefs(gpbdev_vecchia* h) {
+  const int64_t nnz = (int64_t)h->n * h->m;  // upper bound of the CSC length (padded slots are not in it)
+  int32_t cnt = 0;
+  CUDA_TRY(cudaMemcpyAsync(&cnt, h->colptr + h->n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (!h->A_csc) {
+    CUDA_TRY(cudaMalloc(&h->A_csc, sizeof(double) * std::max<int64_t>(nnz, 1)));
+    CUDA_TRY(cudaMalloc(&h->csc_row, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+  }
+  const int gb = (int)std::min<int64_t>(((int64_t)cnt + 255) / 256 + 1, (int64_t)h->num_sms * 16);
+  gpl::csc_gather_kernel<<<gb, 256, 0, h->stream>>>(h->A, h->csc_pos, h->m, cnt, h->A_csc, h->csc_row);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 // V = (B^T D^-1 B + W) X, dots[c] = X[:,c] . V[:,c]
 int lap_apply_op(gpbdev_vecchia* h, int t, const double* X, double* V, double* Tbuf, double* dots) {
   gpb_laplace_state* L = h->lap;
@@ -775,10 +1054,10 @@ int lap_apply_op(gpbdev_vecchia* h, int t, const double* X, double* V, double* T
   const int G = lap_groups(t), grid = lap_grid(L->grid_mv, G);
   if (t == 1) {
     gpl::v_mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, h->Dinv, X, Tbuf);
-    gpl::v_mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, Tbuf, L->W, X, V, L->partial);
+    gpl::v_mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A_csc, h->colptr, h->csc_row, n, Tbuf, L->W, X, V, L->partial);
   } else {
-    gpl::mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, X, Tbuf);
-    gpl::mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, Tbuf, L->W, X, V, L->partial);
+    gpl::mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, X, Tbuf, L->order);
+    gpl::mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, Tbuf, L->W, X, V, L->partial, L->order);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
@@ -799,8 +1078,26 @@ int lap_precond(gpbdev_vecchia* h, int t, const double* R, double* Z, double* Yb
     gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Z, n);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
-    if (coop_launch(h, L->grid_v, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
-    if (coop_launch(h, L->grid_v, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
+    if (L->trs_variant == 0) {  // GPB200_TRS_VARIANT=0: first generation (every row polled through L2, one row per warp)
+      if (coop_launch(h, L->grid_v, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
+      if (coop_launch(h, L->grid_v, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
+      return laplace_colsums(h, t, dots, L->grid_v * (gpl::kBlock / 32));
+    }
+    // head (first K rows) in one CTA's shared memory, tail on the persistent grid, four rows per warp
+    int K = (int)std::min<int64_t>(n, L->head_rows);
+    int64_t row0 = K;
+    const size_t hsm = sizeof(double) * (size_t)K;
+    const double* Ac = h->A_csc; const int32_t* crow = h->csc_row;
+    if (coop_launch(h, L->grid_v2, gpl::v_trs_bwd_tail_kernel, Ac, colptr, crow, nn_, row0, R, Ybuf, err)) return -1;
+    const int gg = (int)std::min<int64_t>(((int64_t)K * 32 + gpl::kBlock - 1) / gpl::kBlock, (int64_t)h->num_sms * 8);
+    gpl::trs_head_bwd_gather_kernel<<<gg, gpl::kBlock, 0, h->stream>>>(Ac, colptr, crow, K, 1, R, Ybuf);
+    gpl::trs_head_bwd_kernel<<<1, gpl::kHeadThreads, hsm, h->stream>>>(Ac, colptr, crow, K, 1, Ybuf, err);
+    const int prow = L->grid_v2 * (gpl::kBlock / 32);
+    gpl::trs_head_fwd_kernel<<<1, gpl::kHeadThreads, hsm, h->stream>>>(A, nn, m, K, 1, dw, Yc, R, Z, partial + (size_t)prow * gpl::kMaxCols, err);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 3;
+    if (coop_launch(h, L->grid_v2, gpl::v_trs_fwd_tail_kernel, A, nn, m, nn_, row0, dw, Yc, R, Z, partial, err)) return -1;
+    return laplace_colsums(h, t, dots, prow + 1);
   } else {
     const int64_t len = n * t;
     const int fb = (int)std::min<int64_t>((len + 255) / 256, (int64_t)h->num_sms * 16);
@@ -890,6 +1187,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
   // latent factor B, D^-1 (Vecchia_utils.cpp:1367-1699 with gauss_likelihood = false)
   if (launch_eval(h, cov_type, var, range, gpb::MODE_STORE, true)) return -1;
   if (ensure_csc(h)) return -1;
+  if (lap_refresh_csc_coefs(h)) return -1;
   const int eb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 16);
   if (fixed_effects_host) {
     std::memcpy(L->stage, fixed_effects_host, sizeof(double) * n);
@@ -924,7 +1222,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       } else {
         if (lap_apply_op(h, 1, L->upd, L->v, L->tt, &dot)) return -1;
         gpl::Coef one; one.v[0] = 1.;
-        gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, one, L->v, L->r, nullptr, nullptr, L->partial);
+        gpl::v_axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, one.v[0], L->v, L->r, nullptr, nullptr, L->partial);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
       }
@@ -935,7 +1233,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
       for (j = 0; j < cg_max; ++j) {
         if (lap_apply_op(h, 1, L->hv, L->v, L->tt, &hv)) return -1;
         gpl::Coef a; a.v[0] = rz / hv;
-        gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, a, L->v, L->r, L->hv, L->upd, L->partial);
+        gpl::v_axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, a.v[0], L->v, L->r, L->hv, L->upd, L->partial);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
         if (laplace_colsums(h, 1, &rr, L->grid_mv * (gpl::kBlock / 32))) return -1;
@@ -994,7 +1292,7 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
     gpl::scale_transpose_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->probes, L->dw, L->T);
     CUDA_TRY(cudaGetLastError());
     const int G = lap_groups(t), gridg = lap_grid(L->grid_mv, G), prow = gridg * (gpl::kBlock / 32) / G;
-    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial);
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial, L->order);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
     // ---- CGTridiagVecchiaLaplace
@@ -1060,6 +1358,36 @@ int gpbdev_vecchia_laplace_eval(gpbdev_vecchia_t h, int cov_type, double var, do
   return 0;
 }
 
+// bench hook: device time of one operator application (B^T D^-1 B + W) X and of one preconditioner application B^-1 (D^-1 + W)^-1 B^-T R
+// on t columns (t = 1: the Newton system's vectors, t = the probe count: the SLQ block), after gpbdev_vecchia_laplace_eval. CUDA events
+// on the engine's stream; mean over `reps` applications after one warm-up. out_ms = {operator, preconditioner}.
+int gpbdev_vecchia_laplace_time_ops(gpbdev_vecchia_t h, int t, int reps, float* out_ms) {
+  if (!h || !out_ms || reps < 1) return fail("gpbdev_vecchia_laplace_time_ops: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gpb_laplace_state* L = h->lap;
+  if (!L || !h->A_csc) return fail("gpbdev_vecchia_laplace_time_ops: run gpbdev_vecchia_laplace_eval first");
+  if (t != 1 && t != L->t) return fail("gpbdev_vecchia_laplace_time_ops: t must be 1 or the number of probe columns");
+  double dots[gpl::kMaxCols];
+  float acc[2] = {0.f, 0.f};
+  for (int r = 0; r < reps + 1; ++r) {
+    for (int which = 0; which < 2; ++which) {
+      CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+      int rc;
+      if (which == 0) rc = t == 1 ? lap_apply_op(h, 1, L->hv, L->v, L->tt, dots) : lap_apply_op(h, t, L->H, L->V, L->T, dots);
+      else rc = t == 1 ? lap_precond(h, 1, L->r, L->z, L->yy, dots) : lap_precond(h, t, L->R, L->Z, L->Y, dots);
+      if (rc) return -1;
+      CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+      CUDA_TRY(cudaEventSynchronize(h->ev1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      if (r > 0) acc[which] += ms;
+    }
+  }
+  if (lap_check_err(h)) return -1;
+  out_ms[0] = acc[0] / reps; out_ms[1] = acc[1] / reps;
+  return 0;
+}
+
 // The next evaluation keeps what the gradient needs (the SLQ's CG solutions); costs one more n x t buffer.
 int gpbdev_vecchia_laplace_keep_solutions(gpbdev_vecchia_t h, int keep) {
   if (!h) return fail("gpbdev_vecchia_laplace_keep_solutions: null argument");
@@ -1111,13 +1439,13 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
   // Zp = B^T (sqrt(dw) probes) -> R;  PI_Z = P^-1 Zp -> Z
   std::vector<double> dots(t), zA(t), zP(t);
   gpl::scale_transpose_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->probes, L->dw, L->T);
-  gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial);
+  gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->T, L->R, L->partial, L->order);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
   CUDA_TRY(cudaMemsetAsync(L->err, 0, sizeof(int), h->stream));
   if (lap_precond(h, t, L->R, L->Z, L->Y, dots.data())) return -1;
   // d mll / d mode -> rhs;  x = (Sigma^-1 + W)^-1 rhs -> upd (PCG from zero, Inv_SigmaI_plus_ZtWZ_Vecchia_iterative_given_PC)
-  gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, nullptr, L->Z, L->T);
+  gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, nullptr, L->Z, L->T, L->order);
   gpl::stoch_dmode_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, t, L->U, L->Z, L->T, L->dWv, L->dw, L->rhs);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
@@ -1131,7 +1459,7 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
     for (int j = 0; j < cg_max; ++j) {
       if (lap_apply_op(h, 1, L->hv, L->v, L->tt, &hv)) return -1;
       gpl::Coef a; a.v[0] = rz / hv;
-      gpl::axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, 1, 1, a, L->v, L->r, L->hv, L->upd, L->partial);
+      gpl::v_axpy_norm_kernel<<<L->grid_mv, gpl::kBlock, 0, h->stream>>>(n, a.v[0], L->v, L->r, L->hv, L->upd, L->partial);
       CUDA_TRY(cudaGetLastError());
       h->launches += 1;
       if (laplace_colsums(h, 1, &rr, L->grid_mv * (gpl::kBlock / 32))) return -1;
@@ -1158,8 +1486,8 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
   // ---- j = 0, marginal variance: dSigma^-1 = -Sigma^-1
   double m_v = 0., x_v = 0.;
   {
-    gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, L->Z, L->T);     // T1 = D^-1 B PI_Z
-    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->Z, L->V, L->partial);  // V = Sigma^-1 PI_Z
+    gpl::mv_B_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, L->Z, L->T, L->order);     // T1 = D^-1 B PI_Z
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->T, nullptr, L->Z, L->V, L->partial, L->order);  // V = Sigma^-1 PI_Z
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
     if (laplace_colsums(h, t, zP.data(), prow)) return -1;  // PI_Z . V
@@ -1169,8 +1497,8 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
     if (laplace_colsums(h, t, zA.data(), prow)) return -1;
     for (int c = 0; c < t; ++c) { zA[c] = -zA[c]; zP[c] = -zP[c]; }
     // single vector: Sigma^-1 mode -> v
-    gpl::mv_B_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, 1, 1, h->Dinv, L->mode, L->tt);
-    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->tt, nullptr, L->mode, L->v, L->partial);
+    gpl::mv_B_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, 1, 1, h->Dinv, L->mode, L->tt, L->order);
+    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->tt, nullptr, L->mode, L->v, L->partial, L->order);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
     if (laplace_colsums(h, 1, &m_v, prow1)) return -1;
@@ -1188,7 +1516,7 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
     // T = D^-1 B PI_Z (still valid), Y = Bg PI_Z, H = D^-1 Y - D^-1 dD T, V = B^T H + Bg^T T
     gpl::mv_Bg_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->nn, h->m, n, t, G, L->Z, L->Y);
     gpl::rowscale2_kernel<<<lb, 256, 0, h->stream>>>(n, t, h->Dinv, L->Y, L->c1, L->T, L->H);
-    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->V, L->partial);
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->V, L->partial, L->order);
     gpl::mv_Bgt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, t, G, L->T, L->V, 1);
     gpl::coldot_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, L->U, L->V, L->partial);
     CUDA_TRY(cudaGetLastError());
@@ -1196,7 +1524,7 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
     if (laplace_colsums(h, t, zA.data(), prow)) return -1;
     // dP = dSigma^-1 + B^T W Bg + Bg^T W B:  R = B^T ((D^-1 + W) Y - D^-1 dD T) + Bg^T ((1 + W / D^-1) T)
     gpl::rowscale2_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->c2, L->Y, L->c1, L->T, L->H);
-    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->R, L->partial);
+    gpl::mv_Bt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, L->H, nullptr, L->Z, L->R, L->partial, L->order);
     gpl::rowscale1_kernel<<<lb, 256, 0, h->stream>>>(n, t, L->c3, L->T, L->H);
     gpl::mv_Bgt_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, t, G, L->H, L->R, 1);
     gpl::coldot_kernel<<<gridg, gpl::kBlock, 0, h->stream>>>(n, t, G, L->Z, L->R, L->partial);
@@ -1206,7 +1534,7 @@ int gpbdev_vecchia_laplace_grad(gpbdev_vecchia_t h, int cov_type, double var, do
     // single vector: tt = D^-1 B mode (still valid), yy = Bg mode, z = D^-1 yy - D^-1 dD tt, v = B^T z + Bg^T tt
     gpl::mv_Bg_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->dA, h->nn, h->m, n, 1, 1, L->mode, L->yy);
     gpl::rowscale2_kernel<<<eb, 256, 0, h->stream>>>(n, 1, h->Dinv, L->yy, L->c1, L->tt, L->z);
-    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->z, nullptr, L->mode, L->v, L->partial);
+    gpl::mv_Bt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, 1, 1, L->z, nullptr, L->mode, L->v, L->partial, L->order);
     gpl::mv_Bgt_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(h->dA, h->colptr, h->csc_pos, h->m, n, 1, 1, L->tt, L->v, 1);
     gpl::coldot_kernel<<<grid1, gpl::kBlock, 0, h->stream>>>(n, 1, 1, L->mode, L->v, L->partial);
     CUDA_TRY(cudaGetLastError());

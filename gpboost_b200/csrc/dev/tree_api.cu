@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
 // GPU budget was spent): opt-in with GPB200_HIST_KERNEL=3, not part of the parity tests until it has passed them once.
 constexpr int kHist3Stride = kHistTile + 8;
 static inline size_t hist3_smem(int nw) { return (size_t)nw * 4 * kBins * 12 + 64 * kHist3Stride + kHistTile * 8; }
+// PLAIN_COUNT: the leader updates the integer counter with an ordinary load / add / store like the gradient sum (it is the only lane
+// that touches the counter in a step, and steps are separated by __syncwarp) instead of a shared-memory RED: a spread-address
+// ATOMS costs ~2 cycles per lane on this part (B300_MICROARCH.md), more than everything else in the step together.
+template <bool PLAIN_COUNT>
 __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist3_kernel(const uint8_t* __restrict__ bins, int Fpad, int F,
                                                                       const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                       int64_t rows_per_chunk, const double* __restrict__ grad,
@@ -377,7 +381,9 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist3_kernel(const uint
           if (pa_hi & 0x80000000u) v += gd.y;
         }
         myg[mybin] = v;
-        atomicAdd(&myc[mybin], 1u + (uint32_t)__popc(pa_lo) + (uint32_t)__popc(pa_hi));
+        const uint32_t members = 1u + (uint32_t)__popc(pa_lo) + (uint32_t)__popc(pa_hi);
+        if (PLAIN_COUNT) myc[mybin] += members;
+        else atomicAdd(&myc[mybin], members);
       }
       __syncwarp();  // the next step's leaders may read counters written by other lanes in this one
     }
@@ -1219,10 +1225,11 @@ struct gpbdev_tree {
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
   int fused_scan = 2;              // GPB200_FUSED_SCAN = 2 (default): reduce_scan2_kernel | 1: reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
+  int sharded_graph = 0;           // GPB200_SHARDED_LOOP = graph: capture the data-parallel leaf loop (NCCL kernels included) in a CUDA graph
   int sharded_host_loop = 0;       // GPB200_SHARDED_LOOP = host: data-parallel learners use the host-driven leaf loop (one blocking all-reduce and one
                                    // D2H per split, CUB partition) instead of the device-resident / graph loop with in-stream all-reduces
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
-  int hist_kernel_version = 3;     // GPB200_HIST_KERNEL = 3 (default): hist3_kernel | 2: hist2_kernel | 1: single-warp hist_kernel
+  int hist_kernel_version = 4;     // GPB200_HIST_KERNEL = 4 (default): hist3_kernel with plain counter updates | 3: hist3_kernel with RED counters | 2: hist2_kernel | 1: single-warp hist_kernel
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -1333,7 +1340,8 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
   TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
   TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist2_smem(hist2_warps(F))));
-  TCUDA(cudaFuncSetAttribute(hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist3_smem(hist2_warps(F))));
+  TCUDA(cudaFuncSetAttribute(hist3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist3_smem(hist2_warps(F))));
+  TCUDA(cudaFuncSetAttribute(hist3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist3_smem(hist2_warps(F))));
   h->max_seg = h->num_sms * 4;
   TCUDA(cudaMalloc(&h->flag8, (size_t)n));
   TCUDA(cudaMalloc(&h->seg_left, sizeof(int32_t) * h->max_seg));
@@ -1343,9 +1351,9 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 1 ? 1 : 2);
-  if (const char* e = std::getenv("GPB200_SHARDED_LOOP")) h->sharded_host_loop = std::string(e) == "host" ? 1 : 0;
+  if (const char* e = std::getenv("GPB200_SHARDED_LOOP")) { h->sharded_host_loop = std::string(e) == "host" ? 1 : 0; h->sharded_graph = std::string(e) == "graph" ? 1 : 0; }
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
-  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) == 1 ? 1 : (std::atoi(e) == 2 ? 2 : 3);
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 4;
   *out = h;
   return 0;
 }
@@ -1392,7 +1400,10 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   const DevJob* job = &st->job;
   // GPB200_TREE_LOOP=graph: the whole tree (root sums included) is one CUDA graph, captured once per (gradient buffer,
   // hessian) and replayed every boosting iteration — one graph launch instead of ~8 launches per split
-  const bool use_graph = h->device_loop == 2;
+  // Data-parallel learners enqueue the same sequence eagerly (kernels and NCCL all-reduces, no host round trip per split); replaying
+  // NCCL collectives from a captured graph is opt-in (GPB200_SHARDED_LOOP=graph) — the first two-GPU run of that combination did
+  // not complete (profiles/r02_mgpu_session.log).
+  const bool use_graph = h->device_loop == 2 && (h->allreduce == nullptr || h->sharded_graph);
   if (use_graph && h->graph_exec && (h->graph_grad != grad || h->graph_hess != hess_const)) {
     cudaGraphExecDestroy(h->graph_exec);
     h->graph_exec = nullptr;
@@ -1407,7 +1418,15 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   // a second latency-bound collective per split for the best-split exchange and scan no faster (one CTA per feature either way).
   const bool sharded = h->allreduce != nullptr;
   const int n_glob = sharded ? (int)h->n_global : (int)n;
-  if (sharded && !h->stage) TCUDA(cudaMalloc(&h->stage, sizeof(double) * slot_stride));
+  if (sharded && !h->stage) {
+    TCUDA(cudaMalloc(&h->stage, sizeof(double) * slot_stride));
+    TCUDA(cudaMemsetAsync(h->stage, 0, sizeof(double) * slot_stride, h->stream));
+    // one eager exchange of each message size before anything is captured: the communicator sets up its channels / buffers for a
+    // (size, algorithm) at the first call, which must not happen inside a stream capture
+    if (h->allreduce(h->allreduce_ctx, h->stage, (int64_t)slot_stride, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
+    if (h->allreduce(h->allreduce_ctx, h->stage, 1, (void*)h->stream)) return tfail("gpbdev_tree_train: device all-reduce failed");
+    TCUDA(cudaStreamSynchronize(h->stream));
+  }
   if (use_graph && !replay) TCUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   bool coll_failed = false;
   if (!replay) {
@@ -1424,8 +1443,10 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   const int cgrid = h->num_sms * 4;
   for (int split = 0; split < L - 1 && !coll_failed; ++split) {
     tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
-    if (h->hist_kernel_version == 3)
-      hist3_kernel<<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+    if (h->hist_kernel_version == 4)
+      hist3_kernel<true><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+    else if (h->hist_kernel_version == 3)
+      hist3_kernel<false><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
     else
       hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
     LeafArgs dummy;
@@ -1500,7 +1521,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
   const bool sharded = h->allreduce != nullptr;
   const int64_t n_glob = sharded ? h->n_global : n;
   const bool dev_loop_sharded = !sharded || !h->sharded_host_loop;
-  if (h->device_loop == 2 && dev_loop_sharded && L <= kMaxLeavesDev && grad_on_device)  // everything, root sums included, is in the graph
+  if (h->device_loop == 2 && (!sharded || (dev_loop_sharded && h->sharded_graph)) && L <= kMaxLeavesDev && grad_on_device)  // everything, root sums included, is in the graph
     return tree_train_device_loop(h, grad, hess_const, num_leaves_out, split_feature, threshold_bin, left_child, right_child, split_gain,
                                   leaf_value, leaf_count);
   iota_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->idx, n);
@@ -1548,8 +1569,11 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
         rpc = std::max<int64_t>(128, ((cnt + h->num_sms - 1) / h->num_sms + 7) / 8 * 8);  // whole 8-row steps per chunk
         nchunks = (int)((cnt + rpc - 1) / rpc);
         const int nw = hist2_warps(F);
-        if (h->hist_kernel_version == 3)
-          hist3_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
+        if (h->hist_kernel_version == 4)
+          hist3_kernel<true><<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
+              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
+        else if (h->hist_kernel_version == 3)
+          hist3_kernel<false><<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
               h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
         else
         hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
@@ -1727,6 +1751,44 @@ int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_le
   add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, score_dev, leaf_of_row_dev);
   TCUDA(cudaGetLastError());
   h->launches += 1;
+  return 0;
+}
+
+// bench hook: device time of the root-pass histogram kernel alone (all n rows, the learner's default kernel), L2 flushed before each
+// of `reps` launches; CUDA events on the learner's stream. Algorithmic bytes per launch: n * (Fpad + 8).
+int gpbdev_tree_time_root_hist(gpbdev_tree_t h, const double* grad_dev, int reps, float* mean_ms) {
+  if (!h || !grad_dev || !mean_ms || reps < 1) return tfail("gpbdev_tree_time_root_hist: bad argument");
+  TCUDA(cudaSetDevice(h->device));
+  const int F = h->F, Fpad = h->Fpad;
+  const int64_t n = h->n;
+  cudaEvent_t e0, e1;
+  TCUDA(cudaEventCreate(&e0)); TCUDA(cudaEventCreate(&e1));
+  double* flush = nullptr;
+  const size_t flush_bytes = (size_t)256 << 20;
+  TCUDA(cudaMalloc(&flush, flush_bytes));
+  const int nw = hist2_warps(F);
+  const int64_t rpc = std::max<int64_t>(128, ((n + h->num_sms - 1) / h->num_sms + 7) / 8 * 8);
+  const int nchunks = (int)((n + rpc - 1) / rpc);
+  const dim3 grid(nchunks, (Fpad + 63) / 64);
+  double total = 0.;
+  for (int r = 0; r < reps + 1; ++r) {
+    TCUDA(cudaMemsetAsync(flush, r, flush_bytes, h->stream));
+    TCUDA(cudaEventRecord(e0, h->stream));
+    if (h->hist_kernel_version == 4)
+      hist3_kernel<true><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+    else if (h->hist_kernel_version == 3)
+      hist3_kernel<false><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+    else
+      hist2_kernel<<<grid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+    TCUDA(cudaEventRecord(e1, h->stream));
+    TCUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    TCUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0) total += ms;  // first launch = warm-up
+  }
+  h->launches += reps + 1;
+  cudaFree(flush); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *mean_ms = (float)(total / reps);
   return 0;
 }
 

@@ -291,6 +291,13 @@ bool Booster::TrainOneIter() {
   return false;
 }
 
+void Booster::TimeRootHistogram(int reps, float* mean_ms, int* row_bytes, int64_t* rows) const {
+  if (learner_ == nullptr) Fatal("This Booster has no training data");
+  TreeCheck(gpbdev_tree_time_root_hist(learner_, grad_dev_ + row_begin_, reps, mean_ms));
+  *row_bytes = train_->bins_row_stride() + 8;  // bins of the row + its gradient (F + 8 bytes per row at the root)
+  *rows = row_end_ - row_begin_;
+}
+
 void Booster::GetTrainingScore(double* out) {
   if (learner_ == nullptr) Fatal("This Booster was loaded from a model string / file and has no training data (prediction only)");
   TreeCheck(gpbdev_vec_download(learner_, out, score_dev_, n_)); }

@@ -57,6 +57,8 @@ class Booster {
   std::vector<double> FeatureImportance(int num_iteration, int importance_type) const;
   double LeafValue(int tree_idx, int leaf_idx) const;
   gpbdev_tree_t learner() const { return learner_; }
+  // bench hook: mean device time of the root-pass histogram kernel on this rank's rows with the current gradient (bench.py roofline)
+  void TimeRootHistogram(int reps, float* mean_ms, int* row_bytes, int64_t* rows) const;
 
  private:
   void Boosting();  // gradients for the next tree (+ covariance-parameter fit when a GP model is attached)

@@ -501,6 +501,12 @@ int GPB200_DatasetGetFeatureBins(DatasetHandle handle, int real_feature, int* nu
   API_END();
 }
 
+int GPB200_BoosterTimeRootHistogram(BoosterHandle handle, int reps, float* mean_ms, int* row_bytes, int64_t* rows) {
+  API_BEGIN();
+  B(handle)->TimeRootHistogram(reps, mean_ms, row_bytes, rows);
+  API_END();
+}
+
 int GPB200_SetDevice(int device) {
   API_BEGIN();
   if (device < 0 || device >= gpbdev_device_count())

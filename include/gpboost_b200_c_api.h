@@ -112,6 +112,8 @@ GPB200_EXPORT int LGBM_BoosterSaveModelToString(BoosterHandle handle, int start_
 /* ---- extensions of the B200 build (no counterpart in the reference's exported API) ---------------------- */
 /* test hook: the bin boundaries the host search found for one feature (upper_bounds: room for 256 doubles) */
 GPB200_EXPORT int GPB200_DatasetGetFeatureBins(DatasetHandle handle, int real_feature, int* num_bin, int* is_trivial, double* upper_bounds);
+/* bench hook: mean device time (ms) of the root-pass histogram kernel over this rank's `rows` rows of `row_bytes` algorithmic bytes each */
+GPB200_EXPORT int GPB200_BoosterTimeRootHistogram(BoosterHandle handle, int reps, float* mean_ms, int* row_bytes, int64_t* rows);
 /* device ordinal used by models created afterwards in this process (default 0) */
 GPB200_EXPORT int GPB200_SetDevice(int device);
 /* Row sharding of observations over `world_size` processes (one per GPU) + the sum-all-reduce used on shard

@@ -82,6 +82,9 @@ GPBDEV_EXPORT int gpbdev_vecchia_yaux(gpbdev_vecchia_t h, double* yaux_host);
 /* Same as gpbdev_vecchia_yaux but the result (times `scale`) stays on the device, original order, written to out_dev
  * (may alias the engine-external gradient buffer of the boosting driver). */
 GPBDEV_EXPORT int gpbdev_vecchia_yaux_device(gpbdev_vecchia_t h, double* out_dev, double scale);
+/* bench hook (after gpbdev_vecchia_laplace_eval): mean device time of one operator application and of one VADU preconditioner
+ * application on t columns (t = 1 or the probe count); out_ms = {operator, preconditioner} */
+GPBDEV_EXPORT int gpbdev_vecchia_laplace_time_ops(gpbdev_vecchia_t h, int t, int reps, float* out_ms);
 /* Vecchia prediction at new locations: CalcPredVecchiaObservedFirstOrder with CondObsOnly = true
  * (src/GPBoost/Vecchia_utils.cpp:1701-2100), Gaussian likelihood, responses of the last gpbdev_vecchia_set_y*. coords_pred_host: np x d
  * row-major. num_neighbors_pred <= 60 (the reference's default is twice the model's num_neighbors, re_model_template.h:299).
@@ -240,6 +243,9 @@ GPBDEV_EXPORT int gpbdev_tree_train(gpbdev_tree_t h, const double* grad, int gra
  * score_updater.hpp); optionally also writes the leaf index of every row (GetDataLeafIndices). Either pointer may be NULL. */
 GPBDEV_EXPORT int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_leaves, double* score_dev,
                                         int32_t* leaf_of_row_dev);
+/* bench hook: mean device time (CUDA events on the learner's stream, L2 flushed before every launch) of the root-pass histogram kernel
+ * over all n rows; algorithmic bytes per launch n * (Fpad + 8) */
+GPBDEV_EXPORT int gpbdev_tree_time_root_hist(gpbdev_tree_t h, const double* grad_dev, int reps, float* mean_ms);
 /* leaf index of every row of the last trained tree (TreeLearner::GetDataLeafIndices, serial_tree_learner.cpp:818): device pointer to n
  * int32 owned by the learner, valid until the next call / tree */
 GPBDEV_EXPORT int gpbdev_tree_leaf_indices(gpbdev_tree_t h, const int32_t** leaf_of_row_dev);

@@ -41,6 +41,8 @@ params = {"objective": "regression_l2", "learning_rate": 0.1, "num_leaves": 8, "
 bst = gpb.train(params=params, train_set=ds, gp_model=m2, num_boost_round=6)
 out["cov_pars_boost"] = np.asarray(m2.get_cov_pars()).reshape(-1).tolist()
 txt = bst.model_to_string()
+if txt.lstrip().startswith("{"):   # with a GP model the package wraps the tree model text and the GPModel's state in JSON
+    txt = json.loads(txt)["booster_str"]
 out["num_trees"] = bst.num_trees()
 out["split_feature"] = [ln for ln in txt.split("\\n") if ln.startswith("split_feature=")]
 out["threshold"] = [ln for ln in txt.split("\\n") if ln.startswith("threshold=")]
