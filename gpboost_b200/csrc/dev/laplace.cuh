@@ -621,6 +621,160 @@ __global__ void csc_gather_kernel(const double* __restrict__ A, const int32_t* _
   }
 }
 
+// ---- tiled operator kernels: neighbour blocks staged in shared memory by bulk async copies --------------------------------
+// mv_B / mv_Bt gather m + 1 rows of the multi-vector per row of B: at t = 50 that is 12.4 KB through L2 per row although rows that
+// are close in space share most of their neighbours. Here 32 rows that are consecutive on the Morton curve form a TILE; the
+// distinct source rows of a tile (~205 of 992 gathers at n = 1e6, m = 30; the lists are a static property of the pattern, built
+// once) are brought into shared memory ONCE, each by one cp.async.bulk (TMA bulk engine, 8 t contiguous bytes) signalling an
+// mbarrier with complete_tx, and the 32 x (m + 1) products are taken from shared memory (lane = column: conflict-free). Two
+// CTAs per SM alternate between their load and compute phases. L2 -> SM traffic drops from (m + 1) rows per row to ~6.4.
+// Sources beyond the tile's capacity (early points with far neighbours; rare) are marked in the slot table and read from global.
+constexpr int kTileRows = 32;
+constexpr int kTileCap = 272;          // source rows held per tile: 272 * 400 B = 108.8 KB at t = 50 -> two CTAs per SM
+constexpr int kTileThreads = 128;
+constexpr uint16_t kSlotNone = 0xFFFF;  // padded neighbour slot
+constexpr uint16_t kSlotGlobal = 0xFFFE;  // source did not fit the tile: read from global memory
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(smem_u32(b)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+
+// T[i,:] = s_i (X[i,:] - sum_k A[i,k] X[nn[i,k],:]) for the rows of tile `tile` (positions 32 tile .. of `order`)
+// tile_ptr / tile_src: sources of each tile; slot[p * (m + 1) + 0] = slot of the row itself, + 1 + k = slot of neighbour k
+__global__ void __launch_bounds__(kTileThreads) mv_B_tiled_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int t,
+                                                                 const double* __restrict__ Dinv, const double* __restrict__ X, double* __restrict__ T,
+                                                                 const int32_t* __restrict__ order, int ntiles, const int32_t* __restrict__ tile_ptr,
+                                                                 const int32_t* __restrict__ tile_src, const uint16_t* __restrict__ slot) {
+  extern __shared__ __align__(128) double tbuf[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t row_bytes = (uint32_t)t * 8u;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t parity = 0;
+  const int c0 = lane, c1 = 32 + lane;
+  const bool on0 = c0 < t, on1 = c1 < t;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s0 = tile_ptr[tile];
+    const int nd = min(tile_ptr[tile + 1] - s0, kTileCap);
+    if (tid == 0) mbar_expect_tx(&bar, (uint32_t)nd * row_bytes);
+    for (int k = tid; k < nd; k += kTileThreads) bulk_g2s(tbuf + (size_t)k * t, X + (size_t)tile_src[s0 + k] * t, row_bytes, &bar);
+    // the rows' own data while the copies fly
+    const int64_t pbase = (int64_t)tile * kTileRows + w * (kTileRows / 4);
+    while (!mbar_try_wait(&bar, parity)) {}
+    parity ^= 1u;
+    for (int r = 0; r < kTileRows / 4; ++r) {
+      const int64_t p = pbase + r;
+      if (p >= n) break;
+      const int64_t i = order[p];
+      const uint16_t sl = lane <= m ? slot[p * (m + 1) + lane] : kSlotNone;   // lane 0: own row, lane 1 + k: neighbour k
+      const double ak = (lane >= 1 && lane <= m && sl != kSlotNone) ? A[i * m + lane - 1] : 0.;
+      const int32_t jn = (lane >= 1 && lane <= m) ? nn[i * m + lane - 1] : -1;
+      const unsigned s_self = __shfl_sync(0xffffffffu, (unsigned)sl, 0);
+      double acc0 = 0., acc1 = 0.;
+      if (s_self == kSlotGlobal) { if (on0) acc0 = X[i * t + c0]; if (on1) acc1 = X[i * t + c1]; }
+      else { if (on0) acc0 = tbuf[(size_t)s_self * t + c0]; if (on1) acc1 = tbuf[(size_t)s_self * t + c1]; }
+      for (int k = 1; k <= m; ++k) {
+        const unsigned sk = __shfl_sync(0xffffffffu, (unsigned)sl, k);
+        const double a = __shfl_sync(0xffffffffu, ak, k);
+        const int32_t j = __shfl_sync(0xffffffffu, jn, k);
+        if (sk == kSlotNone) continue;
+        if (sk == kSlotGlobal) {
+          if (on0) acc0 -= a * X[(int64_t)j * t + c0];
+          if (on1) acc1 -= a * X[(int64_t)j * t + c1];
+        } else {
+          if (on0) acc0 -= a * tbuf[(size_t)sk * t + c0];
+          if (on1) acc1 -= a * tbuf[(size_t)sk * t + c1];
+        }
+      }
+      const double s = Dinv ? Dinv[i] : 1.;
+      if (on0) T[i * t + c0] = s * acc0;
+      if (on1) T[i * t + c1] = s * acc1;
+    }
+    __syncthreads();  // every warp is done with the buffer before the next tile's copies land in it
+  }
+}
+
+// V[j,:] = T[j,:] - sum_{e in column j} A_csc[e] T[row_e,:] + W[j] X[j,:];  per-warp partial dots X[j,c] V[j,c] (columns c, 32 + c)
+// slot_e[e]: slot of the source row of CSC entry e within the tile of its column
+__global__ void __launch_bounds__(kTileThreads) mv_Bt_tiled_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr,
+                                                                  const int32_t* __restrict__ csc_row, int64_t n, int t,
+                                                                  const double* __restrict__ T, const double* __restrict__ W,
+                                                                  const double* __restrict__ X, double* __restrict__ V, double* __restrict__ partial,
+                                                                  const int32_t* __restrict__ order, int ntiles, const int32_t* __restrict__ tile_ptr,
+                                                                  const int32_t* __restrict__ tile_src, const uint16_t* __restrict__ slot_e) {
+  extern __shared__ __align__(128) double tbuf[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t row_bytes = (uint32_t)t * 8u;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t parity = 0;
+  const int c0 = lane, c1 = 32 + lane;
+  const bool on0 = c0 < t, on1 = c1 < t;
+  double dot0 = 0., dot1 = 0.;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int s0 = tile_ptr[tile];
+    const int nd = min(tile_ptr[tile + 1] - s0, kTileCap);
+    if (tid == 0) mbar_expect_tx(&bar, (uint32_t)nd * row_bytes);
+    for (int k = tid; k < nd; k += kTileThreads) bulk_g2s(tbuf + (size_t)k * t, T + (size_t)tile_src[s0 + k] * t, row_bytes, &bar);
+    const int64_t pbase = (int64_t)tile * kTileRows + w * (kTileRows / 4);
+    while (!mbar_try_wait(&bar, parity)) {}
+    parity ^= 1u;
+    for (int r = 0; r < kTileRows / 4; ++r) {
+      const int64_t p = pbase + r;
+      if (p >= n) break;
+      const int64_t j = order[p];
+      double acc0 = on0 ? T[j * t + c0] : 0., acc1 = on1 ? T[j * t + c1] : 0.;
+      const int e0 = colptr[j], e1 = colptr[j + 1];
+      for (int eb = e0; eb < e1; eb += 32) {
+        const int e = eb + lane;
+        const unsigned sl = e < e1 ? (unsigned)slot_e[e] : (unsigned)kSlotNone;
+        const double ae = e < e1 ? A_csc[e] : 0.;
+        const int32_t re = e < e1 ? csc_row[e] : 0;
+        const int cnt = min(32, e1 - eb);
+        for (int q = 0; q < cnt; ++q) {
+          const unsigned sk = __shfl_sync(0xffffffffu, sl, q);
+          const double a = __shfl_sync(0xffffffffu, ae, q);
+          const int32_t row = __shfl_sync(0xffffffffu, re, q);
+          if (sk == kSlotGlobal) {
+            if (on0) acc0 -= a * T[(int64_t)row * t + c0];
+            if (on1) acc1 -= a * T[(int64_t)row * t + c1];
+          } else {
+            if (on0) acc0 -= a * tbuf[(size_t)sk * t + c0];
+            if (on1) acc1 -= a * tbuf[(size_t)sk * t + c1];
+          }
+        }
+      }
+      const double wj = W ? W[j] : 0.;
+      if (on0) { const double xj = X[j * t + c0]; const double v = acc0 + wj * xj; V[j * t + c0] = v; dot0 += xj * v; }
+      if (on1) { const double xj = X[j * t + c1]; const double v = acc1 + wj * xj; V[j * t + c1] = v; dot1 += xj * v; }
+    }
+    __syncthreads();
+  }
+  const size_t gw = (size_t)blockIdx.x * (kTileThreads / 32) + w;
+  if (on0) partial[gw * kMaxCols + c0] = dot0;
+  if (on1) partial[gw * kMaxCols + c1] = dot1;
+}
+
 // ---- bernoulli_logit pieces (DF_utils.h:37-60, likelihoods.h:11401, 12477, 13307) ----------------------------
 __device__ __forceinline__ double sigmoid_stable(double x) {
   if (x >= 0.) { const double e = exp(-x); return 1. / (1. + e); }
@@ -875,8 +1029,13 @@ struct gpb_laplace_state {
   int grid_mv = 0;        // grid of the ordinary (non-polling) row kernels
   int grid_v = 0;         // cooperative grid of the single-vector polling kernels (few registers: more resident warps)
   int grid_v2 = 0;        // cooperative grid of the second-generation tail kernels
+  // tiles of 32 Morton-consecutive rows with their distinct source rows (tiled operator kernels; built once per model, lazily)
+  int ntiles = 0, tiled = -1;      // tiled: -1 not decided, 0 off (GPB200_LAPLACE_TILED=0, no Morton order, ...), 1 on
+  int32_t *tb_ptr = nullptr, *tb_src = nullptr, *tt_ptr = nullptr, *tt_src = nullptr;
+  uint16_t *tb_slot = nullptr, *tt_slot = nullptr;
   int32_t* order = nullptr;  // n: processing order of the order-free row kernels (Morton order of the locations); null = by index
-  int trs_variant = 1;    // GPB200_TRS_VARIANT = 1 (default): shared-memory head + sub-warp tail | 0: first generation
+  int trs_variant = 0;    // GPB200_TRS_VARIANT = 0 (default): every row polled through L2, one row per warp | 1: shared-memory head + sub-warp tail
+                          // (measured slower at the default head size: one CTA cannot hide the global-load latency of 16 384 rows; profiles/r02_laplace_variants.log)
   int head_rows = gpl::kHeadRows;  // GPB200_TRS_HEAD_ROWS (<= 16384): rows solved in shared memory (tests shrink it to exercise the tail on small models)
   int nwarps = 0;
   double *mode = nullptr, *mode_new = nullptr, *upd = nullptr, *dir = nullptr, *rhs = nullptr, *W = nullptr, *dw = nullptr, *fe = nullptr;
@@ -905,6 +1064,7 @@ void laplace_release(gpbdev_vecchia* h) {
   for (double* b : bufs) cudaFree(b);
   cudaFree(L->err);
   cudaFree(L->order);
+  cudaFree(L->tb_ptr); cudaFree(L->tb_src); cudaFree(L->tt_ptr); cudaFree(L->tt_src); cudaFree(L->tb_slot); cudaFree(L->tt_slot);
   cudaFreeHost(L->colsum_host);
   cudaFreeHost(L->stage);
   delete L;
@@ -939,7 +1099,7 @@ int laplace_ensure(gpbdev_vecchia* h) {
   int cap_v2 = 6;
   if (const char* e = std::getenv("GPB200_TRS_CTAS_PER_SM")) cap_v2 = std::max(1, std::atoi(e));
   L->grid_v2 = std::max(1, std::min(std::min(per_t, per_t2), cap_v2)) * h->num_sms;
-  if (const char* e = std::getenv("GPB200_TRS_VARIANT")) L->trs_variant = std::atoi(e) == 0 ? 0 : 1;
+  if (const char* e = std::getenv("GPB200_TRS_VARIANT")) L->trs_variant = std::atoi(e) == 1 ? 1 : 0;
   if (const char* e = std::getenv("GPB200_TRS_HEAD_ROWS")) L->head_rows = std::max(1, std::min(gpl::kHeadRows, std::atoi(e)));
   if (const char* e = std::getenv("GPB200_TRS_SLEEP_NS")) {
     const int ns = std::max(0, std::atoi(e));
@@ -1046,6 +1206,139 @@ int lap_refresh_csc_coefs(gpbdev_vecchia* h) {
   return 0;
 }
 
+// Builds the tile lists of the tiled operator kernels (once per model; the pattern is static): for every tile of 32 Morton-consecutive
+// rows the sorted distinct source rows of B (the rows and their neighbours) and of B^T (the columns' dependents), and for every
+// (row, neighbour) / CSC entry the slot of its source inside the tile (or kSlotGlobal beyond the tile's capacity).
+int lap_build_tiles(gpbdev_vecchia* h) {
+  gpb_laplace_state* L = h->lap;
+  if (L->tiled >= 0) return 0;
+  L->tiled = 0;
+  const char* te = std::getenv("GPB200_LAPLACE_TILED");
+  if (!L->order || (te && std::string(te) == "0") || h->m > 30) return 0;
+  const int64_t n = h->n;
+  const int m = h->m;
+  std::vector<int32_t> ord((size_t)n);
+  CUDA_TRY(cudaMemcpy(ord.data(), L->order, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  if (h->nn_host.empty()) {
+    h->nn_host.resize((size_t)n * m);
+    CUDA_TRY(cudaMemcpy(h->nn_host.data(), h->nn, sizeof(int32_t) * n * m, cudaMemcpyDeviceToHost));
+  }
+  const std::vector<int32_t>& nnh = h->nn_host;
+  std::vector<int32_t> colptr((size_t)n + 1), crow;
+  CUDA_TRY(cudaMemcpy(colptr.data(), h->colptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+  crow.resize((size_t)colptr[n]);
+  {
+    std::vector<int32_t> pos((size_t)colptr[n]);
+    CUDA_TRY(cudaMemcpy(pos.data(), h->csc_pos, sizeof(int32_t) * pos.size(), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < pos.size(); ++e) crow[e] = pos[e] / m;
+  }
+  const int ntiles = (int)((n + gpl::kTileRows - 1) / gpl::kTileRows);
+  std::vector<std::vector<int32_t>> srcB((size_t)ntiles), srcT((size_t)ntiles);
+  std::vector<uint16_t> slotB((size_t)n * (m + 1), gpl::kSlotNone), slotT((size_t)colptr[n], gpl::kSlotNone);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int tl = 0; tl < ntiles; ++tl) {
+    const int64_t p0 = (int64_t)tl * gpl::kTileRows, p1 = std::min<int64_t>(p0 + gpl::kTileRows, n);
+    auto slot_of = [](const std::vector<int32_t>& u, int32_t id) -> uint16_t {
+      const int k = (int)(std::lower_bound(u.begin(), u.end(), id) - u.begin());
+      return k < gpl::kTileCap ? (uint16_t)k : gpl::kSlotGlobal;
+    };
+    {  // B: rows + neighbours
+      std::vector<int32_t>& u = srcB[(size_t)tl];
+      for (int64_t p = p0; p < p1; ++p) {
+        const int32_t i = ord[(size_t)p];
+        u.push_back(i);
+        for (int k = 0; k < m; ++k) { const int32_t j = nnh[(size_t)i * m + k]; if (j >= 0) u.push_back(j); }
+      }
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      for (int64_t p = p0; p < p1; ++p) {
+        const int32_t i = ord[(size_t)p];
+        slotB[(size_t)p * (m + 1)] = slot_of(u, i);
+        for (int k = 0; k < m; ++k) { const int32_t j = nnh[(size_t)i * m + k]; if (j >= 0) slotB[(size_t)p * (m + 1) + 1 + k] = slot_of(u, j); }
+      }
+      if ((int)u.size() > gpl::kTileCap) u.resize(gpl::kTileCap);
+    }
+    {  // B^T: the dependents of the tile's columns
+      std::vector<int32_t>& u = srcT[(size_t)tl];
+      for (int64_t p = p0; p < p1; ++p) {
+        const int32_t j = ord[(size_t)p];
+        for (int32_t e = colptr[(size_t)j]; e < colptr[(size_t)j + 1]; ++e) u.push_back(crow[(size_t)e]);
+      }
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      for (int64_t p = p0; p < p1; ++p) {
+        const int32_t j = ord[(size_t)p];
+        for (int32_t e = colptr[(size_t)j]; e < colptr[(size_t)j + 1]; ++e) slotT[(size_t)e] = slot_of(u, crow[(size_t)e]);
+      }
+      if ((int)u.size() > gpl::kTileCap) u.resize(gpl::kTileCap);
+    }
+  }
+  std::vector<int32_t> pb((size_t)ntiles + 1, 0), pt((size_t)ntiles + 1, 0);
+  for (int tl = 0; tl < ntiles; ++tl) { pb[(size_t)tl + 1] = pb[(size_t)tl] + (int32_t)srcB[(size_t)tl].size(); pt[(size_t)tl + 1] = pt[(size_t)tl] + (int32_t)srcT[(size_t)tl].size(); }
+  std::vector<int32_t> fb((size_t)pb[(size_t)ntiles]), ft((size_t)std::max(pt[(size_t)ntiles], 1));
+  for (int tl = 0; tl < ntiles; ++tl) {
+    std::copy(srcB[(size_t)tl].begin(), srcB[(size_t)tl].end(), fb.begin() + pb[(size_t)tl]);
+    std::copy(srcT[(size_t)tl].begin(), srcT[(size_t)tl].end(), ft.begin() + pt[(size_t)tl]);
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+    if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    return e;
+  };
+  CUDA_TRY(up((void**)&L->tb_ptr, pb.data(), sizeof(int32_t) * pb.size()));
+  CUDA_TRY(up((void**)&L->tt_ptr, pt.data(), sizeof(int32_t) * pt.size()));
+  CUDA_TRY(up((void**)&L->tb_src, fb.data(), sizeof(int32_t) * fb.size()));
+  CUDA_TRY(up((void**)&L->tt_src, ft.data(), sizeof(int32_t) * (size_t)pt[(size_t)ntiles]));
+  CUDA_TRY(up((void**)&L->tb_slot, slotB.data(), sizeof(uint16_t) * slotB.size()));
+  CUDA_TRY(up((void**)&L->tt_slot, slotT.data(), sizeof(uint16_t) * slotT.size()));
+  const int max_smem = (int)(sizeof(double) * gpl::kTileCap * 64);
+  CUDA_TRY(cudaFuncSetAttribute(gpl::mv_B_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  CUDA_TRY(cudaFuncSetAttribute(gpl::mv_Bt_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  L->ntiles = ntiles;
+  L->tiled = 1;
+  return 0;
+}
+
+// multi-vector products with B and B^T: tiled kernels (bulk-copy staging) when the tile lists exist and the rows are 16-byte
+// multiples, the gather kernels otherwise. *prow = rows of the per-warp partial dots the B^T product leaves behind.
+inline bool lap_use_tiles(gpbdev_vecchia* h, int t) {
+  gpb_laplace_state* L = h->lap;
+  return L->tiled == 1 && t > 1 && (t % 2) == 0 && t <= 64;
+}
+int lap_mv_B(gpbdev_vecchia* h, int t, const double* Dinv, const double* X, double* T) {
+  gpb_laplace_state* L = h->lap;
+  if (L->tiled < 0 && lap_build_tiles(h)) return -1;
+  if (lap_use_tiles(h, t)) {
+    const size_t smem = sizeof(double) * (size_t)gpl::kTileCap * t;
+    const int grid = std::min(L->ntiles, 2 * h->num_sms);
+    gpl::mv_B_tiled_kernel<<<grid, gpl::kTileThreads, smem, h->stream>>>(h->A, h->nn, h->m, h->n, t, Dinv, X, T, L->order, L->ntiles, L->tb_ptr, L->tb_src, L->tb_slot);
+  } else {
+    const int G = lap_groups(t), grid = lap_grid(L->grid_mv, G);
+    gpl::mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, h->n, t, G, Dinv, X, T, L->order);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+int lap_mv_Bt(gpbdev_vecchia* h, int t, const double* Tin, const double* W, const double* X, double* V, int* prow) {
+  gpb_laplace_state* L = h->lap;
+  if (L->tiled < 0 && lap_build_tiles(h)) return -1;
+  if (lap_use_tiles(h, t)) {
+    const size_t smem = sizeof(double) * (size_t)gpl::kTileCap * t;
+    const int grid = std::min(L->ntiles, 2 * h->num_sms);
+    gpl::mv_Bt_tiled_kernel<<<grid, gpl::kTileThreads, smem, h->stream>>>(h->A_csc, h->colptr, h->csc_row, h->n, t, Tin, W, X, V, L->partial, L->order, L->ntiles,
+                                                                         L->tt_ptr, L->tt_src, L->tt_slot);
+    *prow = grid * (gpl::kTileThreads / 32);
+  } else {
+    const int G = lap_groups(t), grid = lap_grid(L->grid_mv, G);
+    gpl::mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, h->n, t, G, Tin, W, X, V, L->partial, L->order);
+    *prow = grid * (gpl::kBlock / 32) / G;
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 // V = (B^T D^-1 B + W) X, dots[c] = X[:,c] . V[:,c]
 int lap_apply_op(gpbdev_vecchia* h, int t, const double* X, double* V, double* Tbuf, double* dots) {
   gpb_laplace_state* L = h->lap;
@@ -1056,8 +1349,10 @@ int lap_apply_op(gpbdev_vecchia* h, int t, const double* X, double* V, double* T
     gpl::v_mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, h->Dinv, X, Tbuf);
     gpl::v_mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A_csc, h->colptr, h->csc_row, n, Tbuf, L->W, X, V, L->partial);
   } else {
-    gpl::mv_B_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->nn, h->m, n, t, G, h->Dinv, X, Tbuf, L->order);
-    gpl::mv_Bt_kernel<<<grid, gpl::kBlock, 0, h->stream>>>(h->A, h->colptr, h->csc_pos, h->m, n, t, G, Tbuf, L->W, X, V, L->partial, L->order);
+    int prow = 0;
+    if (lap_mv_B(h, t, h->Dinv, X, Tbuf)) return -1;
+    if (lap_mv_Bt(h, t, Tbuf, L->W, X, V, &prow)) return -1;
+    return laplace_colsums(h, t, dots, prow);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;

@@ -1229,7 +1229,8 @@ struct gpbdev_tree {
   int sharded_host_loop = 0;       // GPB200_SHARDED_LOOP = host: data-parallel learners use the host-driven leaf loop (one blocking all-reduce and one
                                    // D2H per split, CUB partition) instead of the device-resident / graph loop with in-stream all-reduces
   int partition_version = 2;       // GPB200_PARTITION = 2 (default): part_count_kernel + part_scatter_kernel | 1: flag + CUB scan + scatter
-  int hist_kernel_version = 4;     // GPB200_HIST_KERNEL = 4 (default): hist3_kernel with plain counter updates | 3: hist3_kernel with RED counters | 2: hist2_kernel | 1: single-warp hist_kernel
+  int hist_kernel_version = 3;     // GPB200_HIST_KERNEL = 3 (default): hist3_kernel, RED counters | 4: hist3_kernel with plain counter updates (measured 7 % slower:
+                                   // profiles/r02_hist_variants.log) | 2: hist2_kernel | 1: single-warp hist_kernel
   double* sum_part = nullptr;
   SplitOut* split_dev = nullptr;
   SplitOut* cand_dev = nullptr;    // 2 x F per-feature candidates
@@ -1353,7 +1354,7 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 1 ? 1 : 2);
   if (const char* e = std::getenv("GPB200_SHARDED_LOOP")) { h->sharded_host_loop = std::string(e) == "host" ? 1 : 0; h->sharded_graph = std::string(e) == "graph" ? 1 : 0; }
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
-  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 4;
+  if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 3;
   *out = h;
   return 0;
 }

@@ -103,6 +103,18 @@ int GPB_OptimCovPar(REModelHandle handle, const double* y_data, const double* fi
   API_END();
 }
 
+// c_api.h:1490 — with covariates the reference also estimates linear regression coefficients (not part of the hot path: refused);
+// without any it is the same optimisation as GPB_OptimCovPar (REModel::OptimLinRegrCoefCovPar, re_model.cpp:543-600)
+int GPB_OptimLinRegrCoefCovPar(REModelHandle handle, const double* y_data, const double* covariate_data, int num_covariates,
+                               const double* fixed_effects) {
+  API_BEGIN();
+  if (covariate_data != nullptr && num_covariates > 0)
+    throw std::runtime_error("GPB_OptimLinRegrCoefCovPar: linear regression coefficients (covariates) are not supported by the B200 build; "
+                             "use GPB_OptimCovPar on the response minus the fixed effects");
+  M(handle)->OptimCovPar(y_data, fixed_effects, false, false);
+  API_END();
+}
+
 int GPB_EvalNegLogLikelihood(REModelHandle handle, const double* y_data, double* cov_pars, const double* fixed_effects,
                              double* negll) {
   API_BEGIN();

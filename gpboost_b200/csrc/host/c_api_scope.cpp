@@ -102,13 +102,6 @@ int GPB_GetResponseData(REModelHandle handle, double* response_data) {
   API_END();
 }
 
-int GPB_OptimLinRegrCoefCovPar(REModelHandle handle, const double* y_data, const double* covariate_data, int num_covariates, const double* fixed_effects) {
-  API_BEGIN();
-  (void)handle; (void)y_data; (void)covariate_data; (void)num_covariates; (void)fixed_effects;
-  Unsupported("GPB_OptimLinRegrCoefCovPar");
-  API_END();
-}
-
 int GPB_PredictREModelTrainingDataRandomEffects(REModelHandle handle, const double* cov_pars_pred, const double* y_obs, double* out_predict, const double* fixed_effects, bool calc_var) {
   API_BEGIN();
   (void)handle; (void)cov_pars_pred; (void)y_obs; (void)out_predict; (void)fixed_effects; (void)calc_var;
