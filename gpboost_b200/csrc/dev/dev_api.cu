@@ -15,6 +15,7 @@
 #include "knn.cuh"
 #include "vecchia_factor.cuh"
 #include "vecchia_big.cuh"
+#include "vecchia_nll2.cuh"
 
 namespace {
 
@@ -287,6 +288,31 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
       if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
     }
     if (mode == gpb::MODE_STORE) h->factor_stored = true;
+    return 0;
+  }
+  // likelihood pass at the headline shape (d = 2, 20 < m <= 30): two observations per warp (vecchia_nll2.cuh); GPB200_NLL_KERNEL=1
+  // keeps the one-observation kernel
+  static const bool nll1_only = []() { const char* e = std::getenv("GPB200_NLL_KERNEL"); return e && std::string(e) == "1"; }();
+  if (mode == gpb::MODE_NLL && h->d == 2 && h->m > 20 && !nll1_only) {
+    FactorKernel k2 = cov_type == gpb::COV_EXPONENTIAL ? gpb::vecchia_nll2_kernel<gpb::COV_EXPONENTIAL>
+                      : cov_type == gpb::COV_MATERN15  ? gpb::vecchia_nll2_kernel<gpb::COV_MATERN15>
+                      : cov_type == gpb::COV_MATERN25  ? gpb::vecchia_nll2_kernel<gpb::COV_MATERN25>
+                                                       : gpb::vecchia_nll2_kernel<gpb::COV_GAUSSIAN>;
+    const size_t smem2 = sizeof(double) * gpb::kWarpsPerBlock * 2 * (gpb::kNll2Half + 64);
+    CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm2 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k2, gpb::kWarpsPerBlock * 32, smem2));
+    int grid2 = std::max(per_sm2, 1) * h->num_sms;
+    grid2 = std::max(1, std::min(grid2, h->grid_cap / 2));  // two partial rows per warp
+    k2<<<grid2, gpb::kWarpsPerBlock * 32, smem2, h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->partials, (int64_t)grid2 * gpb::kWarpsPerBlock * 2, h->sums);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    if (h->allreduce && !latent) {
+      if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
+    }
     return 0;
   }
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);

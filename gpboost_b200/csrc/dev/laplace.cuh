@@ -428,190 +428,6 @@ __global__ void v_trs_fwd_kernel(const double* __restrict__ A, const int32_t* __
   if (lane == 0) partial[(size_t)gw * kMaxCols] = dot;
 }
 
-// ---- single-vector solves, second generation: head in shared memory + sub-warp tail ---------------------------------
-// The dependency DAG of B is deep where it is thin: at n = 1e6, m = 30 (random ordering) 310 of the 517 levels lie in the first
-// 16 384 rows. Polled through L2 every level costs microseconds (a store that has to become visible on the other die, a back-off
-// period, a load), through shared memory a few hundred cycles. So the first K rows — the HEAD — are solved by ONE CTA that keeps
-// its K unknowns in shared memory (same value-is-the-flag protocol, volatile shared loads), and the remaining rows — the TAIL,
-// ~200 levels — by the persistent grid with FOUR rows per warp (eight lanes per row, four dependencies per lane), which
-// quadruples the rows in flight. Head kernels take a column of an n x t row-major multi-vector (blockIdx.x = column), t = 1 here.
-constexpr int kHeadRows = 16384;
-constexpr int kHeadThreads = 1024;
-
-__device__ __forceinline__ double poll_shared(volatile double* p, int* err) {
-  double v = *p;
-  int spins = 0;
-  while (is_sent(v)) {
-    if (++spins > kSpinLimit) { atomicExch(err, 1); return 0.; }
-    v = *p;
-  }
-  return v;
-}
-
-// rows [0, K): z_i = y_i / dw_i + sum_k A[i,k] z[nn[i,k]]; warp per row, rows taken in order by the CTA's warps
-__global__ void __launch_bounds__(kHeadThreads) trs_head_fwd_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int K,
-                                                                   int t, const double* __restrict__ dw, const double* __restrict__ Y,
-                                                                   const double* __restrict__ R, double* Z, double* __restrict__ partial_row,
-                                                                   int* err) {
-  extern __shared__ double xs_raw[];
-  volatile double* xs = xs_raw;
-  const int c = blockIdx.x;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const double sent = __longlong_as_double((long long)kSentinel);
-  for (int e = threadIdx.x; e < K; e += blockDim.x) xs_raw[e] = sent;
-  __syncthreads();
-  double dot = 0.;
-  int32_t jn = -1; double an = 0., yn = 0., rn = 0.;
-  if (w < K) {
-    if (lane < m) { jn = nn[(int64_t)w * m + lane]; an = A[(int64_t)w * m + lane]; }
-    yn = Y[(int64_t)w * t + c] / dw[w]; rn = R[(int64_t)w * t + c];
-  }
-  for (int i = w; i < K; i += nw) {
-    const int32_t j = jn; const double a = an, yi = yn, ri = rn;
-    const int ni = i + nw;
-    if (ni < K) {  // next row's pattern and right-hand side: in flight while this row waits
-      jn = lane < m ? nn[(int64_t)ni * m + lane] : -1;
-      an = lane < m ? A[(int64_t)ni * m + lane] : 0.;
-      yn = Y[(int64_t)ni * t + c] / dw[ni]; rn = R[(int64_t)ni * t + c];
-    }
-    double s = 0.;
-    if (j >= 0) s = a * poll_shared(xs + j, err);
-    s = wsum(s);
-    if (lane == 0) {
-      const double zi = yi + s;
-      xs[i] = zi;
-      Z[(int64_t)i * t + c] = zi;
-      dot += ri * zi;
-    }
-  }
-  // block sum of the per-warp dots, fixed order
-  __shared__ double wd[kHeadThreads / 32];
-  if (lane == 0) wd[w] = dot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double sacc = 0.;
-    for (int k = 0; k < nw; ++k) sacc += wd[k];
-    partial_row[c] = sacc;
-  }
-}
-
-// tail rows [row0, n): eight lanes per row, four dependencies per lane; dependencies in the head are final (the head kernel ran first)
-__global__ void v_trs_fwd_tail_kernel(const double* __restrict__ A, const int32_t* __restrict__ nn, int m, int64_t n, int64_t row0,
-                                      const double* __restrict__ dw, const double* __restrict__ y, const double* __restrict__ r,
-                                      double* z, double* __restrict__ partial, int* err) {
-  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
-  const unsigned smask = 0xffu << (sub * 8);
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  // subgroups of one warp take rows nw apart: neighbouring rows (the likeliest dependencies) sit in different warps
-  double dot = 0.;
-  for (int64_t i = row0 + sub * nw + gw; i < n; i += 4 * nw) {
-    int32_t j[4]; double a[4], v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = sl + 8 * q;
-      j[q] = k < m ? nn[i * m + k] : -1;
-      a[q] = (k < m && j[q] >= 0) ? A[i * m + k] : 0.;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = j[q] >= 0 ? ld_gpu_nc(z + j[q]) : 0.;
-    double s = 0.;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (j[q] >= 0) { if (is_sent(v[q])) v[q] = poll(z + j[q], err); s += a[q] * v[q]; }
-    }
-    s += __shfl_xor_sync(smask, s, 4);
-    s += __shfl_xor_sync(smask, s, 2);
-    s += __shfl_xor_sync(smask, s, 1);
-    if (sl == 0) {
-      const double zi = y[i] / dw[i] + s;
-      st_gpu(z + i, zi);
-      dot += r[i] * zi;
-    }
-  }
-  // the four subgroup dots of the warp in subgroup order
-  double d1 = __shfl_sync(0xffffffffu, dot, 8), d2 = __shfl_sync(0xffffffffu, dot, 16), d3 = __shfl_sync(0xffffffffu, dot, 24);
-  if (lane == 0) partial[(size_t)gw * kMaxCols] = ((dot + d1) + d2) + d3;
-}
-
-// backward solve y = B^-T r, tail rows j = n-1 .. row0 (all their dependents are tail rows): eight lanes per column
-__global__ void v_trs_bwd_tail_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
-                                      int64_t n, int64_t row0, const double* __restrict__ r, double* y, int* err) {
-  const int lane = threadIdx.x & 31, sub = lane >> 3, sl = lane & 7;
-  const unsigned smask = 0xffu << (sub * 8);
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t jj = sub * nw + gw; jj < n - row0; jj += 4 * nw) {
-    const int64_t j = n - 1 - jj;
-    const int e0 = colptr[j], e1 = colptr[j + 1];
-    double s = 0.;
-    // far rows (finished long ago) first, the rows just above j last; four entries per lane in flight
-    int e = e1 - 1 - sl;
-    for (; e - 24 >= e0; e -= 32) {
-      int32_t row[4]; double a[4], v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { row[q] = csc_row[e - 8 * q]; a[q] = A_csc[e - 8 * q]; }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = ld_gpu_nc(y + row[q]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s += a[q] * (is_sent(v[q]) ? poll(y + row[q], err) : v[q]);
-    }
-    for (; e >= e0; e -= 8) s += A_csc[e] * poll(y + csc_row[e], err);
-    s += __shfl_xor_sync(smask, s, 4);
-    s += __shfl_xor_sync(smask, s, 2);
-    s += __shfl_xor_sync(smask, s, 1);
-    if (sl == 0) st_gpu(y + j, r[j] + s);
-  }
-}
-
-// first entry of column j (entries sorted by row) whose row is >= K
-__device__ __forceinline__ int col_split(const int32_t* __restrict__ csc_row, int e0, int e1, int K) {
-  int lo = e0, hi = e1;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (csc_row[mid] < K) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-
-// head columns j < K, contributions of the (finished) tail rows: Yacc[j,c] = R[j,c] + sum_{entries with row >= K} A Y[row,c]; warp per (j, c)
-__global__ void trs_head_bwd_gather_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
-                                           int K, int t, const double* __restrict__ R, double* Y) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t u = gw; u < (int64_t)K * t; u += nw) {
-    const int j = (int)(u / t), c = (int)(u % t);
-    const int e1 = colptr[j + 1];
-    const int es = col_split(csc_row, colptr[j], e1, K);
-    double s = 0.;
-    for (int e = es + lane; e < e1; e += 32) s += A_csc[e] * Y[(int64_t)csc_row[e] * t + c];
-    s = wsum(s);
-    if (lane == 0) Y[(int64_t)j * t + c] = R[(int64_t)j * t + c] + s;
-  }
-}
-
-// head columns j = K-1 .. 0 from shared memory: y_j = Yacc_j + sum_{entries with row < K} A y_row; one CTA per column of the multi-vector
-__global__ void __launch_bounds__(kHeadThreads) trs_head_bwd_kernel(const double* __restrict__ A_csc, const int32_t* __restrict__ colptr,
-                                                                   const int32_t* __restrict__ csc_row, int K, int t, double* Y, int* err) {
-  extern __shared__ double xs_raw[];
-  volatile double* xs = xs_raw;
-  const int c = blockIdx.x;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const double sent = __longlong_as_double((long long)kSentinel);
-  for (int e = threadIdx.x; e < K; e += blockDim.x) xs_raw[e] = sent;
-  __syncthreads();
-  for (int jj = w; jj < K; jj += nw) {
-    const int j = K - 1 - jj;
-    const int e0 = colptr[j];
-    const int es = col_split(csc_row, e0, colptr[j + 1], K);  // head entries: [e0, es)
-    const double acc = Y[(int64_t)j * t + c];
-    double s = 0.;
-    // far rows first (the rows just above j finish last)
-    for (int e = es - 1 - lane; e >= e0; e -= 32) s += A_csc[e] * poll_shared(xs + csc_row[e], err);
-    s = wsum(s);
-    if (lane == 0) {
-      const double yj = acc + s;
-      xs[j] = yj;
-      Y[(int64_t)j * t + c] = yj;
-    }
-  }
-}
-
 __global__ void csc_gather_kernel(const double* __restrict__ A, const int32_t* __restrict__ csc_pos, int m, int64_t cnt,
                                   double* __restrict__ A_csc, int32_t* __restrict__ csc_row) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (int64_t)gridDim.x * blockDim.x) {
@@ -621,7 +437,7 @@ __global__ void csc_gather_kernel(const double* __restrict__ A, const int32_t* _
   }
 }
 
-// ---- tiled operator kernels: neighbour blocks staged in shared memory by bulk async copies --------------------------------
+// ---- tiled operator kernels (opt-in, see lap_build_tiles): neighbour blocks staged in shared memory by bulk async copies ---
 // mv_B / mv_Bt gather m + 1 rows of the multi-vector per row of B: at t = 50 that is 12.4 KB through L2 per row although rows that
 // are close in space share most of their neighbours. Here 32 rows that are consecutive on the Morton curve form a TILE; the
 // distinct source rows of a tile (~205 of 992 gathers at n = 1e6, m = 30; the lists are a static property of the pattern, built
@@ -1028,15 +844,11 @@ struct gpb_laplace_state {
   int grid = 0;           // persistent cooperative grid (blocks): what is co-resident for the polling kernels
   int grid_mv = 0;        // grid of the ordinary (non-polling) row kernels
   int grid_v = 0;         // cooperative grid of the single-vector polling kernels (few registers: more resident warps)
-  int grid_v2 = 0;        // cooperative grid of the second-generation tail kernels
   // tiles of 32 Morton-consecutive rows with their distinct source rows (tiled operator kernels; built once per model, lazily)
   int ntiles = 0, tiled = -1;      // tiled: -1 not decided, 0 off (GPB200_LAPLACE_TILED=0, no Morton order, ...), 1 on
   int32_t *tb_ptr = nullptr, *tb_src = nullptr, *tt_ptr = nullptr, *tt_src = nullptr;
   uint16_t *tb_slot = nullptr, *tt_slot = nullptr;
   int32_t* order = nullptr;  // n: processing order of the order-free row kernels (Morton order of the locations); null = by index
-  int trs_variant = 0;    // GPB200_TRS_VARIANT = 0 (default): every row polled through L2, one row per warp | 1: shared-memory head + sub-warp tail
-                          // (measured slower at the default head size: one CTA cannot hide the global-load latency of 16 384 rows; profiles/r02_laplace_variants.log)
-  int head_rows = gpl::kHeadRows;  // GPB200_TRS_HEAD_ROWS (<= 16384): rows solved in shared memory (tests shrink it to exercise the tail on small models)
   int nwarps = 0;
   double *mode = nullptr, *mode_new = nullptr, *upd = nullptr, *dir = nullptr, *rhs = nullptr, *W = nullptr, *dw = nullptr, *fe = nullptr;
   double *r = nullptr, *z = nullptr, *hv = nullptr, *v = nullptr, *tt = nullptr, *yy = nullptr;  // n-vectors of the Newton CG
@@ -1093,21 +905,11 @@ int laplace_ensure(gpbdev_vecchia* h) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v, gpl::v_trs_bwd_kernel, gpl::kBlock, 0));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_v2, gpl::v_trs_fwd_kernel, gpl::kBlock, 0));
   L->grid_v = std::max(1, std::min(std::min(per_v, per_v2), 4)) * h->num_sms;
-  int per_t = 0, per_t2 = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_t, gpl::v_trs_bwd_tail_kernel, gpl::kBlock, 0));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_t2, gpl::v_trs_fwd_tail_kernel, gpl::kBlock, 0));
-  int cap_v2 = 6;
-  if (const char* e = std::getenv("GPB200_TRS_CTAS_PER_SM")) cap_v2 = std::max(1, std::atoi(e));
-  L->grid_v2 = std::max(1, std::min(std::min(per_t, per_t2), cap_v2)) * h->num_sms;
-  if (const char* e = std::getenv("GPB200_TRS_VARIANT")) L->trs_variant = std::atoi(e) == 1 ? 1 : 0;
-  if (const char* e = std::getenv("GPB200_TRS_HEAD_ROWS")) L->head_rows = std::max(1, std::min(gpl::kHeadRows, std::atoi(e)));
   if (const char* e = std::getenv("GPB200_TRS_SLEEP_NS")) {
     const int ns = std::max(0, std::atoi(e));
     CUDA_TRY(cudaMemcpyToSymbol(gpl::g_sleep_ns, &ns, sizeof(int)));
   }
-  CUDA_TRY(cudaFuncSetAttribute(gpl::trs_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * gpl::kHeadRows)));
-  CUDA_TRY(cudaFuncSetAttribute(gpl::trs_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * gpl::kHeadRows)));
-  L->nwarps = std::max(std::max(std::max(L->grid, L->grid_mv), L->grid_v), L->grid_v2) * (gpl::kBlock / 32) + 1;
+  L->nwarps = std::max(std::max(L->grid, L->grid_mv), L->grid_v) * (gpl::kBlock / 32) + 1;
   double** vecs[] = {&L->mode, &L->mode_new, &L->upd, &L->dir, &L->rhs, &L->W, &L->dw, &L->fe, &L->r, &L->z, &L->hv, &L->v, &L->tt, &L->yy};
   for (double** p : vecs) {
     CUDA_TRY(cudaMalloc(p, sizeof(double) * n));
@@ -1213,8 +1015,11 @@ int lap_build_tiles(gpbdev_vecchia* h) {
   gpb_laplace_state* L = h->lap;
   if (L->tiled >= 0) return 0;
   L->tiled = 0;
+  // opt-in (GPB200_LAPLACE_TILED=1): on the B200 the staged kernels lose to the plain gather kernels in Morton order — 4.1 vs 3.8 ms
+  // (B) and 6.6 vs 3.4 ms (B^T) per application at n = 1e6, t = 50 (profiles/r02_laplace_variants2.log): ~200 bulk copies of 400
+  // bytes per tile cost more than they save while two 4-warp CTAs per SM cannot match the gather kernels' memory-level parallelism
   const char* te = std::getenv("GPB200_LAPLACE_TILED");
-  if (!L->order || (te && std::string(te) == "0") || h->m > 30) return 0;
+  if (!L->order || !(te && std::string(te) == "1") || h->m > 30) return 0;
   const int64_t n = h->n;
   const int m = h->m;
   std::vector<int32_t> ord((size_t)n);
@@ -1373,26 +1178,8 @@ int lap_precond(gpbdev_vecchia* h, int t, const double* R, double* Z, double* Yb
     gpl::fill_sentinel_kernel<<<fb, 256, 0, h->stream>>>(Z, n);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
-    if (L->trs_variant == 0) {  // GPB200_TRS_VARIANT=0: first generation (every row polled through L2, one row per warp)
-      if (coop_launch(h, L->grid_v, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
-      if (coop_launch(h, L->grid_v, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
-      return laplace_colsums(h, t, dots, L->grid_v * (gpl::kBlock / 32));
-    }
-    // head (first K rows) in one CTA's shared memory, tail on the persistent grid, four rows per warp
-    int K = (int)std::min<int64_t>(n, L->head_rows);
-    int64_t row0 = K;
-    const size_t hsm = sizeof(double) * (size_t)K;
-    const double* Ac = h->A_csc; const int32_t* crow = h->csc_row;
-    if (coop_launch(h, L->grid_v2, gpl::v_trs_bwd_tail_kernel, Ac, colptr, crow, nn_, row0, R, Ybuf, err)) return -1;
-    const int gg = (int)std::min<int64_t>(((int64_t)K * 32 + gpl::kBlock - 1) / gpl::kBlock, (int64_t)h->num_sms * 8);
-    gpl::trs_head_bwd_gather_kernel<<<gg, gpl::kBlock, 0, h->stream>>>(Ac, colptr, crow, K, 1, R, Ybuf);
-    gpl::trs_head_bwd_kernel<<<1, gpl::kHeadThreads, hsm, h->stream>>>(Ac, colptr, crow, K, 1, Ybuf, err);
-    const int prow = L->grid_v2 * (gpl::kBlock / 32);
-    gpl::trs_head_fwd_kernel<<<1, gpl::kHeadThreads, hsm, h->stream>>>(A, nn, m, K, 1, dw, Yc, R, Z, partial + (size_t)prow * gpl::kMaxCols, err);
-    CUDA_TRY(cudaGetLastError());
-    h->launches += 3;
-    if (coop_launch(h, L->grid_v2, gpl::v_trs_fwd_tail_kernel, A, nn, m, nn_, row0, dw, Yc, R, Z, partial, err)) return -1;
-    return laplace_colsums(h, t, dots, prow + 1);
+    if (coop_launch(h, L->grid_v, gpl::v_trs_bwd_kernel, A, colptr, csc, m, nn_, R, Ybuf, err)) return -1;
+    if (coop_launch(h, L->grid_v, gpl::v_trs_fwd_kernel, A, nn, m, nn_, dw, Yc, R, Z, partial, err)) return -1;
   } else {
     const int64_t len = n * t;
     const int fb = (int)std::min<int64_t>((len + 255) / 256, (int64_t)h->num_sms * 16);

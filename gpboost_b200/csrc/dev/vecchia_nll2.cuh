@@ -1,0 +1,181 @@
+// Likelihood pass of the Vecchia factor with TWO observations per warp (one per half-warp) — the dominant kernel of
+// GPB_EvalNegLogLikelihood at the headline configuration (n = 1e6, m = 30, d = 2).
+//
+// Same mathematics as vecchia_factor_kernel<COV, MODE_NLL, 2, 30> (vecchia_factor.cuh: augmented (q+2) x (q+2) matrix, one
+// right-looking Cholesky with look-ahead, D_i = pivot q, (By)_i^2 / D_i = L[q+1][q]^2; reference: CalcCovFactorGradientVecchia,
+// src/GPBoost/Vecchia_utils.cpp:1461-1684 + re_model_template.h:9957-9964, :2947), different mapping:
+//   * a half-warp owns one observation; lane hl of the half owns matrix rows hl ("lo", columns 0..15 matter) and hl + 16 ("hi"),
+//     48 register doubles per lane instead of 32 for twice the observations;
+//   * a rank-1 update step costs (30 - k) DFMA for the hi rows plus (15 - k) for the lo rows per TWO observations (616 warp
+//     instructions per pair instead of 2 x 496), the pivot chain (shuffle, rsqrt, scale) is issued once for both, and every
+//     LDS.128 that broadcasts two entries of L's column serves both halves (the two matrices are offset by 16 bytes modulo 128, so
+//     the two 16-byte addresses of an instruction fall into different banks: one wavefront). ncu of the one-observation kernel
+//     (profiles/r01_ncu_raw_summary.txt) has the LSU pipe at 78 % and the FP64 pipe at 54 %: both counts drop here;
+//   * the 465 pair covariances of an observation take 30 circulant rounds of 16 lanes (both halves in the same instruction).
+// Partial sums are kept per half-warp (partials row = 2 * warp + half) and reduced in fixed order as before.
+#pragma once
+#include "vecchia_factor.cuh"
+
+namespace gpb {
+
+constexpr int kNll2Half = 32 * kLd + 2;  // doubles per half: 32 x 33 matrix + 2 pad -> halves 16 bytes apart modulo 128 bytes
+#ifndef GPB_NLL2_BLOCKS
+#define GPB_NLL2_BLOCKS 3
+#endif
+
+template <int COV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_nll2_kernel(const FactorArgs p) {
+  constexpr int MT = 30, P = 31;
+  extern __shared__ __align__(16) double smem_raw[];
+  const int lane = threadIdx.x & 31, hl = lane & 15, hh = lane >> 4, wib = threadIdx.x >> 5;
+  const int hbase = lane & 16;  // first lane of my half
+  // per-warp shared layout: two halves of [matrix 32 x kLd + 2 | points 32 x 2]
+  double* S = smem_raw + (size_t)wib * (2 * (kNll2Half + 64)) + (size_t)hh * kNll2Half;
+  double* pts = smem_raw + (size_t)wib * (2 * (kNll2Half + 64)) + 2 * kNll2Half + (size_t)hh * 64;
+  const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib, nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  const int m = p.m;
+  const double var = p.var, range = p.range;
+  double acc0 = 0., acc1 = 0., acc2 = 0.;
+
+  // source observation of point slot s of row ii (-1: dummy slot)
+  auto slot_src = [&](int64_t ii, int s) -> int64_t {
+    const int qq = ii < m ? (int)ii : m;
+    if (s < qq) return (int64_t)p.nn[ii * m + s];
+    return s == MT ? ii : (int64_t)-1;
+  };
+  auto row_of = [&](int64_t it) -> int64_t { return p.row_begin + 2 * it + hh; };
+  // software pipeline: the gather of the next pair of observations is in flight while this one is computed
+  int64_t it = gwarp;
+  int64_t i = row_of(it);
+  bool active = i < p.row_end;
+  int64_t s_lo = -1, s_hi = -1;
+  double2 c_lo = make_double2(0., 0.), c_hi = c_lo;
+  double y_lo = 0., y_hi = 0.;
+  auto gather = [&](int64_t ii, bool act) {
+    s_lo = -1; s_hi = -1; y_lo = 0.; y_hi = 0.;
+    if (act) {
+      s_lo = slot_src(ii, hl);
+      s_hi = hl + 16 <= MT ? slot_src(ii, hl + 16) : -1;  // slot 31 does not exist (row 31 = responses)
+      if (s_lo >= 0) { y_lo = p.y[s_lo]; c_lo = *reinterpret_cast<const double2*>(p.coords + s_lo * 2); }
+      if (s_hi >= 0) { y_hi = p.y[s_hi]; c_hi = *reinterpret_cast<const double2*>(p.coords + s_hi * 2); }
+    }
+  };
+  gather(i, active);
+
+  for (; __any_sync(0xffffffffu, active); ) {
+    const int q = i < m ? (int)i : m;
+    const bool real_lo = s_lo >= 0, real_hi = s_hi >= 0;
+    const double2 my_lo = c_lo, my_hi = c_hi;
+    const double yl = y_lo, yh = y_hi;
+    if (real_lo) *reinterpret_cast<double2*>(pts + hl * 2) = my_lo;
+    if (real_hi) *reinterpret_cast<double2*>(pts + (hl + 16) * 2) = my_hi;
+    // which point slots of my half are real (bit s): slots 0..q-1 and slot MT
+    const unsigned blo = __ballot_sync(0xffffffffu, real_lo), bhi = __ballot_sync(0xffffffffu, real_hi);
+    const unsigned real_mask = ((blo >> hbase) & 0xffffu) | (((bhi >> hbase) & 0xffffu) << 16);
+    const bool full = (__all_sync(0xffffffffu, (q == MT) || !active)) != 0;  // no dummy slots anywhere in the warp
+    const bool was_active = active;
+    // next pair
+    const int64_t it_n = it + nwarps;
+    const int64_t i_n = row_of(it_n);
+    const bool active_n = i_n < p.row_end;
+    __syncwarp();
+
+    // ---- pair covariances: round r -> offset t = r / 2 + 1, own point pi = hl + 16 (r & 1)
+#pragma unroll
+    for (int r = 0; r < 2 * (MT / 2); ++r) {
+      const int t = (r >> 1) + 1;
+      const bool odd = (r & 1) != 0;
+      const int pi = hl + (odd ? 16 : 0);
+      const bool valid = pi < P;
+      int o = pi + t;
+      if (o >= P) o -= P;
+      if (!valid) o = 0;
+      const double2 po = *reinterpret_cast<const double2*>(pts + o * 2);
+      const double2 me = odd ? my_hi : my_lo;
+      const double dx = me.x - po.x, dy = me.y - po.y;
+      const double d2 = fma(dy, dy, dx * dx);
+      const double dist = d2 * rsqrt_fast(d2 + 1e-300);
+      double g = 0.;
+      double val = cov_eval<COV, false>(dist, var, range, g);
+      if (!full) {
+        const bool both = (odd ? real_hi : real_lo) && ((real_mask >> o) & 1u);
+        val = both ? val : 0.;
+      }
+      if (valid) S[min(pi, o) * kLd + max(pi, o)] = val;
+    }
+    // prefetch the next pair's gather (consumed at the top of the next iteration)
+    gather(i_n, active_n);
+    // diagonal and response row (row 31): S[c][c], S[c][31] = y_c for c <= 30
+    S[hl * kLd + hl] = real_lo ? p.diag_nb : 1.;
+    S[hl * kLd + (MT + 1)] = yl;
+    if (hl + 16 <= MT) {
+      S[(hl + 16) * kLd + (hl + 16)] = real_hi ? (hl + 16 == MT ? p.diag_obs : p.diag_nb) : 1.;
+      S[(hl + 16) * kLd + (MT + 1)] = yh;
+    }
+    __syncwarp();
+
+    // ---- my two rows of the lower triangle -> registers (entries above the diagonal: don't-care values)
+    double lo[16], hi[MT + 1];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) lo[c] = S[c * kLd + hl];
+#pragma unroll
+    for (int c = 0; c <= MT; ++c) hi[c] = S[c * kLd + hl + 16];
+    __syncwarp();
+
+    // ---- right-looking Cholesky with look-ahead, pivots 0..MT
+    double Di, lk_lo, lk_hi;
+    {
+      const double d0 = __shfl_sync(0xffffffffu, lo[0], hbase);
+      const double r0 = rsqrt_fast(d0);
+      lk_lo = lo[0] * r0; lk_hi = hi[0] * r0;
+      S[hl] = lk_lo; S[hl + 16] = lk_hi;
+      Di = d0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < MT; ++k) {
+      // column k of L is visible in shared memory; lk_* = L[my rows][k]
+      {
+        const double m1 = S[k * kLd + k + 1];
+        hi[k + 1] -= lk_hi * m1;
+        if (k + 1 < 16) lo[k + 1] -= lk_lo * m1;
+      }
+      // look-ahead: pivot chain of column k+1 (owner: lane k+1 of the half for k+1 < 16, lane k+1-16 otherwise)
+      const double dn = (k + 1 < 16) ? __shfl_sync(0xffffffffu, lo[k + 1], hbase + k + 1) : __shfl_sync(0xffffffffu, hi[k + 1], hbase + k + 1 - 16);
+      if (k + 1 == MT) Di = dn;
+      const double rn = rsqrt_fast(dn);
+      double lk1_lo = 0.;
+      if (k + 1 < 16) { lk1_lo = lo[k + 1] * rn; S[(k + 1) * kLd + hl] = lk1_lo; }
+      const double lk1_hi = hi[k + 1] * rn;
+      S[(k + 1) * kLd + hl + 16] = lk1_hi;
+      // remaining rank-1 updates of step k: columns k+2..MT (pairs; the pair load may touch column MT+1: harmless)
+#pragma unroll
+      for (int c = k + 2; c <= MT; c += 2) {
+        const double2 l2 = *reinterpret_cast<const double2*>(&S[k * kLd + c]);
+        hi[c] -= lk_hi * l2.x;
+        if (c + 1 <= MT) hi[c + 1] -= lk_hi * l2.y;
+        if (c < 16) lo[c] -= lk_lo * l2.x;
+        if (c + 1 < 16) lo[c + 1] -= lk_lo * l2.y;
+      }
+      __syncwarp();
+      lk_lo = lk1_lo; lk_hi = lk1_hi;
+    }
+    // lane hl = 15 (row 31) wrote L[31][30] = (By)_i / sqrt(D_i) into column 30
+    const double r_over_sd = S[MT * kLd + (MT + 1)];
+    if (hl == 0 && was_active) {
+      acc0 += r_over_sd * r_over_sd;
+      acc1 += log(Di);
+      acc2 += !(Di > 0.) ? 1. : 0.;
+    }
+    __syncwarp();
+    it = it_n; i = i_n; active = active_n;
+  }
+  if (hl == 0) {
+    double* out = p.partials + (size_t)(gwarp * 2 + hh) * kNumAcc;
+    out[0] = acc0; out[1] = acc1; out[2] = acc2;
+#pragma unroll
+    for (int k = 3; k < kNumAcc; ++k) out[k] = 0.;
+  }
+}
+
+}  // namespace gpb

@@ -47,15 +47,13 @@ def test_negll_matches_reference_golden(idx):
     assert abs(v - c["negll_cholesky"]) <= 2e-3 * abs(c["negll_cholesky"])
 
 
-@pytest.mark.parametrize("variant", ["first_generation", "small_head", "tiny_head", "untiled", "index_order"])
+@pytest.mark.parametrize("variant", ["tiled", "index_order"])
 @pytest.mark.parametrize("idx", [1, 3, 5])
-def test_negll_matches_reference_golden_for_every_solve_variant(idx, variant, monkeypatch):
-    """The sparse triangular solves of the preconditioner exist in two generations (GPB200_TRS_VARIANT) and the second one splits the
-    rows into a shared-memory head and a polled tail (GPB200_TRS_HEAD_ROWS): the golden models are smaller than the default head, so
-    the head is shrunk here to push most rows through the tail kernels. Same bar as the default path."""
-    env = {"first_generation": {"GPB200_TRS_VARIANT": "0"}, "small_head": {"GPB200_TRS_VARIANT": "1", "GPB200_TRS_HEAD_ROWS": "700"},
-           "tiny_head": {"GPB200_TRS_VARIANT": "1", "GPB200_TRS_HEAD_ROWS": "33"},
-           "untiled": {"GPB200_LAPLACE_TILED": "0"}, "index_order": {"GPB200_LAPLACE_ORDER": "index"}}[variant]
+def test_negll_matches_reference_golden_for_every_operator_variant(idx, variant, monkeypatch):
+    """The multi-vector products with B and B^T exist as gather kernels (rows taken in Morton order by default, by index with
+    GPB200_LAPLACE_ORDER=index) and as tiled kernels that stage the neighbour rows in shared memory with bulk async copies
+    (GPB200_LAPLACE_TILED=1). Same bar as the default path."""
+    env = {"tiled": {"GPB200_LAPLACE_TILED": "1"}, "index_order": {"GPB200_LAPLACE_ORDER": "index"}}[variant]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     c = GOLD[idx]
