@@ -435,13 +435,25 @@ def main():
         chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, y_ptr, cp_ptr, None, C.byref(negll)))
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
+    # the same call with the response in ordinary (pageable) numpy memory — what a ctypes caller of the reference's package passes;
+    # the engine stages it through its pinned buffer (dev_api.cu: gpbdev_vecchia_set_y)
+    y_page = np.ascontiguousarray(y.copy())
+    yp_ptr = y_page.ctypes.data_as(C.POINTER(C.c_double))
+    for _ in range(W):
+        chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, yp_ptr, cp_ptr, None, C.byref(negll)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk(lib.GPB_EvalNegLogLikelihood(mdl.handle, yp_ptr, cp_ptr, None, C.byref(negll)))
+    barrier()
+    e2e_page_s = (time.perf_counter() - t0) / args.steps
     sampler.stop_flag = True; sampler.join(2)
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, e2e_page_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
+        dev_ms, e2e_s, e2e_page_s = float(t[0]), float(t[1]), float(t[2])
 
     # Laplace-Vecchia (configs[4]); all ranks take part (probe columns are sharded), rank 0 reports
     laplace_res = None
@@ -494,12 +506,14 @@ def main():
                        "sharding": "rows of the ordered observations over %d rank(s); 9 fp64 sums all-reduced" % world,
                        "model_creation_s": t_create},
             "e2e": {"value": 1.0 / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(8 * N_OBS + 24), "d2h_bytes_per_step": 72 + 8,
-                    "ms_per_step": e2e_s * 1e3, "call": "GPB_EvalNegLogLikelihood(handle, y_host_pinned, cov_pars, NULL, &negll)"},
+                    "ms_per_step": e2e_s * 1e3, "call": "GPB_EvalNegLogLikelihood(handle, y_host_pinned, cov_pars, NULL, &negll)",
+                    "pageable_y": {"value": 1.0 / e2e_page_s, "ms_per_step": e2e_page_s * 1e3,
+                                   "note": "same call with y in ordinary numpy memory (staged through the engine's pinned buffer)"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": ncu_traffic_bytes() if world == 1 else None, "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_raw_summary.txt)",
-                         "kernel": "vecchia_factor_kernel<MATERN15, MODE_NLL, DIM=2>", "kernel_ms": dev_ms,
+                         "kernel": "vecchia_nll2_kernel<MATERN15> (two observations per warp)", "kernel_ms": dev_ms,
                          "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS, "peak_source": peak_src,
                          "note": "this kernel is FP64-pipe bound, not HBM bound (SURVEY §8d, DESIGN.md): see roofline_fp64"},
             "roofline_fp64": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak.value, "unit": "TFLOP/s",

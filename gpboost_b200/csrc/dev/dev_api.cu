@@ -290,14 +290,21 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
     if (mode == gpb::MODE_STORE) h->factor_stored = true;
     return 0;
   }
-  // likelihood pass at the headline shape (d = 2, 20 < m <= 30): two observations per warp (vecchia_nll2.cuh); GPB200_NLL_KERNEL=1
-  // keeps the one-observation kernel
+  // likelihood and gradient passes at the headline shape (d = 2, 20 < m <= 30): two observations per warp (vecchia_nll2.cuh);
+  // GPB200_NLL_KERNEL=1 keeps the one-observation kernel
   static const bool nll1_only = []() { const char* e = std::getenv("GPB200_NLL_KERNEL"); return e && std::string(e) == "1"; }();
-  if (mode == gpb::MODE_NLL && h->d == 2 && h->m > 20 && !nll1_only) {
-    FactorKernel k2 = cov_type == gpb::COV_EXPONENTIAL ? gpb::vecchia_nll2_kernel<gpb::COV_EXPONENTIAL>
-                      : cov_type == gpb::COV_MATERN15  ? gpb::vecchia_nll2_kernel<gpb::COV_MATERN15>
-                      : cov_type == gpb::COV_MATERN25  ? gpb::vecchia_nll2_kernel<gpb::COV_MATERN25>
-                                                       : gpb::vecchia_nll2_kernel<gpb::COV_GAUSSIAN>;
+  if ((mode == gpb::MODE_NLL || mode == gpb::MODE_STORE || (mode == gpb::MODE_GRAD && !latent)) && h->d == 2 && h->m > 20 && !nll1_only) {
+    FactorKernel k2 = nullptr;
+#define GPB_PICK2(COVID)                                                                                                              \
+    k2 = mode == gpb::MODE_NLL ? gpb::vecchia_nll2_kernel<COVID, gpb::MODE_NLL>                                                      \
+         : (mode == gpb::MODE_STORE ? gpb::vecchia_nll2_kernel<COVID, gpb::MODE_STORE> : gpb::vecchia_nll2_kernel<COVID, gpb::MODE_GRAD>)
+    switch (cov_type) {
+      case gpb::COV_EXPONENTIAL: GPB_PICK2(gpb::COV_EXPONENTIAL); break;
+      case gpb::COV_MATERN15: GPB_PICK2(gpb::COV_MATERN15); break;
+      case gpb::COV_MATERN25: GPB_PICK2(gpb::COV_MATERN25); break;
+      default: GPB_PICK2(gpb::COV_GAUSSIAN); break;
+    }
+#undef GPB_PICK2
     const size_t smem2 = sizeof(double) * gpb::kWarpsPerBlock * 2 * (gpb::kNll2Half + 64);
     CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -313,6 +320,7 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
     if (h->allreduce && !latent) {
       if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
     }
+    if (mode == gpb::MODE_STORE) h->factor_stored = true;
     return 0;
   }
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);
@@ -464,25 +472,42 @@ int gpbdev_vecchia_set_y_device(gpbdev_vecchia_t h, const double* y_dev) {
   return 0;
 }
 
+// zero x outside [b, e)
+__global__ void zero_outside_range_kernel(double* __restrict__ x, int64_t n, int64_t b, int64_t e) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (i < b || i >= e) x[i] = 0.;
+}
+
 int gpbdev_vecchia_set_y(gpbdev_vecchia_t h, const double* y_host) {
   if (!h || !y_host) return fail("gpbdev_vecchia_set_y: null argument");
   CUDA_TRY(cudaSetDevice(h->device));
+  // Row-sharded engine with the device collective: every rank uploads only ITS slice of the response (the same index range as its
+  // row shard, taken over the original order) and the slices are exchanged over NVLink (zero elsewhere + sum all-reduce) instead
+  // of N full host-to-device copies of the same vector.
+  const bool sliced = h->allreduce != nullptr && (h->row_begin != 0 || h->row_end != h->n);
+  const int64_t b = sliced ? h->row_begin : 0, e = sliced ? h->row_end : h->n;
   cudaPointerAttributes attr;
   const bool pinned = cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   if (pinned) {  // page-locked caller buffer: DMA straight from it
-    CUDA_TRY(cudaMemcpyAsync(h->y_in, y_host, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->y_in + b, y_host + b, sizeof(double) * (e - b), cudaMemcpyHostToDevice, h->stream));
   } else {
     // pageable caller memory: stage through the engine's pinned buffer (parallel copy) so the H2D runs at link speed
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    const int64_t n = h->n;
+    const int64_t len = e - b;
     const int64_t chunk = 1 << 16;
 #pragma omp parallel for schedule(static) num_threads(8)
-    for (int64_t b = 0; b < (n + chunk - 1) / chunk; ++b) {
-      const int64_t lo = b * chunk, len = std::min(chunk, n - lo);
-      std::memcpy(h->stage_host + lo, y_host + lo, sizeof(double) * len);
+    for (int64_t c = 0; c < (len + chunk - 1) / chunk; ++c) {
+      const int64_t lo = b + c * chunk, cl = std::min(chunk, e - lo);
+      std::memcpy(h->stage_host + lo, y_host + lo, sizeof(double) * cl);
     }
-    CUDA_TRY(cudaMemcpyAsync(h->y_in, h->stage_host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->y_in + b, h->stage_host + b, sizeof(double) * len, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (sliced) {
+    zero_outside_range_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->y_in, h->n, b, e);
+    CUDA_TRY(cudaGetLastError());
+    if (h->allreduce(h->allreduce_ctx, h->y_in, h->n, (void*)h->stream)) return fail("gpbdev_vecchia_set_y: device all-reduce failed");
+    h->launches += 1;
   }
   return gpbdev_vecchia_set_y_device(h, h->y_in);
 }

@@ -23,8 +23,17 @@ constexpr int kNll2Half = 32 * kLd + 2;  // doubles per half: 32 x 33 matrix + 2
 #define GPB_NLL2_BLOCKS 3
 #endif
 
-template <int COV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_nll2_kernel(const FactorArgs p) {
+// GRAD = true: the gradient pass (MODE_GRAD of vecchia_factor_kernel: adjoint identities dD_k = b^T dSigma~_k b,
+// (dB_k y)_i = -b^T dSigma~_k w~ with b = [-A_i, 1], w~ = [S^-1 y_N, 0]; re_model_template.h:1988-2010, Vecchia_utils.cpp:1636-1652) in
+// the same layout: the range-derivative pair values stay in the registers of the lane that computed them (30 per lane), the two
+// back substitutions (A_i and S^-1 y_N) run with lane hl owning unknowns hl and hl + 16, b and w~ are exchanged through the
+// (by then free) point buffer. 4 warps x 2 CTAs per SM = 16 observations in flight (one-observation kernel: 12).
+// MODE = MODE_STORE: one back substitution, A_i / D_i^-1 / u_i written like vecchia_factor_kernel<MODE_STORE>.
+template <int COV, int MODE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : GPB_NLL2_BLOCKS) vecchia_nll2_kernel(const FactorArgs p) {
+  constexpr bool GRAD = MODE == MODE_GRAD;
+  constexpr bool SOLVE = MODE != MODE_NLL;
+  static_assert(MODE == MODE_NLL || MODE == MODE_STORE || MODE == MODE_GRAD, "modes: NLL, STORE, GRAD");
   constexpr int MT = 30, P = 31;
   extern __shared__ __align__(16) double smem_raw[];
   const int lane = threadIdx.x & 31, hl = lane & 15, hh = lane >> 4, wib = threadIdx.x >> 5;
@@ -36,6 +45,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_
   const int m = p.m;
   const double var = p.var, range = p.range;
   double acc0 = 0., acc1 = 0., acc2 = 0.;
+  double accg[GRAD ? 6 : 1];
+#pragma unroll
+  for (int k = 0; k < (GRAD ? 6 : 1); ++k) accg[k] = 0.;
 
   // source observation of point slot s of row ii (-1: dummy slot)
   auto slot_src = [&](int64_t ii, int s) -> int64_t {
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_
     __syncwarp();
 
     // ---- pair covariances: round r -> offset t = r / 2 + 1, own point pi = hl + 16 (r & 1)
+    double gp[GRAD ? 2 * (MT / 2) : 1];
 #pragma unroll
     for (int r = 0; r < 2 * (MT / 2); ++r) {
       const int t = (r >> 1) + 1;
@@ -96,12 +109,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_
       const double d2 = fma(dy, dy, dx * dx);
       const double dist = d2 * rsqrt_fast(d2 + 1e-300);
       double g = 0.;
-      double val = cov_eval<COV, false>(dist, var, range, g);
+      double val = cov_eval<COV, GRAD>(dist, var, range, g);
       if (!full) {
         const bool both = (odd ? real_hi : real_lo) && ((real_mask >> o) & 1u);
         val = both ? val : 0.;
+        g = both ? g : 0.;
       }
       if (valid) S[min(pi, o) * kLd + max(pi, o)] = val;
+      if (GRAD) gp[r] = valid ? g : 0.;
     }
     // prefetch the next pair's gather (consumed at the top of the next iteration)
     gather(i_n, active_n);
@@ -167,6 +182,84 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_
       acc1 += log(Di);
       acc2 += !(Di > 0.) ? 1. : 0.;
     }
+    if (SOLVE) {
+      // ---- back substitution L_NN^T x = L[30][.] (-> A_i) and L_NN^T x = L[31][.] (-> w = S^-1 y_N): lane hl owns unknowns hl, hl + 16
+      const bool has_hi = hl + 16 < MT;
+      double xa_lo = S[hl * kLd + MT], xw_lo = GRAD ? S[hl * kLd + (MT + 1)] : 0.;
+      double xa_hi = has_hi ? S[(hl + 16) * kLd + MT] : 0., xw_hi = (GRAD && has_hi) ? S[(hl + 16) * kLd + (MT + 1)] : 0.;
+      const double dinv_lo = 1. / S[hl * kLd + hl];
+      const double dinv_hi = has_hi ? 1. / S[(hl + 16) * kLd + hl + 16] : 0.;
+#pragma unroll
+      for (int r = MT - 1; r >= 0; --r) {
+        double fa, fw = 0.;
+        if (r < 16) {
+          fa = __shfl_sync(0xffffffffu, xa_lo * dinv_lo, hbase + r);
+          if (GRAD) fw = __shfl_sync(0xffffffffu, xw_lo * dinv_lo, hbase + r);
+          if (hl == r) { xa_lo = fa; xw_lo = fw; }
+        } else {
+          fa = __shfl_sync(0xffffffffu, xa_hi * dinv_hi, hbase + r - 16);
+          if (GRAD) fw = __shfl_sync(0xffffffffu, xw_hi * dinv_hi, hbase + r - 16);
+          if (hl + 16 == r) { xa_hi = fa; xw_hi = fw; }
+        }
+        const double l_lo = hl < r ? S[hl * kLd + r] : 0.;             // L[r][hl]
+        xa_lo -= l_lo * fa; xw_lo -= l_lo * fw;
+        if (r > 16) {  // unknowns hl + 16 only couple to rows r > hl + 16 >= 16
+          const double l_hi = (has_hi && hl + 16 < r) ? S[(hl + 16) * kLd + r] : 0.;  // L[r][hl+16]
+          xa_hi -= l_hi * fa; xw_hi -= l_hi * fw;
+        }
+      }
+      if (MODE == MODE_STORE && was_active) {
+        if (hl < m) p.A[i * m + hl] = hl < q ? xa_lo : 0.;
+        if (hl + 16 < m) p.A[i * m + hl + 16] = hl + 16 < q ? xa_hi : 0.;
+        if (hl == 0) { const double Dinv_i = 1. / Di; p.Dinv[i] = Dinv_i; p.w[i] = r_over_sd * sqrt(Di) * Dinv_i; }
+      }
+      if (GRAD) {
+      // b = [-A, 1], w~ = [w, 0] over the 31 points, exchanged through the point buffer (free after the pair phase)
+      __syncwarp();
+      double* xb = pts;
+      double* xwt = pts + 32;
+      xb[hl] = -xa_lo; xwt[hl] = xw_lo;
+      if (hl + 16 <= MT) { xb[hl + 16] = has_hi ? -xa_hi : 1.; xwt[hl + 16] = has_hi ? xw_hi : 0.; }
+      __syncwarp();
+      const double b_lo = xb[hl], w_lo = xwt[hl];
+      const double b_hi = hl + 16 <= MT ? xb[hl + 16] : 0., w_hi = hl + 16 <= MT ? xwt[hl + 16] : 0.;
+      double bgb = 0., bgw = 0.;
+#pragma unroll
+      for (int r = 0; r < 2 * (MT / 2); ++r) {
+        const int t = (r >> 1) + 1;
+        const bool odd = (r & 1) != 0;
+        const int pi = hl + (odd ? 16 : 0);
+        int o = pi + t;
+        if (o >= P) o -= P;
+        if (pi >= P) o = 0;
+        const double g = gp[r];  // 0 for padded / inactive pairs
+        const double bo = xb[o], wo = xwt[o];
+        const double bm = odd ? b_hi : b_lo, wm = odd ? w_hi : w_lo;
+        bgb += g * (bm * bo);
+        bgw += g * (bm * wo + bo * wm);
+      }
+      double aa = xa_lo * xa_lo + xa_hi * xa_hi, aw = xa_lo * xw_lo + xa_hi * xw_hi;  // dummy unknowns are exactly 0
+#pragma unroll
+      for (int ofs = 8; ofs > 0; ofs >>= 1) {
+        bgb += __shfl_xor_sync(0xffffffffu, bgb, ofs);
+        bgw += __shfl_xor_sync(0xffffffffu, bgw, ofs);
+        aa += __shfl_xor_sync(0xffffffffu, aa, ofs);
+        aw += __shfl_xor_sync(0xffffffffu, aw, ofs);
+      }
+      if (hl == 0 && was_active) {
+        const double Dinv_i = 1. / Di;
+        const double u = r_over_sd * sqrt(Di) * Dinv_i;  // (D^-1 B y)_i
+        const double dD0 = var - aa - (1. + var - Di);   // Vecchia_utils.cpp:1623
+        const double dD1 = 2. * bgb;
+        accg[0] += -aw * u;
+        accg[1] += -bgw * u;
+        accg[2] += u * u * dD0;
+        accg[3] += u * u * dD1;
+        accg[4] += dD0 * Dinv_i;
+        accg[5] += dD1 * Dinv_i;
+      }
+      }  // GRAD
+    }    // SOLVE
     __syncwarp();
     it = it_n; i = i_n; active = active_n;
   }
@@ -174,7 +267,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GPB_NLL2_BLOCKS) vecchia_
     double* out = p.partials + (size_t)(gwarp * 2 + hh) * kNumAcc;
     out[0] = acc0; out[1] = acc1; out[2] = acc2;
 #pragma unroll
-    for (int k = 3; k < kNumAcc; ++k) out[k] = 0.;
+    for (int k = 3; k < kNumAcc; ++k) out[k] = GRAD ? accg[k - 3] : 0.;
   }
 }
 
