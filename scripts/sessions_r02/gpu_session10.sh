@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 10 (1 GPU): the round's bench command (both arms) + ncu evidence for profiles/
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 ( time timeout 900 python bench.py --steps 20 --warmup 3 ) > gpurun_out/s10_bench.json 2> gpurun_out/s10_bench.err
 # launch list of the same command (headline part: first 400 launches after the model creation)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/s10_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --laplace-n 0 --dense-n 0 > gpurun_out/s10_ncu_launches.log 2>&1

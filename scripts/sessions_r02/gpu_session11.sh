@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 11 (1 GPU): gradient pass with two observations per warp: parity (GP fits, GPBoost goldens), timing of the boosting iteration
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_vecchia_gpu.py tests/test_tree_gpu.py tests/test_dropin_reference_package.py tests/test_predict_gpu.py -q -m gpu --tb=short 2>&1 | tail -30 | cut -c1-300 > gpurun_out/s11_pytest.log
 timeout 300 python scripts/mgpu_boost_bench.py 1e6 50 2>&1 | grep "^\[N=" > gpurun_out/s11_boost_grad2.log
 GPB200_NLL_KERNEL=1 timeout 300 python scripts/mgpu_boost_bench.py 1e6 50 2>&1 | grep "^\[N=" > gpurun_out/s11_boost_grad1.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 12 (1 GPU): full suite on the final code (STORE pass in the two-observation layout, sliced y upload), smoke, bench
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -25 | cut -c1-300 > gpurun_out/s12_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s12_smoke.log 2>&1
 ( time timeout 900 python bench.py --steps 20 --warmup 3 ) > gpurun_out/s12_bench.json 2> gpurun_out/s12_bench.err

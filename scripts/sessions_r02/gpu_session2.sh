@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 2: full GPU suite with the new defaults + device binning; launch lists of the Laplace evaluation at n=1e6
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/s2_pytest.log
 cat > /tmp/lap.py <<'PY'
 import sys, time

@@ -1,6 +1,6 @@
 #!/bin/bash
 # two GPUs: multi-GPU parity with the device-resident data-parallel leaf loop (default) and with the host loop; boosting timings
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -25 | cut -c1-600 > gpurun_out/s5_mgpu_device.log
 GPB200_SHARDED_LOOP=host timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -12 | cut -c1-400 > gpurun_out/s5_mgpu_host.log
 timeout 300 python scripts/mgpu_boost_bench.py 1e6 50 > gpurun_out/s5_boost_n1.log 2>&1

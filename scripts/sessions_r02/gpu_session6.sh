@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 6 (1 GPU): full suite with the new defaults; Laplace n=1e6 timings per solve / order variant; histogram variants
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -40 | cut -c1-300 > gpurun_out/s6_pytest.log
 cat > /tmp/lap.py <<'PY'
 import sys, time

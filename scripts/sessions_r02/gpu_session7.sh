@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 7 (1 GPU): tiled operator kernels (bulk-copy staging): parity + timings; head-size sweep of the t=1 solves
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_laplace_gpu.py -q -m gpu --tb=short 2>&1 | tail -30 | cut -c1-300 > gpurun_out/s7_pytest.log
 cat > /tmp/lap.py <<'PY'
 import sys, time

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session 8 (1 GPU): two-observations-per-warp likelihood kernel: parity + timing against the one-observation kernel; full suite
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_vecchia_gpu.py tests/test_laplace_gpu.py -q -m gpu --tb=short 2>&1 | tail -30 | cut -c1-300 > gpurun_out/s8_pytest.log
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --boost-n 0 --laplace-n 0 --dense-n 0 > gpurun_out/s8_bench_nll2.json 2> gpurun_out/s8_bench_nll2.err
 GPB200_NLL_KERNEL=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --boost-n 0 --laplace-n 0 --dense-n 0 > gpurun_out/s8_bench_nll1.json 2> gpurun_out/s8_bench_nll1.err
