@@ -72,6 +72,9 @@ struct DevJob {
   LeafArgs a0, a1;
   int parent_row;
   int part_on, part_begin, part_cnt, part_feature, part_threshold, part_seg, part_nseg;
+  // ping-pong row-index buffers of the device-resident leaf loop: a split reads its leaf's rows from one buffer and writes the two
+  // children (same positions) into the other — no copy back. hist_buf / part_buf: which buffer holds the leaf in question.
+  int hist_buf, part_buf;
 };
 
 // ---- histogram: lane = feature, private shared histograms, rows of the chunk in order
@@ -176,10 +179,11 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist2_kernel(const uint
                                                                       const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                       int64_t rows_per_chunk, const double* __restrict__ grad,
                                                                       double* __restrict__ part_g, uint32_t* __restrict__ part_c,
-                                                                      const DevJob* __restrict__ job) {
+                                                                      const DevJob* __restrict__ job, const int32_t* __restrict__ idx_alt) {
   if (job) {  // device-resident leaf loop: the leaf's row range comes from the planner kernel
     if (job->done || !job->do_find || (int)blockIdx.x >= job->hist_nchunks) return;
     begin = job->hist_begin; count = job->hist_cnt; rows_per_chunk = job->hist_rpc;
+    if (job->hist_buf && idx_alt) idx = idx_alt;
     if (!job->hist_use_idx) idx = nullptr;
   }
   extern __shared__ __align__(16) unsigned char sm[];
@@ -292,10 +296,11 @@ __global__ void __launch_bounds__(kHistMaxWarps * 32, 1) hist3_kernel(const uint
                                                                       const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                       int64_t rows_per_chunk, const double* __restrict__ grad,
                                                                       double* __restrict__ part_g, uint32_t* __restrict__ part_c,
-                                                                      const DevJob* __restrict__ job) {
+                                                                      const DevJob* __restrict__ job, const int32_t* __restrict__ idx_alt) {
   if (job) {  // device-resident leaf loop: the leaf's row range comes from the planner kernel
     if (job->done || !job->do_find || (int)blockIdx.x >= job->hist_nchunks) return;
     begin = job->hist_begin; count = job->hist_cnt; rows_per_chunk = job->hist_rpc;
+    if (job->hist_buf && idx_alt) idx = idx_alt;
     if (!job->hist_use_idx) idx = nullptr;
   }
   extern __shared__ __align__(16) unsigned char sm[];
@@ -924,10 +929,11 @@ constexpr int kPartThreads = 256;
 __global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t* __restrict__ bins, int Fpad, int feature, int threshold,
                                                                   const int32_t* __restrict__ idx, int64_t begin, int64_t count,
                                                                   int64_t seg, uint8_t* __restrict__ flag, int32_t* __restrict__ seg_left,
-                                                                  const DevJob* __restrict__ job) {
+                                                                  const DevJob* __restrict__ job, const int32_t* __restrict__ idx_alt) {
   if (job) {
     if (job->done || !job->part_on || (int)blockIdx.x >= job->part_nseg) return;
     feature = job->part_feature; threshold = job->part_threshold; begin = job->part_begin; count = job->part_cnt; seg = job->part_seg;
+    if (job->part_buf && idx_alt) idx = idx_alt;
   }
   __shared__ int wsum[kPartThreads / 32];
   const int64_t j0 = (int64_t)blockIdx.x * seg, j1 = min(j0 + seg, count);
@@ -950,10 +956,18 @@ __global__ void __launch_bounds__(kPartThreads) part_count_kernel(const uint8_t*
 __global__ void __launch_bounds__(kPartThreads) part_scatter_kernel(const int32_t* __restrict__ idx, int64_t begin, int64_t count, int64_t seg,
                                                                     const uint8_t* __restrict__ flag, const int32_t* __restrict__ seg_left,
                                                                     int nseg, int32_t* __restrict__ out, int32_t* __restrict__ nleft_out,
-                                                                    const DevJob* __restrict__ job) {
+                                                                    const DevJob* __restrict__ job, int32_t* __restrict__ idx_alt) {
+  // host-driven loop: out = a scratch buffer holding the leaf from position 0. Device-resident loop (idx_alt != null): the two row
+  // index buffers alternate — read the leaf from the buffer that holds it, write the children at the same positions of the other one.
+  int64_t out_off = 0;
   if (job) {
     if (job->done || !job->part_on || (int)blockIdx.x >= job->part_nseg) return;
     begin = job->part_begin; count = job->part_cnt; seg = job->part_seg; nseg = job->part_nseg;
+    if (idx_alt) {
+      int32_t* a = const_cast<int32_t*>(idx);
+      if (job->part_buf) { idx = idx_alt; out = a; } else { out = idx_alt; }
+      out_off = begin;
+    }
   }
   __shared__ int red[2][kPartThreads / 32];
   __shared__ int woff[kPartThreads / 32];
@@ -993,7 +1007,7 @@ __global__ void __launch_bounds__(kPartThreads) part_scatter_kernel(const int32_
     if (in) {
       const int lb = lefts_before + wbefore + __popc(bal & ((1u << lane) - 1u));  // lefts in front of row j
       const int64_t dst = left ? (int64_t)lb : (int64_t)nleft + (j - lb);
-      out[dst] = idx[begin + j];
+      out[out_off + dst] = idx[begin + j];
     }
     lefts_before += tile_left;
     __syncthreads();  // woff is rewritten by the next tile
@@ -1024,12 +1038,14 @@ __global__ void sum_stage2_kernel(const double* __restrict__ part, int np, doubl
   if (threadIdx.x == 0) out[0] = sh[0];
 }
 // score[row] += value[leaf] for the rows of every leaf of the last tree (Tree::AddPredictionToScore via the data partition)
-__global__ void add_score_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ leaf_begin,
+__global__ void add_score_kernel(const int32_t* __restrict__ idx0, const int32_t* __restrict__ idx1, const int32_t* __restrict__ leaf_buf,
+                                 const int32_t* __restrict__ leaf_begin,
                                  const int32_t* __restrict__ leaf_cnt, const double* __restrict__ value, double* __restrict__ score,
                                  int32_t* __restrict__ leaf_of_row) {
   const int l = blockIdx.y;
   const int64_t b = leaf_begin[l], c = leaf_cnt[l];
   const double v = value[l];
+  const int32_t* __restrict__ idx = leaf_buf[l] ? idx1 : idx0;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < c; j += (int64_t)gridDim.x * blockDim.x) {
     const int32_t r = idx[b + j];
     if (score) score[r] += v;
@@ -1056,6 +1072,7 @@ struct TreeDevState {
   // leaf_begin / leaf_cnt: this rank's rows of the leaf (partition and histogram ranges); leaf_cnt_g: rows over all ranks — every
   // decision uses the global counts so that all ranks of a data-parallel learner grow the same tree (equal on one GPU)
   int leaf_begin[kMaxLeavesDev], leaf_cnt[kMaxLeavesDev], leaf_cnt_g[kMaxLeavesDev], leaf_depth[kMaxLeavesDev], leaf_parent[kMaxLeavesDev], slot_of[kMaxLeavesDev];
+  int leaf_buf[kMaxLeavesDev];  // which of the two row-index buffers holds the leaf's rows
   double leaf_sg[kMaxLeavesDev], leaf_sh[kMaxLeavesDev];
   SplitOut best[kMaxLeavesDev];
   int split_feature[kMaxLeavesDev], threshold_bin[kMaxLeavesDev], left_child[kMaxLeavesDev], right_child[kMaxLeavesDev];
@@ -1070,7 +1087,7 @@ __global__ void tree_init_kernel(TreeDevState* __restrict__ st, const double* __
   st->job.done = 0; st->job.error = 0; st->job.do_find = 0; st->job.part_on = 0;
   st->num_leaves = 1; st->left_leaf = 0; st->right_leaf = -1; st->next_slot = 0;
   for (int l = 0; l < L; ++l) {
-    st->leaf_begin[l] = 0; st->leaf_cnt[l] = 0; st->leaf_cnt_g[l] = 0; st->leaf_depth[l] = 0; st->leaf_parent[l] = -1; st->slot_of[l] = -1;
+    st->leaf_begin[l] = 0; st->leaf_cnt[l] = 0; st->leaf_cnt_g[l] = 0; st->leaf_buf[l] = 0; st->leaf_depth[l] = 0; st->leaf_parent[l] = -1; st->slot_of[l] = -1;
     st->leaf_sg[l] = 0.; st->leaf_sh[l] = 0.;
     st->best[l].gain = -INFINITY; st->best[l].feature = -1;
     st->split_feature[l] = 0; st->threshold_bin[l] = 0; st->left_child[l] = 0; st->right_child[l] = 0; st->split_gain[l] = 0.f;
@@ -1084,11 +1101,11 @@ __global__ void tree_init_kernel(TreeDevState* __restrict__ st, const double* __
 }
 
 // BeforeFindBestSplit (serial_tree_learner.cpp:283-322): may the two newest leaves be examined, which one gets a histogram pass
-__global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, int min_data_in_leaf, int num_chunk_ctas) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// keep_part: called from tree_advance_kernel BEFORE the partition of the split that was just selected ran — its job must stay armed
+__device__ void tree_plan_body(TreeDevState* __restrict__ st, int max_depth, int min_data_in_leaf, int num_chunk_ctas, bool keep_part) {
   DevJob& job = st->job;
   job.do_find = 0;
-  job.part_on = 0;
+  if (!keep_part) job.part_on = 0;
   if (job.done) return;
   const int left_leaf = st->left_leaf, right_leaf = st->right_leaf;
   bool do_find = true;
@@ -1119,17 +1136,21 @@ __global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, i
   job.parent_row = left_leaf;
   const int cnt = st->leaf_cnt[smaller];
   job.hist_begin = st->leaf_begin[smaller]; job.hist_cnt = cnt; job.hist_use_idx = st->num_leaves > 1 ? 1 : 0;
+  job.hist_buf = st->leaf_buf[smaller];
   int rpc = ((cnt + num_chunk_ctas - 1) / num_chunk_ctas + 7) / 8 * 8;  // same chunking as the host-driven loop
   if (rpc < 128) rpc = 128;
   job.hist_rpc = rpc; job.hist_nchunks = (cnt + rpc - 1) / rpc;
   job.do_find = 1;
 }
 
+__global__ void tree_plan_kernel(TreeDevState* __restrict__ st, int max_depth, int min_data_in_leaf, int num_chunk_ctas) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  tree_plan_body(st, max_depth, min_data_in_leaf, num_chunk_ctas, false);
+}
+
 // best leaf (ArrayArgs::ArgMax with SplitInfo::operator>), Tree::Split (tree.h:533-575), the partition job
 // sharded != 0: the children's LOCAL row ranges are not known before the partition ran (tree_local_ranges_kernel sets them)
-__global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ split_dev, double min_gain_to_split, int max_seg,
-                                   int sharded) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void tree_select_body(TreeDevState* __restrict__ st, const SplitOut* split_dev, double min_gain_to_split, int max_seg, int sharded) {
   DevJob& job = st->job;
   job.part_on = 0;
   if (job.done) return;
@@ -1148,10 +1169,12 @@ __global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut
   const int nleft = bs.left_count, nright = st->leaf_cnt_g[best_leaf] - nleft;
   if (nleft <= 0 || nright <= 0) { job.error = 1; job.done = 1; return; }
   job.part_on = 1; job.part_begin = b; job.part_cnt = c; job.part_feature = bs.feature; job.part_threshold = bs.threshold;
+  job.part_buf = st->leaf_buf[best_leaf];
   int seg = ((c + max_seg - 1) / max_seg + kPartThreads - 1) / kPartThreads * kPartThreads;
   if (seg < 4 * kPartThreads) seg = 4 * kPartThreads;
   job.part_seg = seg; job.part_nseg = (c + seg - 1) / seg;
   const int new_leaf = num_leaves;
+  st->leaf_buf[best_leaf] = st->leaf_buf[new_leaf] = 1 - job.part_buf;  // the children are written into the other buffer
   st->leaf_cnt_g[best_leaf] = nleft; st->leaf_cnt_g[new_leaf] = nright;
   if (!sharded) { st->leaf_cnt[best_leaf] = nleft; st->leaf_begin[new_leaf] = b + nleft; st->leaf_cnt[new_leaf] = nright; }
   const int node = num_leaves - 1;
@@ -1172,6 +1195,47 @@ __global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut
   st->left_leaf = best_leaf; st->right_leaf = new_leaf;
 }
 
+__global__ void tree_select_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ split_dev, double min_gain_to_split, int max_seg,
+                                   int sharded) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  tree_select_body(st, split_dev, min_gain_to_split, max_seg, sharded);
+}
+
+// One launch instead of three between the split scan and the partition (single GPU): arg-max over the per-feature candidates of both
+// children (split_argmax_kernel), the selector (tree_select_kernel) and the planner of the NEXT split (tree_plan_kernel — on one GPU it
+// needs nothing the partition produces: the children's ranges follow from the split's counts).
+__global__ void __launch_bounds__(128) tree_advance_kernel(TreeDevState* __restrict__ st, const SplitOut* __restrict__ cand, int F, double min_gain_to_split,
+                                                           int max_seg, int max_depth, int min_data_in_leaf, int num_chunk_ctas, int plan_next) {
+  __shared__ SplitOut sh[128];
+  __shared__ SplitOut best2[2];
+  const int child = threadIdx.x >> 6, t = threadIdx.x & 63;
+  SplitOut best;
+  best.gain = -INFINITY; best.feature = -1; best.threshold = 0; best.left_count = best.right_count = 0;
+  best.left_output = best.right_output = 0.;
+  best.left_sum_gradient = best.left_sum_hessian = best.right_sum_gradient = best.right_sum_hessian = 0.;
+  const bool find = !st->job.done && st->job.do_find;
+  if (find) {
+    for (int f = t; f < F; f += 64) {
+      const SplitOut c = cand[child * F + f];
+      if (split_better(c.gain, c.feature, best.gain, best.feature)) best = c;
+    }
+  }
+  sh[threadIdx.x] = best;
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (t < o) {
+      const SplitOut& c = sh[threadIdx.x + o];
+      if (split_better(c.gain, c.feature, sh[threadIdx.x].gain, sh[threadIdx.x].feature)) sh[threadIdx.x] = c;
+    }
+    __syncthreads();
+  }
+  if (t == 0) best2[child] = sh[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  tree_select_body(st, best2, min_gain_to_split, max_seg, 0);
+  if (plan_next) tree_plan_body(st, max_depth, min_data_in_leaf, num_chunk_ctas, true);
+}
+
 // data-parallel learner: after the local partition, the children's ranges on THIS rank (lefts counted by part_count_kernel)
 __global__ void tree_local_ranges_kernel(TreeDevState* __restrict__ st, const int32_t* __restrict__ seg_left) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1185,11 +1249,6 @@ __global__ void tree_local_ranges_kernel(TreeDevState* __restrict__ st, const in
   st->leaf_cnt[new_leaf] = job.part_cnt - nl;
 }
 
-__global__ void part_copyback_kernel(int32_t* __restrict__ idx, const int32_t* __restrict__ tmp, const DevJob* __restrict__ job) {
-  if (job->done || !job->part_on) return;
-  const int64_t b = job->part_begin, c = job->part_cnt;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < c; j += (int64_t)gridDim.x * blockDim.x) idx[b + j] = tmp[j];
-}
 }  // namespace
 
 struct gpbdev_tree {
@@ -1225,6 +1284,7 @@ struct gpbdev_tree {
   TreeDevState* state_dev = nullptr;
   TreeDevState* state_host = nullptr;  // pinned
   int fused_scan = 2;              // GPB200_FUSED_SCAN = 2 (default): reduce_scan2_kernel | 1: reduce_scan_kernel | 0: hist_reduce_kernel + split_scan_kernel
+  int fused_advance = 1;           // GPB200_FUSED_ADVANCE = 1 (default): arg-max + selector + next planner in one launch (single GPU) | 0: three launches
   int sharded_graph = 0;           // GPB200_SHARDED_LOOP = graph: capture the data-parallel leaf loop (NCCL kernels included) in a CUDA graph
   int sharded_host_loop = 0;       // GPB200_SHARDED_LOOP = host: data-parallel learners use the host-driven leaf loop (one blocking all-reduce and one
                                    // D2H per split, CUB partition) instead of the device-resident / graph loop with in-stream all-reduces
@@ -1238,7 +1298,8 @@ struct gpbdev_tree {
   double* scalar_host = nullptr;   // pinned
   void* scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
-  int32_t *leaf_begin_dev = nullptr, *leaf_cnt_dev = nullptr;
+  int32_t *leaf_begin_dev = nullptr, *leaf_cnt_dev = nullptr, *leaf_buf_dev = nullptr;
+  std::vector<int> leaf_buf;  // per leaf of the last tree: which row-index buffer holds its rows
   double* leaf_val_dev = nullptr;
   std::vector<int> leaf_begin, leaf_cnt;
   int last_num_leaves = 0;
@@ -1338,6 +1399,8 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   TCUDA(cudaMalloc(&h->scan_tmp, h->scan_tmp_bytes));
   TCUDA(cudaMalloc(&h->leaf_begin_dev, sizeof(int32_t) * h->L));
   TCUDA(cudaMalloc(&h->leaf_cnt_dev, sizeof(int32_t) * h->L));
+  TCUDA(cudaMalloc(&h->leaf_buf_dev, sizeof(int32_t) * h->L));
+  h->leaf_buf.assign(h->L, 0);
   TCUDA(cudaMalloc(&h->leaf_val_dev, sizeof(double) * h->L));
   TCUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 257 * 12));
   TCUDA(cudaFuncSetAttribute(hist2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist2_smem(hist2_warps(F))));
@@ -1352,6 +1415,7 @@ static int tree_create_common(gpbdev_tree_t* out, int device, int64_t n, int F, 
   TCUDA(cudaMallocHost(&h->state_host, sizeof(TreeDevState)));
   if (const char* e = std::getenv("GPB200_TREE_LOOP")) h->device_loop = std::string(e) == "device" ? 1 : (std::string(e) == "host" ? 0 : 2);
   if (const char* e = std::getenv("GPB200_FUSED_SCAN")) h->fused_scan = std::atoi(e) == 0 ? 0 : (std::atoi(e) == 1 ? 1 : 2);
+  if (const char* e = std::getenv("GPB200_FUSED_ADVANCE")) h->fused_advance = std::atoi(e) == 0 ? 0 : 1;
   if (const char* e = std::getenv("GPB200_SHARDED_LOOP")) { h->sharded_host_loop = std::string(e) == "host" ? 1 : 0; h->sharded_graph = std::string(e) == "graph" ? 1 : 0; }
   if (const char* e = std::getenv("GPB200_PARTITION")) h->partition_version = std::atoi(e) == 1 ? 1 : 2;
   if (const char* e = std::getenv("GPB200_HIST_KERNEL")) h->hist_kernel_version = std::atoi(e) >= 1 && std::atoi(e) <= 4 ? std::atoi(e) : 3;
@@ -1376,7 +1440,7 @@ int gpbdev_tree_free(gpbdev_tree_t h) {
   cudaSetDevice(h->device);
   cudaFree(h->bins_owned); cudaFree(h->leaf_of_row); cudaFree(h->stage); cudaFree(h->num_bin); cudaFree(h->idx); cudaFree(h->idx_tmp); cudaFree(h->flag); cudaFree(h->pos);
   cudaFree(h->grad); cudaFree(h->hist); cudaFree(h->splittable); cudaFree(h->parent_flags); cudaFree(h->part_g); cudaFree(h->part_c); cudaFree(h->sum_part);
-  cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_val_dev);
+  cudaFree(h->split_dev); cudaFree(h->cand_dev); cudaFree(h->scan_tmp); cudaFree(h->leaf_begin_dev); cudaFree(h->leaf_cnt_dev); cudaFree(h->leaf_buf_dev); cudaFree(h->leaf_val_dev);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   cudaFree(h->state_dev); cudaFreeHost(h->state_host);
   cudaFree(h->flag8); cudaFree(h->seg_left); cudaFree(h->nleft_dev); cudaFreeHost(h->nleft_host);
@@ -1441,15 +1505,16 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   tree_init_kernel<<<1, 32, 0, h->stream>>>(st, h->sum_part + 1023, (int)n, n_glob, hess_const, L);
   const int nw = hist2_warps(F);
   const dim3 hgrid(h->num_sms, (Fpad + 63) / 64);
-  const int cgrid = h->num_sms * 4;
+  const bool fused_advance = !sharded && h->fused_advance;
+  if (fused_advance) tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);  // first split; later ones: tree_advance_kernel
   for (int split = 0; split < L - 1 && !coll_failed; ++split) {
-    tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
+    if (!fused_advance) tree_plan_kernel<<<1, 32, 0, h->stream>>>(st, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms);
     if (h->hist_kernel_version == 4)
-      hist3_kernel<true><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+      hist3_kernel<true><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job, h->idx_tmp);
     else if (h->hist_kernel_version == 3)
-      hist3_kernel<false><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+      hist3_kernel<false><<<hgrid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job, h->idx_tmp);
     else
-      hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job);
+      hist2_kernel<<<hgrid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, h->idx, 0, 0, 0, grad, h->part_g, h->part_c, job, h->idx_tmp);
     LeafArgs dummy;
     dummy.leaf = -1; dummy.hist_slot = 0; dummy.inherit = 0; dummy.num_data = 0; dummy.sum_gradients = 0.; dummy.sum_hessians = 0.;
     if (sharded) {
@@ -1466,11 +1531,15 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
                                                                  h->num_bin, dummy, dummy, 0, cfg.min_data_in_leaf,
                                                                  cfg.min_sum_hessian_in_leaf, cfg.lambda_l2, cfg.min_gain_to_split,
                                                                  h->splittable, h->cand_dev, job);
-    split_argmax_kernel<<<2, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
-    tree_select_kernel<<<1, 32, 0, h->stream>>>(st, h->split_dev, cfg.min_gain_to_split, h->max_seg, sharded ? 1 : 0);
-    part_count_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, 0, 0, h->idx, 0, 0, 0, h->flag8, h->seg_left, job);
-    part_scatter_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->idx, 0, 0, 0, h->flag8, h->seg_left, 0, h->idx_tmp, nullptr, job);
-    part_copyback_kernel<<<cgrid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, job);
+    if (fused_advance) {
+      tree_advance_kernel<<<1, 128, 0, h->stream>>>(st, h->cand_dev, F, cfg.min_gain_to_split, h->max_seg, cfg.max_depth, cfg.min_data_in_leaf, h->num_sms,
+                                                    split + 1 < L - 1 ? 1 : 0);
+    } else {
+      split_argmax_kernel<<<2, 64, 0, h->stream>>>(h->cand_dev, F, h->split_dev);
+      tree_select_kernel<<<1, 32, 0, h->stream>>>(st, h->split_dev, cfg.min_gain_to_split, h->max_seg, sharded ? 1 : 0);
+    }
+    part_count_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, 0, 0, h->idx, 0, 0, 0, h->flag8, h->seg_left, job, h->idx_tmp);
+    part_scatter_kernel<<<h->max_seg, kPartThreads, 0, h->stream>>>(h->idx, 0, 0, 0, h->flag8, h->seg_left, 0, nullptr, nullptr, job, h->idx_tmp);
     if (sharded) tree_local_ranges_kernel<<<1, 32, 0, h->stream>>>(st, h->seg_left);
   }
   TCUDA(cudaMemcpyAsync(h->state_host, st, sizeof(TreeDevState), cudaMemcpyDeviceToHost, h->stream));
@@ -1487,7 +1556,8 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   if (!use_graph && coll_failed) return tfail("gpbdev_tree_train: device all-reduce failed");
   if (!replay) TCUDA(cudaGetLastError());
   if (use_graph) TCUDA(cudaGraphLaunch(h->graph_exec, h->stream));
-  h->launches += (sharded ? 11 : 8) * (L - 1) + (use_graph ? (sharded ? 4 : 3) : 0);
+  const bool one_advance = !sharded && h->fused_advance;
+  h->launches += (sharded ? 10 : (one_advance ? 5 : 7)) * (L - 1) + (use_graph ? (sharded ? 4 : 3) : 0) + (one_advance ? 1 : 0);
   TCUDA(cudaStreamSynchronize(h->stream));
   const TreeDevState& r = *h->state_host;
   if (r.job.error) return tfail("gpbdev_tree_train: inconsistent split counts");
@@ -1499,6 +1569,7 @@ static int tree_train_device_loop(gpbdev_tree_t h, const double* grad, double he
   for (int i = 0; i < num_leaves; ++i) { leaf_value[i] = r.leaf_value[i]; leaf_count[i] = r.leaf_count[i]; }
   h->leaf_begin.assign(r.leaf_begin, r.leaf_begin + L);
   h->leaf_cnt.assign(r.leaf_cnt, r.leaf_cnt + L);
+  h->leaf_buf.assign(r.leaf_buf, r.leaf_buf + L);
   h->last_num_leaves = num_leaves;
   *num_leaves_out = num_leaves;
   return 0;
@@ -1572,13 +1643,13 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
         const int nw = hist2_warps(F);
         if (h->hist_kernel_version == 4)
           hist3_kernel<true><<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
-              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
+              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr, nullptr);
         else if (h->hist_kernel_version == 3)
           hist3_kernel<false><<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist3_smem(nw), h->stream>>>(
-              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
+              h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr, nullptr);
         else
         hist2_kernel<<<dim3(nchunks, (Fpad + 63) / 64), nw * 32, hist2_smem(nw), h->stream>>>(
-            h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr);
+            h->bins, Fpad, F, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt, rpc, grad, h->part_g, h->part_c, nullptr, nullptr);
       }
       else
         hist_kernel<<<grid, 32, 32 * 257 * 12, h->stream>>>(h->bins, Fpad, (num_leaves == 1) ? nullptr : h->idx, leaf_begin[leaf], cnt,
@@ -1684,9 +1755,9 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     if (c > 0 && h->partition_version == 2 && !sharded) {  // the host loop of a data-parallel learner keeps the CUB path
       const int64_t seg = std::max<int64_t>(4 * kPartThreads, ((c + h->max_seg - 1) / h->max_seg + kPartThreads - 1) / kPartThreads * kPartThreads);
       const int nseg = (int)((c + seg - 1) / seg);
-      part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr);
+      part_count_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->bins, Fpad, bs.feature, bs.threshold, h->idx, b, c, seg, h->flag8, h->seg_left, nullptr, nullptr);
       part_scatter_kernel<<<nseg, kPartThreads, 0, h->stream>>>(h->idx, b, c, seg, h->flag8, h->seg_left, nseg, h->idx_tmp,
-                                                                sharded ? h->nleft_dev : nullptr, nullptr);
+                                                                sharded ? h->nleft_dev : nullptr, nullptr, nullptr);
       TCUDA(cudaGetLastError());
       TCUDA(cudaMemcpyAsync(h->idx + b, h->idx_tmp, sizeof(int32_t) * c, cudaMemcpyDeviceToDevice, h->stream));
       if (sharded) {  // this rank's share of the left child
@@ -1735,6 +1806,7 @@ int gpbdev_tree_train(gpbdev_tree_t h, const double* grad_in, int grad_on_device
     left_leaf = best_leaf; right_leaf = new_leaf;
   }
   h->leaf_begin = leaf_begin; h->leaf_cnt = leaf_cnt; h->last_num_leaves = num_leaves;
+  h->leaf_buf.assign(L, 0);  // the host-driven loop copies every partition back into the first buffer
   *num_leaves_out = num_leaves;
   return 0;
 }
@@ -1746,10 +1818,12 @@ int gpbdev_tree_add_score(gpbdev_tree_t h, const double* leaf_values, int num_le
   std::vector<int32_t> lb(h->leaf_begin.begin(), h->leaf_begin.begin() + num_leaves), lc(h->leaf_cnt.begin(), h->leaf_cnt.begin() + num_leaves);
   TCUDA(cudaMemcpyAsync(h->leaf_begin_dev, lb.data(), sizeof(int32_t) * num_leaves, cudaMemcpyHostToDevice, h->stream));
   TCUDA(cudaMemcpyAsync(h->leaf_cnt_dev, lc.data(), sizeof(int32_t) * num_leaves, cudaMemcpyHostToDevice, h->stream));
+  std::vector<int32_t> lbuf(h->leaf_buf.begin(), h->leaf_buf.begin() + num_leaves);
+  TCUDA(cudaMemcpyAsync(h->leaf_buf_dev, lbuf.data(), sizeof(int32_t) * num_leaves, cudaMemcpyHostToDevice, h->stream));
   TCUDA(cudaMemcpyAsync(h->leaf_val_dev, leaf_values, sizeof(double) * num_leaves, cudaMemcpyHostToDevice, h->stream));
   TCUDA(cudaStreamSynchronize(h->stream));  // the host vectors above are temporaries
   dim3 grid((unsigned)std::min<int64_t>((h->n / num_leaves + 255) / 256 + 1, 1024), num_leaves);
-  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, score_dev, leaf_of_row_dev);
+  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, h->leaf_buf_dev, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, score_dev, leaf_of_row_dev);
   TCUDA(cudaGetLastError());
   h->launches += 1;
   return 0;
@@ -1776,11 +1850,11 @@ int gpbdev_tree_time_root_hist(gpbdev_tree_t h, const double* grad_dev, int reps
     TCUDA(cudaMemsetAsync(flush, r, flush_bytes, h->stream));
     TCUDA(cudaEventRecord(e0, h->stream));
     if (h->hist_kernel_version == 4)
-      hist3_kernel<true><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+      hist3_kernel<true><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr, nullptr);
     else if (h->hist_kernel_version == 3)
-      hist3_kernel<false><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+      hist3_kernel<false><<<grid, nw * 32, hist3_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr, nullptr);
     else
-      hist2_kernel<<<grid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr);
+      hist2_kernel<<<grid, nw * 32, hist2_smem(nw), h->stream>>>(h->bins, Fpad, F, nullptr, 0, n, rpc, grad_dev, h->part_g, h->part_c, nullptr, nullptr);
     TCUDA(cudaEventRecord(e1, h->stream));
     TCUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1802,9 +1876,11 @@ int gpbdev_tree_leaf_indices(gpbdev_tree_t h, const int32_t** leaf_of_row_dev) {
   std::vector<int32_t> lb(h->leaf_begin.begin(), h->leaf_begin.begin() + nl), lc(h->leaf_cnt.begin(), h->leaf_cnt.begin() + nl);
   TCUDA(cudaMemcpyAsync(h->leaf_begin_dev, lb.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
   TCUDA(cudaMemcpyAsync(h->leaf_cnt_dev, lc.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
+  std::vector<int32_t> lbuf(h->leaf_buf.begin(), h->leaf_buf.begin() + nl);
+  TCUDA(cudaMemcpyAsync(h->leaf_buf_dev, lbuf.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
   TCUDA(cudaStreamSynchronize(h->stream));
   dim3 grid((unsigned)std::min<int64_t>((h->n / nl + 255) / 256 + 1, 1024), nl);
-  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, nullptr, h->leaf_of_row);
+  add_score_kernel<<<grid, 256, 0, h->stream>>>(h->idx, h->idx_tmp, h->leaf_buf_dev, h->leaf_begin_dev, h->leaf_cnt_dev, h->leaf_val_dev, nullptr, h->leaf_of_row);
   TCUDA(cudaGetLastError());
   TCUDA(cudaStreamSynchronize(h->stream));
   h->launches += 1;
