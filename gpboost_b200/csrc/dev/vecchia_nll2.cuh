@@ -19,6 +19,84 @@
 namespace gpb {
 
 constexpr int kNll2Half = 32 * kLd + 2;  // doubles per half: 32 x 33 matrix + 2 pad -> halves 16 bytes apart modulo 128 bytes
+// ---- covariance evaluation of this kernel. ncu of the first version (profiles/r02_ncu_raw_summary.txt, source page) had 52 % of
+// the stall samples in the pair-covariance rounds: every round a serial chain of ~33 dependent FP64 instructions (the shared-memory
+// store of round r ordered the load of round r + 1 behind it), issued at the DFMA latency. Here
+//   * the rounds run in groups whose values stay in registers until the group is done (no store between the point loads of a
+//     group: its chains interleave);
+//   * the points are pre-scaled by the range parameter (distance in units of the range comes out of the square root directly);
+//   * sqrt(x) = x * rsqrt(x) with the correction applied to x * y (one multiply less);
+//   * exp() reduces the argument to |r| <= ln2 / 64 with a 32-entry table of 2^(j/32) held one entry per lane: degree-6 instead of
+//     degree-13 polynomial (truncation 3.5e-18 relative); underflow is caught on the integer pipe.
+// Matern-1.5 pair: 22 FP64 instructions instead of 33.
+__constant__ double kExp2Tab32[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924, 1.1387886347566916,
+    1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332, 1.2968395546510096,
+    1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993,
+    1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,
+    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
+    1.9571441241754002};
+
+// exp(ax) for |ax| <= 700 (the caller zeroes the result below -700): n = rint(ax * 32 / ln2), r = ax - n ln2 / 32 (two-step,
+// n * hi exact), e^r by Taylor to r^6, 2^(n/32) = 2^(n >> 5) * tab[n & 31] with the power of two added into the exponent field.
+// tab_lane: lane l of the warp holds 2^(l/32) — the lookup is a register shuffle (a shared-memory table would order every lookup
+// behind the preceding stores of covariance values: same address space, run-time indices). All 32 lanes must call this together.
+__device__ __forceinline__ double exp_tab32(double ax, double tab_lane) {
+  const double t = fma(ax, 46.16624130844683, 6755399441055744.0);
+  const double n = t - 6755399441055744.0;
+  double r = fma(n, -6.93147180369123816490e-01 / 32., ax);
+  r = fma(n, -1.90821492927058770002e-10 / 32., r);
+  const int ni = __double2loint(t);
+  double pl = 1. / 720.;
+  pl = fma(pl, r, 1. / 120.);
+  pl = fma(pl, r, 1. / 24.);
+  pl = fma(pl, r, 1. / 6.);
+  pl = fma(pl, r, 0.5);
+  pl = fma(pl, r, 1.0);
+  pl = fma(pl, r, 1.0);
+  const double v = pl * __shfl_sync(0xffffffffu, tab_lane, ni & 31);
+  return __hiloint2double(__double2hiint(v) + ((ni >> 5) << 20), __double2loint(v));
+}
+// ax < -700 by the high word alone (sign-magnitude order of negative doubles; -700 = 0xC085E000_00000000)
+__device__ __forceinline__ bool below_m700(double ax) { return (unsigned)__double2hiint(ax) > 0xC085E000u; }
+
+// covariance (and d / d log range) from the SCALED squared distance d2s = (range * dist)^2 (Gaussian: range * dist^2), guarded
+// away from 0 by the caller; logvar = log(var). Same closed forms as cov_eval (cov_fcts.h:2100-2118, :2154, :2535-2563).
+template <int COV, bool GRAD>
+__device__ __forceinline__ double cov_eval_scaled(double d2s, double var, double logvar, double tab, double& grad) {
+  double val;
+  if (COV == COV_GAUSSIAN) {
+    const double ax = logvar - d2s;
+    val = exp_tab32(ax, tab);
+    if (below_m700(ax)) val = 0.;
+    if (GRAD) grad = -d2s * val;
+    return val;
+  }
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2s));
+  const double g = d2s * y;
+  const double e = fma(-g, y, 1.0);
+  const double rd = fma(g * e, fma(0.375, e, 0.5), g);  // sqrt(d2s)
+  if (COV == COV_EXPONENTIAL) {
+    const double ax = logvar - rd;
+    val = exp_tab32(ax, tab);
+    if (below_m700(ax)) val = 0.;
+    if (GRAD) grad = -rd * val;
+  } else {
+    double ex = exp_tab32(-rd, tab);
+    if (below_m700(-rd)) ex = 0.;
+    if (COV == COV_MATERN15) {
+      val = fma(var, rd, var) * ex;
+      if (GRAD) grad = -(var * d2s) * ex;
+    } else {
+      const double q1 = 1. + rd;
+      val = (var * fma(d2s, 1. / 3., q1)) * ex;
+      if (GRAD) grad = -(var * (1. / 3.)) * d2s * q1 * ex;
+    }
+  }
+  return val;
+}
+
 #ifndef GPB_NLL2_BLOCKS
 #define GPB_NLL2_BLOCKS 3
 #endif
@@ -43,7 +121,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
   double* pts = smem_raw + (size_t)wib * (2 * (kNll2Half + 64)) + 2 * kNll2Half + (size_t)hh * 64;
   const int64_t gwarp = (int64_t)blockIdx.x * kWarpsPerBlock + wib, nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
   const int m = p.m;
-  const double var = p.var, range = p.range;
+  const double var = p.var;
+  const double sc = COV == COV_GAUSSIAN ? sqrt(p.range) : p.range;  // points are kept scaled: pair distances in units of the range
+  const double logvar = log(var);
+  const double tab = kExp2Tab32[lane];
   double acc0 = 0., acc1 = 0., acc2 = 0.;
   double accg[GRAD ? 6 : 1];
 #pragma unroll
@@ -77,7 +158,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
   for (; __any_sync(0xffffffffu, active); ) {
     const int q = i < m ? (int)i : m;
     const bool real_lo = s_lo >= 0, real_hi = s_hi >= 0;
-    const double2 my_lo = c_lo, my_hi = c_hi;
+    const double2 my_lo = make_double2(c_lo.x * sc, c_lo.y * sc), my_hi = make_double2(c_hi.x * sc, c_hi.y * sc);
     const double yl = y_lo, yh = y_hi;
     if (real_lo) *reinterpret_cast<double2*>(pts + hl * 2) = my_lo;
     if (real_hi) *reinterpret_cast<double2*>(pts + (hl + 16) * 2) = my_hi;
@@ -93,30 +174,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
     __syncwarp();
 
     // ---- pair covariances: round r -> offset t = r / 2 + 1, own point pi = hl + 16 (r & 1)
-    double gp[GRAD ? 2 * (MT / 2) : 1];
+    // The rounds run in groups of G: the G values stay in registers until the group's rounds are done, then they are stored — a
+    // store between two point loads would order the second load behind it (same address space, run-time indices) and serialise the
+    // rounds' dependent FP64 chains (the state of the first version of this kernel).
+    constexpr int NR = 2 * (MT / 2);
+#ifndef GPB_NLL2_GROUP
+#define GPB_NLL2_GROUP 10
+#endif
+    constexpr int G = GRAD ? 6 : GPB_NLL2_GROUP;
+    static_assert(NR % G == 0, "group size must divide the number of rounds");
+    double gp[GRAD ? NR : 1];
 #pragma unroll
-    for (int r = 0; r < 2 * (MT / 2); ++r) {
-      const int t = (r >> 1) + 1;
-      const bool odd = (r & 1) != 0;
-      const int pi = hl + (odd ? 16 : 0);
-      const bool valid = pi < P;
-      int o = pi + t;
-      if (o >= P) o -= P;
-      if (!valid) o = 0;
-      const double2 po = *reinterpret_cast<const double2*>(pts + o * 2);
-      const double2 me = odd ? my_hi : my_lo;
-      const double dx = me.x - po.x, dy = me.y - po.y;
-      const double d2 = fma(dy, dy, dx * dx);
-      const double dist = d2 * rsqrt_fast(d2 + 1e-300);
-      double g = 0.;
-      double val = cov_eval<COV, GRAD>(dist, var, range, g);
-      if (!full) {
-        const bool both = (odd ? real_hi : real_lo) && ((real_mask >> o) & 1u);
-        val = both ? val : 0.;
-        g = both ? g : 0.;
+    for (int r0 = 0; r0 < NR; r0 += G) {
+      double val[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int r = r0 + j;
+        const int t = (r >> 1) + 1;
+        const bool odd = (r & 1) != 0;
+        const int pi = hl + (odd ? 16 : 0);
+        int o = pi + t;
+        if (o >= P) o -= P;
+        if (pi >= P) o = 0;
+        const double2 po = *reinterpret_cast<const double2*>(pts + o * 2);
+        const double2 me = odd ? my_hi : my_lo;
+        const double dx = me.x - po.x, dy = me.y - po.y;
+        const double d2s = fma(dy, dy, fma(dx, dx, 1e-300));
+        double g = 0.;
+        val[j] = cov_eval_scaled<COV, GRAD>(d2s, var, logvar, tab, g);
+        if (GRAD) gp[r] = g;
       }
-      if (valid) S[min(pi, o) * kLd + max(pi, o)] = val;
-      if (GRAD) gp[r] = valid ? g : 0.;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int r = r0 + j;
+        const int t = (r >> 1) + 1;
+        const bool odd = (r & 1) != 0;
+        const int pi = hl + (odd ? 16 : 0);
+        const bool valid = pi < P;
+        int o = pi + t;
+        if (o >= P) o -= P;
+        if (!valid) o = 0;
+        // dummy slots: zero unless the whole warp is free of them; the one padded pair (lane 15, odd rounds) goes to the unused column 31
+        const bool keep = ((full ? 1u : 0u) | ((odd ? (unsigned)real_hi : (unsigned)real_lo) & (real_mask >> o) & 1u)) != 0u;  // no branches
+        const double v = keep ? val[j] : 0.;
+        if (GRAD) gp[r] = (keep && valid) ? gp[r] : 0.;
+        S[valid ? min(pi, o) * kLd + max(pi, o) : 31 * kLd + hl] = v;
+      }
     }
     // prefetch the next pair's gather (consumed at the top of the next iteration)
     gather(i_n, active_n);
@@ -149,14 +252,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < MT; ++k) {
-      // column k of L is visible in shared memory; lk_* = L[my rows][k]
+      // column k of L is visible in shared memory; lk_* = L[my rows][k].
+      // Pivot chain of column k+1 first, from registers only: the owner of row k+1 (lane k+1 of the half for k+1 < 16, lane k+1-16
+      // otherwise) holds L[k+1][k] itself, so its updated diagonal does not wait for the shared-memory broadcast of the column
+      const double dself = (k + 1 < 16) ? fma(-lk_lo, lk_lo, lo[k + 1]) : fma(-lk_hi, lk_hi, hi[k + 1]);
+      const double dn = (k + 1 < 16) ? __shfl_sync(0xffffffffu, dself, hbase + k + 1) : __shfl_sync(0xffffffffu, dself, hbase + k + 1 - 16);
       {
         const double m1 = S[k * kLd + k + 1];
         hi[k + 1] -= lk_hi * m1;
         if (k + 1 < 16) lo[k + 1] -= lk_lo * m1;
       }
-      // look-ahead: pivot chain of column k+1 (owner: lane k+1 of the half for k+1 < 16, lane k+1-16 otherwise)
-      const double dn = (k + 1 < 16) ? __shfl_sync(0xffffffffu, lo[k + 1], hbase + k + 1) : __shfl_sync(0xffffffffu, hi[k + 1], hbase + k + 1 - 16);
       if (k + 1 == MT) Di = dn;
       const double rn = rsqrt_fast(dn);
       double lk1_lo = 0.;

@@ -7,7 +7,8 @@ _LIB = None
 
 
 def find_lib_path():
-    p = os.path.join(_HERE, "lib_gpboost_b200.so")
+    # GPB200_LIB: a variant build of the same library (gpboost_b200.build.build(extra_flags=..., out_name=...)), tuning runs only
+    p = os.environ.get("GPB200_LIB") or os.path.join(_HERE, "lib_gpboost_b200.so")
     if not os.path.exists(p):
         raise RuntimeError("lib_gpboost_b200.so not found at %s — build it with `python -m gpboost_b200.build` "
                            "(or __graft_entry__.build()); there is no fallback implementation" % p)
