@@ -131,29 +131,36 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
   for (int k = 0; k < (GRAD ? 6 : 1); ++k) accg[k] = 0.;
 
   // source observation of point slot s of row ii (-1: dummy slot)
-  auto slot_src = [&](int64_t ii, int s) -> int64_t {
+  auto slot_src = [&](int64_t ii, int s) -> int {  // observation indices fit 32 bits (the neighbour table is int32)
     const int qq = ii < m ? (int)ii : m;
-    if (s < qq) return (int64_t)p.nn[ii * m + s];
-    return s == MT ? ii : (int64_t)-1;
+    if (s < qq) return p.nn[ii * m + s];
+    return s == MT ? (int)ii : -1;
   };
   auto row_of = [&](int64_t it) -> int64_t { return p.row_begin + 2 * it + hh; };
-  // software pipeline: the gather of the next pair of observations is in flight while this one is computed
+  // software pipeline, two deep: the neighbour indices of the pair after the next one and the responses / coordinates of the next
+  // pair (addressed by indices that were loaded one iteration earlier) are in flight while this pair is computed — a gather whose
+  // data loads wait for its own index load stalls the warp for a full memory latency (12 % of the samples of the first version)
   int64_t it = gwarp;
   int64_t i = row_of(it);
   bool active = i < p.row_end;
-  int64_t s_lo = -1, s_hi = -1;
+  int s_lo = -1, s_hi = -1, sn_lo = -1, sn_hi = -1;
   double2 c_lo = make_double2(0., 0.), c_hi = c_lo;
   double y_lo = 0., y_hi = 0.;
-  auto gather = [&](int64_t ii, bool act) {
-    s_lo = -1; s_hi = -1; y_lo = 0.; y_hi = 0.;
+  auto fetch_idx = [&](int64_t ii, bool act, int& a_lo, int& a_hi) {
+    a_lo = -1; a_hi = -1;
     if (act) {
-      s_lo = slot_src(ii, hl);
-      s_hi = hl + 16 <= MT ? slot_src(ii, hl + 16) : -1;  // slot 31 does not exist (row 31 = responses)
-      if (s_lo >= 0) { y_lo = p.y[s_lo]; c_lo = *reinterpret_cast<const double2*>(p.coords + s_lo * 2); }
-      if (s_hi >= 0) { y_hi = p.y[s_hi]; c_hi = *reinterpret_cast<const double2*>(p.coords + s_hi * 2); }
+      a_lo = slot_src(ii, hl);
+      a_hi = hl + 16 <= MT ? slot_src(ii, hl + 16) : -1;  // slot 31 does not exist (row 31 = responses)
     }
   };
-  gather(i, active);
+  auto fetch_data = [&]() {  // of the slots named by s_lo / s_hi
+    y_lo = 0.; y_hi = 0.;
+    if (s_lo >= 0) { y_lo = p.y[s_lo]; c_lo = *reinterpret_cast<const double2*>(p.coords + (int64_t)s_lo * 2); }
+    if (s_hi >= 0) { y_hi = p.y[s_hi]; c_hi = *reinterpret_cast<const double2*>(p.coords + (int64_t)s_hi * 2); }
+  };
+  fetch_idx(i, active, s_lo, s_hi);
+  fetch_data();
+  fetch_idx(row_of(it + nwarps), row_of(it + nwarps) < p.row_end, sn_lo, sn_hi);
 
   for (; __any_sync(0xffffffffu, active); ) {
     const int q = i < m ? (int)i : m;
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
     // rounds' dependent FP64 chains (the state of the first version of this kernel).
     constexpr int NR = 2 * (MT / 2);
 #ifndef GPB_NLL2_GROUP
-#define GPB_NLL2_GROUP 10
+#define GPB_NLL2_GROUP 6
 #endif
     constexpr int G = GRAD ? 6 : GPB_NLL2_GROUP;
     static_assert(NR % G == 0, "group size must divide the number of rounds");
@@ -221,8 +228,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
         S[valid ? min(pi, o) * kLd + max(pi, o) : 31 * kLd + hl] = v;
       }
     }
-    // prefetch the next pair's gather (consumed at the top of the next iteration)
-    gather(i_n, active_n);
+    // prefetch: data of the next pair (its indices arrived during the previous iteration), indices of the pair after it
+    s_lo = sn_lo; s_hi = sn_hi;
+    fetch_data();
+    {
+      const int64_t i_n2 = row_of(it_n + nwarps);
+      fetch_idx(i_n2, i_n2 < p.row_end, sn_lo, sn_hi);
+    }
     // diagonal and response row (row 31): S[c][c], S[c][31] = y_c for c <= 30
     S[hl * kLd + hl] = real_lo ? p.diag_nb : 1.;
     S[hl * kLd + (MT + 1)] = yl;
@@ -242,6 +254,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
 
     // ---- right-looking Cholesky with look-ahead, pivots 0..MT
     double Di, lk_lo, lk_hi;
+    double dg_lo = S[hl * kLd + hl], dg_hi = S[(hl + 16) * kLd + hl + 16];  // my diagonals (row 31 has none: never a pivot)
     {
       const double d0 = __shfl_sync(0xffffffffu, lo[0], hbase);
       const double r0 = rsqrt_fast(d0);
@@ -253,10 +266,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
 #pragma unroll
     for (int k = 0; k < MT; ++k) {
       // column k of L is visible in shared memory; lk_* = L[my rows][k].
-      // Pivot chain of column k+1 first, from registers only: the owner of row k+1 (lane k+1 of the half for k+1 < 16, lane k+1-16
-      // otherwise) holds L[k+1][k] itself, so its updated diagonal does not wait for the shared-memory broadcast of the column
-      const double dself = (k + 1 < 16) ? fma(-lk_lo, lk_lo, lo[k + 1]) : fma(-lk_hi, lk_hi, hi[k + 1]);
-      const double dn = (k + 1 < 16) ? __shfl_sync(0xffffffffu, dself, hbase + k + 1) : __shfl_sync(0xffffffffu, dself, hbase + k + 1 - 16);
+      // Pivot chain of column k+1 first, from registers only: every lane keeps the diagonal entries of its own two rows up to date
+      // with its own column values (a[r][r] -= L[r][k]^2 needs nothing from the other lanes), so the next pivot is one DFMA and a
+      // shuffle away from lk — no shared-memory round trip on the chain that serialises the 31 steps
+      dg_lo = fma(-lk_lo, lk_lo, dg_lo);
+      dg_hi = fma(-lk_hi, lk_hi, dg_hi);
+      const double dn = (k + 1 < 16) ? __shfl_sync(0xffffffffu, dg_lo, hbase + k + 1) : __shfl_sync(0xffffffffu, dg_hi, hbase + k + 1 - 16);
       {
         const double m1 = S[k * kLd + k + 1];
         hi[k + 1] -= lk_hi * m1;
@@ -264,10 +279,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
       }
       if (k + 1 == MT) Di = dn;
       const double rn = rsqrt_fast(dn);
-      double lk1_lo = 0.;
-      if (k + 1 < 16) { lk1_lo = lo[k + 1] * rn; S[(k + 1) * kLd + hl] = lk1_lo; }
+      const double lk1_lo = (k + 1 < 16) ? lo[k + 1] * rn : 0.;
       const double lk1_hi = hi[k + 1] * rn;
-      S[(k + 1) * kLd + hl + 16] = lk1_hi;
       // remaining rank-1 updates of step k: columns k+2..MT (pairs; the pair load may touch column MT+1: harmless)
 #pragma unroll
       for (int c = k + 2; c <= MT; c += 2) {
@@ -277,6 +290,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
         if (c < 16) lo[c] -= lk_lo * l2.x;
         if (c + 1 < 16) lo[c + 1] -= lk_lo * l2.y;
       }
+      // column k+1 goes out LAST: a store in front of the loads above would order them behind it (run-time row index: the compiler
+      // cannot tell the two columns apart), i.e. behind the whole pivot chain — with it the next step's pivot would wait for
+      // store -> load -> update of column k+2 instead of running from registers
+      if (k + 1 < 16) S[(k + 1) * kLd + hl] = lk1_lo;
+      S[(k + 1) * kLd + hl + 16] = lk1_hi;
       __syncwarp();
       lk_lo = lk1_lo; lk_hi = lk1_hi;
     }

@@ -251,7 +251,8 @@ def test_full_size_properties_n1e6(lib):
     assert np.abs(yb - (2. * ya - 0.5 * yc)).max() <= 1e-10 * np.abs(ya).max()
     # modes agree with each other on the shared sums
     chk(lib, lib.gpbdev_vecchia_eval(h, cid, C.c_double(pt[0]), C.c_double(pt[1]), 2, P(out1)))
-    assert out1[0] == out2[0] and out1[1] == out2[1]
+    # (the passes run on different grids — resident CTAs per SM differ — so the fixed summation order differs between modes)
+    assert abs(out1[0] - out2[0]) <= 1e-13 * out2[0] and abs(out1[1] - out2[1]) <= 1e-13 * abs(out2[1])
     lib.gpbdev_vecchia_free(h)
 
 
