@@ -16,7 +16,6 @@
 #include "vecchia_factor.cuh"
 #include "vecchia_big.cuh"
 #include "vecchia_nll2.cuh"
-#include "vecchia_nll3.cuh"
 
 namespace {
 
@@ -291,18 +290,14 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
     if (mode == gpb::MODE_STORE) h->factor_stored = true;
     return 0;
   }
-  // likelihood and gradient passes at the headline shape (d = 2, 20 < m <= 30): two observations per warp. NLL / STORE run the
-  // kernel that computes the next pair's covariances inside the factorisation (vecchia_nll3.cuh), GRAD the plain two-observation
-  // kernel (vecchia_nll2.cuh). GPB200_NLL_KERNEL=2: vecchia_nll2 for all three; =1: the one-observation kernel
-  static const int nll_kernel_env = []() { const char* e = std::getenv("GPB200_NLL_KERNEL"); return e ? std::atoi(e) : 0; }();
-  const bool nll1_only = nll_kernel_env == 1;
+  // likelihood and gradient passes at the headline shape (d = 2, 20 < m <= 30): two observations per warp (vecchia_nll2.cuh);
+  // GPB200_NLL_KERNEL=1 keeps the one-observation kernel
+  static const bool nll1_only = []() { const char* e = std::getenv("GPB200_NLL_KERNEL"); return e && std::string(e) == "1"; }();
   if ((mode == gpb::MODE_NLL || mode == gpb::MODE_STORE || (mode == gpb::MODE_GRAD && !latent)) && h->d == 2 && h->m > 20 && !nll1_only) {
     FactorKernel k2 = nullptr;
-    const bool overlap = nll_kernel_env != 2;
 #define GPB_PICK2(COVID)                                                                                                              \
-    k2 = mode == gpb::MODE_NLL ? (overlap ? gpb::vecchia_nll3_kernel<COVID, gpb::MODE_NLL> : gpb::vecchia_nll2_kernel<COVID, gpb::MODE_NLL>)     \
-         : (mode == gpb::MODE_STORE ? (overlap ? gpb::vecchia_nll3_kernel<COVID, gpb::MODE_STORE> : gpb::vecchia_nll2_kernel<COVID, gpb::MODE_STORE>) \
-                                    : gpb::vecchia_nll2_kernel<COVID, gpb::MODE_GRAD>)
+    k2 = mode == gpb::MODE_NLL ? gpb::vecchia_nll2_kernel<COVID, gpb::MODE_NLL>                                                      \
+         : (mode == gpb::MODE_STORE ? gpb::vecchia_nll2_kernel<COVID, gpb::MODE_STORE> : gpb::vecchia_nll2_kernel<COVID, gpb::MODE_GRAD>)
     switch (cov_type) {
       case gpb::COV_EXPONENTIAL: GPB_PICK2(gpb::COV_EXPONENTIAL); break;
       case gpb::COV_MATERN15: GPB_PICK2(gpb::COV_MATERN15); break;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 19 (1 GPU): likelihood / store pass with the next pair's covariance rounds inside the factorisation (vecchia_nll3):
+# round 2, sessions 19-20 (1 GPU): likelihood / store pass with the next pair's covariance rounds inside the factorisation (vecchia_nll3):
 # parity tests, headline timing against the plain two-observation kernel (GPB200_NLL_KERNEL=2), GPBoost iteration
 cd "$(dirname "$0")/../.." && mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_vecchia_gpu.py tests/test_predict_gpu.py -q -m gpu --tb=short 2>&1 | tail -30 | cut -c1-300 > gpurun_out/s19_pytest.log
