@@ -100,6 +100,15 @@ __device__ __forceinline__ double cov_eval_scaled(double d2s, double var, double
 #ifndef GPB_NLL2_BLOCKS
 #define GPB_NLL2_BLOCKS 3
 #endif
+// gradient pass: the range-derivative pair values are parked in the strict upper triangle of the shared matrix buffer (the
+// factorisation only uses column c, rows >= c) instead of 60 registers per lane held across the elimination: the pass fits the
+// register budget of three resident CTAs per SM like the likelihood pass. GPB_NLL2_GRAD_SMEM=0: registers, two CTAs (first version).
+#ifndef GPB_NLL2_GRAD_SMEM
+#define GPB_NLL2_GRAD_SMEM 1
+#endif
+#ifndef GPB_NLL2_GRAD_BLOCKS
+#define GPB_NLL2_GRAD_BLOCKS (GPB_NLL2_GRAD_SMEM ? 3 : 2)
+#endif
 
 // GRAD = true: the gradient pass (MODE_GRAD of vecchia_factor_kernel: adjoint identities dD_k = b^T dSigma~_k b,
 // (dB_k y)_i = -b^T dSigma~_k w~ with b = [-A_i, 1], w~ = [S^-1 y_N, 0]; re_model_template.h:1988-2010, Vecchia_utils.cpp:1636-1652) in
@@ -108,7 +117,8 @@ __device__ __forceinline__ double cov_eval_scaled(double d2s, double var, double
 // (by then free) point buffer. 4 warps x 2 CTAs per SM = 16 observations in flight (one-observation kernel: 12).
 // MODE = MODE_STORE: one back substitution, A_i / D_i^-1 / u_i written like vecchia_factor_kernel<MODE_STORE>.
 template <int COV, int MODE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : GPB_NLL2_BLOCKS) vecchia_nll2_kernel(const FactorArgs p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? GPB_NLL2_GRAD_BLOCKS : GPB_NLL2_BLOCKS) vecchia_nll2_kernel(const FactorArgs p) {
+  constexpr bool GP_SMEM = GPB_NLL2_GRAD_SMEM != 0;
   constexpr bool GRAD = MODE == MODE_GRAD;
   constexpr bool SOLVE = MODE != MODE_NLL;
   static_assert(MODE == MODE_NLL || MODE == MODE_STORE || MODE == MODE_GRAD, "modes: NLL, STORE, GRAD");
@@ -190,10 +200,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
 #endif
     constexpr int G = GRAD ? 6 : GPB_NLL2_GROUP;
     static_assert(NR % G == 0, "group size must divide the number of rounds");
-    double gp[GRAD ? NR : 1];
+    double gp[(GRAD && !GP_SMEM) ? NR : 1];
 #pragma unroll
     for (int r0 = 0; r0 < NR; r0 += G) {
-      double val[G];
+      double val[G], gval[(GRAD && GP_SMEM) ? G : 1];
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const int r = r0 + j;
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
         const double d2s = fma(dy, dy, fma(dx, dx, 1e-300));
         double g = 0.;
         val[j] = cov_eval_scaled<COV, GRAD>(d2s, var, logvar, tab, g);
-        if (GRAD) gp[r] = g;
+        if (GRAD) { if (GP_SMEM) gval[j] = g; else gp[r] = g; }
       }
 #pragma unroll
       for (int j = 0; j < G; ++j) {
@@ -224,8 +234,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
         // dummy slots: zero unless the whole warp is free of them; the one padded pair (lane 15, odd rounds) goes to the unused column 31
         const bool keep = ((full ? 1u : 0u) | ((odd ? (unsigned)real_hi : (unsigned)real_lo) & (real_mask >> o) & 1u)) != 0u;  // no branches
         const double v = keep ? val[j] : 0.;
-        if (GRAD) gp[r] = (keep && valid) ? gp[r] : 0.;
         S[valid ? min(pi, o) * kLd + max(pi, o) : 31 * kLd + hl] = v;
+        if (GRAD) {  // derivative value: 0 for padded / dummy pairs; pair (a, b), a < b -> column b, row a (padded pair: column 31)
+          if (GP_SMEM) S[valid ? max(pi, o) * kLd + min(pi, o) : 31 * kLd + 16 + hl] = keep ? gval[j] : 0.;
+          else gp[r] = (keep && valid) ? gp[r] : 0.;
+        }
       }
     }
     // prefetch: data of the next pair (its indices arrived during the previous iteration), indices of the pair after it
@@ -293,8 +306,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
       // column k+1 goes out LAST: a store in front of the loads above would order them behind it (run-time row index: the compiler
       // cannot tell the two columns apart), i.e. behind the whole pivot chain — with it the next step's pivot would wait for
       // store -> load -> update of column k+2 instead of running from registers
-      if (k + 1 < 16) S[(k + 1) * kLd + hl] = lk1_lo;
-      S[(k + 1) * kLd + hl + 16] = lk1_hi;
+      // (rows above the diagonal are not stored: in the gradient pass those slots hold the derivative values)
+      if (k + 1 < 16 && (!(GRAD && GP_SMEM) || hl >= k + 1)) S[(k + 1) * kLd + hl] = lk1_lo;
+      if (!(GRAD && GP_SMEM) || k + 1 <= 16 || hl + 16 >= k + 1) S[(k + 1) * kLd + hl + 16] = lk1_hi;
       __syncwarp();
       lk_lo = lk1_lo; lk_hi = lk1_hi;
     }
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? 2 : G
         int o = pi + t;
         if (o >= P) o -= P;
         if (pi >= P) o = 0;
-        const double g = gp[r];  // 0 for padded / inactive pairs
+        const double g = GP_SMEM ? ((pi < P) ? S[max(pi, o) * kLd + min(pi, o)] : 0.) : gp[r];  // 0 for padded / inactive pairs
         const double bo = xb[o], wo = xwt[o];
         const double bm = odd ? b_hi : b_lo, wm = odd ? w_hi : w_lo;
         bgb += g * (bm * bo);
