@@ -1028,6 +1028,18 @@ __global__ void sum_stage1_kernel(const double* __restrict__ x, int64_t n, doubl
   for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
+// deterministic dot product: fixed block partials (sum_stage2_kernel finishes it)
+__global__ void dot_stage1_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, double* __restrict__ part) {
+  __shared__ double sh[256];
+  double s = 0.;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t b = (int64_t)blockIdx.x * per, e = min(b + per, n);
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) s = fma(x[i], y[i], s);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
 __global__ void sum_stage2_kernel(const double* __restrict__ part, int np, double* __restrict__ out) {
   __shared__ double sh[256];
   double s = 0.;
@@ -1930,6 +1942,32 @@ int gpbdev_vec_add_const(gpbdev_tree_t h, double* a_dev, double c, int64_t n) {
   add_const_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(a_dev, c, n);
   TCUDA(cudaGetLastError());
   h->launches += 1;
+  return 0;
+}
+
+int gpbdev_vec_dot(gpbdev_tree_t h, const double* a_dev, const double* b_dev, int64_t n, double* out_host) {
+  if (!h || !a_dev || !b_dev || !out_host) return tfail("gpbdev_vec_dot: null argument");
+  TCUDA(cudaSetDevice(h->device));
+  const int nb1 = (int)std::min<int64_t>(1023, (n + 4095) / 4096);
+  dot_stage1_kernel<<<nb1, 256, 0, h->stream>>>(a_dev, b_dev, n, h->sum_part);
+  sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->sum_part, nb1, h->sum_part + 1023);
+  TCUDA(cudaGetLastError());
+  TCUDA(cudaMemcpyAsync(h->scalar_host, h->sum_part + 1023, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  TCUDA(cudaStreamSynchronize(h->stream));
+  *out_host = h->scalar_host[0];
+  h->launches += 2;
+  return 0;
+}
+int gpbdev_vec_zero(gpbdev_tree_t h, double* a_dev, int64_t n) {
+  if (!h || !a_dev) return tfail("gpbdev_vec_zero: null argument");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaMemsetAsync(a_dev, 0, sizeof(double) * n, h->stream));
+  return 0;
+}
+int gpbdev_vec_copy(gpbdev_tree_t h, double* dst_dev, const double* src_dev, int64_t n) {
+  if (!h || !dst_dev || !src_dev) return tfail("gpbdev_vec_copy: null argument");
+  TCUDA(cudaSetDevice(h->device));
+  TCUDA(cudaMemcpyAsync(dst_dev, src_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
   return 0;
 }
 

@@ -77,7 +77,8 @@ Booster::Booster(const Dataset* train, const char* parameters, REModel* re_model
   leaves_newton_update_ = params_.GetBool("leaves_newton_update", false);
   if (leaves_newton_update_ && re_model_ == nullptr)
     Fatal("leaves_newton_update can only be 'true' if Gaussian process boosting is done ");  // c_api.cpp:226-228
-  if (params_.GetBool("line_search_step_length", false)) Fatal("line_search_step_length is not supported by the B200 booster yet");
+  line_search_step_length_ = params_.GetBool("line_search_step_length", false);
+  if (line_search_step_length_ && re_model_ == nullptr) line_search_step_length_ = false;  // gbdt.cpp:480: only with a GP model
   gpbdev_tree_config cfg;
   cfg.num_leaves = num_leaves_;
   cfg.min_data_in_leaf = params_.GetInt("min_data_in_leaf", 20, {"min_data_per_leaf", "min_data", "min_child_samples"});
@@ -212,6 +213,8 @@ Booster::~Booster() {
     gpbdev_vec_free(learner_, score_dev_);
     gpbdev_vec_free(learner_, label_dev_);
     gpbdev_vec_free(learner_, grad_dev_);
+    if (new_score_dev_) gpbdev_vec_free(learner_, new_score_dev_);
+    if (new_score_aux_dev_) gpbdev_vec_free(learner_, new_score_aux_dev_);
     gpbdev_tree_free(learner_);
   }
 }
@@ -276,8 +279,31 @@ bool Booster::TrainOneIter() {
     TreeCheck(gpbdev_tree_leaf_indices(learner_, &leaf_of_row));
     re_model_->NewtonUpdateLeafValuesDevice(leaf_of_row, nl, grad_dev_, tree->leaf_value.data());
   }
+  double step = 1.;
+  if (line_search_step_length_) {
+    // gbdt.cpp:480-492 -> REModelTemplate::OptimLinRegrCoefCovPar(find_learning_rate_for_GPBoost_algo), re_model_template.h:1163-1181:
+    // Gaussian likelihood, closed form  lr = -(F - y)' Psi^-1 f / (f' Psi^-1 f),  f = the new tree's (unshrunk) training predictions.
+    // (F - y)' Psi^-1 f = f' [Psi^-1 (F - y)]: the bracket is the gradient vector already in HBM; Psi^-1 f costs one more pass
+    // over the factor (REModel::CalcGradientDevice — like the reference's SetY(f) it leaves f as the engine's response)
+    if (!re_model_->DevicePathReady()) Fatal("line_search_step_length: no device-resident path for this GP model");
+    if (new_score_dev_ == nullptr) {
+      TreeCheck(gpbdev_vec_alloc(learner_, &new_score_dev_, n_));
+      TreeCheck(gpbdev_vec_alloc(learner_, &new_score_aux_dev_, n_));
+    }
+    TreeCheck(gpbdev_vec_zero(learner_, new_score_dev_, n_));
+    TreeCheck(gpbdev_tree_add_score(learner_, tree->leaf_value.data(), nl, new_score_dev_ + row_begin_, nullptr));
+    if (sharded_) TreeCheck(gpbdev_vec_allgather_rows(learner_, new_score_dev_, n_, row_begin_, row_end_));
+    double numer = 0., denom = 0.;
+    TreeCheck(gpbdev_vec_dot(learner_, new_score_dev_, grad_dev_, n_, &numer));
+    TreeCheck(gpbdev_vec_copy(learner_, new_score_aux_dev_, new_score_dev_, n_));
+    TreeCheck(gpbdev_tree_sync(learner_));
+    re_model_->CalcGradientDevice(new_score_aux_dev_);
+    TreeCheck(gpbdev_vec_dot(learner_, new_score_dev_, new_score_aux_dev_, n_, &denom));
+    step = -numer / denom;  // both inner products carry the same 1 / sigma^2
+    for (int i = 0; i < nl; ++i) tree->leaf_value[i] *= step;  // Tree::Shrinkage(optimal_lr_)
+  }
   for (int i = 0; i < nl; ++i) tree->leaf_value[i] *= learning_rate_;  // Tree::Shrinkage
-  tree->shrinkage = learning_rate_;
+  tree->shrinkage = step * learning_rate_;
   TreeCheck(gpbdev_tree_add_score(learner_, tree->leaf_value.data(), nl, score_dev_ + row_begin_, nullptr));  // UpdateScore
   if (sharded_) TreeCheck(gpbdev_vec_allgather_rows(learner_, score_dev_, n_, row_begin_, row_end_));  // scores stay replicated
   if (std::fabs(init_score) > (double)1e-15f) {  // Tree::AddBias (tree.h): stored model only

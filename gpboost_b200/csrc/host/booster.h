@@ -74,6 +74,9 @@ class Booster {
   bool boost_from_average_ = true;
   bool train_gp_model_cov_pars_ = true;
   bool leaves_newton_update_ = false;   // config.h: Newton step for the leaf values after the structure search (GPBoost only)
+  bool line_search_step_length_ = false;  // config.h:177: step length of every tree from a line search on the GP likelihood (GPBoost only)
+  double* new_score_dev_ = nullptr;     // the new tree's unshrunk predictions / Psi^-1 of them (line search scratch, n each)
+  double* new_score_aux_dev_ = nullptr;
   gpbdev_tree_t learner_ = nullptr;
   double *score_dev_ = nullptr, *label_dev_ = nullptr, *grad_dev_ = nullptr;
   std::vector<double> host_buf_;

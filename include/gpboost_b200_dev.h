@@ -257,6 +257,10 @@ GPBDEV_EXPORT int gpbdev_vec_download(gpbdev_tree_t h, double* dst_host, const d
 /* out = a - b: the L2 objective's gradient score - label (regression_objective.hpp:158-162) */
 GPBDEV_EXPORT int gpbdev_vec_sub(gpbdev_tree_t h, const double* a_dev, const double* b_dev, double* out_dev, int64_t n);
 GPBDEV_EXPORT int gpbdev_vec_add_const(gpbdev_tree_t h, double* a_dev, double c, int64_t n);
+/* a . b in a fixed summation order (the line search's two inner products: re_model_template.h:1165-1178), zero fill, copy */
+GPBDEV_EXPORT int gpbdev_vec_dot(gpbdev_tree_t h, const double* a_dev, const double* b_dev, int64_t n, double* out_host);
+GPBDEV_EXPORT int gpbdev_vec_zero(gpbdev_tree_t h, double* a_dev, int64_t n);
+GPBDEV_EXPORT int gpbdev_vec_copy(gpbdev_tree_t h, double* dst_dev, const double* src_dev, int64_t n);
 /* data-parallel mode: this learner holds a contiguous shard of the rows; the root gradient sum and the smaller child's histogram of
  * every split are summed over the ranks through `fn` on the learner's stream (DataParallelTreeLearner,
  * src/LightGBM/treelearner/data_parallel_tree_learner.cpp:155-175). n_global = rows over all ranks. */

@@ -167,6 +167,31 @@ def test_gpboost_iteration_matches_reference_golden(lib, tree_golden):
     assert np.abs(score[:64] - np.array(rec["score_head"])).max() <= 2e-3 * np.abs(rec["score_head"]).max()
 
 
+@pytest.mark.parametrize("name", ["gpboost_vecchia_line_search", "gpboost_vecchia_newton_line_search"])
+def test_gpboost_line_search_step_length_matches_reference_golden(lib, tree_golden, name):
+    """line_search_step_length (gbdt.cpp:480-492, re_model_template.h:1163-1181): every tree is scaled by
+    -(F - y)' Psi^-1 f / f' Psi^-1 f before the learning rate, two inner products against the device-resident factor. The reference only
+    supports it with trained covariance parameters (it reads F - y from its last OptimCovPar call), so the comparison carries the
+    optimiser tolerance of test_gpboost_iteration_matches_reference_golden: first tree's structure bit-exact, its values (which contain
+    the first step length) to 1e-3, the later step lengths (the stored shrinkage) to 2 %. After a Newton leaf update the step is 1."""
+    rec = [r for r in tree_golden["cases"] if r["spec"]["name"] == name][0]
+    trees, score, gp, _, _ = _run_product(rec["spec"])
+    assert len(trees) == len(rec["trees"])
+    g0 = rec["trees"][0]
+    assert np.array_equal(trees[0]["split_feature"], np.array(g0["split_feature"])) and np.array_equal(trees[0]["threshold"], np.array(g0["threshold"]))
+    assert np.array_equal(trees[0]["leaf_count"], np.array(g0["leaf_count"]))
+    assert np.max(np.abs(trees[0]["leaf_value"] - np.array(g0["leaf_value"]))) <= 1e-3 * np.max(np.abs(g0["leaf_value"]))
+    for t, g in zip(trees[1:], rec["trees"][1:]):
+        assert abs(t["shrinkage"] - g["shrinkage"]) <= 2e-2 * abs(g["shrinkage"]), (t["shrinkage"], g["shrinkage"])
+    if rec["spec"].get("newton"):
+        assert all(abs(t["shrinkage"] - 0.1) <= 1e-6 for t in trees[1:])
+    else:
+        assert all(abs(t["shrinkage"] - 0.1) > 1e-3 for t in trees[1:])  # the step length is not a no-op
+    cp = gp.get_cov_pars()
+    assert np.all(np.abs(cp - np.array(rec["cov_pars"])) <= 1e-2 * np.abs(rec["cov_pars"])), (cp, rec["cov_pars"])
+    assert np.abs(score[:64] - np.array(rec["score_head"])).max() <= 5e-3 * np.abs(rec["score_head"]).max()
+
+
 @pytest.mark.parametrize("name", ["gpboost_vecchia_fixed_pars", "gpboost_vecchia_newton", "gpboost_vecchia_newton_many_leaves"])
 def test_gpboost_fixed_parameters_all_trees_match_reference(lib, tree_golden, name):
     """GPBoost iterations at fixed covariance parameters (train_gp_model_cov_pars = false): gradient Psi^-1 (F - y) / sigma^2 from the

@@ -18,6 +18,13 @@ CASES = [
      "gp": True, "num_neighbors": 20, "train_cov": False, "init_cov_pars": [0.12, 0.3, 0.15], "newton": True},
     {"name": "gpboost_vecchia_newton_many_leaves", "n": 6000, "F": 4, "kind": "real", "num_leaves": 80, "min_data_in_leaf": 10, "num_iter": 2, "seed": 10,
      "gp": True, "num_neighbors": 10, "train_cov": False, "init_cov_pars": [0.1, 0.4, 0.1], "newton": True},
+    # step length of every tree from the closed-form line search -(F - y)' Psi^-1 f / f' Psi^-1 f (line_search_step_length),
+    # alone and behind the Newton leaf update. The covariance parameters are trained: the reference takes F - y from its last
+    # OptimCovPar call (re_model_template.h:1211-1214) and reads an empty vector when train_gp_model_cov_pars = false.
+    {"name": "gpboost_vecchia_line_search", "n": 4000, "F": 6, "kind": "real", "num_leaves": 12, "min_data_in_leaf": 20, "num_iter": 3, "seed": 11,
+     "gp": True, "num_neighbors": 20, "line_search": True},
+    {"name": "gpboost_vecchia_newton_line_search", "n": 4000, "F": 6, "kind": "real", "num_leaves": 12, "min_data_in_leaf": 20, "num_iter": 3, "seed": 12,
+     "gp": True, "num_neighbors": 20, "newton": True, "line_search": True},
 ]
 
 
@@ -55,6 +62,8 @@ def booster_params(spec, reference):
         p["train_gp_model_cov_pars"] = False
     if spec.get("newton"):
         p["leaves_newton_update"] = True
+    if spec.get("line_search"):
+        p["line_search_step_length"] = True
     if reference:  # make the reference's summation order deterministic (column-wise histograms, fixed threads)
         p.update({"force_col_wise": True, "deterministic": True, "num_threads": 4})
     return p
