@@ -273,13 +273,13 @@ def time_laplace(n, lib, threads, reps=1, barrier=None):
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the factor kernel (NLL, n=1e6, one launch) from the committed
-    `ncu --set full` capture summary (profiles/r01_ncu_raw_summary.txt); None when the file is not there."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel (n=1e6, one launch) from the committed
+    `ncu --set full` capture summary (profiles/r02_ncu_raw_summary.txt, section prof_nll2); None when the file is not there."""
     try:
         tot, inside = 0.0, False
-        for ln in open(os.path.join(ROOT, "profiles", "r01_ncu_raw_summary.txt")):
+        for ln in open(os.path.join(ROOT, "profiles", "r02_ncu_raw_summary.txt")):
             if ln.startswith("=="):
-                inside = "prof_factor" in ln
+                inside = "prof_nll2" in ln
             elif inside and ("dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln):
                 val, unit = ln.split("=")[1].split()[:2]
                 tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
@@ -512,7 +512,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": ncu_traffic_bytes() if world == 1 else None, "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_ncu_raw_summary.txt)",
+                         "traffic": ncu_traffic_bytes() if world == 1 else None, "traffic_unit": "bytes per launch (ncu --set full, profiles/r02_ncu_raw_summary.txt)",
                          "kernel": "vecchia_nll2_kernel<MATERN15> (two observations per warp)", "kernel_ms": dev_ms,
                          "algorithmic_bytes_per_obs": ALGO_BYTES_PER_OBS, "peak_source": peak_src,
                          "note": "this kernel is FP64-pipe bound, not HBM bound (SURVEY §8d, DESIGN.md): see roofline_fp64"},
