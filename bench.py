@@ -169,7 +169,7 @@ def hist_roofline(booster):
         return {"error": L.LGBM_GetLastError().decode()}
     hbm_peak, src = measured_hbm_peak()
     ach = rows.value * row_bytes.value / (ms.value * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "hist3_kernel<plain counters> (root pass, all rows of this rank)", "kernel_ms": ms.value,
+    return {"bound": "hbm", "kernel": "hist3_kernel (root pass, all rows of this rank)", "kernel_ms": ms.value,
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
             "algorithmic_bytes_per_row": row_bytes.value, "rows": rows.value, "peak_source": src,
             "note": "shared-memory (LSU) bound: one read-modify-write per (row, feature) on private fp64 histograms"}
