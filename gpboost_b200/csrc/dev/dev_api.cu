@@ -188,6 +188,11 @@ struct gpbdev_vecchia {
   int grid_cap = 0;
   int64_t launches = 0;
   bool factor_stored = false;
+  // parameters of the stored factor and of the last pass (whose sums sit in `sums`): a STORE request for exactly this state is
+  // already satisfied — the gradient pass of the two-observation kernel writes A, D^-1, u as well once the buffers exist
+  int stored_cov = -1, last_cov = -1;
+  bool stored_latent = false, last_latent = false;
+  double stored_var = 0., stored_range = 0., last_var = 0., last_range = 0.;
   int knn_replayed = 0;  // queries whose neighbour set was re-derived by the exact replay of the reference walk
   std::vector<int32_t> nn_host;  // kept for the lazy CSC build
 };
@@ -243,9 +248,19 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   if (mode < 0 || mode > 3) return fail("gpbdev_vecchia_eval: unknown mode");
   if (!(var > 0.) || !(range > 0.)) return fail("gpbdev_vecchia_eval: covariance parameters must be positive");
   CUDA_TRY(cudaSetDevice(h->device));
+  // GPBoost iteration: OptimCovPar's last accepted trial was a gradient pass at the final parameters on this response, and
+  // CalcGradient asks for the factor at the same state right after (regression_objective.hpp:164-165): nothing to recompute.
+  // GPB200_GRAD_STORES=0 switches the shortcut (and the extra stores of the gradient pass) off.
+  static const bool grad_stores = []() { const char* e = std::getenv("GPB200_GRAD_STORES"); return !(e && std::string(e) == "0"); }();
+  if (mode == gpb::MODE_STORE && !latent && grad_stores && h->factor_stored && h->stored_cov == cov_type && h->stored_latent == latent &&
+      h->stored_var == var && h->stored_range == range && h->last_cov == cov_type && h->last_latent == latent && h->last_var == var &&
+      h->last_range == range)
+    return 0;
   if (mode == gpb::MODE_STORE || mode == gpb::MODE_STORE_GRAD) {
     if (ensure_store_buffers(h)) return -1;
   }
+  h->last_cov = cov_type; h->last_latent = latent; h->last_var = var; h->last_range = range;
+  if (mode == gpb::MODE_STORE || mode == gpb::MODE_STORE_GRAD) { h->stored_cov = cov_type; h->stored_latent = latent; h->stored_var = var; h->stored_range = range; }
   if (mode == gpb::MODE_STORE_GRAD && !h->dA) {
     CUDA_TRY(cudaMalloc(&h->dA, sizeof(double) * h->n * h->m));
     CUDA_TRY(cudaMalloc(&h->dD, sizeof(double) * h->n));
@@ -255,6 +270,7 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
   gpb::FactorArgs a;
   a.coords = h->coords; a.nn = h->nn; a.y = h->y;
   a.A = h->A; a.Dinv = h->Dinv; a.w = h->u;
+  if (mode == gpb::MODE_GRAD && !grad_stores) a.A = nullptr;  // (only the two-observation gradient pass looks at it)
   a.partials = h->partials;
   a.n = h->n; a.row_begin = h->row_begin; a.row_end = h->row_end;
   a.m = h->m; a.d = h->d; a.var = var; a.range = range;
@@ -321,6 +337,10 @@ int launch_eval(gpbdev_vecchia* h, int cov_type, double var, double range, int m
       if (h->allreduce(h->allreduce_ctx, h->sums, gpb::kNumAcc, (void*)h->stream)) return fail("gpbdev_vecchia_eval: device all-reduce failed");
     }
     if (mode == gpb::MODE_STORE) h->factor_stored = true;
+    if (mode == gpb::MODE_GRAD && a.A != nullptr) {  // the pass also wrote A, D^-1, u (vecchia_nll2_kernel<GRAD>)
+      h->factor_stored = true;
+      h->stored_cov = cov_type; h->stored_latent = false; h->stored_var = var; h->stored_range = range;
+    }
     return 0;
   }
   FactorKernel k = pick_kernel(cov_type, mode, h->d, h->m);

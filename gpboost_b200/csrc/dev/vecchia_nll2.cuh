@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MODE == MODE_GRAD ? GPB_N
           xa_hi -= l_hi * fa; xw_hi -= l_hi * fw;
         }
       }
-      if (MODE == MODE_STORE && was_active) {
+      // (the gradient pass writes the factor as well when the store buffers exist: the GPBoost iteration asks for it right after)
+      if ((MODE == MODE_STORE || (GRAD && p.A != nullptr)) && was_active) {
         if (hl < m) p.A[i * m + hl] = hl < q ? xa_lo : 0.;
         if (hl + 16 < m) p.A[i * m + hl + 16] = hl + 16 < q ? xa_hi : 0.;
         if (hl == 0) { const double Dinv_i = 1. / Di; p.Dinv[i] = Dinv_i; p.w[i] = r_over_sd * sqrt(Di) * Dinv_i; }
