@@ -229,7 +229,7 @@ void Booster::Boosting() {
       // writes the gradient back in place (both calls return with their stream synchronised)
       TreeCheck(gpbdev_tree_sync(learner_));
       if (train_gp_model_cov_pars_) re_model_->OptimCovParDevice(grad_dev_, true, true);
-      re_model_->CalcGradientDevice(grad_dev_);
+      re_model_->CalcGradientDevice(grad_dev_, /*response_is_current=*/train_gp_model_cov_pars_);
     } else {  // first iteration (initial covariance parameters need the response on the host) / backends without a device entry
       TreeCheck(gpbdev_vec_download(learner_, host_buf_.data(), grad_dev_, n_));
       if (train_gp_model_cov_pars_) re_model_->OptimCovPar(host_buf_.data(), nullptr, true, true);

@@ -775,16 +775,18 @@ void REModel::CalcGradient(double* y, const double* fixed_effects, bool /*calc_c
   for (int32_t i = 0; i < num_data_; ++i) y[i] *= inv_s2;
 }
 
-void REModel::CalcGradientDevice(double* y_dev) {
+void REModel::CalcGradientDevice(double* y_dev, bool response_is_current) {
   if (!gauss_) Fatal("CalcGradient for likelihood '" + likelihood_ + "' is not built on the device yet");
   if (y_dev == nullptr) Fatal("Check failed: y != nullptr");
   if (!DevicePathReady()) Fatal("CalcGradientDevice: no device-resident path for this model state (use CalcGradient)");
   if (grouped_) {
-    GrpCheck(gpbdev_grouped_set_y_device(grouped_, y_dev));
+    if (!response_is_current) GrpCheck(gpbdev_grouped_set_y_device(grouped_, y_dev));
     GrpCheck(gpbdev_grouped_yaux_device(grouped_, cov_pars_[1], 1. / cov_pars_[0], y_dev));
     return;
   }
-  DevCheck(gpbdev_vecchia_set_y_device(engine_, y_dev));
+  // (with the response still installed, a store request at the parameters of the optimiser's last gradient pass costs no launch:
+  // that pass wrote A, D^-1 and u already — gpbdev_vecchia_eval)
+  if (!response_is_current) DevCheck(gpbdev_vecchia_set_y_device(engine_, y_dev));
   DevicePass(cov_pars_[1], cov_pars_[2], GPBDEV_MODE_STORE);
   DevCheck(gpbdev_vecchia_yaux_device(engine_, y_dev, 1. / cov_pars_[0]));
 }

@@ -52,7 +52,9 @@ class REModel {
   // regression_objective.hpp:164-165): y_dev is a device pointer to n doubles in original order, complete on the
   // caller's side (the caller synchronised its stream). No host copy of the response is made.
   void OptimCovParDevice(const double* y_dev, bool called_in_GPBoost_algorithm, bool reuse_learning_rates_from_previous_call);
-  void CalcGradientDevice(double* y_dev);
+  // response_is_current: y_dev is the vector the last OptimCovParDevice call installed (the boosting objective calls both on the same
+  // F - y, regression_objective.hpp:164-165): it is not installed again, and the factor of the optimiser's last gradient pass is reused
+  void CalcGradientDevice(double* y_dev, bool response_is_current = false);
   bool DevicePathReady() const;
   // REModel::NewtonUpdateLeafValues (re_model.cpp:1298-1310 -> re_model_template.h:4982-5063), device-resident: leaf ids and the
   // gradient of the tree that was just grown stay in HBM; only the L x L system comes to the host. After CalcGradient*.
